@@ -1,0 +1,390 @@
+/* pandaseq_b200.h -- C ABI of libpandaseq_b200.so
+ *
+ * A Blackwell (sm_100a) implementation of ONE path of PANDAseq: what happens
+ * behind panda_assembler_assemble() -- primer location, k-mer seeded overlap
+ * selection, and reconstruction of the merged read with posterior qualities,
+ * for the simple_bayesian / pear / rdp_mle / flash scoring algorithms.
+ *
+ * Two layers, both plain C (no C++/torch types cross this boundary):
+ *
+ *   1. panda_*  -- the reference's own object API for this path, same names,
+ *      argument meaning and error behaviour, so a program written against
+ *      <pandaseq.h> links against this library for assembling pairs.  Each
+ *      declaration cites the reference declaration/definition it replaces.
+ *      The structs below are ABI-compatible with the reference's (they have to
+ *      be: callers allocate panda_qual arrays and read panda_result_seq).
+ *
+ *   2. pb_*  -- the batch layer the panda_* calls sit on: a device context, a
+ *      flat batch format, and launch entry points that take either host
+ *      buffers (copies inside) or device pointers (for callers that already
+ *      keep reads in HBM, e.g. bench.py via torch allocations).
+ *
+ * There is no CPU fallback: every entry point that computes needs a CUDA device
+ * and returns an error (NULL / negative pb_status) without one.
+ */
+#ifndef PANDASEQ_B200_H
+#define PANDASEQ_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ======================================================================
+ * Shared data types (ABI-compatible with the reference)
+ * ====================================================================== */
+
+/* pandaseq-common.h:176 -- 4-bit one-hot IUPAC code in a char: A=1 C=2 G=4 T=8,
+ * degenerate = OR, N = 15, 0 = invalid (pandaseq-nt.h:35-51). */
+typedef char panda_nt;
+#define PANDA_NT_Z ((panda_nt) 0)
+#define PANDA_NT_A ((panda_nt) 1)
+#define PANDA_NT_C ((panda_nt) 2)
+#define PANDA_NT_G ((panda_nt) 4)
+#define PANDA_NT_T ((panda_nt) 8)
+#define PANDA_NT_N ((panda_nt) 15)
+
+/* pandaseq-common.h:210-219 */
+typedef struct {
+	panda_nt nt;
+	char qual;
+} panda_qual;
+
+/* pandaseq-common.h:224-233 */
+typedef struct {
+	panda_nt nt;
+	double p; /* log probability that the base is right */
+} panda_result;
+
+#define PANDA_TAG_LEN 50
+/* pandaseq-common.h:238-247 (368 bytes; carried through, never interpreted here) */
+typedef struct {
+	char instrument[100];
+	char run[100];
+	char flowcell[100];
+	int lane;
+	int tile;
+	int x;
+	int y;
+	char tag[PANDA_TAG_LEN];
+} panda_seq_identifier;
+
+/* pandaseq-common.h:277-330 */
+typedef struct {
+	double quality;
+	size_t degenerates;
+	panda_seq_identifier name;
+	panda_result *sequence;
+	size_t sequence_length;
+	panda_qual const *forward;
+	size_t forward_length;
+	panda_qual const *reverse;
+	size_t reverse_length;
+	size_t forward_offset;
+	size_t reverse_offset;
+	size_t overlap_mismatches;
+	size_t overlaps_examined;
+	size_t overlap;
+	double estimated_overlap_probability;
+} panda_result_seq;
+
+typedef struct panda_algorithm *PandaAlgorithm;
+typedef const struct panda_algorithm_class *PandaAlgorithmClass;
+typedef struct panda_assembler *PandaAssembler;
+typedef struct panda_log_proxy *PandaLogProxy; /* accepted and ignored: logging is out of scope */
+
+/* pandaseq-common.h:335-340, 366-397, 402-403 */
+typedef PandaAlgorithm (*PandaAlgorithmCreate) (const char *args);
+typedef double (*PandaComputeMatch) (void *private_data, bool match, char a, char b);
+typedef double (*PandaComputeOverlap) (void *private_data, const panda_qual *forward, size_t forward_length,
+                                       const panda_qual *reverse, size_t reverse_length, size_t overlap);
+typedef void (*PandaDestroy) (void *user_data);
+/* pandaseq-common.h:481-497 -- pull source; arrays valid until the next call */
+typedef bool (*PandaNextSeq) (panda_seq_identifier *id, const panda_qual **forward, size_t *forward_length,
+                              const panda_qual **reverse, size_t *reverse_length, void *user_data);
+/* pandaseq-common.h:499-507 */
+typedef bool (*PandaOutputSeq) (const panda_result_seq *sequence, void *user_data);
+/* pandaseq-common.h:408-426 */
+typedef void (*PandaFailAlign) (PandaAssembler assembler, const panda_seq_identifier *id,
+                                const panda_qual *forward, size_t forward_length,
+                                const panda_qual *reverse, size_t reverse_length, void *user_data);
+/* pandaseq-common.h:342-354 -- the shape panda_diff() takes for control/experiment */
+typedef const panda_result_seq *(*PandaAssemble) (void *user_data, panda_seq_identifier *id,
+                                                  const panda_qual *forward, size_t forward_length,
+                                                  const panda_qual *reverse, size_t reverse_length);
+
+/* pandaseq-common.h:594-605.  The two function pointers are HOST functions; the
+ * device path never calls them.  It dispatches on class identity to the four
+ * built-in device scorers and refuses any other class (PB_ERR_UNSUPPORTED). */
+struct panda_algorithm_class {
+	size_t data_size;
+	const char *name;
+	PandaAlgorithmCreate create;
+	PandaDestroy data_destroy;
+	PandaComputeOverlap overlap_probability;
+	PandaComputeMatch match_probability;
+	const double prob_unpaired;
+};
+
+#define PANDA_API 3
+#define PANDA_DEFAULT_NUM_KMERS 2
+/* misc.c:36-39; configure.ac:8 */
+size_t panda_max_len(void);
+#define PANDA_MAX_LEN (panda_max_len())
+
+/* ======================================================================
+ * Layer 1a: algorithms (pandaseq-algorithm.h:33-228, algo.c:27-133)
+ * ====================================================================== */
+extern PandaAlgorithmClass *panda_algorithms;           /* algo.c:85, sorted by name */
+extern size_t panda_algorithms_length;                  /* algo.c:86 */
+void panda_algorithm_register(PandaAlgorithmClass clazz);               /* algo.c:95-110 */
+PandaAlgorithm panda_algorithm_new(PandaAlgorithmClass clazz);          /* algo.c:73-83 */
+PandaAlgorithmClass panda_algorithm_class(PandaAlgorithm algo);         /* algo.c:38-41 */
+void *panda_algorithm_data(PandaAlgorithm algo);                        /* algo.c:33-36 */
+double panda_algorithm_quality_compare(PandaAlgorithm algorithm, const panda_qual *a, const panda_qual *b); /* algo.c:26-31 */
+bool panda_algorithm_is_a(PandaAlgorithm algo, PandaAlgorithmClass clazz);  /* algo.c:43-47 */
+PandaAlgorithm panda_algorithm_ref(PandaAlgorithm algo);                /* algo.c:49-59 */
+void panda_algorithm_unref(PandaAlgorithm algo);                        /* algo.c:61-83 */
+
+extern const struct panda_algorithm_class panda_algorithm_simple_bayes_class; /* algo_simple_bayes.c:100-108 */
+PandaAlgorithm panda_algorithm_simple_bayes_new(void);                  /* algo_simple_bayes.c:110-115 */
+double panda_algorithm_simple_bayes_get_error_estimation(PandaAlgorithm algorithm); /* :117-124 */
+void panda_algorithm_simple_bayes_set_error_estimation(PandaAlgorithm algorithm, double q); /* :126-135 */
+
+extern const struct panda_algorithm_class panda_algorithm_pear_class;   /* algo_pear.c:89-97 */
+PandaAlgorithm panda_algorithm_pear_new(void);                          /* algo_pear.c:99-104 */
+double panda_algorithm_pear_get_random_base_log_p(PandaAlgorithm algorithm); /* :114-121 */
+void panda_algorithm_pear_set_random_base_log_p(PandaAlgorithm algorithm, double log_p); /* :106-112 */
+
+extern const struct panda_algorithm_class panda_algorithm_rdp_mle_class; /* algo_rdp_mle.c:84-92 */
+PandaAlgorithm panda_algorithm_rdp_mle_new(void);                        /* algo_rdp_mle.c:94-98 */
+
+extern const struct panda_algorithm_class panda_algorithm_flash_class;   /* algo_flash.c:91-99 */
+PandaAlgorithm panda_algorithm_flash_new(void);                          /* algo_flash.c:101-104 */
+
+/* ======================================================================
+ * Layer 1b: assembler (pandaseq-assembler.h:37-405, assembler.c, assembler_support.c)
+ * ====================================================================== */
+/* assembler_support.c:26-99.  `logger` may be NULL.  Returns NULL when no CUDA
+ * device is usable or num_kmers != 2 (the reference's table indexing is only
+ * self-consistent for 2). */
+PandaAssembler panda_assembler_new(PandaNextSeq next, void *next_data, PandaDestroy next_destroy, PandaLogProxy logger);
+PandaAssembler panda_assembler_new_kmer(PandaNextSeq next, void *next_data, PandaDestroy next_destroy, PandaLogProxy logger, size_t num_kmers);
+PandaAssembler panda_assembler_ref(PandaAssembler assembler);           /* assembler_support.c:139-149 */
+void panda_assembler_unref(PandaAssembler assembler);                   /* assembler_support.c:151-175 */
+void panda_assembler_copy_configuration(PandaAssembler dest, PandaAssembler src); /* assembler_support.c:119-137 */
+
+/* assembler.c:368-383.  A batch of one on the device; result is (transfer none),
+ * valid until the next call on this assembler.  NULL = rejected, reason in the counters. */
+const panda_result_seq *panda_assembler_assemble(PandaAssembler assembler, panda_seq_identifier *id,
+                                                 const panda_qual *forward, size_t forward_length,
+                                                 const panda_qual *reverse, size_t reverse_length);
+/* assembler.c:350-366.  Pulls pairs from `next` in device-sized batches; returns
+ * assembled pairs one at a time in input order, NULL when the source is dry. */
+const panda_result_seq *panda_assembler_next(PandaAssembler assembler);
+
+/* NEW (no reference counterpart; what a batching caller -- the replacement for
+ * pool.c:71-108 do_assembly -- uses).  Assembles n pairs given as arrays of
+ * pointers, calls `output` for every accepted pair in input order (may be NULL
+ * to only update counters).  ids may be NULL.  Returns the number accepted, or
+ * (size_t)-1 on a device/configuration error. */
+size_t panda_assembler_assemble_batch(PandaAssembler assembler, size_t n, const panda_seq_identifier *ids,
+                                      const panda_qual *const *forward, const size_t *forward_length,
+                                      const panda_qual *const *reverse, const size_t *reverse_length,
+                                      PandaOutputSeq output, void *output_data);
+
+PandaAlgorithm panda_assembler_get_algorithm(PandaAssembler assembler);        /* assembler_support.c:177-180 */
+void panda_assembler_set_algorithm(PandaAssembler assembler, PandaAlgorithm algorithm); /* :182-189 */
+long panda_assembler_get_bad_read_count(PandaAssembler assembler);             /* :191-194 */
+long panda_assembler_get_count(PandaAssembler assembler);                      /* :196-199 */
+void panda_assembler_set_fail_alignment(PandaAssembler assembler, PandaFailAlign handler, void *handler_data, PandaDestroy handler_destroy); /* :215-224 */
+long panda_assembler_get_failed_alignment_count(PandaAssembler assembler);     /* :226-229 */
+panda_nt *panda_assembler_get_forward_primer(PandaAssembler assembler, size_t *length); /* :231-237 */
+void panda_assembler_set_forward_primer(PandaAssembler assembler, panda_nt *sequence, size_t length); /* :201-213 */
+size_t panda_assembler_get_forward_trim(PandaAssembler assembler);             /* :239-242 */
+void panda_assembler_set_forward_trim(PandaAssembler assembler, size_t trim);  /* :244-249 */
+size_t panda_assembler_get_longest_overlap(PandaAssembler assembler);          /* :256-259 */
+long panda_assembler_get_low_quality_count(PandaAssembler assembler);          /* :266-269 */
+int panda_assembler_get_minimum_overlap(PandaAssembler assembler);             /* :271-274 */
+void panda_assembler_set_minimum_overlap(PandaAssembler assembler, int overlap); /* :276-282 */
+int panda_assembler_get_maximum_overlap(PandaAssembler assembler);             /* :284-287 */
+void panda_assembler_set_maximum_overlap(PandaAssembler assembler, int overlap); /* :289-295 */
+const char *panda_assembler_get_name(PandaAssembler assembler);                /* :297-302 */
+void panda_assembler_set_name(PandaAssembler assembler, const char *name);     /* :304-313 */
+long panda_assembler_get_no_forward_primer_count(PandaAssembler assembler);    /* :315-318 */
+long panda_assembler_get_no_reverse_primer_count(PandaAssembler assembler);    /* :320-323 */
+size_t panda_assembler_get_num_kmer(PandaAssembler assembler);                 /* :251-254 */
+long panda_assembler_get_ok_count(PandaAssembler assembler);                   /* :325-328 */
+long panda_assembler_get_overlap_count(PandaAssembler assembler, size_t overlap); /* :330-334 */
+bool panda_assembler_get_primers_after(PandaAssembler assembler);              /* :336-339 */
+void panda_assembler_set_primers_after(PandaAssembler assembler, bool after);  /* :341-345 */
+panda_nt *panda_assembler_get_reverse_primer(PandaAssembler assembler, size_t *length); /* :361-367 */
+void panda_assembler_set_reverse_primer(PandaAssembler assembler, panda_nt *sequence, size_t length); /* :347-359 */
+size_t panda_assembler_get_reverse_trim(PandaAssembler assembler);             /* :369-372 */
+void panda_assembler_set_reverse_trim(PandaAssembler assembler, size_t trim);  /* :374-379 */
+long panda_assembler_get_slow_count(PandaAssembler assembler);                 /* :381-384 */
+double panda_assembler_get_threshold(PandaAssembler assembler);                /* :386-389 */
+void panda_assembler_set_threshold(PandaAssembler assembler, double threshold); /* :391-397 */
+PandaLogProxy panda_assembler_get_logger(PandaAssembler assembler);            /* :261-264 */
+double panda_assembler_get_primer_penalty(PandaAssembler assembler);           /* :399-402 */
+void panda_assembler_set_primer_penalty(PandaAssembler assembler, double threshold); /* :404-410 */
+
+/* offset.c:103-112.  Runs the device primer scan on one read (batch of one). */
+size_t panda_compute_offset_qual(double threshold, double penalty, bool reverse,
+                                 const panda_qual *haystack, size_t haystack_length,
+                                 const panda_nt *needle, size_t needle_length);
+
+/* ======================================================================
+ * Layer 2: batch / device layer
+ * ====================================================================== */
+
+typedef enum {
+	PB_OK = 0,
+	PB_ERR_NO_DEVICE = -1,    /* no CUDA device / driver: there is no CPU fallback */
+	PB_ERR_CUDA = -2,         /* a CUDA call failed; see pb_last_error() */
+	PB_ERR_UNSUPPORTED = -3,  /* configuration the device path does not implement */
+	PB_ERR_ARGUMENT = -4,
+	PB_ERR_NOMEM = -5
+} pb_status;
+
+#define PB_MAX_LEN 450  /* == panda_max_len() */
+#define PB_PHREDMAX 46
+
+enum pb_algo { PB_SIMPLE_BAYES = 0, PB_PEAR = 1, PB_RDP_MLE = 2, PB_FLASH = 3 };
+
+/* Why a pair was not emitted, in assemble_seq order (assembler.c:252-348). */
+enum pb_pair_status { PB_PAIR_OK = 0, PB_PAIR_BADR = 1, PB_PAIR_NOFP = 2, PB_PAIR_NORP = 3, PB_PAIR_NOALGN = 4, PB_PAIR_LOWQ = 5 };
+
+/* Everything assemble_seq/align read from struct panda_assembler (assembler.h:28-79)
+ * plus the algorithm's private data, as one plain struct.  panda_* objects are
+ * flattened into this before every launch. */
+typedef struct {
+	int32_t algo;             /* enum pb_algo */
+	int32_t post_primers;     /* must be 0 (primers-after path: SURVEY.md §8f rank 3, not built yet) */
+	int64_t minoverlap;
+	int64_t maxoverlap;
+	int64_t num_kmers;        /* must be 2 */
+	int64_t forward_trim;
+	int64_t reverse_trim;
+	int64_t forward_primer_length;
+	int64_t reverse_primer_length;
+	double threshold;         /* log space */
+	double primer_penalty;
+	double sb_q;              /* simple_bayes error estimation */
+	double pear_random_base;  /* pear: log p of a random base */
+	panda_nt forward_primer[PB_MAX_LEN];
+	panda_nt reverse_primer[PB_MAX_LEN]; /* as the assembler stores it (already complemented) */
+} pb_config;
+
+void pb_config_default(pb_config *cfg, int algo);
+
+/* Counter vector; [PB_C_LONGEST] merges by max, everything else by sum
+ * (the host-side STAT merge across shards). */
+enum {
+	PB_C_COUNT = 0, PB_C_OK, PB_C_LOWQ, PB_C_NOALGN, PB_C_BADR, PB_C_NOFP, PB_C_NORP, PB_C_SLOW,
+	PB_C_LONGEST,
+	PB_C_OVERLAPS = 16,
+	PB_NCOUNTERS = 16 + 2 * PB_MAX_LEN
+};
+void pb_counters_merge(int64_t *dst, const int64_t *src);
+
+/* --- packed device layout -------------------------------------------------
+ * meta[i]   : {u32 off16; u16 flen; u16 rlen}, record i starts at reads + 16*off16
+ * record    : [fwd nt, 4 bit/base, base 2k in the low nibble, padded to 4 B]
+ *             [rev nt, same, stored in TEMPLATE order: element j is reverse[rlen-1-j]]
+ *             [fwd qual, 1 B/base, raw char, padded to 4 B]
+ *             [rev qual, template order, padded to 4 B]      then padded to 16 B
+ */
+typedef struct {
+	uint32_t off16;
+	uint16_t flen;
+	uint16_t rlen;
+} pb_pair_meta;
+
+static inline size_t pb_record_bytes(size_t flen, size_t rlen) {
+	size_t b = ((flen + 7) / 8) * 4 + ((rlen + 7) / 8) * 4 + ((flen + 3) / 4) * 4 + ((rlen + 3) / 4) * 4;
+	return (b + 15) & ~(size_t) 15;
+}
+
+/* 32-byte result record, one per pair. */
+typedef struct {
+	uint8_t status;       /* enum pb_pair_status */
+	uint8_t slow;         /* align() counted this pair as SLOW (assembler.c:135-137) */
+	uint16_t overlap;
+	uint16_t seq_len;
+	uint16_t mismatches;
+	uint16_t degenerates;
+	uint16_t examined;
+	uint16_t fwd_offset;
+	uint16_t rev_offset;
+	double quality;
+	double est_prob;
+} pb_pair_result;
+
+typedef struct pb_context pb_context;
+
+/* One context per (process, GPU).  Owns a stream, LUTs in HBM, staging buffers. */
+pb_status pb_context_create(int device, pb_context **out);
+void pb_context_destroy(pb_context *ctx);
+const char *pb_last_error(void);
+int pb_device_count(void);
+/* the cudaStream_t the context launches on, as an opaque pointer (for event timing by the caller) */
+void *pb_context_stream(pb_context *ctx);
+
+/* Device-resident entry points: every pointer is a DEVICE pointer.
+ * pb_pack_device:  flat AoS (panda_qual) -> packed records + meta.
+ *   f_off/r_off have n+1 entries (element offsets into f_data/r_data, read order).
+ *   rec_off16 has n entries (record offsets in 16 B units; a host/device exclusive
+ *   scan of pb_record_bytes/16 -- pb_layout_host computes it). */
+pb_status pb_pack_device(pb_context *ctx, size_t n,
+                         const panda_qual *d_f_data, const uint64_t *d_f_off,
+                         const panda_qual *d_r_data, const uint64_t *d_r_off,
+                         const uint32_t *d_rec_off16, uint8_t *d_reads, pb_pair_meta *d_meta);
+
+/* pb_assemble_device: the hot path.  d_seq_nt [n][seq_stride] receives one panda_nt
+ * per merged base (may be NULL); d_seq_p [n][seq_stride] the per-base log p (may be
+ * NULL: only FASTQ output and quality plugins need it); d_counters PB_NCOUNTERS
+ * int64, accumulated.  max_read_len = longest read in the batch (selects the kernel's
+ * shared-memory class; 0 = assume PB_MAX_LEN).  Asynchronous on the context's stream. */
+pb_status pb_assemble_device(pb_context *ctx, const pb_config *cfg, size_t n, int max_read_len,
+                             const uint8_t *d_reads, const pb_pair_meta *d_meta,
+                             pb_pair_result *d_results, uint8_t *d_seq_nt, double *d_seq_p,
+                             size_t seq_stride, int64_t *d_counters);
+pb_status pb_synchronize(pb_context *ctx);
+
+/* Host helpers for the layout (pure integer bookkeeping, no compute on reads). */
+/* fills rec_off16[n] and returns total packed bytes */
+size_t pb_layout_host(size_t n, const uint64_t *f_off, const uint64_t *r_off, uint32_t *rec_off16);
+
+/* Host-buffer entry point (the e2e path): flat AoS batch in HOST memory, results in
+ * HOST memory; H2D copy, pack, assemble and D2H copy happen inside, chunked and
+ * double-buffered on the context's streams.  Output arrays may be NULL except results.
+ * counters (host, PB_NCOUNTERS) is accumulated. */
+pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, size_t n,
+                           const panda_qual *f_data, const uint64_t *f_off,
+                           const panda_qual *r_data, const uint64_t *r_off,
+                           pb_pair_result *results, uint8_t *seq_nt, double *seq_p,
+                           size_t seq_stride, int64_t *counters);
+
+/* The LUTs the kernels use (regenerated with the reference's formulas and "%g"
+ * rounding, mktable.c:23-155 + tablebuilder.c:73-183), exposed for the table parity test. */
+typedef struct {
+	double qual_nn;
+	double match_sb[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
+	double mismatch_sb[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
+	double match_pear[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
+	double mismatch_pear[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
+	double mismatch_rdp[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
+	double mismatch_rdp_asm[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
+	double score[PB_PHREDMAX + 1];
+	double score_err[PB_PHREDMAX + 1];
+} pb_tables;
+const pb_tables *pb_get_tables(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,263 @@
+/* ref_harness.c -- drives the UNMODIFIED reference (oracle/_ref/libpandaseq_ref.so)
+ * over a flat batch, through the reference's own public API
+ * (panda_assembler_assemble, assembler.c:368-383), and writes the same
+ * structure-of-arrays output as oracle/panda_oracle.c.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Compiled by `make ref` against the headers in
+ * /root/reference; the built oracle/_ref/libref_harness.so travels to the GPU box,
+ * the reference sources do not.  One PandaAssembler per thread, created the way
+ * diff.c:180 does (no reader, null-writer logger), panda_debug_flags = 0 so the
+ * per-pair "INFO BESTOLP" formatting stays out of the timing.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pandaseq.h>
+#include "panda_oracle.h"
+
+typedef struct {
+	const po_config *cfg;
+	size_t begin, end;
+	const po_qual *f_data;
+	const uint64_t *f_off;
+	const po_qual *r_data;
+	const uint64_t *r_off;
+	po_flat_out *out;
+	int64_t counters[PO_NCOUNTERS];
+	int failed;
+} ref_job;
+
+static PandaAssembler make_assembler(const po_config *cfg) {
+	PandaLogProxy logger = panda_log_proxy_new(panda_writer_new_null());
+	PandaAssembler a = panda_assembler_new_kmer(NULL, NULL, NULL, logger, (size_t) cfg->num_kmers);
+	PandaAlgorithm algo = NULL;
+	panda_log_proxy_unref(logger);
+	if (a == NULL)
+		return NULL;
+	switch (cfg->algo) {
+	case PO_SIMPLE_BAYES:
+		algo = panda_algorithm_simple_bayes_new();
+		panda_algorithm_simple_bayes_set_error_estimation(algo, cfg->sb_q);
+		break;
+	case PO_PEAR:
+		algo = panda_algorithm_pear_new();
+		panda_algorithm_pear_set_random_base_log_p(algo, cfg->pear_random_base);
+		break;
+	case PO_RDP_MLE:
+		algo = panda_algorithm_rdp_mle_new();
+		break;
+	case PO_FLASH:
+		algo = panda_algorithm_flash_new();
+		break;
+	}
+	if (algo == NULL) {
+		panda_assembler_unref(a);
+		return NULL;
+	}
+	panda_assembler_set_algorithm(a, algo);
+	panda_algorithm_unref(algo);
+	{
+		/* The setter takes a probability and stores log(p) (assembler_support.c:384-390);
+		 * find the p whose log is bit-identical to the requested log-threshold. */
+		double want = cfg->threshold, p = exp(want), lo = p, hi = p;
+		int found = (log(p) == want);
+		for (int k = 0; k < 8 && !found; k++) {
+			lo = nextafter(lo, 0.0);
+			hi = nextafter(hi, 2.0);
+			if (log(lo) == want) { p = lo; found = 1; }
+			else if (log(hi) == want) { p = hi; found = 1; }
+		}
+		if (!found) {
+			panda_assembler_unref(a);
+			return NULL;
+		}
+		panda_assembler_set_threshold(a, p);
+	}
+	panda_assembler_set_minimum_overlap(a, (int) cfg->minoverlap);
+	panda_assembler_set_maximum_overlap(a, (int) cfg->maxoverlap);
+	panda_assembler_set_primer_penalty(a, cfg->primer_penalty);
+	panda_assembler_set_primers_after(a, cfg->post_primers != 0);
+	if (cfg->forward_primer_length > 0)
+		panda_assembler_set_forward_primer(a, (panda_nt *) cfg->forward_primer, (size_t) cfg->forward_primer_length);
+	else
+		panda_assembler_set_forward_trim(a, (size_t) cfg->forward_trim);
+	if (cfg->reverse_primer_length > 0)
+		panda_assembler_set_reverse_primer(a, (panda_nt *) cfg->reverse_primer, (size_t) cfg->reverse_primer_length);
+	else
+		panda_assembler_set_reverse_trim(a, (size_t) cfg->reverse_trim);
+	return a;
+}
+
+/* The reference's threshold setter takes a probability and stores its log
+ * (assembler_support.c:384-390); exp(log x) may not round-trip bit-exactly, so the
+ * harness also exposes what the reference ended up with. */
+double ref_effective_threshold(const po_config *cfg) {
+	PandaAssembler a = make_assembler(cfg);
+	double t;
+	if (a == NULL)
+		return 0;
+	t = log(panda_assembler_get_threshold(a));
+	panda_assembler_unref(a);
+	return t;
+}
+
+static void *run_job(void *arg) {
+	ref_job *job = arg;
+	po_flat_out *o = job->out;
+	PandaAssembler a = make_assembler(job->cfg);
+	panda_seq_identifier id;
+	panda_qual fpad[PO_MAX_LEN];
+	memset(job->counters, 0, sizeof job->counters);
+	memset(&id, 0, sizeof id);
+	if (a == NULL) {
+		job->failed = 1;
+		return NULL;
+	}
+	for (size_t i = job->begin; i < job->end; i++) {
+		size_t flen = job->f_off[i + 1] - job->f_off[i];
+		size_t rlen = job->r_off[i + 1] - job->r_off[i];
+		const panda_qual *F = (const panda_qual *) (job->f_data + job->f_off[i]);
+		const panda_qual *R = (const panda_qual *) (job->r_data + job->r_off[i]);
+		long slow_before = panda_assembler_get_slow_count(a);
+		long lowq_before = panda_assembler_get_low_quality_count(a);
+		long badr_before = panda_assembler_get_bad_read_count(a);
+		long nofp_before = panda_assembler_get_no_forward_primer_count(a);
+		long norp_before = panda_assembler_get_no_reverse_primer_count(a);
+		if (job->cfg->algo == PO_PEAR) {
+			/* algo_pear.c:52,54 read forward[rindex]; pin the out-of-range case to zeros. */
+			memset(fpad, 0, sizeof fpad);
+			memcpy(fpad, F, flen * sizeof(panda_qual));
+			F = fpad;
+		}
+		const panda_result_seq *res = panda_assembler_assemble(a, &id, F, flen, R, rlen);
+		int status;
+		if (res != NULL)
+			status = PO_OK;
+		else if (panda_assembler_get_low_quality_count(a) != lowq_before)
+			status = PO_LOWQ;
+		else if (panda_assembler_get_bad_read_count(a) != badr_before)
+			status = PO_BADR;
+		else if (panda_assembler_get_no_forward_primer_count(a) != nofp_before)
+			status = PO_NOFP;
+		else if (panda_assembler_get_no_reverse_primer_count(a) != norp_before)
+			status = PO_NORP;
+		else
+			status = PO_NOALGN;
+		if (o->status) o->status[i] = (uint8_t) status;
+		if (o->slow) o->slow[i] = (uint8_t) (panda_assembler_get_slow_count(a) != slow_before);
+		/* On LOWQ the reference returns NULL but has filled its result; that object is
+		 * not reachable through the public API, so only OK rows carry the fields. */
+		int emitted = (res != NULL);
+		if (o->overlap) o->overlap[i] = emitted ? (int32_t) res->overlap : 0;
+		if (o->seq_len) o->seq_len[i] = emitted ? (int32_t) res->sequence_length : 0;
+		if (o->mismatches) o->mismatches[i] = emitted ? (int32_t) res->overlap_mismatches : 0;
+		if (o->degenerates) o->degenerates[i] = emitted ? (int32_t) res->degenerates : 0;
+		if (o->examined) o->examined[i] = emitted ? (int32_t) res->overlaps_examined : 0;
+		if (o->fwd_offset) o->fwd_offset[i] = emitted ? (int32_t) res->forward_offset : 0;
+		if (o->rev_offset) o->rev_offset[i] = emitted ? (int32_t) res->reverse_offset : 0;
+		if (o->quality) o->quality[i] = emitted ? res->quality : 0;
+		if (o->est_prob) o->est_prob[i] = emitted ? res->estimated_overlap_probability : 0;
+		if (o->seq_nt) {
+			uint8_t *dst = o->seq_nt + i * (size_t) o->seq_stride;
+			memset(dst, 0, (size_t) o->seq_stride);
+			if (emitted && (size_t) o->seq_stride >= res->sequence_length)
+				for (size_t k = 0; k < res->sequence_length; k++)
+					dst[k] = (uint8_t) res->sequence[k].nt;
+		}
+		if (o->seq_p) {
+			double *dst = o->seq_p + i * (size_t) o->seq_stride;
+			memset(dst, 0, (size_t) o->seq_stride * sizeof(double));
+			if (emitted && (size_t) o->seq_stride >= res->sequence_length)
+				for (size_t k = 0; k < res->sequence_length; k++)
+					dst[k] = res->sequence[k].p;
+		}
+	}
+	job->counters[PO_C_COUNT] = panda_assembler_get_count(a);
+	job->counters[PO_C_OK] = panda_assembler_get_ok_count(a);
+	job->counters[PO_C_LOWQ] = panda_assembler_get_low_quality_count(a);
+	job->counters[PO_C_NOALGN] = panda_assembler_get_failed_alignment_count(a);
+	job->counters[PO_C_BADR] = panda_assembler_get_bad_read_count(a);
+	job->counters[PO_C_NOFP] = panda_assembler_get_no_forward_primer_count(a);
+	job->counters[PO_C_NORP] = panda_assembler_get_no_reverse_primer_count(a);
+	job->counters[PO_C_SLOW] = panda_assembler_get_slow_count(a);
+	job->counters[PO_C_LONGEST] = (int64_t) panda_assembler_get_longest_overlap(a);
+	for (size_t k = 0; k < 2 * PO_MAX_LEN; k++)
+		job->counters[PO_C_OVERLAPS + k] = panda_assembler_get_overlap_count(a, k);
+	panda_assembler_unref(a);
+	return NULL;
+}
+
+int ref_assemble_flat(const po_config *cfg, size_t n,
+                      const po_qual *f_data, const uint64_t *f_off,
+                      const po_qual *r_data, const uint64_t *r_off,
+                      po_flat_out *out, int threads) {
+	panda_debug_flags = 0;
+	if (threads < 1)
+		threads = 1;
+	if ((size_t) threads > n)
+		threads = n ? (int) n : 1;
+	ref_job *jobs = calloc((size_t) threads, sizeof(ref_job));
+	pthread_t *tids = calloc((size_t) threads, sizeof(pthread_t));
+	for (int k = 0; k < threads; k++) {
+		jobs[k].cfg = cfg;
+		jobs[k].begin = n * (size_t) k / (size_t) threads;
+		jobs[k].end = n * (size_t) (k + 1) / (size_t) threads;
+		jobs[k].f_data = f_data;
+		jobs[k].f_off = f_off;
+		jobs[k].r_data = r_data;
+		jobs[k].r_off = r_off;
+		jobs[k].out = out;
+		if (k > 0)
+			pthread_create(&tids[k], NULL, run_job, &jobs[k]);
+	}
+	run_job(&jobs[0]);
+	int failed = jobs[0].failed;
+	for (int k = 1; k < threads; k++) {
+		pthread_join(tids[k], NULL);
+		failed |= jobs[k].failed;
+	}
+	if (out->counters) {
+		for (int k = 0; k < threads; k++)
+			for (int c = 0; c < PO_NCOUNTERS; c++) {
+				if (c == PO_C_LONGEST) {
+					if (out->counters[c] < jobs[k].counters[c])
+						out->counters[c] = jobs[k].counters[c];
+				} else {
+					out->counters[c] += jobs[k].counters[c];
+				}
+			}
+	}
+	free(jobs);
+	free(tids);
+	return failed ? -1 : 0;
+}
+
+/* Raw access to the reference's generated LUTs (table.c) for the table parity test. */
+extern const double qual_match_simple_bayesian[][47];
+extern const double qual_mismatch_simple_bayesian[][47];
+extern const double qual_match_pear[][47];
+extern const double qual_mismatch_pear[][47];
+extern const double qual_mismatch_rdp_mle[][47];
+extern const double qual_mismatch_assembled_rdp_mle[][47];
+extern const double qual_score[47];
+extern const double qual_score_err[47];
+
+void ref_get_tables(po_tables *t) {
+	t->qual_nn = panda_algorithm_simple_bayes_class.prob_unpaired;
+	memcpy(t->match_sb, qual_match_simple_bayesian, sizeof t->match_sb);
+	memcpy(t->mismatch_sb, qual_mismatch_simple_bayesian, sizeof t->mismatch_sb);
+	memcpy(t->match_pear, qual_match_pear, sizeof t->match_pear);
+	memcpy(t->mismatch_pear, qual_mismatch_pear, sizeof t->mismatch_pear);
+	memcpy(t->mismatch_rdp, qual_mismatch_rdp_mle, sizeof t->mismatch_rdp);
+	memcpy(t->mismatch_rdp_asm, qual_mismatch_assembled_rdp_mle, sizeof t->mismatch_rdp_asm);
+	memcpy(t->score, qual_score, sizeof t->score);
+	memcpy(t->score_err, qual_score_err, sizeof t->score_err);
+}
+
+/* Direct calls into the reference's callbacks / primer scan, for unit parity. */
+size_t ref_compute_offset_qual(double threshold, double penalty, int reverse,
+                               const po_qual *hay, size_t hay_len, const char *needle, size_t needle_len) {
+	return panda_compute_offset_qual(threshold, penalty, reverse != 0, (const panda_qual *) hay, hay_len, (const panda_nt *) needle, needle_len);
+}

@@ -1,0 +1,236 @@
+"""pandaseq_b200 -- Python binding (ctypes) of libpandaseq_b200.so.
+
+The product is the shared library (``include/pandaseq_b200.h``); this module is
+the thin host-side mirror used by the tests and ``bench.py``.  PyTorch is used
+only for device memory, streams and ``torch.distributed`` plumbing: every
+compute call goes through the C ABI into the hand-written sm_100a kernels.
+
+There is no fallback: if the library has not been built, importing the binding
+symbols raises; if no GPU is present, compute calls raise ``PandaseqError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpandaseq_b200.so")
+
+PB_MAX_LEN = 450
+PB_PHREDMAX = 46
+PB_NCOUNTERS = 16 + 2 * PB_MAX_LEN
+ALGOS = {"simple_bayesian": 0, "pear": 1, "rdp_mle": 2, "flash": 3}
+STATUS = {0: "OK", 1: "BADR", 2: "NOFP", 3: "NORP", 4: "NOALGN", 5: "LOWQ"}
+C_COUNT, C_OK, C_LOWQ, C_NOALGN, C_BADR, C_NOFP, C_NORP, C_SLOW, C_LONGEST = range(9)
+C_OVERLAPS = 16
+
+
+class PandaseqError(RuntimeError):
+    pass
+
+
+class PbConfig(C.Structure):
+    """mirror of pb_config (and, by construction, of oracle/panda_oracle.h po_config)"""
+    _fields_ = [
+        ("algo", C.c_int32), ("post_primers", C.c_int32),
+        ("minoverlap", C.c_int64), ("maxoverlap", C.c_int64), ("num_kmers", C.c_int64),
+        ("forward_trim", C.c_int64), ("reverse_trim", C.c_int64),
+        ("forward_primer_length", C.c_int64), ("reverse_primer_length", C.c_int64),
+        ("threshold", C.c_double), ("primer_penalty", C.c_double),
+        ("sb_q", C.c_double), ("pear_random_base", C.c_double),
+        ("forward_primer", C.c_char * PB_MAX_LEN), ("reverse_primer", C.c_char * PB_MAX_LEN),
+    ]
+
+
+NQ = PB_PHREDMAX + 1
+
+
+class PbTables(C.Structure):
+    _fields_ = [
+        ("qual_nn", C.c_double),
+        ("match_sb", C.c_double * NQ * NQ), ("mismatch_sb", C.c_double * NQ * NQ),
+        ("match_pear", C.c_double * NQ * NQ), ("mismatch_pear", C.c_double * NQ * NQ),
+        ("mismatch_rdp", C.c_double * NQ * NQ), ("mismatch_rdp_asm", C.c_double * NQ * NQ),
+        ("score", C.c_double * NQ), ("score_err", C.c_double * NQ),
+    ]
+
+    def as_dict(self):
+        d = {"qual_nn": np.float64(self.qual_nn)}
+        for name, _ in self._fields_[1:]:
+            d[name] = np.ctypeslib.as_array(getattr(self, name)).copy()
+        return d
+
+
+PAIR_META_DTYPE = np.dtype([("off16", "<u4"), ("flen", "<u2"), ("rlen", "<u2")])
+PAIR_RESULT_DTYPE = np.dtype([
+    ("status", "u1"), ("slow", "u1"), ("overlap", "<u2"), ("seq_len", "<u2"), ("mismatches", "<u2"),
+    ("degenerates", "<u2"), ("examined", "<u2"), ("fwd_offset", "<u2"), ("rev_offset", "<u2"),
+    ("quality", "<f8"), ("est_prob", "<f8")])
+assert PAIR_RESULT_DTYPE.itemsize == 32 and PAIR_META_DTYPE.itemsize == 8
+
+
+def make_config(algo="simple_bayesian", *, threshold=0.6, minoverlap=2, maxoverlap=0, forward_primer=None,
+                reverse_primer=None, forward_trim=0, reverse_trim=0, primer_penalty=0.0, sb_q=0.36,
+                pear_random_base=None, post_primers=False, num_kmers=2) -> PbConfig:
+    """Flat assembler configuration.  Primers are sequences of panda_nt codes *as the assembler
+    stores them* (the reverse primer already complemented, args_assembler.c:222)."""
+    cfg = PbConfig()
+    cfg.algo = ALGOS[algo] if isinstance(algo, str) else int(algo)
+    cfg.post_primers = int(post_primers)
+    cfg.minoverlap, cfg.maxoverlap, cfg.num_kmers = int(minoverlap), int(maxoverlap), int(num_kmers)
+    cfg.threshold = math.log(threshold)
+    cfg.primer_penalty = float(primer_penalty)
+    cfg.sb_q = float(sb_q)
+    cfg.pear_random_base = math.log(0.25) if pear_random_base is None else float(pear_random_base)
+    if forward_primer is not None and len(forward_primer):
+        fp = bytes(int(x) & 0xFF for x in forward_primer)
+        cfg.forward_primer_length = len(fp)
+        C.memmove(C.byref(cfg, PbConfig.forward_primer.offset), fp, len(fp))
+    else:
+        cfg.forward_trim = int(forward_trim)
+    if reverse_primer is not None and len(reverse_primer):
+        rp = bytes(int(x) & 0xFF for x in reverse_primer)
+        cfg.reverse_primer_length = len(rp)
+        C.memmove(C.byref(cfg, PbConfig.reverse_primer.offset), rp, len(rp))
+    else:
+        cfg.reverse_trim = int(reverse_trim)
+    return cfg
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libpandaseq_b200.so (built in-tree by ``__graft_entry__.build()`` / csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PandaseqError(f"{LIB_PATH} is missing: build it with `make -C pandaseq_b200/csrc` "
+                            "(there is no Python or CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    L.pb_last_error.restype = C.c_char_p
+    L.pb_device_count.restype = i32
+    L.pb_context_create.argtypes = [i32, C.POINTER(vp)]
+    L.pb_context_create.restype = i32
+    L.pb_context_destroy.argtypes = [vp]
+    L.pb_context_stream.argtypes = [vp]
+    L.pb_context_stream.restype = vp
+    L.pb_synchronize.argtypes = [vp]
+    L.pb_synchronize.restype = i32
+    L.pb_config_default.argtypes = [C.POINTER(PbConfig), i32]
+    L.pb_get_tables.restype = C.POINTER(PbTables)
+    L.pb_layout_host.argtypes = [sz, vp, vp, vp]
+    L.pb_layout_host.restype = sz
+    L.pb_pack_device.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
+    L.pb_pack_device.restype = i32
+    L.pb_assemble_device.argtypes = [vp, C.POINTER(PbConfig), sz, i32, vp, vp, vp, vp, vp, sz, vp]
+    L.pb_assemble_device.restype = i32
+    L.pb_assemble_host.argtypes = [vp, C.POINTER(PbConfig), sz, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.pb_assemble_host.restype = i32
+    L.pb_counters_merge.argtypes = [vp, vp]
+    L.panda_max_len.restype = sz
+    _lib = L
+    return L
+
+
+def _check(status: int, what: str):
+    if status != 0:
+        raise PandaseqError(f"{what}: status {status}: {lib().pb_last_error().decode(errors='replace')}")
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def record_bytes(flen, rlen):
+    flen, rlen = np.asarray(flen, dtype=np.int64), np.asarray(rlen, dtype=np.int64)
+    b = ((flen + 7) // 8) * 4 + ((rlen + 7) // 8) * 4 + ((flen + 3) // 4) * 4 + ((rlen + 3) // 4) * 4
+    return (b + 15) & ~15
+
+
+class Context:
+    """One device context (stream + LUT block + staging) on a GPU."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().pb_context_create(int(device), C.byref(self._h)), "pb_context_create")
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            lib().pb_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream_handle(self) -> int:
+        return int(lib().pb_context_stream(self._h))
+
+    def synchronize(self):
+        _check(lib().pb_synchronize(self._h), "pb_synchronize")
+
+    # ---- host-buffer (e2e) path ----------------------------------------------------
+    def assemble_host(self, cfg: PbConfig, batch, *, want_nt=True, want_p=False, seq_stride=None):
+        """batch: synth.FlatBatch.  Returns dict(results, seq_nt, seq_p, counters) of numpy arrays."""
+        n = batch.n
+        if seq_stride is None:
+            fl, rl = batch.lengths()
+            seq_stride = int((fl + rl).max()) if n else 0
+            seq_stride = (seq_stride + 15) & ~15
+        res = np.zeros(n, dtype=PAIR_RESULT_DTYPE)
+        nt = np.zeros((n, seq_stride), dtype=np.uint8) if want_nt else None
+        p = np.zeros((n, seq_stride), dtype=np.float64) if want_p else None
+        counters = np.zeros(PB_NCOUNTERS, dtype=np.int64)
+        f_data, r_data = np.ascontiguousarray(batch.f_data), np.ascontiguousarray(batch.r_data)
+        f_off, r_off = np.ascontiguousarray(batch.f_off, dtype=np.uint64), np.ascontiguousarray(batch.r_off, dtype=np.uint64)
+        _check(lib().pb_assemble_host(self._h, C.byref(cfg), n, _np_ptr(f_data), _np_ptr(f_off), _np_ptr(r_data), _np_ptr(r_off),
+                                      _np_ptr(res), _np_ptr(nt), _np_ptr(p), seq_stride, _np_ptr(counters)), "pb_assemble_host")
+        return dict(results=res, seq_nt=nt, seq_p=p, counters=counters, seq_stride=seq_stride)
+
+    # ---- device-resident path (torch tensors own the HBM) ---------------------------
+    def pack_device(self, f_data, f_off, r_data, r_off):
+        """flat AoS torch CUDA tensors -> (reads u8, meta (n,2) i32 view, max_len, record bytes).
+        The record offsets (an exclusive scan of the record sizes) are computed with torch on the device."""
+        import torch
+        n = f_off.numel() - 1
+        flen, rlen = f_off[1:] - f_off[:-1], r_off[1:] - r_off[:-1]
+        rb = ((flen + 7) // 8) * 4 + ((rlen + 7) // 8) * 4 + ((flen + 3) // 4) * 4 + ((rlen + 3) // 4) * 4
+        rb16 = (rb + 15) // 16
+        rec_off = torch.zeros(n + 1, dtype=torch.int64, device=f_data.device)
+        rec_off[1:] = torch.cumsum(rb16, 0)
+        total = int(rec_off[-1].item()) * 16
+        rec_off32 = rec_off[:-1].to(torch.int32).contiguous()   # < 2^31 units of 16 B
+        reads = torch.empty(total + 16, dtype=torch.uint8, device=f_data.device)
+        meta = torch.empty((n, 2), dtype=torch.int32, device=f_data.device)
+        max_len = int(torch.maximum(flen.max(), rlen.max()).item()) if n else 0
+        self._sync_from_torch()
+        _check(lib().pb_pack_device(self._h, n, f_data.data_ptr(), f_off.data_ptr(), r_data.data_ptr(), r_off.data_ptr(),
+                                    rec_off32.data_ptr(), reads.data_ptr(), meta.data_ptr()), "pb_pack_device")
+        self.synchronize()
+        return reads, meta, max_len, total
+
+    def _sync_from_torch(self):
+        import torch
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def assemble_device(self, cfg: PbConfig, n, max_len, reads, meta, results, seq_nt, seq_p, seq_stride, counters):
+        """Asynchronous launch on the context's stream; all tensors are torch CUDA tensors
+        (results: (n,32) uint8, counters: (PB_NCOUNTERS,) int64)."""
+        _check(lib().pb_assemble_device(self._h, C.byref(cfg), int(n), int(max_len), reads.data_ptr(), meta.data_ptr(),
+                                        results.data_ptr(), seq_nt.data_ptr() if seq_nt is not None else None,
+                                        seq_p.data_ptr() if seq_p is not None else None, int(seq_stride), counters.data_ptr()),
+               "pb_assemble_device")
+
+
+def tables() -> dict:
+    return lib().pb_get_tables().contents.as_dict()

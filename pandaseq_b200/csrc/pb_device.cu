@@ -1,0 +1,411 @@
+/* pb_device.cu -- device context, launch wrappers and the host-buffer (e2e) path.
+ *
+ * extern "C" entry points declared in include/pandaseq_b200.h.  One pb_context
+ * per (process, GPU): a stream, the parameter/LUT block in HBM, and staging
+ * buffers for the host-buffer path.  Nothing here computes on reads on the CPU:
+ * the host only lays out offsets and moves bytes.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "pb_kernels.cuh"
+
+struct pb_context {
+	int device;
+	int sm_count;
+	cudaStream_t stream;
+	cudaStream_t copy_stream;
+	pb_device_params *d_params;      /* in HBM */
+	pb_device_params *h_params;      /* pinned mirror */
+	pb_config cached_cfg;
+	bool cfg_valid;
+	unsigned long long *d_counters;  /* scratch counters for the host path */
+	/* host-path staging (grown on demand) */
+	struct Slot {
+		size_t cap_pairs, cap_bases;
+		uint8_t *h_f, *h_r;              /* pinned AoS */
+		unsigned long long *h_foff, *h_roff;
+		uint32_t *h_recoff;
+		uint8_t *d_f, *d_r;
+		unsigned long long *d_foff, *d_roff;
+		uint32_t *d_recoff;
+		uint8_t *d_reads;
+		size_t cap_reads;
+		pb_pair_meta *d_meta;
+		pb_pair_result *d_res, *h_res;
+		uint8_t *d_nt, *h_nt;
+		double *d_p, *h_p;
+		size_t cap_nt, cap_p;
+		cudaEvent_t done;
+	} slot[2];
+};
+
+#define CUDA_TRY(expr)                                                                         \
+	do {                                                                                       \
+		cudaError_t e_ = (expr);                                                               \
+		if (e_ != cudaSuccess) {                                                               \
+			pb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+			return PB_ERR_CUDA;                                                                \
+		}                                                                                      \
+	} while (0)
+
+extern "C" int pb_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess)
+		return 0;
+	return n;
+}
+
+extern "C" pb_status pb_context_create(int device, pb_context **out) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		pb_set_error("no CUDA device available (%s); libpandaseq_b200 has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+		return PB_ERR_NO_DEVICE;
+	}
+	if (device < 0 || device >= n) {
+		pb_set_error("device %d out of range (0..%d)", device, n - 1);
+		return PB_ERR_ARGUMENT;
+	}
+	CUDA_TRY(cudaSetDevice(device));
+	pb_context *ctx = (pb_context *) calloc(1, sizeof(pb_context));
+	if (!ctx)
+		return PB_ERR_NOMEM;
+	ctx->device = device;
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	ctx->sm_count = prop.multiProcessorCount;
+	if (prop.major < 10) {
+		pb_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+		free(ctx);
+		return PB_ERR_NO_DEVICE;
+	}
+	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaMalloc(&ctx->d_params, sizeof(pb_device_params)));
+	CUDA_TRY(cudaMallocHost(&ctx->h_params, sizeof(pb_device_params)));
+	CUDA_TRY(cudaMalloc(&ctx->d_counters, PB_NCOUNTERS * sizeof(unsigned long long)));
+	for (int s = 0; s < 2; s++)
+		CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot[s].done, cudaEventDisableTiming));
+	*out = ctx;
+	return PB_OK;
+}
+
+static void free_slot(pb_context::Slot &s) {
+	cudaFreeHost(s.h_f); cudaFreeHost(s.h_r); cudaFreeHost(s.h_foff); cudaFreeHost(s.h_roff); cudaFreeHost(s.h_recoff);
+	cudaFree(s.d_f); cudaFree(s.d_r); cudaFree(s.d_foff); cudaFree(s.d_roff); cudaFree(s.d_recoff);
+	cudaFree(s.d_reads); cudaFree(s.d_meta); cudaFree(s.d_res); cudaFreeHost(s.h_res);
+	cudaFree(s.d_nt); cudaFreeHost(s.h_nt); cudaFree(s.d_p); cudaFreeHost(s.h_p);
+	cudaEvent_t ev = s.done;
+	memset(&s, 0, sizeof s);
+	s.done = ev;
+}
+
+extern "C" void pb_context_destroy(pb_context *ctx) {
+	if (!ctx)
+		return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	cudaStreamSynchronize(ctx->copy_stream);
+	for (int s = 0; s < 2; s++) {
+		free_slot(ctx->slot[s]);
+		cudaEventDestroy(ctx->slot[s].done);
+	}
+	cudaFree(ctx->d_params);
+	cudaFreeHost(ctx->h_params);
+	cudaFree(ctx->d_counters);
+	cudaStreamDestroy(ctx->stream);
+	cudaStreamDestroy(ctx->copy_stream);
+	free(ctx);
+}
+
+extern "C" void *pb_context_stream(pb_context *ctx) {
+	return (void *) ctx->stream;
+}
+
+extern "C" pb_status pb_synchronize(pb_context *ctx) {
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	return PB_OK;
+}
+
+static pb_status upload_params(pb_context *ctx, const pb_config *cfg) {
+	if (ctx->cfg_valid && memcmp(&ctx->cached_cfg, cfg, sizeof *cfg) == 0)
+		return PB_OK;
+	/* the pinned mirror may still be in flight from the previous upload */
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	pb_status st = pb_build_device_params(cfg, ctx->h_params);
+	if (st != PB_OK)
+		return st;
+	CUDA_TRY(cudaMemcpyAsync(ctx->d_params, ctx->h_params, sizeof(pb_device_params), cudaMemcpyHostToDevice, ctx->stream));
+	ctx->cached_cfg = *cfg;
+	ctx->cfg_valid = true;
+	return PB_OK;
+}
+
+template <int ML, bool OVER, int WARPS>
+static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
+                                 pb_pair_result *d_results, uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride,
+                                 unsigned long long *d_counters) {
+	auto kern = pb::assemble_kernel<ML, OVER, WARPS>;
+	constexpr size_t smem = pb::assemble_smem_bytes<ML, OVER, WARPS>();
+	static bool configured[16] = { false };
+	if (!configured[ctx->device & 15]) {
+		CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		configured[ctx->device & 15] = true;
+	}
+	int per_sm = 0;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+	if (per_sm < 1) {
+		pb_set_error("assemble kernel does not fit on an SM (smem %zu)", smem);
+		return PB_ERR_CUDA;
+	}
+	/* persistent grid: a whole number of CTAs per SM; warps stride over the batch */
+	long long want = ((long long) n + WARPS - 1) / WARPS;
+	long long grid = (long long) ctx->sm_count * per_sm;
+	if (grid > want)
+		grid = want;
+	if (grid < 1)
+		grid = 1;
+	kern<<<(unsigned) grid, WARPS * 32, smem, ctx->stream>>>(ctx->d_params, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p,
+	                                                           (long long) seq_stride, d_counters);
+	CUDA_TRY(cudaGetLastError());
+	return PB_OK;
+}
+
+static pb_status assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int max_len,
+                                   const uint8_t *d_reads, const pb_pair_meta *d_meta, pb_pair_result *d_results,
+                                   uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride, unsigned long long *d_counters) {
+	const bool over = cfg->algo == PB_PEAR || cfg->algo == PB_RDP_MLE;
+	if (max_len <= 0 || max_len > PB_MAX_LEN)
+		max_len = PB_MAX_LEN;
+#define PB_GO(ML, OVER, W) return launch_assemble<ML, OVER, W>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters)
+	if (max_len <= 160) {
+		if (over) PB_GO(160, true, 16); else PB_GO(160, false, 16);
+	} else if (max_len <= 256) {
+		if (over) PB_GO(256, true, 16); else PB_GO(256, false, 16);
+	} else {
+		if (over) PB_GO(456, true, 16); else PB_GO(456, false, 16);
+	}
+#undef PB_GO
+}
+
+extern "C" pb_status pb_assemble_device(pb_context *ctx, const pb_config *cfg, size_t n, int max_read_len,
+                                        const uint8_t *d_reads, const pb_pair_meta *d_meta,
+                                        pb_pair_result *d_results, uint8_t *d_seq_nt, double *d_seq_p,
+                                        size_t seq_stride, int64_t *d_counters) {
+	if (!ctx || !cfg || !d_results || !d_counters || n > 0x7FFFFFFFull) {
+		pb_set_error("pb_assemble_device: bad argument");
+		return PB_ERR_ARGUMENT;
+	}
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	pb_status st = upload_params(ctx, cfg);
+	if (st != PB_OK)
+		return st;
+	if (n == 0)
+		return PB_OK;
+	return assemble_dispatch(ctx, cfg, (int) n, max_read_len, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride,
+	                         (unsigned long long *) d_counters);
+}
+
+extern "C" pb_status pb_pack_device(pb_context *ctx, size_t n,
+                                    const panda_qual *d_f_data, const uint64_t *d_f_off,
+                                    const panda_qual *d_r_data, const uint64_t *d_r_off,
+                                    const uint32_t *d_rec_off16, uint8_t *d_reads, pb_pair_meta *d_meta) {
+	if (!ctx || n > 0x7FFFFFFFull) {
+		pb_set_error("pb_pack_device: bad argument");
+		return PB_ERR_ARGUMENT;
+	}
+	if (n == 0)
+		return PB_OK;
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	const int threads = 256;
+	const unsigned blocks = (unsigned) (((long long) n * 32 + threads - 1) / threads);
+	pb::pack_kernel<<<blocks, threads, 0, ctx->stream>>>((int) n, (const uint8_t *) d_f_data, (const unsigned long long *) d_f_off,
+	                                                      (const uint8_t *) d_r_data, (const unsigned long long *) d_r_off,
+	                                                      d_rec_off16, d_reads, d_meta);
+	CUDA_TRY(cudaGetLastError());
+	return PB_OK;
+}
+
+/* ---- host-buffer path ------------------------------------------------------------ */
+
+template <typename T> static cudaError_t regrow_dev(T **p, size_t *cap, size_t need) {
+	if (need <= *cap)
+		return cudaSuccess;
+	cudaFree(*p);
+	*p = nullptr;
+	*cap = 0;
+	cudaError_t e = cudaMalloc((void **) p, need * sizeof(T));
+	if (e == cudaSuccess)
+		*cap = need;
+	return e;
+}
+
+static pb_status ensure_slot(pb_context::Slot &s, size_t pairs, size_t fbases, size_t rbases, size_t reads_bytes,
+                             size_t nt_bytes, size_t p_elems) {
+	size_t bases = fbases > rbases ? fbases : rbases;
+	if (pairs > s.cap_pairs) {
+		size_t cap = pairs + pairs / 4 + 16;
+		cudaFreeHost(s.h_foff); cudaFreeHost(s.h_roff); cudaFreeHost(s.h_recoff); cudaFreeHost(s.h_res);
+		cudaFree(s.d_foff); cudaFree(s.d_roff); cudaFree(s.d_recoff); cudaFree(s.d_meta); cudaFree(s.d_res);
+		CUDA_TRY(cudaMallocHost(&s.h_foff, (cap + 1) * 8));
+		CUDA_TRY(cudaMallocHost(&s.h_roff, (cap + 1) * 8));
+		CUDA_TRY(cudaMallocHost(&s.h_recoff, cap * 4));
+		CUDA_TRY(cudaMallocHost(&s.h_res, cap * sizeof(pb_pair_result)));
+		CUDA_TRY(cudaMalloc(&s.d_foff, (cap + 1) * 8));
+		CUDA_TRY(cudaMalloc(&s.d_roff, (cap + 1) * 8));
+		CUDA_TRY(cudaMalloc(&s.d_recoff, cap * 4));
+		CUDA_TRY(cudaMalloc(&s.d_meta, cap * sizeof(pb_pair_meta)));
+		CUDA_TRY(cudaMalloc(&s.d_res, cap * sizeof(pb_pair_result)));
+		s.cap_pairs = cap;
+	}
+	if (bases > s.cap_bases) {
+		size_t cap = bases + bases / 4 + 64;
+		cudaFreeHost(s.h_f); cudaFreeHost(s.h_r); cudaFree(s.d_f); cudaFree(s.d_r);
+		CUDA_TRY(cudaMallocHost(&s.h_f, cap * 2));
+		CUDA_TRY(cudaMallocHost(&s.h_r, cap * 2));
+		CUDA_TRY(cudaMalloc(&s.d_f, cap * 2));
+		CUDA_TRY(cudaMalloc(&s.d_r, cap * 2));
+		s.cap_bases = cap;
+	}
+	CUDA_TRY(regrow_dev(&s.d_reads, &s.cap_reads, reads_bytes + 16));
+	if (nt_bytes > s.cap_nt) {
+		cudaFree(s.d_nt); cudaFreeHost(s.h_nt);
+		CUDA_TRY(cudaMalloc(&s.d_nt, nt_bytes));
+		CUDA_TRY(cudaMallocHost(&s.h_nt, nt_bytes));
+		s.cap_nt = nt_bytes;
+	}
+	if (p_elems > s.cap_p) {
+		cudaFree(s.d_p); cudaFreeHost(s.h_p);
+		CUDA_TRY(cudaMalloc(&s.d_p, p_elems * sizeof(double)));
+		CUDA_TRY(cudaMallocHost(&s.h_p, p_elems * sizeof(double)));
+		s.cap_p = p_elems;
+	}
+	return PB_OK;
+}
+
+/* Chunked, double-buffered: while chunk k runs on the GPU, chunk k+1 is staged into pinned
+ * memory by the host and chunk k-1's results are copied out. */
+extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, size_t n,
+                                      const panda_qual *f_data, const uint64_t *f_off,
+                                      const panda_qual *r_data, const uint64_t *r_off,
+                                      pb_pair_result *results, uint8_t *seq_nt, double *seq_p,
+                                      size_t seq_stride, int64_t *counters) {
+	if (!ctx || !cfg || (!results && n) || (n && (!f_data || !f_off || !r_data || !r_off))) {
+		pb_set_error("pb_assemble_host: bad argument");
+		return PB_ERR_ARGUMENT;
+	}
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	pb_status st = upload_params(ctx, cfg);
+	if (st != PB_OK)
+		return st;
+	if (n == 0)
+		return PB_OK;
+	CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, PB_NCOUNTERS * sizeof(unsigned long long), ctx->stream));
+	const size_t CHUNK = 1u << 20;       /* pairs per chunk */
+	struct Pending { bool live; size_t begin, count; } pend[2] = { { false, 0, 0 }, { false, 0, 0 } };
+	auto drain = [&](int si) -> pb_status {
+		if (!pend[si].live)
+			return PB_OK;
+		pb_context::Slot &s = ctx->slot[si];
+		CUDA_TRY(cudaEventSynchronize(s.done));
+		memcpy(results + pend[si].begin, s.h_res, pend[si].count * sizeof(pb_pair_result));
+		if (seq_nt)
+			memcpy(seq_nt + pend[si].begin * seq_stride, s.h_nt, pend[si].count * seq_stride);
+		if (seq_p)
+			memcpy(seq_p + pend[si].begin * seq_stride, s.h_p, pend[si].count * seq_stride * sizeof(double));
+		pend[si].live = false;
+		return PB_OK;
+	};
+	int si = 0;
+	for (size_t begin = 0; begin < n; begin += CHUNK, si ^= 1) {
+		const size_t count = (n - begin < CHUNK) ? (n - begin) : CHUNK;
+		st = drain(si);
+		if (st != PB_OK)
+			return st;
+		pb_context::Slot &s = ctx->slot[si];
+		const uint64_t fb = f_off[begin], rb = r_off[begin];
+		const size_t fbases = (size_t) (f_off[begin + count] - fb), rbases = (size_t) (r_off[begin + count] - rb);
+		/* layout (integer bookkeeping only) */
+		size_t max_len = 0;
+		for (size_t i = 0; i < count; i++) {
+			size_t fl = (size_t) (f_off[begin + i + 1] - f_off[begin + i]), rl = (size_t) (r_off[begin + i + 1] - r_off[begin + i]);
+			if (fl > max_len) max_len = fl;
+			if (rl > max_len) max_len = rl;
+		}
+		if (max_len > PB_MAX_LEN) {
+			pb_set_error("read longer than PANDA_MAX_LEN (%zu > %d)", max_len, PB_MAX_LEN);
+			return PB_ERR_ARGUMENT;
+		}
+		st = ensure_slot(s, count, fbases, rbases, 0, seq_nt ? count * seq_stride : 0, seq_p ? count * seq_stride : 0);
+		if (st != PB_OK)
+			return st;
+		for (size_t i = 0; i <= count; i++) {
+			s.h_foff[i] = f_off[begin + i] - fb;
+			s.h_roff[i] = r_off[begin + i] - rb;
+		}
+		const size_t reads_bytes = pb_layout_host(count, (const uint64_t *) s.h_foff, (const uint64_t *) s.h_roff, s.h_recoff);
+		st = ensure_slot(s, count, fbases, rbases, reads_bytes, 0, 0);
+		if (st != PB_OK)
+			return st;
+		memcpy(s.h_f, f_data + fb, fbases * 2);
+		memcpy(s.h_r, r_data + rb, rbases * 2);
+		CUDA_TRY(cudaMemcpyAsync(s.d_f, s.h_f, fbases * 2, cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(cudaMemcpyAsync(s.d_r, s.h_r, rbases * 2, cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(cudaMemcpyAsync(s.d_foff, s.h_foff, (count + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(cudaMemcpyAsync(s.d_roff, s.h_roff, (count + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(cudaMemcpyAsync(s.d_recoff, s.h_recoff, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+		st = pb_pack_device(ctx, count, (const panda_qual *) s.d_f, (const uint64_t *) s.d_foff, (const panda_qual *) s.d_r,
+		                    (const uint64_t *) s.d_roff, s.d_recoff, s.d_reads, s.d_meta);
+		if (st != PB_OK)
+			return st;
+		st = assemble_dispatch(ctx, cfg, (int) count, (int) max_len, s.d_reads, s.d_meta, s.d_res,
+		                       seq_nt ? s.d_nt : nullptr, seq_p ? s.d_p : nullptr, seq_stride, ctx->d_counters);
+		if (st != PB_OK)
+			return st;
+		CUDA_TRY(cudaMemcpyAsync(s.h_res, s.d_res, count * sizeof(pb_pair_result), cudaMemcpyDeviceToHost, ctx->stream));
+		if (seq_nt)
+			CUDA_TRY(cudaMemcpyAsync(s.h_nt, s.d_nt, count * seq_stride, cudaMemcpyDeviceToHost, ctx->stream));
+		if (seq_p)
+			CUDA_TRY(cudaMemcpyAsync(s.h_p, s.d_p, count * seq_stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(cudaEventRecord(s.done, ctx->stream));
+		pend[si].live = true;
+		pend[si].begin = begin;
+		pend[si].count = count;
+	}
+	for (int k = 0; k < 2; k++) {
+		st = drain(k);
+		if (st != PB_OK)
+			return st;
+	}
+	if (counters) {
+		unsigned long long hc[PB_NCOUNTERS];
+		CUDA_TRY(cudaMemcpyAsync(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+		int64_t tmp[PB_NCOUNTERS];
+		for (int i = 0; i < PB_NCOUNTERS; i++)
+			tmp[i] = (int64_t) hc[i];
+		pb_counters_merge(counters, tmp);
+	}
+	return PB_OK;
+}
+
+/* process-wide default context for the panda_* object layer */
+static pb_context *g_shared = nullptr;
+static pthread_mutex_t g_shared_lock = PTHREAD_MUTEX_INITIALIZER;
+
+extern "C" pb_status pb_shared_context(pb_context **out) {
+	pb_status st = PB_OK;
+	pthread_mutex_lock(&g_shared_lock);
+	if (!g_shared) {
+		int dev = 0;
+		const char *env = getenv("PANDASEQ_B200_DEVICE");
+		if (env)
+			dev = atoi(env);
+		st = pb_context_create(dev, &g_shared);
+	}
+	*out = g_shared;
+	pthread_mutex_unlock(&g_shared_lock);
+	return st;
+}

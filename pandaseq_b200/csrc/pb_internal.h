@@ -1,0 +1,66 @@
+/* pb_internal.h -- declarations shared by the host C files and the CUDA file.
+ * Not installed; the public ABI is include/pandaseq_b200.h. */
+#ifndef PB_INTERNAL_H
+#define PB_INTERNAL_H
+#include "pandaseq_b200.h"
+#include <pthread.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_NQ (PB_PHREDMAX + 1)   /* 47 PHRED values */
+#define PB_NQM (PB_NQ + 1)        /* + index 47 = "masked / absent read" */
+
+/* What the kernels read, built on the host from a pb_config (pb_luts.c) and kept in HBM.
+ *  recon[k][a][b]  : per-base log p during reconstruction (assembler.c:162-243), k = bases match;
+ *                    a/b = clamped PHRED of the forward/reverse base, or 47 when that read is absent
+ *                    (forward-only / reverse-only stretch) or B-cliff masked (assembler.c:176-210).
+ *  over[k][a][b]   : per-base term of the overlap score for pear / rdp_mle (algo_pear.c:52-54,
+ *                    algo_rdp_mle.c:68-70); unused by simple_bayes / flash.
+ */
+typedef struct {
+	double recon[2][PB_NQM][PB_NQM];
+	double over[2][PB_NQ][PB_NQ];
+	double score[PB_NQM];       /* qual_score, [47] unused (0) */
+	double score_err[PB_NQM];   /* qual_score_err */
+	double qual_nn;
+	double sb_pmatch;           /* algo_simple_bayes.c:132-133 */
+	double sb_pmismatch;
+	double pear_random_base;
+	double threshold;
+	double primer_penalty;
+	int32_t algo;
+	int32_t minoverlap;
+	int32_t maxoverlap;
+	int32_t forward_trim;
+	int32_t reverse_trim;
+	int32_t forward_primer_length;
+	int32_t reverse_primer_length;
+	int32_t pad0;
+	uint8_t forward_primer[PB_MAX_LEN + 2];
+	uint8_t reverse_primer[PB_MAX_LEN + 2];
+} pb_device_params;
+
+/* pb_luts.c */
+pb_status pb_build_device_params(const pb_config *cfg, pb_device_params *out);
+double pb_host_match_probability(int algo, bool match, char a, char b);
+void pb_set_error(const char *fmt, ...);
+
+/* pb_algorithm.c */
+struct panda_algorithm {
+	PandaAlgorithmClass clazz;
+	volatile size_t refcnt;
+	pthread_mutex_t mutex;
+	/* private data of clazz->data_size bytes follows; aligned like a pointer, as in algo.h:27-34 */
+	void *end;
+};
+int pb_algorithm_fill_config(PandaAlgorithm algo, pb_config *cfg);
+
+/* pb_device.cu */
+pb_status pb_shared_context(pb_context **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
