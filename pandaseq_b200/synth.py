@@ -190,15 +190,18 @@ def generate(n: int, rl=(150, 150), tmpl=(180, 280), seed=1, device="cpu", mixed
         rp = torch.from_numpy(np.log2(encode(revcomp(REV_PRIMER))).astype(np.int64)).to(device)
         L = L + len(fp) + len(rp)
     Lmax = int(L.max().item())
-    tcode = torch.randint(0, 4, (n, Lmax), generator=gen, device=device)
+    # Extended template: the insert occupies [rlr, rlr+L); what lies outside is random sequence, so an
+    # insert shorter than a read ("read-through") simply runs on into unrelated bases.
+    width = rlr + max(Lmax, rlf) + rlf
+    tcode = torch.randint(0, 4, (n, width), generator=gen, device=device)
     if primers:
-        tcode[:, :len(fp)] = fp[None, :]
-        idx = (L - len(rp))[:, None] + torch.arange(len(rp), device=device)[None, :]
+        tcode[:, rlr:rlr + len(fp)] = fp[None, :]
+        idx = (rlr + L - len(rp))[:, None] + torch.arange(len(rp), device=device)[None, :]
         tcode.scatter_(1, idx, rp[None, :].expand(n, -1))
-    # forward read: template[0:RL]; reverse read k: template[L-1-k] (complemented, read order)
-    fpos = torch.arange(rlf, device=device)[None, :].expand(n, -1).clamp(max=Lmax - 1)
+    # forward read i: insert[i]; reverse read k: insert[L-1-k] (complemented, read order)
+    fpos = (rlr + torch.arange(rlf, device=device))[None, :].expand(n, -1)
     f_true = torch.gather(tcode, 1, fpos)
-    rpos = (L[:, None] - 1 - torch.arange(rlr, device=device)[None, :]).clamp(min=0)
+    rpos = rlr + L[:, None] - 1 - torch.arange(rlr, device=device)[None, :]
     r_true = torch.gather(tcode, 1, rpos)
     f_q = _btail(gen, _quals(gen, n, rlf, flen, device), flen, device, btail_rate)
     r_q = _btail(gen, _quals(gen, n, rlr, rlen, device), rlen, device, btail_rate)
