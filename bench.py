@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- read-pairs/s of the paired-end assembly hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2] [--pairs P]
+
+A "step" is one pass of the hot path (primer scan when configured, k-mer seeded overlap selection,
+reconstruction with posterior qualities) over one batch of synthetic read pairs.  At N = 1 the batch is
+BASELINE config 2: 10 M synthetic 2x150 bp pairs, simple_bayesian.  With N > 1 (launched by torchrun,
+one rank per GPU) every rank assembles its own 10 M-pair shard -- weak scaling, no collective on the
+data path; the per-rank counter vectors are merged once at the end (the STAT merge).
+
+value      whole-job Mpairs/s with the packed batch already resident in HBM (CUDA events on the
+           library's launch stream, max over ranks).
+e2e        the same metric through the C ABI with HOST buffers: pb_assemble_host() copies the flat
+           panda_qual arrays host->device, packs, assembles, and copies results + merged reads back.
+roofline   algorithmic HBM read bytes per pair (458 B at 2x150) x pairs / kernel time vs the measured
+           copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline / --impl reference
+           the reference's own CPU implementation (oracle/_ref, compiled from the reference sources)
+           or the oracle port if that is absent, all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GEN_CHUNK = 1_000_000
+
+
+def algorithmic_read_bytes(flen, rlen):
+    """4-bit nt + 8-bit PHRED for both reads + 8 B of pair metadata."""
+    return (flen + 1) // 2 + (rlen + 1) // 2 + flen + rlen + 8
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(cfg_id):
+    from pandaseq_b200 import synth
+    c = synth.CONFIGS[cfg_id]
+    kw = {}
+    if c.get("primers"):
+        fwd = synth.encode(synth.FWD_PRIMER)
+        rev = synth.encode("".join(synth._COMP[ch] for ch in synth.REV_PRIMER))
+        kw = dict(forward_primer=fwd, reverse_primer=rev)
+    return c, kw
+
+
+def cpu_rate(cfg, flat, threads):
+    """Mpairs/s of the CPU reference on `flat`, and which implementation ran."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    which = "ref" if oracle_lib.have_ref() else "port"
+    t0 = time.perf_counter()
+    oracle_lib.assemble(which, cfg, flat, want_seq=False, threads=threads)
+    dt = time.perf_counter() - t0
+    return flat.n / dt / 1e6, ("reference" if which == "ref" else "port")
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU path on this box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import pandaseq_b200 as pb
+    from pandaseq_b200 import synth
+    c, kw = workload(args.config)
+    cfg = pb.make_config(c["algo"], **kw)
+    cores = os.cpu_count() or 1
+    probe = synth.generate_config(args.config, n=20_000, device="cpu").to_flat()
+    rate, kind = cpu_rate(cfg, probe, cores)
+    sample = int(min(max(rate * 1e6 * 6.0, 20_000), 4_000_000))        # ~6 s per step
+    flat = synth.generate_config(args.config, n=sample, device="cpu", chunk_index=1).to_flat()
+    for _ in range(args.warmup):
+        cpu_rate(cfg, flat.slice(0, min(sample, 50_000)), cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_rate(cfg, flat, cores)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt / 1e6
+    fl, rl = flat.lengths()
+    line = {
+        "impl": "reference", "metric": "read-pairs/s (Mpairs/s), pair assembly hot path", "value": value, "unit": "Mpairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE config {args.config}: synthetic 2x{int(fl[0])} bp pairs, {c['algo']}, "
+                               f"bounded sample of {sample} pairs per step on the host CPU"},
+        "cpu_baseline": {"value": value, "unit": "Mpairs/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} pairs x {args.steps} steps, panda_assembler_assemble loop, one assembler per thread, logging off"},
+        "e2e": {"value": value, "unit": "Mpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU (default: the config's, capped at 10 M per GPU)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import pandaseq_b200 as pb
+    from pandaseq_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    c, kw = workload(args.config)
+    cfg = pb.make_config(c["algo"], **kw)
+    n = args.pairs if args.pairs is not None else min(c["n"], 10_000_000)
+    ctx = pb.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle, device=dev)
+
+    # ---- build the resident batch: generate on the device, pack with the library's pack kernel ------
+    reads_parts, meta_parts, alg_bytes, max_len, base16 = [], [], 0, 0, 0
+    keep_flat = []          # AoS chunks kept (on the host) for the e2e leg
+    e2e_pairs = 0 if args.no_e2e else min(n, 4_000_000)
+    for ci, start in enumerate(range(0, n, GEN_CHUNK)):
+        cnt = min(GEN_CHUNK, n - start)
+        rect = synth.generate_config(args.config, n=cnt, device=dev, chunk_index=rank * 100_000 + ci)
+        f_data, f_off, r_data, r_off = rect.to_flat_tensors()
+        alg_bytes += int(algorithmic_read_bytes(rect.flen, rect.rlen).sum().item())
+        reads, meta, ml, total = ctx.pack_device(f_data, f_off, r_data, r_off)
+        meta[:, 0] += base16
+        base16 += total // 16
+        max_len = max(max_len, ml)
+        reads_parts.append(reads[:total])
+        meta_parts.append(meta)
+        if start < e2e_pairs:
+            keep_flat.append(synth.FlatBatch(f_data.cpu().numpy(), f_off.cpu().numpy().astype(np.uint64),
+                                             r_data.cpu().numpy(), r_off.cpu().numpy().astype(np.uint64)))
+        del rect, f_data, r_data
+    reads = torch.cat(reads_parts + [torch.zeros(16, dtype=torch.uint8, device=dev)])
+    meta = torch.cat(meta_parts)
+    del reads_parts, meta_parts
+    seq_stride = (2 * max_len + 15) & ~15
+    results = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    seq_nt = torch.empty((n, seq_stride), dtype=torch.uint8, device=dev)
+    counters = torch.zeros(pb.PB_NCOUNTERS, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize(dev)
+
+    def step():
+        ctx.assemble_device(cfg, n, max_len, reads, meta, results, seq_nt, None, seq_stride, counters)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    ctx.synchronize()
+    counters.zero_()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for k in range(args.steps):
+        step()
+        evs[k + 1].record(stream)
+    ctx.synchronize()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    total_ms = evs[0].elapsed_time(evs[-1])
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = n * world * args.steps / (total_ms / 1e3) / 1e6
+    # the step is one launch of the assemble kernel: its average duration is the kernel duration
+    kern_ms = float(np.mean(step_ms))
+    achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    # ---- counters: the STAT merge ---------------------------------------------------------------
+    ctot = counters.clone()
+    if dist is not None:
+        longest = ctot[pb.C_LONGEST].clone()
+        dist.all_reduce(ctot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(longest, op=dist.ReduceOp.MAX)
+        ctot[pb.C_LONGEST] = longest
+    ctot = ctot.cpu().numpy()
+    stat = {k: int(ctot[i]) // args.steps for k, i in (("count", pb.C_COUNT), ("ok", pb.C_OK), ("lowq", pb.C_LOWQ),
+                                                      ("noalgn", pb.C_NOALGN), ("badr", pb.C_BADR), ("slow", pb.C_SLOW))}
+
+    # ---- e2e: host buffers through pb_assemble_host -----------------------------------------------
+    e2e = None
+    if not args.no_e2e and keep_flat:
+        flat = synth.FlatBatch.concat(keep_flat)
+        del keep_flat
+        ne = flat.n
+        res_h = np.zeros(ne, dtype=pb.PAIR_RESULT_DTYPE)
+        nt_h = np.zeros((ne, seq_stride), dtype=np.uint8)
+        cnt_h = np.zeros(pb.PB_NCOUNTERS, dtype=np.int64)
+        import ctypes as C
+        L = pb.lib()
+
+        def e2e_step():
+            rc = L.pb_assemble_host(ctx._h, C.byref(cfg), ne, flat.f_data.ctypes.data, flat.f_off.ctypes.data, flat.r_data.ctypes.data,
+                                    flat.r_off.ctypes.data, res_h.ctypes.data, nt_h.ctypes.data, None, seq_stride, cnt_h.ctypes.data)
+            if rc != 0:
+                raise RuntimeError(L.pb_last_error().decode())
+
+        e2e_step()
+        barrier()
+        ksteps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_step()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = flat.f_data.nbytes + flat.r_data.nbytes + flat.f_off.nbytes + flat.r_off.nbytes + 4 * ne
+        d2h = res_h.nbytes + nt_h.nbytes
+        e2e = {"value": ne * world * ksteps / dt / 1e6, "unit": "Mpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "pairs_per_step_per_gpu": ne, "steps": ksteps,
+               "note": "pb_assemble_host(): pageable host panda_qual arrays -> pinned staging -> H2D -> pack -> assemble -> D2H (results + merged reads)"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        probe = synth.generate_config(args.config, n=20_000, device="cpu").to_flat()
+        r0, kind = cpu_rate(cfg, probe, cores)
+        sample = int(min(max(r0 * 1e6 * 12.0, 20_000), 8_000_000))
+        flat_c = synth.generate_config(args.config, n=sample, device="cpu", chunk_index=1).to_flat()
+        r1, kind = cpu_rate(cfg, flat_c, cores)
+        cpu = {"value": r1, "unit": "Mpairs/s", "cores": cores, "kind": kind,
+               "sample": f"{sample} synthetic pairs of the same config, panda_assembler_assemble loop, one assembler per thread, logging off"}
+
+    if rank == 0:
+        fl = int(meta[0, 1].item()) & 0xFFFF
+        line = {
+            "metric": "read-pairs/s (Mpairs/s), pair assembly hot path", "value": value, "unit": "Mpairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 (4-bit nt, 8-bit PHRED) + f64 log-probabilities", "data": "synthetic",
+            "config": {"workload": f"BASELINE config {args.config}: {n} synthetic 2x{fl} bp pairs per GPU, {c['algo']}"
+                                   + (", primer strip" if kw else ""),
+                       "pairs_per_gpu": n, "l2_policy": f"inputs larger than L2 ({reads.numel() / 1e6:.0f} MB packed per GPU), no flush",
+                       "outputs": "32 B result record + merged read (1 B/base) per pair; per-base log p not requested",
+                       "parallelism": f"{world} x independent shards, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_pair": alg_bytes / n,
+                         "kernel": "pb::assemble_kernel", "kernel_ms": kern_ms},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "stat": stat,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
