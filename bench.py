@@ -205,7 +205,7 @@ def main():
     del reads_parts, meta_parts
     seq_stride = (2 * max_len + 15) & ~15
     results = torch.empty((n, 32), dtype=torch.uint8, device=dev)
-    seq_nt = torch.empty((n, seq_stride), dtype=torch.uint8, device=dev)
+    seq_nt = torch.empty((n, seq_stride // 2), dtype=torch.uint8, device=dev)
     counters = torch.zeros(pb.PB_NCOUNTERS, dtype=torch.int64, device=dev)
     torch.cuda.synchronize(dev)
 
@@ -267,7 +267,7 @@ def main():
         del keep_flat
         ne = flat.n
         res_h = np.zeros(ne, dtype=pb.PAIR_RESULT_DTYPE)
-        nt_h = np.zeros((ne, seq_stride), dtype=np.uint8)
+        nt_h = np.zeros((ne, seq_stride // 2), dtype=np.uint8)
         cnt_h = np.zeros(pb.PB_NCOUNTERS, dtype=np.int64)
         import ctypes as C
         L = pb.lib()
@@ -316,7 +316,7 @@ def main():
             "config": {"workload": f"BASELINE config {args.config}: {n} synthetic 2x{fl} bp pairs per GPU, {c['algo']}"
                                    + (", primer strip" if kw else ""),
                        "pairs_per_gpu": n, "l2_policy": f"inputs larger than L2 ({reads.numel() / 1e6:.0f} MB packed per GPU), no flush",
-                       "outputs": "32 B result record + merged read (1 B/base) per pair; per-base log p not requested",
+                       "outputs": "32 B result record + merged read (4 bit/base) per pair; per-base log p not requested",
                        "parallelism": f"{world} x independent shards, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_pair": alg_bytes / n,

@@ -344,8 +344,9 @@ pb_status pb_pack_device(pb_context *ctx, size_t n,
                          const panda_qual *d_r_data, const uint64_t *d_r_off,
                          const uint32_t *d_rec_off16, uint8_t *d_reads, pb_pair_meta *d_meta);
 
-/* pb_assemble_device: the hot path.  d_seq_nt [n][seq_stride] receives one panda_nt
- * per merged base (may be NULL); d_seq_p [n][seq_stride] the per-base log p (may be
+/* pb_assemble_device: the hot path.  seq_stride = row capacity in BASES (multiple of 16).
+ * d_seq_nt [n][seq_stride/2] receives the merged read, 4 bit per base (panda_nt codes, base 2k
+ * in the low nibble of byte k; may be NULL); d_seq_p [n][seq_stride] the per-base log p (may be
  * NULL: only FASTQ output and quality plugins need it); d_counters PB_NCOUNTERS
  * int64, accumulated.  max_read_len = longest read in the batch (selects the kernel's
  * shared-memory class; 0 = assume PB_MAX_LEN).  Asynchronous on the context's stream. */

@@ -147,6 +147,14 @@ def _np_ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def unpack_nt(packed: np.ndarray) -> np.ndarray:
+    """(n, stride/2) packed merged reads (4 bit per base, low nibble first) -> (n, stride) panda_nt codes"""
+    out = np.empty((packed.shape[0], packed.shape[1] * 2), dtype=np.uint8)
+    out[:, 0::2] = packed & 0x0F
+    out[:, 1::2] = packed >> 4
+    return out
+
+
 def record_bytes(flen, rlen):
     flen, rlen = np.asarray(flen, dtype=np.int64), np.asarray(rlen, dtype=np.int64)
     b = ((flen + 7) // 8) * 4 + ((rlen + 7) // 8) * 4 + ((flen + 3) // 4) * 4 + ((rlen + 3) // 4) * 4
@@ -188,14 +196,15 @@ class Context:
             seq_stride = int((fl + rl).max()) if n else 0
             seq_stride = (seq_stride + 15) & ~15
         res = np.zeros(n, dtype=PAIR_RESULT_DTYPE)
-        nt = np.zeros((n, seq_stride), dtype=np.uint8) if want_nt else None
+        nt = np.zeros((n, seq_stride // 2), dtype=np.uint8) if want_nt else None
         p = np.zeros((n, seq_stride), dtype=np.float64) if want_p else None
         counters = np.zeros(PB_NCOUNTERS, dtype=np.int64)
         f_data, r_data = np.ascontiguousarray(batch.f_data), np.ascontiguousarray(batch.r_data)
         f_off, r_off = np.ascontiguousarray(batch.f_off, dtype=np.uint64), np.ascontiguousarray(batch.r_off, dtype=np.uint64)
         _check(lib().pb_assemble_host(self._h, C.byref(cfg), n, _np_ptr(f_data), _np_ptr(f_off), _np_ptr(r_data), _np_ptr(r_off),
                                       _np_ptr(res), _np_ptr(nt), _np_ptr(p), seq_stride, _np_ptr(counters)), "pb_assemble_host")
-        return dict(results=res, seq_nt=nt, seq_p=p, counters=counters, seq_stride=seq_stride)
+        return dict(results=res, seq_nt=unpack_nt(nt) if nt is not None else None, seq_nt_packed=nt, seq_p=p, counters=counters,
+                    seq_stride=seq_stride)
 
     # ---- device-resident path (torch tensors own the HBM) ---------------------------
     def pack_device(self, f_data, f_off, r_data, r_off):

@@ -16,7 +16,7 @@
 #include <string.h>
 
 #define NEXT_BATCH 65536	/* pairs pulled from a PandaNextSeq source per launch */
-#define SEQ_CAP (2 * PB_MAX_LEN)
+#define SEQ_CAP (2 * PB_MAX_LEN + 12)	/* 912: multiple of 16 */
 
 struct panda_assembler {
 	volatile size_t refcnt;
@@ -270,7 +270,7 @@ static bool reserve(PandaAssembler a, size_t pairs, size_t fbases, size_t rbases
 		if (ro) a->r_off = ro;
 		void *res = realloc(a->res, cap * sizeof(pb_pair_result));
 		if (res) a->res = res;
-		void *nt = realloc(a->nt, cap * SEQ_CAP);
+		void *nt = realloc(a->nt, cap * (SEQ_CAP / 2));
 		if (nt) a->nt = nt;
 		void *p = realloc(a->p, cap * SEQ_CAP * sizeof(double));
 		if (p) a->p = p;
@@ -329,10 +329,10 @@ static const panda_result_seq *publish(PandaAssembler a, size_t i, const panda_s
 	out->overlaps_examined = r->examined;
 	out->overlap = r->overlap;
 	out->estimated_overlap_probability = r->est_prob;
-	const uint8_t *nt = a->nt + i * SEQ_CAP;
+	const uint8_t *nt = a->nt + i * (SEQ_CAP / 2);	/* 4 bit per base, base 2k in the low nibble */
 	const double *p = a->p + i * SEQ_CAP;
 	for (size_t k = 0; k < r->seq_len; k++) {
-		a->result_seq[k].nt = (panda_nt) nt[k];
+		a->result_seq[k].nt = (panda_nt) ((nt[k >> 1] >> ((k & 1) * 4)) & 0x0F);
 		a->result_seq[k].p = p[k];
 	}
 	return out;

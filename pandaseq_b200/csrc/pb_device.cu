@@ -180,12 +180,13 @@ static pb_status assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n,
 	if (max_len <= 0 || max_len > PB_MAX_LEN)
 		max_len = PB_MAX_LEN;
 #define PB_GO(ML, OVER, W) return launch_assemble<ML, OVER, W>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters)
+	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */
 	if (max_len <= 160) {
-		if (over) PB_GO(160, true, 16); else PB_GO(160, false, 16);
+		if (over) PB_GO(160, true, 20); else PB_GO(160, false, 28);
 	} else if (max_len <= 256) {
-		if (over) PB_GO(256, true, 16); else PB_GO(256, false, 16);
+		if (over) PB_GO(256, true, 10); else PB_GO(256, false, 12);
 	} else {
-		if (over) PB_GO(456, true, 16); else PB_GO(456, false, 16);
+		if (over) PB_GO(456, true, 6); else PB_GO(456, false, 6);
 	}
 #undef PB_GO
 }
@@ -194,8 +195,8 @@ extern "C" pb_status pb_assemble_device(pb_context *ctx, const pb_config *cfg, s
                                         const uint8_t *d_reads, const pb_pair_meta *d_meta,
                                         pb_pair_result *d_results, uint8_t *d_seq_nt, double *d_seq_p,
                                         size_t seq_stride, int64_t *d_counters) {
-	if (!ctx || !cfg || !d_results || !d_counters || n > 0x7FFFFFFFull) {
-		pb_set_error("pb_assemble_device: bad argument");
+	if (!ctx || !cfg || !d_results || !d_counters || n > 0x7FFFFFFFull || ((d_seq_nt || d_seq_p) && (seq_stride % 16) != 0)) {
+		pb_set_error("pb_assemble_device: bad argument (seq_stride must be a multiple of 16)");
 		return PB_ERR_ARGUMENT;
 	}
 	CUDA_TRY(cudaSetDevice(ctx->device));
@@ -292,8 +293,8 @@ extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, siz
                                       const panda_qual *r_data, const uint64_t *r_off,
                                       pb_pair_result *results, uint8_t *seq_nt, double *seq_p,
                                       size_t seq_stride, int64_t *counters) {
-	if (!ctx || !cfg || (!results && n) || (n && (!f_data || !f_off || !r_data || !r_off))) {
-		pb_set_error("pb_assemble_host: bad argument");
+	if (!ctx || !cfg || (!results && n) || (n && (!f_data || !f_off || !r_data || !r_off)) || ((seq_nt || seq_p) && (seq_stride % 16) != 0)) {
+		pb_set_error("pb_assemble_host: bad argument (seq_stride must be a multiple of 16)");
 		return PB_ERR_ARGUMENT;
 	}
 	CUDA_TRY(cudaSetDevice(ctx->device));
@@ -312,7 +313,7 @@ extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, siz
 		CUDA_TRY(cudaEventSynchronize(s.done));
 		memcpy(results + pend[si].begin, s.h_res, pend[si].count * sizeof(pb_pair_result));
 		if (seq_nt)
-			memcpy(seq_nt + pend[si].begin * seq_stride, s.h_nt, pend[si].count * seq_stride);
+			memcpy(seq_nt + pend[si].begin * (seq_stride / 2), s.h_nt, pend[si].count * (seq_stride / 2));
 		if (seq_p)
 			memcpy(seq_p + pend[si].begin * seq_stride, s.h_p, pend[si].count * seq_stride * sizeof(double));
 		pend[si].live = false;
@@ -338,7 +339,7 @@ extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, siz
 			pb_set_error("read longer than PANDA_MAX_LEN (%zu > %d)", max_len, PB_MAX_LEN);
 			return PB_ERR_ARGUMENT;
 		}
-		st = ensure_slot(s, count, fbases, rbases, 0, seq_nt ? count * seq_stride : 0, seq_p ? count * seq_stride : 0);
+		st = ensure_slot(s, count, fbases, rbases, 0, seq_nt ? count * (seq_stride / 2) : 0, seq_p ? count * seq_stride : 0);
 		if (st != PB_OK)
 			return st;
 		for (size_t i = 0; i <= count; i++) {
@@ -366,7 +367,7 @@ extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, siz
 			return st;
 		CUDA_TRY(cudaMemcpyAsync(s.h_res, s.d_res, count * sizeof(pb_pair_result), cudaMemcpyDeviceToHost, ctx->stream));
 		if (seq_nt)
-			CUDA_TRY(cudaMemcpyAsync(s.h_nt, s.d_nt, count * seq_stride, cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(cudaMemcpyAsync(s.h_nt, s.d_nt, count * (seq_stride / 2), cudaMemcpyDeviceToHost, ctx->stream));
 		if (seq_p)
 			CUDA_TRY(cudaMemcpyAsync(s.h_p, s.d_p, count * seq_stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(cudaEventRecord(s.done, ctx->stream));

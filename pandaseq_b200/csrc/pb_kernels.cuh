@@ -1,32 +1,34 @@
-/* pb_kernels.cuh -- sm_100a kernels for the PANDAseq pair-assembly hot path.
+/* pb_kernels.cuh -- sm_100a kernels for the PANDAseq pair-assembly hot path (kernel v2).
  *
- * assemble_kernel<ML>: one warp owns one read pair at a time (persistent grid,
- * warps stride over the batch).  Per pair, following the reference's align()
+ * assemble_kernel<ML>: one warp owns one read pair at a time (persistent grid, warps
+ * stride over the batch).  Per pair, following the reference's align()
  * (assembler.c:48-250) and assemble_seq() (assembler.c:252-348):
  *
- *   stage   the packed record (4-bit nt + 8-bit PHRED, both reads) is pulled from
- *           HBM into this warp's shared-memory stage by ONE bulk async copy
- *           (cp.async.bulk, the 1-D TMA path; SASS UBLKCP) completing on an
- *           mbarrier; the copy for the warp's next pair is in flight while the
- *           current pair is processed (2 stages).
+ *   stage   the packed record (4-bit nt + 8-bit PHRED, both reads) is pulled from HBM
+ *           into this warp's shared-memory stage by ONE bulk async copy (cp.async.bulk,
+ *           the 1-D TMA path; SASS UBLKCP) completing on an mbarrier; the copy for the
+ *           warp's next pair is in flight while the current pair is processed.
  *   primers panda_compute_offset_qual (offset.c:47-112), when primers are set.
- *   planes  three bit-planes per read (hi/lo bit of the 2-bit k-mer code, is-N)
- *           built with warp ballots: 32 bases -> one 32-bit word per plane.
- *   seed    K1-K3 of align(): forward 8-mers go into a per-warp shared-memory hash
- *           (open addressing, write-then-verify instead of atomics); reverse
- *           8-mers probe it and keep the two lowest forward positions per code
- *           (the observable behaviour of the reference's 65536x2 table, SURVEY.md
- *           §8a "table-free statement"); hits set byte flags per candidate overlap.
- *   score   K4/K5: every flagged overlap (or all, if none was flagged) is scored by
- *           the algorithm's overlap_probability, whole warp per candidate.
- *   merge   K6: the merged read, per-base log p (2x48x48 LUT in shared memory),
- *           quality = sum / len, mismatch / degenerate counts; result record out.
+ *   codes   a lane takes one 32-bit word (8 bases) of a read, turns the nibbles into
+ *           2-bit k-mer digits with bit-parallel logic (misc.h:41: T=3 G=2 C=1 else 0),
+ *           and emits the 16-bit code of the eight 8-mers that end in its word.
+ *   seed    K1-K3 of align(): forward 8-mers go into a per-warp bucket table in shared
+ *           memory (4 x 16-bit entries per bucket; same-bucket lanes of a round are
+ *           ranked with match.any so every round is a fixed instruction sequence and
+ *           entries stay in position order); reverse 8-mers read one bucket and keep
+ *           the first two forward positions with their code -- the observable behaviour
+ *           of the reference's 65536x2 table (SURVEY.md §8a "table-free statement").
+ *           A bucket that would need a 5th entry (low-complexity reads) sends the pair
+ *           through an exact open-addressing path in the same memory.
+ *   score   K4/K5: every flagged overlap (or all, if none) is scored, a lane per 8 bases.
+ *   merge   K6: merged read (8 bases per lane, bit-parallel), per-base log p from a
+ *           2x48x48 LUT in shared memory, quality = sum / len, counts; result record.
  *
- * Floating point: compiled with --fmad=false.  simple_bayes / flash scores are
- * closed forms of integer counts and are bit-identical to the reference.  The
- * pear / rdp_mle score and the quality sum are sums of LUT entries; the reference
- * adds them left to right, the warp adds 32 partial sums with a shuffle tree:
- * |difference| <= ~3e-13 (measured), tolerance 1e-6 (BASELINE.json north_star).
+ * Floating point: compiled with --fmad=false.  simple_bayes / flash scores are closed
+ * forms of integer counts and are bit-identical to the reference.  The pear / rdp_mle
+ * score and the quality sum are sums of LUT entries; the reference adds them left to
+ * right, the warp adds per-lane partial sums with a shuffle tree: |difference| ~1e-13,
+ * tolerance 1e-6 (BASELINE.json north_star).
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -38,18 +40,28 @@ namespace pb {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int NSTAGE = 2;
+constexpr unsigned NIB1 = 0x11111111u;
 
 /* ---- per-warp shared memory layout, sized by the read-length class ML -------- */
 template <int ML> struct WarpSmem {
 	static constexpr int NTW = (ML + 7) / 8;                 /* nibble words per read */
 	static constexpr int STAGE_BYTES = ((2 * NTW * 4 + 2 * ((ML + 3) / 4) * 4) + 15) & ~15;
-	static constexpr int SLOTS = (ML <= 160) ? 512 : 1024;   /* >= 2x the most k-mers a read can have */
-	static constexpr int PLANE_WORDS = ML / 32 + 2;
+	static constexpr int PBITS = (ML <= 256) ? 8 : 9;        /* bits of a forward position */
+	static constexpr int IDXBITS = (ML <= 160) ? 9 : (ML <= 256 ? 10 : 11);
+	static constexpr int NB = 1 << IDXBITS;                  /* buckets of 4 entries */
+	static constexpr int TAGBITS = 16 - IDXBITS;
+	static_assert(TAGBITS + PBITS <= 16, "bucket entry must fit 16 bits");
+	static constexpr int SLOTS = NB * 2;                     /* the same memory as 32-bit open-addressing slots */
+	static constexpr int CODEN = NTW * 8 + 8;
 	static constexpr int NFLAG = ((2 * ML + 15) & ~15) + 16;
 	alignas(128) uint8_t stage[NSTAGE][STAGE_BYTES];
-	alignas(16) uint32_t htab[SLOTS];
+	alignas(16) uint64_t btab[NB];
+	alignas(16) uint8_t bcnt[NB];
+	alignas(16) uint16_t code_f[CODEN];
+	alignas(16) uint16_t code_r[CODEN];
+	alignas(16) uint8_t inval_f[(NTW + 19) & ~15];           /* bit t of byte w: k-mer ending at 8w+t is invalid */
+	alignas(16) uint8_t inval_r[(NTW + 19) & ~15];
 	alignas(16) uint8_t cflag[NFLAG];
-	uint32_t plane[6][PLANE_WORDS];   /* f.hi f.lo f.N r.hi r.lo r.N */
 	alignas(8) uint64_t bar[NSTAGE];
 	pb_pair_meta meta[NSTAGE];
 };
@@ -92,18 +104,53 @@ __device__ __forceinline__ double warp_sum(double v) {
 		v += __shfl_xor_sync(FULL, v, s);
 	return v;
 }
-__device__ __forceinline__ int warp_sum_int(int v) {
-	return __reduce_add_sync(FULL, v);
+__device__ __forceinline__ unsigned lanemask_lt() {
+	unsigned m;
+	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+	return m;
 }
-/* bits [pos, pos+32) of a bit array stored as 32-bit words */
-__device__ __forceinline__ unsigned window(const uint32_t *w, int pos) {
-	int k = pos >> 5;
-	return __funnelshift_r(w[k], w[k + 1], pos & 31);
+/* 8 nibbles starting at base `pos` of a nibble array; pos may be negative or run past the read (the
+ * caller masks those nibbles; the loads stay inside this warp's shared memory / the LUT area before it). */
+__device__ __forceinline__ unsigned nibwin(const uint32_t *w32, int pos) {
+	int j = max(pos >> 3, -1);
+	return __funnelshift_r(w32[j], w32[j + 1], (pos & 7) * 4);
 }
-__device__ __forceinline__ unsigned hash16(unsigned code, unsigned mask) {
-	return ((code * 40503u) >> 4) & mask;
+/* low n nibbles set, n in [0, 8] */
+__device__ __forceinline__ unsigned nibmask(int n) {
+	return __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 4 * n);
 }
-
+/* bit 4k set iff nibble k is non-zero */
+__device__ __forceinline__ unsigned nz_nib(unsigned x) {
+	unsigned t = x | (x >> 1);
+	return (t | (t >> 2)) & NIB1;
+}
+/* bit 4k set iff nibble k == 15 (N) */
+__device__ __forceinline__ unsigned n_nib(unsigned x) {
+	unsigned t = x & (x >> 1);
+	return t & (t >> 2) & NIB1;
+}
+/* bit 4k set iff nibble k has exactly one bit set */
+__device__ __forceinline__ unsigned onehot_nib(unsigned x) {
+	unsigned x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
+	unsigned par = x ^ x1 ^ x2 ^ x3;
+	unsigned two = (x & x1) | (x2 & x3) | ((x | x1) & (x2 | x3));
+	return par & ~two & NIB1;
+}
+/* nibble-spaced bits (bit 4k) -> 8 contiguous bits */
+__device__ __forceinline__ unsigned squeeze1(unsigned v) {
+	unsigned t = (v | (v >> 3)) & 0x03030303u;
+	t = (t | (t >> 6)) & 0x000F000Fu;
+	return (t | (t >> 12)) & 0xFFu;
+}
+/* nibble-spaced 2-bit fields (bits 4k, 4k+1) -> 16 contiguous bits */
+__device__ __forceinline__ unsigned squeeze2(unsigned v) {
+	unsigned t = (v | (v >> 2)) & 0x0F0F0F0Fu;
+	t = (t | (t >> 4)) & 0x00FF00FFu;
+	return (t | (t >> 8)) & 0xFFFFu;
+}
+__device__ __forceinline__ unsigned hash_slot(unsigned code, unsigned mask) {
+	return ((code * 40503u) >> 3) & mask;
+}
 /* same arithmetic as pb_record_bytes() in the public header */
 __device__ __forceinline__ unsigned record_bytes(unsigned flen, unsigned rlen) {
 	unsigned b = ((flen + 7) / 8) * 4 + ((rlen + 7) / 8) * 4 + ((flen + 3) / 4) * 4 + ((rlen + 3) / 4) * 4;
@@ -112,20 +159,19 @@ __device__ __forceinline__ unsigned record_bytes(unsigned flen, unsigned rlen) {
 
 struct PairView {
 	const uint8_t *fnt, *rnt;      /* packed nibbles; rnt in template order */
+	const uint32_t *fnt32, *rnt32;
 	const int8_t *fq, *rq;         /* raw PHRED chars; rq in template order */
 	int F, R;
 };
 
-/* offset.c:47-112 for one read, whole warp.  Lane s owns the circular-buffer slot s, s+32, ...
- * (P <= 449 slots, up to 15 per lane, kept in registers is too much -> shared would be needed;
- * instead each START offset is owned by a lane: the alignment that begins at read position s
- * accumulates primer[x] vs read[s+x] for x = 0..P-1 in that order, exactly the order the
- * reference's circular buffer receives its addends, so the sum is bit-identical.)
+/* offset.c:47-112 for one read, whole warp.  Each START offset s is owned by a lane: the alignment that
+ * begins at read position s accumulates primer[x] vs read[s+x] for x = 0..P-1 in that order, exactly the
+ * order the reference's circular buffer receives its addends, so the sum is bit-identical.
  *
  * template_order: the read is stored reversed (reverse read), so read position i is element len-1-i.
  * Returns bestindex as the reference does (0 = not found, else 1 + bases consumed).
- * With penalty == 0 the comparison exp(a) > exp(b) is done as a > b (exp is monotone; SURVEY.md
- * §8a a18 measured 0 differences on 600 k reads); with a penalty, CUDA's exp() is used. */
+ * With penalty == 0 the comparison exp(a) > exp(b) is done as a > b (exp is monotone; SURVEY.md §8a a18
+ * measured 0 differences on 600 k reads); with a penalty, CUDA's exp() is used. */
 __device__ int primer_offset(const uint8_t *nt, const int8_t *q, int len, bool template_order,
                              const uint8_t *primer, int P, double threshold, double penalty,
                              const double *score, const double *score_err, int lane) {
@@ -182,20 +228,323 @@ __device__ int primer_offset(const uint8_t *nt, const int8_t *q, int len, bool t
 	return best_index;
 }
 
+/* ---- k-mer codes ---------------------------------------------------------------------------------
+ * For every position p of a read, the 16-bit code of the 8-mer ending at p (digits of misc.h:41, oldest
+ * base in the low bits -- any fixed injective packing will do, both reads use the same one).
+ * Returns per-lane flags: bit 0 = some nibble is N, bit 1 = some nibble inside the read is not A/C/G/T. */
+template <int NTW>
+__device__ __forceinline__ unsigned gen_codes(const uint32_t *nt32, int len, uint16_t *codes, int lane) {
+	const int nw = (len + 7) >> 3;
+	unsigned flags = 0, carry = 0;
+#pragma unroll
+	for (int w0 = 0; w0 < NTW; w0 += 32) {
+		if (w0 < nw) {               /* warp-uniform */
+			const int w = w0 + lane;
+			const unsigned x = (w < nw) ? nt32[w] : 0u;
+			const unsigned x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
+			const unsigned lo = (x3 ^ x1) & ~x2 & ~x & NIB1;      /* T or C */
+			const unsigned hi = (x3 ^ x2) & ~x1 & ~x & NIB1;      /* T or G */
+			const unsigned isa = x & ~x1 & ~x2 & ~x3 & NIB1;
+			const unsigned inread = nibmask(min(max(len - 8 * w, 0), 8)) & NIB1;
+			if ((x & x1 & x2 & x3 & NIB1) != 0)
+				flags |= 1u;
+			if ((inread & ~(lo | hi | isa)) != 0)
+				flags |= 2u;
+			const unsigned c16 = squeeze2(lo | (hi << 1));
+			unsigned prev = __shfl_up_sync(FULL, c16, 1);
+			if (lane == 0)
+				prev = carry;
+			carry = __shfl_sync(FULL, c16, 31);
+			const unsigned W = prev | (c16 << 16);    /* bases 8w-8 .. 8w+7, two bits each */
+			if (w < nw) {
+				uint4 o;
+				o.x = ((W >> 2) & 0xFFFFu) | ((W >> 4) << 16);
+				o.y = ((W >> 6) & 0xFFFFu) | ((W >> 8) << 16);
+				o.z = ((W >> 10) & 0xFFFFu) | ((W >> 12) << 16);
+				o.w = ((W >> 14) & 0xFFFFu) | ((W >> 16) << 16);
+				reinterpret_cast<uint4 *>(codes)[w] = o;
+			}
+		}
+	}
+	return flags;
+}
+
+/* Rare path (a read contains N): bit t of inval[w] is set when the 9 bases ending at 8w+t contain an N
+ * or 8w+t < 8 -- the `bad` counter of misc.h:41. */
+template <int NTW>
+__device__ void gen_invalid(const uint32_t *nt32, int len, uint8_t *inval, int lane) {
+	const int nw = (len + 7) >> 3;
+	unsigned carry = 0;
+	for (int w0 = 0; w0 < nw; w0 += 32) {
+		const int w = w0 + lane;
+		const unsigned x = (w < nw) ? nt32[w] : 0u;
+		const unsigned n8 = squeeze1(n_nib(x));
+		unsigned prev = __shfl_up_sync(FULL, n8, 1);
+		if (lane == 0)
+			prev = carry;
+		carry = __shfl_sync(FULL, n8, 31);
+		unsigned win = prev | (n8 << 8);          /* N flags of bases 8w-8 .. 8w+7 */
+		unsigned s = win | (win << 1);
+		s |= s << 2;
+		s |= s << 4;
+		s |= win << 8;                            /* bit b: an N among bases b-8 .. b */
+		unsigned bad = (s >> 8) & 0xFFu;
+		if (w == 0)
+			bad = 0xFFu;
+		if (w < nw)
+			inval[w] = (uint8_t) bad;
+	}
+}
+
+/* ---- K1-K3 of align() (assembler.c:92-118): flag every overlap that shares a valid 8-mer between the reads ----
+ * HASN: some base is N, so k-mer validity comes from the inval bitmaps (warp-uniform choice, made per pair). */
+template <int ML, bool HASN>
+__device__ __forceinline__ void seed_candidates(WarpSmem<ML> &ws, int F, int R, int mo, int nbits, int lane) {
+	using WS = WarpSmem<ML>;
+	constexpr unsigned IDXMASK = WS::NB - 1;
+	constexpr unsigned PLIM = (1u << WS::PBITS) - 1u;
+	uint16_t *bt16 = reinterpret_cast<uint16_t *>(ws.btab);
+	const unsigned lt = lanemask_lt();
+	unsigned ovf = 0;
+	/* K1: forward 8-mers into the bucket table, in position order.  Two rounds are prepared together so the
+	 * second round's match.any is in flight while the first round's bucket counters are updated. */
+	for (int p0 = 8 + lane; p0 - lane < F; p0 += 64) {
+		unsigned code[2], idx[2], grp[2];
+		bool live[2];
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const int p = p0 + 32 * h;
+			live[h] = p < F;
+			if (HASN)
+				live[h] = live[h] && ((ws.inval_f[p >> 3] >> (p & 7)) & 1u) == 0;
+			code[h] = ws.code_f[p];
+			idx[h] = code[h] & IDXMASK;
+			grp[h] = __match_any_sync(FULL, live[h] ? idx[h] : (WS::NB + lane));
+		}
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const int p = p0 + 32 * h;
+			const unsigned cnt = ws.bcnt[idx[h]];
+			__syncwarp();
+			const unsigned slot = cnt + __popc(grp[h] & lt);
+			const unsigned entry = ((code[h] >> WS::IDXBITS) << WS::PBITS) | (unsigned) p;
+			if (live[h] && slot < 4u)
+				bt16[idx[h] * 4 + slot] = (uint16_t) entry;
+			ovf |= (live[h] && slot >= 4u) ? 1u : 0u;
+			if (live[h] && (grp[h] >> lane) == 1u)   /* last lane of its group; an 8-bit wrap only happens after ovf is set */
+				ws.bcnt[idx[h]] = (uint8_t) (cnt + __popc(grp[h]));
+			__syncwarp();
+		}
+	}
+	const bool overflow = __any_sync(FULL, ovf != 0);
+	const int cbase = F - mo;                  /* overlap - mo = cbase - p + e */
+	if (!overflow) {
+		/* K2: reverse 8-mers probe one bucket each (assembler.c:104-110); byte flags = BIT_LIST_SET */
+#pragma unroll 2
+		for (int e = 8 + lane; e - lane < R; e += 32) {
+			bool live = e < R;
+			if (HASN)
+				live = live && ((ws.inval_r[e >> 3] >> (e & 7)) & 1u) == 0;
+			const unsigned code = ws.code_r[e];
+			const unsigned tagsh = (code >> WS::IDXBITS) << WS::PBITS;
+			const uint2 b = *reinterpret_cast<const uint2 *>(&ws.btab[code & IDXMASK]);
+			/* entry ^ tagsh is the stored position iff the tags agree (positions are >= 8, empty entries are 0) */
+			const unsigned x0 = (b.x & 0xFFFFu) ^ tagsh, x1 = (b.x >> 16) ^ tagsh;
+			const unsigned x2 = (b.y & 0xFFFFu) ^ tagsh, x3 = (b.y >> 16) ^ tagsh;
+			unsigned m1 = 0x7FFFu, m2 = 0x7FFFu;      /* entries are in position order: first two that match */
+			if (x3 - 1u < PLIM) { m1 = x3; }
+			if (x2 - 1u < PLIM) { m2 = m1; m1 = x2; }
+			if (x1 - 1u < PLIM) { m2 = m1; m1 = x1; }
+			if (x0 - 1u < PLIM) { m2 = m1; m1 = x0; }
+			const unsigned c = live ? (unsigned) (cbase + e) : 0u;   /* dead lanes: index underflows, no flag */
+			const unsigned i1 = c - m1, i2 = c - m2;
+			if (i1 < (unsigned) nbits)
+				ws.cflag[i1] = 1;
+			if (i2 < (unsigned) nbits)
+				ws.cflag[i2] = 1;
+		}
+		__syncwarp();
+		/* K3: clear (assembler.c:113-116) */
+		const uint4 z = make_uint4(0, 0, 0, 0);
+		uint4 *t4 = reinterpret_cast<uint4 *>(ws.btab);
+#pragma unroll
+		for (int k = 0; k < WS::NB * 8 / 16 / 32; k++)
+			t4[k * 32 + lane] = z;
+		uint4 *c4 = reinterpret_cast<uint4 *>(ws.bcnt);
+#pragma unroll
+		for (int k = 0; k < (WS::NB / 16 + 31) / 32; k++)
+			if (k * 32 + lane < WS::NB / 16)
+				c4[k * 32 + lane] = z;
+		return;
+	}
+	/* Exact open-addressing path for pairs whose k-mers crowd a bucket (low-complexity reads): every
+	 * (code, position) is stored; the probe walks the whole chain and keeps the two lowest positions. */
+	constexpr unsigned SMASK = WS::SLOTS - 1;
+	uint32_t *slots = reinterpret_cast<uint32_t *>(ws.btab);
+	for (int k = lane; k < WS::SLOTS; k += 32)
+		slots[k] = 0;
+	for (int k = lane; k < WS::NB; k += 32)
+		ws.bcnt[k] = 0;
+	__syncwarp();
+	for (int base = 8; base < F; base += 32) {
+		const int p = base + lane;
+		bool live = p < F;
+		if (HASN)
+			live = live && ((ws.inval_f[p >> 3] >> (p & 7)) & 1u) == 0;
+		const unsigned code = ws.code_f[p];
+		const unsigned entry = (code << 16) | (unsigned) p;
+		unsigned slot = hash_slot(code, SMASK);
+		bool pending = live;
+		while (__any_sync(FULL, pending)) {
+			bool tryw = false;
+			if (pending) {
+				tryw = slots[slot] == 0u;
+				if (tryw)
+					slots[slot] = entry;
+			}
+			__syncwarp();
+			if (pending) {
+				if (tryw && slots[slot] == entry)
+					pending = false;
+				else
+					slot = (slot + 1) & SMASK;
+			}
+			__syncwarp();
+		}
+	}
+	__syncwarp();
+	for (int base = 8; base < R; base += 32) {
+		const int e = base + lane;
+		bool live = e < R;
+		if (HASN)
+			live = live && ((ws.inval_r[e >> 3] >> (e & 7)) & 1u) == 0;
+		if (live) {
+			const unsigned code = ws.code_r[e];
+			unsigned slot = hash_slot(code, SMASK);
+			unsigned m1 = 0x7FFFu, m2 = 0x7FFFu;
+			for (;;) {
+				const unsigned ent = slots[slot];
+				if (ent == 0u)
+					break;
+				if ((ent >> 16) == code) {
+					const unsigned p = ent & 0xFFFFu;
+					if (p < m1) {
+						m2 = m1;
+						m1 = p;
+					} else if (p < m2) {
+						m2 = p;
+					}
+				}
+				slot = (slot + 1) & SMASK;
+			}
+			const unsigned c = (unsigned) (cbase + e);
+			const unsigned i1 = c - m1, i2 = c - m2;
+			if (i1 < (unsigned) nbits)
+				ws.cflag[i1] = 1;
+			if (i2 < (unsigned) nbits)
+				ws.cflag[i2] = 1;
+		}
+	}
+	__syncwarp();
+	for (int k = lane; k < WS::SLOTS; k += 32)
+		slots[k] = 0;
+}
+
+/* ---- K6 of align() (assembler.c:158-244), 8 output bases per lane ----
+ * Output position idx takes forward base fo+idx while idx < fend and reverse (template) base idx-df from
+ * idx >= dfp on; where both apply the bases are merged (assembler.c:181-228).
+ * GENERAL = false is the common case: no B-cliff masking, no degenerate bases, per-base p not requested. */
+struct ReconArgs {
+	const uint32_t *fnt32, *rnt32;
+	const int8_t *fq, *rq;
+	int fo, df, dfp, fend, seq_len, unmasked_f, lead_r, out_cap;
+	uint8_t *out_nt;
+	double *out_p;
+	const uint16_t *qoff;          /* [0..255]: clamp(q)*48*8, [256..511]: clamp(q)*8, indexed by the raw quality byte */
+};
+
+constexpr unsigned ZERO_OFF = 2 * PB_NQM * PB_NQM * 8;   /* byte offset of the 0.0 that follows recon[2][48][48] in shared memory */
+
+template <bool GENERAL>
+__device__ __forceinline__ double recon_words(const ReconArgs &ra, const double *__restrict__ s_recon, int &mism, int &degen, int lane) {
+	double qsum = 0.0;
+	const int nwords = (ra.seq_len + 7) >> 3;
+	for (int k = lane; k - lane < nwords; k += 32) {
+		if (k < nwords) {
+			const int idx0 = 8 * k;
+			const int nV = min(ra.seq_len - idx0, 8);                 /* positions of this word inside the sequence */
+			const int nF = min(max(ra.fend - idx0, 0), 8);            /* leading positions that use the forward read */
+			const int r0 = min(max(ra.dfp - idx0, 0), 8);             /* positions < r0 do not use the reverse read */
+			const unsigned maskV = nibmask(nV), maskF = nibmask(nF) & maskV, maskR = maskV & ~nibmask(r0);
+			const unsigned fw = nibwin(ra.fnt32, ra.fo + idx0) & maskF;
+			const unsigned rw = nibwin(ra.rnt32, idx0 - ra.df) & maskR;
+			const unsigned both = maskF & maskR;
+			const unsigned andw = fw & rw;
+			const unsigned nzb = nz_nib(andw);                     /* match flags, meaningful where both */
+			unsigned missb = both & NIB1 & ~nzb;                   /* mismatching overlap positions */
+			/* match -> intersection; mismatch -> forward unless the reverse quality is strictly higher (fixed below) */
+			unsigned nt = (fw & ~maskR) | (rw & ~maskF) | andw | (fw & (missb * 15u));
+			const int8_t *fqp = ra.fq + ra.fo + idx0, *rqp = ra.rq + idx0 - ra.df;
+			mism += __popc(missb);
+			while (missb) {                                        /* assembler.c:215-219 */
+				const int t = (__ffs(missb) - 1) >> 2;
+				missb &= missb - 1;
+				if (fqp[t] < rqp[t])
+					nt = (nt & ~(15u << (4 * t))) | (rw & (15u << (4 * t)));
+			}
+			if (GENERAL)
+				degen += __popc(~onehot_nib(nt) & maskV & NIB1);
+			if (ra.out_nt && idx0 < ra.out_cap)
+				reinterpret_cast<uint32_t *>(ra.out_nt)[k] = nt;
+			/* per-base posterior: recon[match][a][b], a/b = clamped PHRED or 47 when that read is absent/masked.
+			 * qoff maps a raw quality byte to the BYTE offset of its clamped row (x 48*8) / column (x 8). */
+			const unsigned char *fqu = reinterpret_cast<const unsigned char *>(fqp), *rqu = reinterpret_cast<const unsigned char *>(rqp);
+			const char *tab = reinterpret_cast<const char *>(s_recon);
+#pragma unroll
+			for (int t = 0; t < 8; t++) {
+				unsigned oa = ra.qoff[fqu[t]], ob = ra.qoff[256 + rqu[t]];
+				if (t >= nF)
+					oa = PB_NQ * PB_NQM * 8;
+				if (t < r0)
+					ob = PB_NQ * 8;
+				if (GENERAL) {                                     /* assembler.c:194-210 */
+					const bool inboth = t < nF && t >= r0;
+					if (inboth && ra.fo + idx0 + t >= ra.unmasked_f)
+						oa = PB_NQ * PB_NQM * 8;
+					if (inboth && idx0 + t - ra.df < ra.lead_r)
+						ob = PB_NQ * 8;
+				}
+				const unsigned om = (nzb & (1u << (4 * t))) ? (unsigned) (PB_NQM * PB_NQM * 8) : 0u;
+				unsigned off = oa + ob + om;
+				if (t >= nV)
+					off = ZERO_OFF;                                /* a 0.0 kept right after the table */
+				const double p = *reinterpret_cast<const double *>(tab + off);
+				qsum += p;
+				if (GENERAL && ra.out_p && t < nV && idx0 + t < ra.out_cap)
+					ra.out_p[idx0 + t] = p;
+			}
+		}
+	}
+	return qsum;
+}
+
 template <int ML>
 __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
                              const pb_device_params *__restrict__ prm,
                              const double *__restrict__ s_recon, const double *__restrict__ s_over,
                              const double *__restrict__ s_score, const double *__restrict__ s_score_err,
+                             const uint16_t *__restrict__ s_qoff,
                              pb_pair_result &res, uint8_t *out_nt, double *out_p, int out_cap, int lane) {
 	using WS = WarpSmem<ML>;
 	PairView v;
 	v.F = F;
 	v.R = R;
-	const int fw = ((F + 7) / 8) * 4, rw = ((R + 7) / 8) * 4;
+	const int fwb = ((F + 7) / 8) * 4, rwb = ((R + 7) / 8) * 4;
 	v.fnt = rec;
-	v.rnt = rec + fw;
-	v.fq = (const int8_t *) (rec + fw + rw);
+	v.rnt = rec + fwb;
+	v.fnt32 = reinterpret_cast<const uint32_t *>(v.fnt);
+	v.rnt32 = reinterpret_cast<const uint32_t *>(v.rnt);
+	v.fq = (const int8_t *) (rec + fwb + rwb);
 	v.rq = v.fq + ((F + 3) / 4) * 4;
 
 	res.status = PB_PAIR_OK;
@@ -255,230 +604,123 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 		maxov = min(F + R - mo - fo - ro - 1, prm->maxoverlap);
 	const int nbits = (mo <= maxov) ? (maxov - mo + 1) : 1;
 
-	/* ---- bit planes (K1/K2 input): misc.h:41 code T=3 G=2 C=1 else 0; N resets the window ---- */
-	const int fwords = (F + 31) >> 5, rwords = (R + 31) >> 5;
-	bool anyN = false;
-	for (int w = 0; w < fwords; w++) {
-		int b = w * 32 + lane;
-		unsigned n = (b < F) ? nib(v.fnt, b) : 0u;
-		unsigned hi = __ballot_sync(FULL, n == 8u || n == 4u);
-		unsigned lo = __ballot_sync(FULL, n == 8u || n == 2u);
-		unsigned nn = __ballot_sync(FULL, n == 15u);
-		anyN |= nn != 0;
-		if (lane == 0) {
-			ws.plane[0][w] = hi;
-			ws.plane[1][w] = lo;
-			ws.plane[2][w] = nn;
-		}
-	}
-	for (int w = 0; w < rwords; w++) {
-		int b = w * 32 + lane;
-		unsigned n = (b < R) ? nib(v.rnt, b) : 0u;
-		unsigned hi = __ballot_sync(FULL, n == 8u || n == 4u);
-		unsigned lo = __ballot_sync(FULL, n == 8u || n == 2u);
-		unsigned nn = __ballot_sync(FULL, n == 15u);
-		anyN |= nn != 0;
-		if (lane == 0) {
-			ws.plane[3][w] = hi;
-			ws.plane[4][w] = lo;
-			ws.plane[5][w] = nn;
-		}
-	}
-	if (lane == 0) {
-		for (int k = 0; k < 6; k++)
-			ws.plane[k][k < 3 ? fwords : rwords] = 0;
+	/* ---- k-mer codes of both reads ---- */
+	unsigned flg = gen_codes<WS::NTW>(v.fnt32, F, ws.code_f, lane) | gen_codes<WS::NTW>(v.rnt32, R, ws.code_r, lane);
+	flg = __reduce_or_sync(FULL, flg);
+	const bool anyN = (flg & 1u) != 0;
+	const bool anyDeg = (flg & 2u) != 0;       /* some base is not A/C/G/T: only then can a merged base be degenerate */
+	if (anyN) {
+		gen_invalid<WS::NTW>(v.fnt32, F, ws.inval_f, lane);
+		gen_invalid<WS::NTW>(v.rnt32, R, ws.inval_r, lane);
 	}
 	__syncwarp();
 
-	/* ---- K1: forward 8-mers into the hash (assembler.c:92-101) ---- */
-	constexpr unsigned MASK = WS::SLOTS - 1;
-	for (int base = 8; base < F; base += 32) {
-		int p = base + lane;
-		bool live = p < F;
-		unsigned code = 0;
-		if (live) {
-			unsigned hi = window(ws.plane[0], p - 7) & 0xFFu;
-			unsigned lo = window(ws.plane[1], p - 7) & 0xFFu;
-			code = (hi << 8) | lo;
-			if (anyN)
-				live = (window(ws.plane[2], p - 8) & 0x1FFu) == 0;
-		}
-		unsigned entry = (code << 16) | (unsigned) p;
-		unsigned slot = hash16(code, MASK);
-		bool pending = live;
-		while (__any_sync(FULL, pending)) {
-			bool tryw = false;
-			if (pending) {
-				tryw = ws.htab[slot] == 0u;
-				if (tryw)
-					ws.htab[slot] = entry;
-			}
-			__syncwarp();
-			if (pending) {
-				if (tryw && ws.htab[slot] == entry)
-					pending = false;
-				else
-					slot = (slot + 1) & MASK;
-			}
-			__syncwarp();
-		}
-	}
-	__syncwarp();
+	/* ---- K1-K3: seed candidate overlaps (assembler.c:92-118) ---- */
+	if (anyN)
+		seed_candidates<ML, true>(ws, F, R, mo, nbits, lane);
+	else
+		seed_candidates<ML, false>(ws, F, R, mo, nbits, lane);
 
-	/* ---- K2: reverse 8-mers probe (assembler.c:104-110); flags = BIT_LIST_SET ---- */
-	for (int base = 8; base < R; base += 32) {
-		int e = base + lane;
-		bool live = e < R;
-		if (live) {
-			unsigned hi = window(ws.plane[3], e - 7) & 0xFFu;
-			unsigned lo = window(ws.plane[4], e - 7) & 0xFFu;
-			unsigned code = (hi << 8) | lo;
-			if (anyN)
-				live = (window(ws.plane[5], e - 8) & 0x1FFu) == 0;
-			if (live) {
-				unsigned slot = hash16(code, MASK);
-				unsigned m1 = 0xFFFFu, m2 = 0xFFFFu;
-				for (;;) {
-					unsigned ent = ws.htab[slot];
-					if (ent == 0u)
-						break;
-					if ((ent >> 16) == code) {
-						unsigned p = ent & 0xFFFFu;
-						if (p < m1) {
-							m2 = m1;
-							m1 = p;
-						} else if (p < m2) {
-							m2 = p;
-						}
-					}
-					slot = (slot + 1) & MASK;
-				}
-				if (m1 != 0xFFFFu) {
-					int idx = F - (int) m1 + e - mo;
-					if (idx >= 0 && idx < nbits)
-						ws.cflag[idx] = 1;
-				}
-				if (m2 != 0xFFFFu) {
-					int idx = F - (int) m2 + e - mo;
-					if (idx >= 0 && idx < nbits)
-						ws.cflag[idx] = 1;
-				}
-			}
-		}
-	}
-	__syncwarp();
-	/* ---- K3: clear the hash for the next pair (assembler.c:113-116) ---- */
-	{
-		uint4 z = make_uint4(0, 0, 0, 0);
-		uint4 *h4 = reinterpret_cast<uint4 *>(ws.htab);
-		for (int k = lane; k < WS::SLOTS / 4; k += 32)
-			h4[k] = z;
-	}
-
-	/* ---- K4/K5: sweep the candidates (assembler.c:118-143) ---- */
+	/* ---- K4/K5: sweep the candidates in increasing overlap (assembler.c:118-143) ---- */
 	const double qual_nn = prm->qual_nn;
 	double best = qual_nn * (double) (unsigned long long) (F + R);   /* assembler.c:60 */
 	int bestov = -1;
 	int examined = 0;
-	/* gather the flag bytes, 16 per lane, into a 16-bit mask per lane, and clear them */
-	const int nflag_chunks = (nbits + 15) >> 4;
-	bool none;
-	{
-		unsigned anyflag = 0;
-		for (int c = lane; c < nflag_chunks; c += 32) {
-			uint4 f = reinterpret_cast<const uint4 *>(ws.cflag)[c];
-			anyflag |= f.x | f.y | f.z | f.w;
-		}
-		none = !__any_sync(FULL, anyflag != 0);
-	}
+	const int nchunks = (nbits + 15) >> 4;     /* 16 flag bytes per chunk; nbits < 900 -> at most 57 chunks */
 	const int algo = prm->algo;
-	for (int cbase = 0; cbase < nflag_chunks; cbase += 32) {
-		int c = cbase + lane;
-		unsigned m16 = 0;
-		if (c < nflag_chunks) {
-			uint4 f = reinterpret_cast<const uint4 *>(ws.cflag)[c];
-			unsigned wv[4] = { f.x, f.y, f.z, f.w };
+	unsigned cm[2];
 #pragma unroll
-			for (int k = 0; k < 4; k++) {
-#pragma unroll
-				for (int b = 0; b < 4; b++)
-					if ((wv[k] >> (8 * b)) & 0xFFu)
-						m16 |= 1u << (k * 4 + b);
-			}
-			if (none)
-				m16 = 0xFFFFu;
-			/* only idx < nbits are candidates */
-			int lim = nbits - c * 16;
-			if (lim < 16)
-				m16 &= (1u << lim) - 1u;
-			reinterpret_cast<uint4 *>(ws.cflag)[c] = make_uint4(0, 0, 0, 0);
+	for (int h = 0; h < 2; h++) {
+		unsigned nzw = 0;
+		if (h * 32 < nchunks && h * 32 + lane < nchunks) {
+			const uint4 f = reinterpret_cast<const uint4 *>(ws.cflag)[h * 32 + lane];
+			nzw = f.x | f.y | f.z | f.w;
 		}
-		unsigned have;
-		while ((have = __ballot_sync(FULL, m16 != 0)) != 0) {
-			int leader = __ffs(have) - 1;
-			unsigned lm = __shfl_sync(FULL, m16, leader);
-			int bit = __ffs(lm) - 1;
-			if (lane == leader)
-				m16 &= m16 - 1;
-			const int ov = (cbase + leader) * 16 + bit + mo;
-			/* overlap_probability for this candidate, whole warp */
-			const int i0 = max(0, ov - F), i1 = min(ov, R);    /* findex = F-ov+i in [0,F), template index i < R */
-			double prob;
-			if (algo == PB_SIMPLE_BAYES || algo == PB_FLASH) {
-				int matches = 0, mism = 0, unk = 0;
-				for (int i = i0 + lane; i < i1; i += 32) {
-					unsigned f = nib(v.fnt, F - ov + i), r = nib(v.rnt, i);
-					if (f == 15u || r == 15u)
-						unk++;
-					else if (f & r)
-						matches++;
-					else
-						mism++;
-				}
-				unsigned packed = (unsigned) matches | ((unsigned) mism << 10) | ((unsigned) unk << 20);
-				packed = __reduce_add_sync(FULL, packed);
-				matches = packed & 1023;
-				mism = (packed >> 10) & 1023;
-				unk = packed >> 20;
-				if (algo == PB_SIMPLE_BAYES) {
-					/* algo_simple_bayes.c:61-65: size_t arithmetic inside the parenthesis */
-					unsigned long long nn_count = (ov >= F && ov >= R)
-						? (unsigned long long) unk
-						: (unsigned long long) ((long long) F + R - 2 * (long long) ov + unk);
-					prob = qual_nn * (double) nn_count + (double) matches * prm->sb_pmatch;
-					prob = prob + (double) mism * prm->sb_pmismatch;
-				} else {
-					/* algo_flash.c:59: integer division inside log() */
-					int real = matches + mism + unk, bad = mism + unk;
-					prob = (real == 0) ? -2.0 : ((bad == real) ? 0.0 : -CUDART_INF);
-				}
-			} else {
-				double acc = 0.0;
-				for (int i = i0 + lane; i < i1; i += 32) {
-					int fi = F - ov + i;
-					unsigned f = nib(v.fnt, fi), r = nib(v.rnt, i);
-					int qa = clampq(v.fq[fi]);
-					if (algo == PB_PEAR) {
-						/* algo_pear.c:52,54 index the FORWARD qualities with rindex = R-1-i; past the
-						 * end of the forward read that is defined as quality 0. */
-						int ri = R - 1 - i;
-						int qb = (ri < F) ? clampq(v.fq[ri]) : 0;
-						if (f == 15u || r == 15u)
-							acc -= prm->pear_random_base;
-						else
-							acc += s_over[(((f & r) ? 1 : 0) * PB_NQ + qa) * PB_NQ + qb];
-					} else {
-						int qb = clampq(v.rq[i]);
-						acc += s_over[(((f & r) ? 1 : 0) * PB_NQ + qa) * PB_NQ + qb];
+		cm[h] = (h * 32 < nchunks) ? __ballot_sync(FULL, nzw != 0) : 0u;
+	}
+	const bool none = (cm[0] | cm[1]) == 0;    /* ALL_BITS_IF_NONE, assembler.c:118 */
+	if (none) {
+		cm[0] = nchunks >= 32 ? FULL : ((1u << nchunks) - 1u);
+		cm[1] = nchunks > 32 ? ((1u << (nchunks - 32)) - 1u) : 0u;
+	}
+#pragma unroll
+	for (int h = 0; h < 2; h++) {
+		unsigned chunks = cm[h];
+		while (chunks) {
+			const int ch = h * 32 + __ffs(chunks) - 1;
+			chunks &= chunks - 1;
+			/* candidate bits of this chunk: lane t < 16 looks at flag byte t */
+			const int idx0 = ch * 16;
+			bool set = false;
+			if (lane < 16 && idx0 + lane < nbits)
+				set = none || ws.cflag[idx0 + lane] != 0;
+			unsigned cand = __ballot_sync(FULL, set);
+			__syncwarp();
+			if (!none && lane == 0)
+				reinterpret_cast<uint4 *>(ws.cflag)[ch] = make_uint4(0, 0, 0, 0);
+			while (cand) {
+				const int ov = idx0 + __ffs(cand) - 1 + mo;
+				cand &= cand - 1;
+				/* overlap_probability for this candidate.  findex = F-ov+i in [0,F), template index i in [0,R) */
+				const int i0 = max(0, ov - F), i1 = min(ov, R);
+				double prob;
+				if (algo == PB_SIMPLE_BAYES || algo == PB_FLASH) {
+					unsigned packed = 0;
+					const int nw = (i1 + 7) >> 3;
+					for (int k0 = 0; k0 < nw; k0 += 32) {
+						const int k = k0 + lane;
+						if (k < nw) {
+							const unsigned M = (nibmask(min(max(i1 - 8 * k, 0), 8)) & ~nibmask(min(max(i0 - 8 * k, 0), 8))) & NIB1;
+							const unsigned r = v.rnt32[k];
+							const unsigned f = nibwin(v.fnt32, F - ov + 8 * k);
+							const unsigned nzb = nz_nib(f & r);
+							const unsigned unk = anyN ? ((n_nib(f) | n_nib(r)) & M) : 0u;
+							const unsigned mt = nzb & ~unk & M, mm = ~nzb & ~unk & M;
+							packed += (unsigned) __popc(mt) | ((unsigned) __popc(mm) << 10) | ((unsigned) __popc(unk) << 20);
+						}
 					}
+					packed = __reduce_add_sync(FULL, packed);
+					const int matches = packed & 1023, mism = (packed >> 10) & 1023, unk = packed >> 20;
+					if (algo == PB_SIMPLE_BAYES) {
+						/* algo_simple_bayes.c:61-65: size_t arithmetic inside the parenthesis */
+						const unsigned long long nn_count = (ov >= F && ov >= R)
+							? (unsigned long long) unk
+							: (unsigned long long) ((long long) F + R - 2 * (long long) ov + unk);
+						prob = qual_nn * (double) nn_count + (double) matches * prm->sb_pmatch;
+						prob = prob + (double) mism * prm->sb_pmismatch;
+					} else {
+						/* algo_flash.c:59: integer division inside log() */
+						const int real = matches + mism + unk, bad = mism + unk;
+						prob = (real == 0) ? -2.0 : ((bad == real) ? 0.0 : -CUDART_INF);
+					}
+				} else {
+					double acc = 0.0;
+					for (int i = i0 + lane; i < i1; i += 32) {
+						const int fi = F - ov + i;
+						const unsigned f = nib(v.fnt, fi), r = nib(v.rnt, i);
+						const int qa = clampq(v.fq[fi]);
+						if (algo == PB_PEAR) {
+							/* algo_pear.c:52,54 index the FORWARD qualities with rindex = R-1-i; past the
+							 * end of the forward read that is defined as quality 0. */
+							const int ri = R - 1 - i;
+							const int qb = (ri < F) ? clampq(v.fq[ri]) : 0;
+							if (f == 15u || r == 15u)
+								acc -= prm->pear_random_base;
+							else
+								acc += s_over[(((f & r) ? 1 : 0) * PB_NQ + qa) * PB_NQ + qb];
+						} else {
+							const int qb = clampq(v.rq[i]);
+							acc += s_over[(((f & r) ? 1 : 0) * PB_NQ + qa) * PB_NQ + qb];
+						}
+					}
+					prob = warp_sum(acc);
 				}
-				prob = warp_sum(acc);
+				if (prob > best) {        /* strict, ascending overlap: assembler.c:128-131 */
+					best = prob;
+					bestov = ov;
+				}
+				examined++;
 			}
-			if (prob > best) {        /* strict, ascending overlap: assembler.c:128-131 */
-				best = prob;
-				bestov = ov;
-			}
-			examined++;
 		}
 	}
 	res.examined = (uint16_t) examined;
@@ -500,67 +742,43 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 	const int nover = bestov + dfn + drn;
 	/* B-cliff: trailing run of '#'/qual 2 in each read (assembler.c:176-177) */
 	int unmasked_f = F, lead_r = 0;
-	for (int base = 0; base < F; base += 32) {
-		int i = F - 1 - base - lane;
-		unsigned notb = __ballot_sync(FULL, !(i >= 0 && v.fq[i] == 2));
-		if (notb) {
-			unmasked_f = F - base - (__ffs(notb) - 1);
-			break;
-		}
-		unmasked_f = max(F - base - 32, 0);
-	}
-	for (int base = 0; base < R; base += 32) {
-		int j = base + lane;      /* template order: reverse[R-1-j] */
-		unsigned notb = __ballot_sync(FULL, !(j < R && v.rq[j] == 2));
-		if (notb) {
-			lead_r = base + (__ffs(notb) - 1);
-			break;
-		}
-		lead_r = min(base + 32, R);
-	}
-	double qsum = 0.0;
-	int mism = 0, degen = 0;
-	for (int base = 0; base < seq_len; base += 32) {
-		int idx = base + lane;
-		if (idx < seq_len) {
-			unsigned nt;
-			int a, b, m = 0;
-			if (idx < dfp) {                       /* forward only, assembler.c:162-173 */
-				int fi = idx + fo;
-				nt = nib(v.fnt, fi);
-				a = clampq(v.fq[fi]);
-				b = PB_NQ;
-			} else if (idx < dfp + nover) {        /* overlap, assembler.c:181-228 */
-				int i = idx - dfp;
-				int fi = fo + dfp + i;
-				int j = i - dfn;                   /* template index of reverse[R-1-i+dfn] */
-				unsigned fn = nib(v.fnt, fi), rn = nib(v.rnt, j);
-				int fqv = v.fq[fi], rqv = v.rq[j];
-				m = (fn & rn) ? 1 : 0;
-				if (!m)
-					mism++;
-				a = (fi >= unmasked_f) ? PB_NQ : clampq(fqv);
-				b = (j < lead_r) ? PB_NQ : clampq(rqv);
-				nt = m ? (fn & rn) : ((fqv < rqv) ? rn : fn);
-			} else {                               /* reverse only, assembler.c:231-243 */
-				int j = bestov + (idx - dfp - nover);
-				nt = nib(v.rnt, j);
-				a = PB_NQ;
-				b = clampq(v.rq[j]);
+	if (v.fq[F - 1] == 2 || v.rq[0] == 2) {       /* warp-uniform: most pairs have no '#' tail */
+		for (int base = 0; base < F; base += 32) {
+			const int i = F - 1 - base - lane;
+			const unsigned notb = __ballot_sync(FULL, !(i >= 0 && v.fq[max(i, 0)] == 2));
+			if (notb) {
+				unmasked_f = F - base - (__ffs(notb) - 1);
+				break;
 			}
-			double p = s_recon[(m * PB_NQM + a) * PB_NQM + b];
-			qsum += p;
-			if (__popc(nt) != 1)
-				degen++;
-			if (out_nt && idx < out_cap)
-				out_nt[idx] = (uint8_t) nt;
-			if (out_p && idx < out_cap)
-				out_p[idx] = p;
+			unmasked_f = max(F - base - 32, 0);
 		}
+		for (int base = 0; base < R; base += 32) {
+			const int j = base + lane;      /* template order: reverse[R-1-j] */
+			const unsigned notb = __ballot_sync(FULL, !(j < R && v.rq[min(j, R - 1)] == 2));
+			if (notb) {
+				lead_r = base + (__ffs(notb) - 1);
+				break;
+			}
+			lead_r = min(base + 32, R);
+		}
+	}
+	const bool cliff = unmasked_f < F || lead_r > 0;
+	/* the per-word work, specialised on the (warp-uniform, rare) B-cliff / per-base-p / degenerate cases */
+	double qsum;
+	int mism = 0, degen = 0;
+	{
+		ReconArgs ra;
+		ra.fnt32 = v.fnt32; ra.rnt32 = v.rnt32; ra.fq = v.fq; ra.rq = v.rq;
+		ra.fo = fo; ra.df = df; ra.dfp = dfp; ra.fend = dfp + nover; ra.seq_len = seq_len;
+		ra.unmasked_f = unmasked_f; ra.lead_r = lead_r; ra.out_nt = out_nt; ra.out_p = out_p; ra.out_cap = out_cap; ra.qoff = s_qoff;
+		if (cliff || anyDeg || out_p != nullptr)
+			qsum = recon_words<true>(ra, s_recon, mism, degen, lane);
+		else
+			qsum = recon_words<false>(ra, s_recon, mism, degen, lane);
 	}
 	qsum = warp_sum(qsum);
-	mism = warp_sum_int(mism);
-	degen = warp_sum_int(degen);
+	mism = __reduce_add_sync(FULL, mism);
+	degen = __reduce_add_sync(FULL, degen);
 	res.quality = qsum / (double) len;               /* assembler.c:244: divides by len, not seq_len */
 	res.overlap = (uint16_t) bestov;
 	res.est_prob = best;
@@ -572,7 +790,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 }
 
 template <int ML, bool OVER, int WARPS_PER_BLOCK>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 assemble_kernel(const pb_device_params *__restrict__ prm, int n,
                 const uint8_t *__restrict__ reads, const pb_pair_meta *__restrict__ meta,
                 pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, double *__restrict__ seq_p,
@@ -582,17 +800,20 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 	/* block-level: LUTs + counters, then the per-warp areas */
 	constexpr int OVER_N = OVER ? 2 * PB_NQ * PB_NQ : 0;
 	double *s_recon = reinterpret_cast<double *>(smem_raw);
-	double *s_over = s_recon + 2 * PB_NQM * PB_NQM;
+	double *s_over = s_recon + 2 * PB_NQM * PB_NQM + 2;        /* [2*48*48] is the 0.0 recon_words() uses for padding positions */
 	double *s_score = s_over + OVER_N;
 	double *s_score_err = s_score + PB_NQM;
 	unsigned *s_cnt = reinterpret_cast<unsigned *>(s_score_err + PB_NQM);
-	constexpr size_t LUT_BYTES = (2 * PB_NQM * PB_NQM + OVER_N + 2 * PB_NQM) * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned);
+	uint16_t *s_qoff = reinterpret_cast<uint16_t *>(s_cnt + PB_NCOUNTERS);
+	constexpr size_t LUT_BYTES = (2 * PB_NQM * PB_NQM + 2 + OVER_N + 2 * PB_NQM) * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned) + 512 * sizeof(uint16_t);
 	constexpr size_t LUT_ALIGNED = (LUT_BYTES + 127) & ~(size_t) 127;
 	WS *wsall = reinterpret_cast<WS *>(smem_raw + LUT_ALIGNED);
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	for (int i = tid; i < 2 * PB_NQM * PB_NQM; i += blockDim.x)
 		s_recon[i] = (&prm->recon[0][0][0])[i];
+	if (tid < 2)
+		s_recon[2 * PB_NQM * PB_NQM + tid] = 0.0;
 	if (OVER)
 		for (int i = tid; i < 2 * PB_NQ * PB_NQ; i += blockDim.x)
 			s_over[i] = (&prm->over[0][0][0])[i];
@@ -602,9 +823,16 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 	}
 	for (int i = tid; i < PB_NCOUNTERS; i += blockDim.x)
 		s_cnt[i] = 0;
+	for (int i = tid; i < 256; i += blockDim.x) {
+		const int q = clampq((int) (signed char) i);
+		s_qoff[i] = (uint16_t) (q * PB_NQM * 8);
+		s_qoff[256 + i] = (uint16_t) (q * 8);
+	}
 	WS &ws = wsall[warp];
-	for (int k = lane; k < WS::SLOTS; k += 32)
-		ws.htab[k] = 0;
+	for (int k = lane; k < WS::NB; k += 32) {
+		ws.btab[k] = 0;
+		ws.bcnt[k] = 0;
+	}
 	for (int k = lane; k < WS::NFLAG; k += 32)
 		ws.cflag[k] = 0;
 	if (lane == 0) {
@@ -616,6 +844,8 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 
 	const int wglobal = blockIdx.x * WARPS_PER_BLOCK + warp;
 	const int wstride = gridDim.x * WARPS_PER_BLOCK;
+	/* merged read rows: 4 bit per base, seq_stride bases per row */
+	const long long nt_row = seq_stride / 2;
 
 	auto issue = [&](int pair, int stage) {
 		if (lane == 0) {
@@ -640,9 +870,9 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 		const pb_pair_meta m = ws.meta[stage];
 		union { pb_pair_result r; uint4 v[2]; } ru;
 		pb_pair_result &res = ru.r;
-		uint8_t *o_nt = seq_nt ? seq_nt + (size_t) pair * seq_stride : nullptr;
+		uint8_t *o_nt = seq_nt ? seq_nt + (size_t) pair * nt_row : nullptr;
 		double *o_p = seq_p ? seq_p + (size_t) pair * seq_stride : nullptr;
-		process_pair<ML>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, res, o_nt, o_p, (int) seq_stride, lane);
+		process_pair<ML>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, s_qoff, res, o_nt, o_p, (int) seq_stride, lane);
 		if (lane == 0) {
 			uint4 *dst = reinterpret_cast<uint4 *>(&results[pair]);
 			dst[0] = ru.v[0];
@@ -678,7 +908,7 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 }
 
 template <int ML, bool OVER, int WARPS_PER_BLOCK> constexpr size_t assemble_smem_bytes() {
-	constexpr size_t LUT_BYTES = (2 * PB_NQM * PB_NQM + (OVER ? 2 * PB_NQ * PB_NQ : 0) + 2 * PB_NQM) * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned);
+	constexpr size_t LUT_BYTES = (2 * PB_NQM * PB_NQM + 2 + (OVER ? 2 * PB_NQ * PB_NQ : 0) + 2 * PB_NQM) * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned) + 512 * sizeof(uint16_t);
 	constexpr size_t LUT_ALIGNED = (LUT_BYTES + 127) & ~(size_t) 127;
 	return LUT_ALIGNED + sizeof(WarpSmem<ML>) * WARPS_PER_BLOCK;
 }
