@@ -250,12 +250,8 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     # ---- counters: the STAT merge ---------------------------------------------------------------
-    ctot = counters.clone()
-    if dist is not None:
-        longest = ctot[pb.C_LONGEST].clone()
-        dist.all_reduce(ctot, op=dist.ReduceOp.SUM)
-        dist.all_reduce(longest, op=dist.ReduceOp.MAX)
-        ctot[pb.C_LONGEST] = longest
+    from pandaseq_b200.shard import dist_merge_counters
+    ctot = dist_merge_counters(counters, dist) if dist is not None else counters.clone()
     ctot = ctot.cpu().numpy()
     stat = {k: int(ctot[i]) // args.steps for k, i in (("count", pb.C_COUNT), ("ok", pb.C_OK), ("lowq", pb.C_LOWQ),
                                                       ("noalgn", pb.C_NOALGN), ("badr", pb.C_BADR), ("slow", pb.C_SLOW))}

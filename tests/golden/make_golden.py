@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libref_harness.so, compiled from
+/root/reference by `make -C oracle ref`).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Each fixture holds a small seeded input batch (flat panda_qual arrays), the configuration, and what
+panda_assembler_assemble() returned for every pair (status, overlap, merged bases, per-base log p, quality,
+counters ...).  The inputs are stored too, so the fixtures do not depend on the random number generator
+of whatever torch version later reads them.  tests/test_golden.py checks the oracle port (CPU) and
+tests/test_gpu_golden.py the CUDA path against these files."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import datasets  # noqa: E402
+import oracle_lib  # noqa: E402
+import pandaseq_b200 as pb  # noqa: E402
+
+CASES = {
+    "cfg1_simple_bayesian": (lambda: datasets.cfg1(600), dict(algo="simple_bayesian")),
+    "cfg1_pear": (lambda: datasets.cfg1(600), dict(algo="pear")),
+    "cfg1_rdp_mle": (lambda: datasets.cfg1(600), dict(algo="rdp_mle")),
+    "cfg1_flash": (lambda: datasets.cfg1(600), dict(algo="flash")),
+    "stress_sb_maxov300": (lambda: datasets.stress(400), dict(algo="simple_bayesian", maxoverlap=300)),
+    "stress_pear_trims": (lambda: datasets.stress(400, seed=3), dict(algo="pear", forward_trim=20, reverse_trim=20, maxoverlap=300)),
+    "mixed_sb": (lambda: datasets.mixed(400), dict(algo="simple_bayesian")),
+    "long250_pear": (lambda: datasets.long250(200), dict(algo="pear")),
+    "primers300_rdp": (lambda: datasets.primers300(150), dict(algo="rdp_mle", primers=True)),
+    "primers300_rdp_penalty": (lambda: datasets.primers300(150), dict(algo="rdp_mle", primers=True, primer_penalty=0.0005)),
+    "lowcomplexity_sb": (lambda: datasets.low_complexity(200), dict(algo="simple_bayesian")),
+    "edge_cases_sb": (lambda: datasets.edge_cases(), dict(algo="simple_bayesian")),
+    "edge_cases_rdp_maxov800": (lambda: datasets.edge_cases(), dict(algo="rdp_mle", maxoverlap=800)),
+}
+
+
+def build_config(spec):
+    kw = dict(spec)
+    algo = kw.pop("algo")
+    if kw.pop("primers", False):
+        fwd, rev = datasets.primer_codes()
+        kw.update(forward_primer=fwd, reverse_primer=rev)
+    return pb.make_config(algo, **kw)
+
+
+def main():
+    if not oracle_lib.have_ref():
+        raise SystemExit("oracle/_ref is not built: run `make -C oracle ref` (needs /root/reference)")
+    for name, (mk, spec) in CASES.items():
+        batch = mk()
+        cfg = build_config(spec)
+        out = oracle_lib.assemble("ref", cfg, batch)
+        ok = out["status"] == 0
+        width = int(out["seq_len"].max()) if ok.any() else 0
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            f_data=batch.f_data, f_off=batch.f_off, r_data=batch.r_data, r_off=batch.r_off,
+            spec=np.array(repr(spec)),
+            status=out["status"], slow=out["slow"], overlap=out["overlap"], seq_len=out["seq_len"],
+            mismatches=out["mismatches"], degenerates=out["degenerates"], examined=out["examined"],
+            fwd_offset=out["fwd_offset"], rev_offset=out["rev_offset"], quality=out["quality"], est_prob=out["est_prob"],
+            seq_nt=out["seq_nt"][:, :width], seq_p=out["seq_p"][:, :width], counters=out["counters"])
+        print(f"{name}: {batch.n} pairs, {int(ok.sum())} assembled, width {width}")
+
+
+if __name__ == "__main__":
+    main()
