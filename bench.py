@@ -262,8 +262,18 @@ def main():
         flat = synth.FlatBatch.concat(keep_flat)
         del keep_flat
         ne = flat.n
-        res_h = np.zeros(ne, dtype=pb.PAIR_RESULT_DTYPE)
-        nt_h = np.zeros((ne, seq_stride // 2), dtype=np.uint8)
+
+        def pinned(arr):
+            """host copy of arr in page-locked memory (what a batching caller would read its FASTQ chunks into)"""
+            t = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0].copy()).dtype, pin_memory=True)
+            t.numpy()[...] = arr
+            return t
+
+        keep = [pinned(flat.f_data), pinned(flat.f_off.view(np.int64)), pinned(flat.r_data), pinned(flat.r_off.view(np.int64))]
+        flat = synth.FlatBatch(keep[0].numpy(), keep[1].numpy().view(np.uint64), keep[2].numpy(), keep[3].numpy().view(np.uint64))
+        res_t = torch.zeros((ne, 32), dtype=torch.uint8, pin_memory=True)
+        nt_t = torch.zeros((ne, seq_stride // 2), dtype=torch.uint8, pin_memory=True)
+        res_h, nt_h = res_t.numpy(), nt_t.numpy()
         cnt_h = np.zeros(pb.PB_NCOUNTERS, dtype=np.int64)
         import ctypes as C
         L = pb.lib()
@@ -289,7 +299,7 @@ def main():
         d2h = res_h.nbytes + nt_h.nbytes
         e2e = {"value": ne * world * ksteps / dt / 1e6, "unit": "Mpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "pairs_per_step_per_gpu": ne, "steps": ksteps,
-               "note": "pb_assemble_host(): pageable host panda_qual arrays -> pinned staging -> H2D -> pack -> assemble -> D2H (results + merged reads)"}
+               "note": "pb_assemble_host(): pinned host panda_qual arrays -> H2D -> pack -> assemble -> D2H (results + merged reads) into pinned host arrays, 2 streams"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
     cpu = None

@@ -23,7 +23,7 @@ struct pb_context {
 	unsigned long long *d_counters;  /* scratch counters for the host path */
 	/* host-path staging (grown on demand) */
 	struct Slot {
-		size_t cap_pairs, cap_bases;
+		size_t cap_pairs, cap_bases, cap_hpairs, cap_hbases, cap_hres;
 		uint8_t *h_f, *h_r;              /* pinned AoS */
 		unsigned long long *h_foff, *h_roff;
 		uint32_t *h_recoff;
@@ -36,7 +36,7 @@ struct pb_context {
 		pb_pair_result *d_res, *h_res;
 		uint8_t *d_nt, *h_nt;
 		double *d_p, *h_p;
-		size_t cap_nt, cap_p;
+		size_t cap_nt, cap_p, cap_dnt, cap_dp;
 		cudaEvent_t done;
 	} slot[2];
 };
@@ -146,7 +146,7 @@ static pb_status upload_params(pb_context *ctx, const pb_config *cfg) {
 template <int ML, bool OVER, int WARPS>
 static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
                                  pb_pair_result *d_results, uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride,
-                                 unsigned long long *d_counters) {
+                                 unsigned long long *d_counters, cudaStream_t stream) {
 	auto kern = pb::assemble_kernel<ML, OVER, WARPS>;
 	constexpr size_t smem = pb::assemble_smem_bytes<ML, OVER, WARPS>();
 	static bool configured[16] = { false };
@@ -167,7 +167,7 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 		grid = want;
 	if (grid < 1)
 		grid = 1;
-	kern<<<(unsigned) grid, WARPS * 32, smem, ctx->stream>>>(ctx->d_params, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p,
+	kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p,
 	                                                           (long long) seq_stride, d_counters);
 	CUDA_TRY(cudaGetLastError());
 	return PB_OK;
@@ -175,11 +175,12 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 
 static pb_status assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int max_len,
                                    const uint8_t *d_reads, const pb_pair_meta *d_meta, pb_pair_result *d_results,
-                                   uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride, unsigned long long *d_counters) {
+                                   uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride, unsigned long long *d_counters,
+                                   cudaStream_t stream) {
 	const bool over = cfg->algo == PB_PEAR || cfg->algo == PB_RDP_MLE;
 	if (max_len <= 0 || max_len > PB_MAX_LEN)
 		max_len = PB_MAX_LEN;
-#define PB_GO(ML, OVER, W) return launch_assemble<ML, OVER, W>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters)
+#define PB_GO(ML, OVER, W) return launch_assemble<ML, OVER, W>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream)
 	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */
 	if (max_len <= 160) {
 		if (over) PB_GO(160, true, 20); else PB_GO(160, false, 28);
@@ -206,7 +207,7 @@ extern "C" pb_status pb_assemble_device(pb_context *ctx, const pb_config *cfg, s
 	if (n == 0)
 		return PB_OK;
 	return assemble_dispatch(ctx, cfg, (int) n, max_read_len, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride,
-	                         (unsigned long long *) d_counters);
+	                         (unsigned long long *) d_counters, ctx->stream);
 }
 
 extern "C" pb_status pb_pack_device(pb_context *ctx, size_t n,
@@ -222,8 +223,8 @@ extern "C" pb_status pb_pack_device(pb_context *ctx, size_t n,
 	CUDA_TRY(cudaSetDevice(ctx->device));
 	const int threads = 256;
 	const unsigned blocks = (unsigned) (((long long) n * 32 + threads - 1) / threads);
-	pb::pack_kernel<<<blocks, threads, 0, ctx->stream>>>((int) n, (const uint8_t *) d_f_data, (const unsigned long long *) d_f_off,
-	                                                      (const uint8_t *) d_r_data, (const unsigned long long *) d_r_off,
+	pb::pack_kernel<<<blocks, threads, 0, ctx->stream>>>((int) n, (const uint8_t *) d_f_data, (const unsigned long long *) d_f_off, 0ull,
+	                                                      (const uint8_t *) d_r_data, (const unsigned long long *) d_r_off, 0ull,
 	                                                      d_rec_off16, d_reads, d_meta);
 	CUDA_TRY(cudaGetLastError());
 	return PB_OK;
@@ -243,17 +244,14 @@ template <typename T> static cudaError_t regrow_dev(T **p, size_t *cap, size_t n
 	return e;
 }
 
-static pb_status ensure_slot(pb_context::Slot &s, size_t pairs, size_t fbases, size_t rbases, size_t reads_bytes,
-                             size_t nt_bytes, size_t p_elems) {
+static pb_status ensure_slot(pb_context::Slot &s, size_t pairs, size_t fbases, size_t rbases, bool stage_in,
+                             bool stage_res, size_t nt_bytes, size_t p_elems) {
 	size_t bases = fbases > rbases ? fbases : rbases;
 	if (pairs > s.cap_pairs) {
 		size_t cap = pairs + pairs / 4 + 16;
-		cudaFreeHost(s.h_foff); cudaFreeHost(s.h_roff); cudaFreeHost(s.h_recoff); cudaFreeHost(s.h_res);
+		cudaFreeHost(s.h_recoff);
 		cudaFree(s.d_foff); cudaFree(s.d_roff); cudaFree(s.d_recoff); cudaFree(s.d_meta); cudaFree(s.d_res);
-		CUDA_TRY(cudaMallocHost(&s.h_foff, (cap + 1) * 8));
-		CUDA_TRY(cudaMallocHost(&s.h_roff, (cap + 1) * 8));
 		CUDA_TRY(cudaMallocHost(&s.h_recoff, cap * 4));
-		CUDA_TRY(cudaMallocHost(&s.h_res, cap * sizeof(pb_pair_result)));
 		CUDA_TRY(cudaMalloc(&s.d_foff, (cap + 1) * 8));
 		CUDA_TRY(cudaMalloc(&s.d_roff, (cap + 1) * 8));
 		CUDA_TRY(cudaMalloc(&s.d_recoff, cap * 4));
@@ -261,33 +259,63 @@ static pb_status ensure_slot(pb_context::Slot &s, size_t pairs, size_t fbases, s
 		CUDA_TRY(cudaMalloc(&s.d_res, cap * sizeof(pb_pair_result)));
 		s.cap_pairs = cap;
 	}
+	if (stage_in && pairs > s.cap_hpairs) {          /* pinned staging for pageable caller offsets */
+		size_t cap = pairs + pairs / 4 + 16;
+		cudaFreeHost(s.h_foff); cudaFreeHost(s.h_roff);
+		CUDA_TRY(cudaMallocHost(&s.h_foff, (cap + 1) * 8));
+		CUDA_TRY(cudaMallocHost(&s.h_roff, (cap + 1) * 8));
+		s.cap_hpairs = cap;
+	}
+	if (stage_res && pairs > s.cap_hres) {
+		size_t cap = pairs + pairs / 4 + 16;
+		cudaFreeHost(s.h_res);
+		CUDA_TRY(cudaMallocHost(&s.h_res, cap * sizeof(pb_pair_result)));
+		s.cap_hres = cap;
+	}
 	if (bases > s.cap_bases) {
 		size_t cap = bases + bases / 4 + 64;
-		cudaFreeHost(s.h_f); cudaFreeHost(s.h_r); cudaFree(s.d_f); cudaFree(s.d_r);
-		CUDA_TRY(cudaMallocHost(&s.h_f, cap * 2));
-		CUDA_TRY(cudaMallocHost(&s.h_r, cap * 2));
+		cudaFree(s.d_f); cudaFree(s.d_r);
 		CUDA_TRY(cudaMalloc(&s.d_f, cap * 2));
 		CUDA_TRY(cudaMalloc(&s.d_r, cap * 2));
 		s.cap_bases = cap;
 	}
-	CUDA_TRY(regrow_dev(&s.d_reads, &s.cap_reads, reads_bytes + 16));
-	if (nt_bytes > s.cap_nt) {
-		cudaFree(s.d_nt); cudaFreeHost(s.h_nt);
-		CUDA_TRY(cudaMalloc(&s.d_nt, nt_bytes));
+	if (stage_in && bases > s.cap_hbases) {
+		size_t cap = bases + bases / 4 + 64;
+		cudaFreeHost(s.h_f); cudaFreeHost(s.h_r);
+		CUDA_TRY(cudaMallocHost(&s.h_f, cap * 2));
+		CUDA_TRY(cudaMallocHost(&s.h_r, cap * 2));
+		s.cap_hbases = cap;
+	}
+	if (nt_bytes > s.cap_nt) {          /* pinned staging, only for pageable caller buffers */
+		cudaFreeHost(s.h_nt);
+		s.h_nt = nullptr;
 		CUDA_TRY(cudaMallocHost(&s.h_nt, nt_bytes));
 		s.cap_nt = nt_bytes;
 	}
 	if (p_elems > s.cap_p) {
-		cudaFree(s.d_p); cudaFreeHost(s.h_p);
-		CUDA_TRY(cudaMalloc(&s.d_p, p_elems * sizeof(double)));
+		cudaFreeHost(s.h_p);
+		s.h_p = nullptr;
 		CUDA_TRY(cudaMallocHost(&s.h_p, p_elems * sizeof(double)));
 		s.cap_p = p_elems;
 	}
 	return PB_OK;
 }
 
-/* Chunked, double-buffered: while chunk k runs on the GPU, chunk k+1 is staged into pinned
- * memory by the host and chunk k-1's results are copied out. */
+static bool is_pinned(const void *p) {
+	if (!p)
+		return false;
+	cudaPointerAttributes attr;
+	if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return attr.type == cudaMemoryTypeHost;
+}
+
+/* Chunked over two slots, each with its own stream: while chunk k is packed/assembled on the GPU, chunk k+1's
+ * host->device copies and chunk k-1's device->host copies run on the other stream.  Caller buffers that are
+ * pinned (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are copied from/to directly; pageable
+ * buffers go through the slot's pinned staging area first. */
 extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, size_t n,
                                       const panda_qual *f_data, const uint64_t *f_off,
                                       const panda_qual *r_data, const uint64_t *r_off,
@@ -304,17 +332,23 @@ extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, siz
 	if (n == 0)
 		return PB_OK;
 	CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, PB_NCOUNTERS * sizeof(unsigned long long), ctx->stream));
-	const size_t CHUNK = 1u << 20;       /* pairs per chunk */
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));      /* parameters + zeroed counters visible to both streams */
+	const bool pin_in = is_pinned(f_data) && is_pinned(r_data) && is_pinned(f_off) && is_pinned(r_off);
+	const bool pin_res = is_pinned(results), pin_nt = is_pinned(seq_nt), pin_p = is_pinned(seq_p);
+	const size_t CHUNK = n > (1u << 21) ? (1u << 20) : (n + 1) / 2 + 1;       /* at least two chunks so the slots overlap */
+	const size_t nt_row = seq_stride / 2;
 	struct Pending { bool live; size_t begin, count; } pend[2] = { { false, 0, 0 }, { false, 0, 0 } };
+	cudaStream_t streams[2] = { ctx->stream, ctx->copy_stream };
 	auto drain = [&](int si) -> pb_status {
 		if (!pend[si].live)
 			return PB_OK;
 		pb_context::Slot &s = ctx->slot[si];
 		CUDA_TRY(cudaEventSynchronize(s.done));
-		memcpy(results + pend[si].begin, s.h_res, pend[si].count * sizeof(pb_pair_result));
-		if (seq_nt)
-			memcpy(seq_nt + pend[si].begin * (seq_stride / 2), s.h_nt, pend[si].count * (seq_stride / 2));
-		if (seq_p)
+		if (!pin_res)
+			memcpy(results + pend[si].begin, s.h_res, pend[si].count * sizeof(pb_pair_result));
+		if (seq_nt && !pin_nt)
+			memcpy(seq_nt + pend[si].begin * nt_row, s.h_nt, pend[si].count * nt_row);
+		if (seq_p && !pin_p)
 			memcpy(seq_p + pend[si].begin * seq_stride, s.h_p, pend[si].count * seq_stride * sizeof(double));
 		pend[si].live = false;
 		return PB_OK;
@@ -326,51 +360,59 @@ extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, siz
 		if (st != PB_OK)
 			return st;
 		pb_context::Slot &s = ctx->slot[si];
+		cudaStream_t stream = streams[si];
 		const uint64_t fb = f_off[begin], rb = r_off[begin];
 		const size_t fbases = (size_t) (f_off[begin + count] - fb), rbases = (size_t) (r_off[begin + count] - rb);
-		/* layout (integer bookkeeping only) */
-		size_t max_len = 0;
+		st = ensure_slot(s, count, fbases, rbases, !pin_in, !pin_res, (seq_nt && !pin_nt) ? count * nt_row : 0, (seq_p && !pin_p) ? count * seq_stride : 0);
+		if (st != PB_OK)
+			return st;
+		/* layout: record offsets (integer bookkeeping only) and the longest read of the chunk */
+		size_t max_len = 0, total16 = 0;
 		for (size_t i = 0; i < count; i++) {
-			size_t fl = (size_t) (f_off[begin + i + 1] - f_off[begin + i]), rl = (size_t) (r_off[begin + i + 1] - r_off[begin + i]);
+			const size_t fl = (size_t) (f_off[begin + i + 1] - f_off[begin + i]), rl = (size_t) (r_off[begin + i + 1] - r_off[begin + i]);
 			if (fl > max_len) max_len = fl;
 			if (rl > max_len) max_len = rl;
+			s.h_recoff[i] = (uint32_t) total16;
+			total16 += pb_record_bytes(fl, rl) / 16;
 		}
 		if (max_len > PB_MAX_LEN) {
 			pb_set_error("read longer than PANDA_MAX_LEN (%zu > %d)", max_len, PB_MAX_LEN);
 			return PB_ERR_ARGUMENT;
 		}
-		st = ensure_slot(s, count, fbases, rbases, 0, seq_nt ? count * (seq_stride / 2) : 0, seq_p ? count * seq_stride : 0);
-		if (st != PB_OK)
-			return st;
-		for (size_t i = 0; i <= count; i++) {
-			s.h_foff[i] = f_off[begin + i] - fb;
-			s.h_roff[i] = r_off[begin + i] - rb;
-		}
-		const size_t reads_bytes = pb_layout_host(count, (const uint64_t *) s.h_foff, (const uint64_t *) s.h_roff, s.h_recoff);
-		st = ensure_slot(s, count, fbases, rbases, reads_bytes, 0, 0);
-		if (st != PB_OK)
-			return st;
-		memcpy(s.h_f, f_data + fb, fbases * 2);
-		memcpy(s.h_r, r_data + rb, rbases * 2);
-		CUDA_TRY(cudaMemcpyAsync(s.d_f, s.h_f, fbases * 2, cudaMemcpyHostToDevice, ctx->stream));
-		CUDA_TRY(cudaMemcpyAsync(s.d_r, s.h_r, rbases * 2, cudaMemcpyHostToDevice, ctx->stream));
-		CUDA_TRY(cudaMemcpyAsync(s.d_foff, s.h_foff, (count + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-		CUDA_TRY(cudaMemcpyAsync(s.d_roff, s.h_roff, (count + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-		CUDA_TRY(cudaMemcpyAsync(s.d_recoff, s.h_recoff, count * 4, cudaMemcpyHostToDevice, ctx->stream));
-		st = pb_pack_device(ctx, count, (const panda_qual *) s.d_f, (const uint64_t *) s.d_foff, (const panda_qual *) s.d_r,
-		                    (const uint64_t *) s.d_roff, s.d_recoff, s.d_reads, s.d_meta);
-		if (st != PB_OK)
-			return st;
-		st = assemble_dispatch(ctx, cfg, (int) count, (int) max_len, s.d_reads, s.d_meta, s.d_res,
-		                       seq_nt ? s.d_nt : nullptr, seq_p ? s.d_p : nullptr, seq_stride, ctx->d_counters);
-		if (st != PB_OK)
-			return st;
-		CUDA_TRY(cudaMemcpyAsync(s.h_res, s.d_res, count * sizeof(pb_pair_result), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(regrow_dev(&s.d_reads, &s.cap_reads, total16 * 16 + 16));
 		if (seq_nt)
-			CUDA_TRY(cudaMemcpyAsync(s.h_nt, s.d_nt, count * (seq_stride / 2), cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(regrow_dev(&s.d_nt, &s.cap_dnt, count * nt_row));
 		if (seq_p)
-			CUDA_TRY(cudaMemcpyAsync(s.h_p, s.d_p, count * seq_stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(cudaEventRecord(s.done, ctx->stream));
+			CUDA_TRY(regrow_dev(&s.d_p, &s.cap_dp, count * seq_stride));
+		const void *src_f = f_data + fb, *src_r = r_data + rb, *src_fo = f_off + begin, *src_ro = r_off + begin;
+		if (!pin_in) {
+			memcpy(s.h_f, src_f, fbases * 2);
+			memcpy(s.h_r, src_r, rbases * 2);
+			memcpy(s.h_foff, src_fo, (count + 1) * 8);
+			memcpy(s.h_roff, src_ro, (count + 1) * 8);
+			src_f = s.h_f; src_r = s.h_r; src_fo = s.h_foff; src_ro = s.h_roff;
+		}
+		CUDA_TRY(cudaMemcpyAsync(s.d_f, src_f, fbases * 2, cudaMemcpyHostToDevice, stream));
+		CUDA_TRY(cudaMemcpyAsync(s.d_r, src_r, rbases * 2, cudaMemcpyHostToDevice, stream));
+		CUDA_TRY(cudaMemcpyAsync(s.d_foff, src_fo, (count + 1) * 8, cudaMemcpyHostToDevice, stream));
+		CUDA_TRY(cudaMemcpyAsync(s.d_roff, src_ro, (count + 1) * 8, cudaMemcpyHostToDevice, stream));
+		CUDA_TRY(cudaMemcpyAsync(s.d_recoff, s.h_recoff, count * 4, cudaMemcpyHostToDevice, stream));
+		{
+			const int threads = 256;
+			const unsigned blocks = (unsigned) (((long long) count * 32 + threads - 1) / threads);
+			pb::pack_kernel<<<blocks, threads, 0, stream>>>((int) count, s.d_f, s.d_foff, fb, s.d_r, s.d_roff, rb, s.d_recoff, s.d_reads, s.d_meta);
+			CUDA_TRY(cudaGetLastError());
+		}
+		st = assemble_dispatch(ctx, cfg, (int) count, (int) max_len, s.d_reads, s.d_meta, s.d_res,
+		                       seq_nt ? s.d_nt : nullptr, seq_p ? s.d_p : nullptr, seq_stride, ctx->d_counters, stream);
+		if (st != PB_OK)
+			return st;
+		CUDA_TRY(cudaMemcpyAsync(pin_res ? (void *) (results + begin) : (void *) s.h_res, s.d_res, count * sizeof(pb_pair_result), cudaMemcpyDeviceToHost, stream));
+		if (seq_nt)
+			CUDA_TRY(cudaMemcpyAsync(pin_nt ? (void *) (seq_nt + begin * nt_row) : (void *) s.h_nt, s.d_nt, count * nt_row, cudaMemcpyDeviceToHost, stream));
+		if (seq_p)
+			CUDA_TRY(cudaMemcpyAsync(pin_p ? (void *) (seq_p + begin * seq_stride) : (void *) s.h_p, s.d_p, count * seq_stride * sizeof(double), cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaEventRecord(s.done, stream));
 		pend[si].live = true;
 		pend[si].begin = begin;
 		pend[si].count = count;
@@ -382,8 +424,7 @@ extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, siz
 	}
 	if (counters) {
 		unsigned long long hc[PB_NCOUNTERS];
-		CUDA_TRY(cudaMemcpyAsync(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+		CUDA_TRY(cudaMemcpy(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost));
 		int64_t tmp[PB_NCOUNTERS];
 		for (int i = 0; i < PB_NCOUNTERS; i++)
 			tmp[i] = (int64_t) hc[i];

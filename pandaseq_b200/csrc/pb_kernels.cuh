@@ -914,15 +914,16 @@ template <int ML, bool OVER, int WARPS_PER_BLOCK> constexpr size_t assemble_smem
 }
 
 /* ---- pack: flat AoS panda_qual -> packed records (one warp per pair) -------------- */
-__global__ void pack_kernel(int n, const uint8_t *__restrict__ f_data, const unsigned long long *__restrict__ f_off,
-                            const uint8_t *__restrict__ r_data, const unsigned long long *__restrict__ r_off,
+__global__ void pack_kernel(int n, const uint8_t *__restrict__ f_data, const unsigned long long *__restrict__ f_off, unsigned long long f_base,
+                            const uint8_t *__restrict__ r_data, const unsigned long long *__restrict__ r_off, unsigned long long r_base,
                             const uint32_t *__restrict__ rec_off16, uint8_t *__restrict__ reads, pb_pair_meta *__restrict__ meta) {
 	const int lane = threadIdx.x & 31;
 	const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (pair >= n)
 		return;
-	const unsigned long long fb = f_off[pair], rb = r_off[pair];
-	const int F = (int) (f_off[pair + 1] - fb), R = (int) (r_off[pair + 1] - rb);
+	/* offsets are absolute; f_data / r_data start at element f_base / r_base (a chunk of a larger batch) */
+	const unsigned long long fb = f_off[pair] - f_base, rb = r_off[pair] - r_base;
+	const int F = (int) (f_off[pair + 1] - f_base - fb), R = (int) (r_off[pair + 1] - r_base - rb);
 	const uint8_t *f = f_data + 2 * fb, *r = r_data + 2 * rb;     /* {nt, qual} byte pairs */
 	uint8_t *rec = reads + (size_t) rec_off16[pair] * 16;
 	const int fw = ((F + 7) / 8) * 4, rw = ((R + 7) / 8) * 4, fqb = ((F + 3) / 4) * 4, rqb = ((R + 3) / 4) * 4;

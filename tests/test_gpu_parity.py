@@ -109,3 +109,52 @@ def test_unsupported_configurations_fail_loudly(ctx):
         ctx.assemble_host(pb.make_config("simple_bayesian", post_primers=True), b)
     with pytest.raises(pb.PandaseqError):
         ctx.assemble_host(pb.make_config(7), b)
+
+
+def test_pinned_host_buffers_take_the_direct_copy_path(ctx):
+    """pb_assemble_host copies straight from/to page-locked caller buffers (two streams); same results as staging."""
+    import ctypes as C
+    import torch
+    b = datasets.cfg1(5000)
+    cfg = pb.make_config("simple_bayesian")
+    want = ctx.assemble_host(cfg, b, want_nt=True, want_p=False)       # pageable numpy -> staged path
+    stride = want["seq_stride"]
+
+    def pin(a, dt=None):
+        t = torch.empty(a.shape, dtype=dt or torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    f, fo = pin(b.f_data), pin(b.f_off.view(np.int64))
+    r, ro = pin(b.r_data), pin(b.r_off.view(np.int64))
+    res = torch.zeros((b.n, 32), dtype=torch.uint8, pin_memory=True)
+    nt = torch.zeros((b.n, stride // 2), dtype=torch.uint8, pin_memory=True)
+    cnt = np.zeros(pb.PB_NCOUNTERS, np.int64)
+    rc = pb.lib().pb_assemble_host(ctx._h, C.byref(cfg), b.n, f.data_ptr(), fo.data_ptr(), r.data_ptr(), ro.data_ptr(),
+                                   res.data_ptr(), nt.data_ptr(), None, stride, cnt.ctypes.data)
+    assert rc == 0, pb.lib().pb_last_error()
+    assert np.array_equal(res.numpy().view(pb.PAIR_RESULT_DTYPE).ravel(), want["results"])
+    assert np.array_equal(nt.numpy(), want["seq_nt_packed"])
+    assert np.array_equal(cnt, want["counters"])
+
+
+def test_device_resident_entry_point(ctx):
+    """pb_pack_device + pb_assemble_device on torch-owned HBM (what bench.py times) == the host-buffer path."""
+    import torch
+    from pandaseq_b200 import synth
+    rect = synth.generate_config(1, n=3000, device="cuda", n_rate=0.001, btail_rate=0.05)
+    f_data, f_off, r_data, r_off = rect.to_flat_tensors()
+    reads, meta, max_len, total = ctx.pack_device(f_data, f_off, r_data, r_off)
+    n = f_off.numel() - 1
+    stride = (2 * max_len + 15) & ~15
+    res = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+    nt = torch.zeros((n, stride // 2), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(pb.PB_NCOUNTERS, dtype=torch.int64, device="cuda")
+    cfg = pb.make_config("simple_bayesian")
+    torch.cuda.synchronize()
+    ctx.assemble_device(cfg, n, max_len, reads, meta, res, nt, None, stride, cnt)
+    ctx.synchronize()
+    flat = synth.FlatBatch(f_data.cpu().numpy(), f_off.cpu().numpy().astype(np.uint64), r_data.cpu().numpy(), r_off.cpu().numpy().astype(np.uint64))
+    got = dict(results=res.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel(), seq_nt=pb.unpack_nt(nt.cpu().numpy()), seq_p=None,
+               counters=cnt.cpu().numpy())
+    rep = compare(got, oracle_lib.assemble("port", cfg, flat))
+    assert rep["ok"], rep
