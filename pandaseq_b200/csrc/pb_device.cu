@@ -183,11 +183,13 @@ static pb_status assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n,
 #define PB_GO(ML, OVER, W) return launch_assemble<ML, OVER, W>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream)
 	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */
 	if (max_len <= 160) {
-		if (over) PB_GO(160, true, 20); else PB_GO(160, false, 28);
+		if (over) PB_GO(160, true, 24); else PB_GO(160, false, 30);
 	} else if (max_len <= 256) {
-		if (over) PB_GO(256, true, 10); else PB_GO(256, false, 12);
+		if (over) PB_GO(256, true, 12); else PB_GO(256, false, 16);
+	} else if (max_len <= 320) {
+		if (over) PB_GO(320, true, 12); else PB_GO(320, false, 15);
 	} else {
-		if (over) PB_GO(456, true, 6); else PB_GO(456, false, 6);
+		if (over) PB_GO(456, true, 6); else PB_GO(456, false, 8);
 	}
 #undef PB_GO
 }

@@ -47,7 +47,7 @@ template <int ML> struct WarpSmem {
 	static constexpr int NTW = (ML + 7) / 8;                 /* nibble words per read */
 	static constexpr int STAGE_BYTES = ((2 * NTW * 4 + 2 * ((ML + 3) / 4) * 4) + 15) & ~15;
 	static constexpr int PBITS = (ML <= 256) ? 8 : 9;        /* bits of a forward position */
-	static constexpr int IDXBITS = (ML <= 160) ? 9 : (ML <= 256 ? 10 : 11);
+	static constexpr int IDXBITS = (ML <= 160) ? 9 : (ML <= 320 ? 10 : 11);
 	static constexpr int NB = 1 << IDXBITS;                  /* buckets of 4 entries */
 	static constexpr int TAGBITS = 16 - IDXBITS;
 	static_assert(TAGBITS + PBITS <= 16, "bucket entry must fit 16 bits");
@@ -56,7 +56,6 @@ template <int ML> struct WarpSmem {
 	static constexpr int NFLAG = ((2 * ML + 15) & ~15) + 16;
 	alignas(128) uint8_t stage[NSTAGE][STAGE_BYTES];
 	alignas(16) uint64_t btab[NB];
-	alignas(16) uint8_t bcnt[NB];
 	alignas(16) uint16_t code_f[CODEN];
 	alignas(16) uint16_t code_r[CODEN];
 	alignas(16) uint8_t inval_f[(NTW + 19) & ~15];           /* bit t of byte w: k-mer ending at 8w+t is invalid */
@@ -168,13 +167,15 @@ struct PairView {
  * begins at read position s accumulates primer[x] vs read[s+x] for x = 0..P-1 in that order, exactly the
  * order the reference's circular buffer receives its addends, so the sum is bit-identical.
  *
- * template_order: the read is stored reversed (reverse read), so read position i is element len-1-i.
+ * TEMPLATE_ORDER: the read is stored reversed (reverse read), so read position i is element len-1-i.
  * Returns bestindex as the reference does (0 = not found, else 1 + bases consumed).
  * With penalty == 0 the comparison exp(a) > exp(b) is done as a > b (exp is monotone; SURVEY.md §8a a18
- * measured 0 differences on 600 k reads); with a penalty, CUDA's exp() is used. */
-__device__ int primer_offset(const uint8_t *nt, const int8_t *q, int len, bool template_order,
+ * measured 0 differences on 600 k reads); with a penalty, CUDA's exp() is used.
+ * score[] and score_err[] are adjacent 48-entry tables; qoff[256 + raw] = clamp(raw) * 8. */
+template <bool TEMPLATE_ORDER>
+__device__ int primer_offset(const uint32_t *nt32, const int8_t *q, int len,
                              const uint8_t *primer, int P, double threshold, double penalty,
-                             const double *score, const double *score_err, int lane) {
+                             const double *score, const uint16_t *qoff, int lane) {
 	if (P > len)
 		return 0;
 	/* The reference tests slot (index % P) at every index before resetting it; the value it sees at
@@ -186,35 +187,42 @@ __device__ int primer_offset(const uint8_t *nt, const int8_t *q, int len, bool t
 		best = exp(best);
 	int best_index = 0;
 	const int nstart = len - P;                    /* starts 0 .. nstart-1 */
+	const char *tab = reinterpret_cast<const char *>(score);
+	const unsigned char *qu = reinterpret_cast<const unsigned char *>(q);
 	for (int base = 0; base < nstart; base += 32) {
-		int s = base + lane;
+		const int s = min(base + lane, nstart - 1);    /* surplus lanes redo the last start; masked below */
 		double sum = 0.0;
-		bool live = s < nstart;
-		if (live) {
-			for (int x = 0; x < P; x++) {
-				unsigned pn = primer[x];
-				if (pn == 15u)
-					continue;
-				int pos = s + x;
-				int el = template_order ? (len - 1 - pos) : pos;
-				unsigned b = nib(nt, el);
-				int ph = clampq(q[el]);
-				sum += (b & pn) ? score[ph] : score_err[ph];
+		for (int x0 = 0; x0 < P; x0 += 8) {
+			/* the 8 read positions s+x0 .. s+x0+7 */
+			const int first = TEMPLATE_ORDER ? (len - 1 - (s + x0) - 7) : (s + x0);
+			const unsigned w = nibwin(nt32, first);
+			const int xn = min(P - x0, 8);
+#pragma unroll
+			for (int t = 0; t < 8; t++) {
+				if (t < xn) {                          /* warp-uniform */
+					const unsigned pn = primer[x0 + t];
+					if (pn != 15u) {                   /* warp-uniform: N in the primer contributes nothing */
+						const unsigned b = TEMPLATE_ORDER ? (w >> (4 * (7 - t))) : (w >> (4 * t));
+						const int el = TEMPLATE_ORDER ? (first + 7 - t) : (first + t);
+						const unsigned off = qoff[256 + qu[el]] + ((b & pn) ? 0u : (unsigned) (PB_NQM * 8));
+						sum += *reinterpret_cast<const double *>(tab + off);
+					}
+				}
 			}
 		}
 		/* The reference scans starts in increasing order and keeps the first strictly better one:
 		 * within a batch that is the maximum value with the lowest start on ties. */
-		int index = s + P;                     /* the index at which this slot is examined */
+		const int index = s + P;                   /* the index at which this slot is examined */
 		double val = sum / (double) (index + 1);
 		if (penalty != 0.0)
 			val = exp(val) - (double) index * penalty;
-		if (!live)
+		if (base + lane >= nstart)
 			val = -CUDART_INF;
 		int who = s;
 #pragma unroll
 		for (int d = 16; d > 0; d >>= 1) {
-			double ov = __shfl_xor_sync(FULL, val, d);
-			int ow = __shfl_xor_sync(FULL, who, d);
+			const double ov = __shfl_xor_sync(FULL, val, d);
+			const int ow = __shfl_xor_sync(FULL, who, d);
 			if (ov > val || (ov == val && ow < who)) {
 				val = ov;
 				who = ow;
@@ -324,15 +332,15 @@ __device__ __forceinline__ void seed_candidates(WarpSmem<ML> &ws, int F, int R, 
 #pragma unroll
 		for (int h = 0; h < 2; h++) {
 			const int p = p0 + 32 * h;
-			const unsigned cnt = ws.bcnt[idx[h]];
+			/* entries fill a bucket from slot 0 upwards, so the count is the number of non-zero halfwords */
+			const uint2 b = *reinterpret_cast<const uint2 *>(&ws.btab[idx[h]]);
+			const unsigned cnt = b.y ? ((b.y >> 16) ? 4u : 3u) : (b.x ? ((b.x >> 16) ? 2u : 1u) : 0u);
 			__syncwarp();
 			const unsigned slot = cnt + __popc(grp[h] & lt);
 			const unsigned entry = ((code[h] >> WS::IDXBITS) << WS::PBITS) | (unsigned) p;
 			if (live[h] && slot < 4u)
 				bt16[idx[h] * 4 + slot] = (uint16_t) entry;
 			ovf |= (live[h] && slot >= 4u) ? 1u : 0u;
-			if (live[h] && (grp[h] >> lane) == 1u)   /* last lane of its group; an 8-bit wrap only happens after ovf is set */
-				ws.bcnt[idx[h]] = (uint8_t) (cnt + __popc(grp[h]));
 			__syncwarp();
 		}
 	}
@@ -370,11 +378,6 @@ __device__ __forceinline__ void seed_candidates(WarpSmem<ML> &ws, int F, int R, 
 #pragma unroll
 		for (int k = 0; k < WS::NB * 8 / 16 / 32; k++)
 			t4[k * 32 + lane] = z;
-		uint4 *c4 = reinterpret_cast<uint4 *>(ws.bcnt);
-#pragma unroll
-		for (int k = 0; k < (WS::NB / 16 + 31) / 32; k++)
-			if (k * 32 + lane < WS::NB / 16)
-				c4[k * 32 + lane] = z;
 		return;
 	}
 	/* Exact open-addressing path for pairs whose k-mers crowd a bucket (low-complexity reads): every
@@ -383,8 +386,6 @@ __device__ __forceinline__ void seed_candidates(WarpSmem<ML> &ws, int F, int R, 
 	uint32_t *slots = reinterpret_cast<uint32_t *>(ws.btab);
 	for (int k = lane; k < WS::SLOTS; k += 32)
 		slots[k] = 0;
-	for (int k = lane; k < WS::NB; k += 32)
-		ws.bcnt[k] = 0;
 	__syncwarp();
 	for (int base = 8; base < F; base += 32) {
 		const int p = base + lane;
@@ -533,7 +534,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
                              const pb_device_params *__restrict__ prm,
                              const double *__restrict__ s_recon, const double *__restrict__ s_over,
                              const double *__restrict__ s_score, const double *__restrict__ s_score_err,
-                             const uint16_t *__restrict__ s_qoff,
+                             const uint16_t *__restrict__ s_qoff, const uint8_t *__restrict__ s_primer,
                              pb_pair_result &res, uint8_t *out_nt, double *out_p, int out_cap, int lane) {
 	using WS = WarpSmem<ML>;
 	PairView v;
@@ -563,8 +564,8 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 	int fo, ro;
 	/* assembler.c:262-284 (primers before assembly) */
 	if (prm->forward_primer_length > 0) {
-		fo = primer_offset(v.fnt, v.fq, F, false, prm->forward_primer, prm->forward_primer_length,
-		                   prm->threshold, prm->primer_penalty, s_score, s_score_err, lane);
+		fo = primer_offset<false>(v.fnt32, v.fq, F, s_primer, prm->forward_primer_length,
+		                          prm->threshold, prm->primer_penalty, s_score, s_qoff, lane);
 		if (fo == 0) {
 			res.status = PB_PAIR_NOFP;
 			return;
@@ -575,8 +576,8 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 	}
 	res.fwd_offset = (uint16_t) fo;
 	if (prm->reverse_primer_length > 0) {
-		ro = primer_offset(v.rnt, v.rq, R, true, prm->reverse_primer, prm->reverse_primer_length,
-		                   prm->threshold, prm->primer_penalty, s_score, s_score_err, lane);
+		ro = primer_offset<true>(v.rnt32, v.rq, R, s_primer + PB_MAX_LEN + 2, prm->reverse_primer_length,
+		                         prm->threshold, prm->primer_penalty, s_score, s_qoff, lane);
 		if (ro == 0) {
 			res.status = PB_PAIR_NORP;
 			return;
@@ -805,7 +806,8 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 	double *s_score_err = s_score + PB_NQM;
 	unsigned *s_cnt = reinterpret_cast<unsigned *>(s_score_err + PB_NQM);
 	uint16_t *s_qoff = reinterpret_cast<uint16_t *>(s_cnt + PB_NCOUNTERS);
-	constexpr size_t LUT_BYTES = (2 * PB_NQM * PB_NQM + 2 + OVER_N + 2 * PB_NQM) * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned) + 512 * sizeof(uint16_t);
+	uint8_t *s_primer = reinterpret_cast<uint8_t *>(s_qoff + 512);    /* forward primer, then the reverse one */
+	constexpr size_t LUT_BYTES = (2 * PB_NQM * PB_NQM + 2 + OVER_N + 2 * PB_NQM) * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned) + 512 * sizeof(uint16_t) + 2 * (PB_MAX_LEN + 2);
 	constexpr size_t LUT_ALIGNED = (LUT_BYTES + 127) & ~(size_t) 127;
 	WS *wsall = reinterpret_cast<WS *>(smem_raw + LUT_ALIGNED);
 
@@ -823,16 +825,16 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 	}
 	for (int i = tid; i < PB_NCOUNTERS; i += blockDim.x)
 		s_cnt[i] = 0;
+	for (int i = tid; i < 2 * (PB_MAX_LEN + 2); i += blockDim.x)
+		s_primer[i] = i < PB_MAX_LEN + 2 ? prm->forward_primer[i] : prm->reverse_primer[i - (PB_MAX_LEN + 2)];
 	for (int i = tid; i < 256; i += blockDim.x) {
 		const int q = clampq((int) (signed char) i);
 		s_qoff[i] = (uint16_t) (q * PB_NQM * 8);
 		s_qoff[256 + i] = (uint16_t) (q * 8);
 	}
 	WS &ws = wsall[warp];
-	for (int k = lane; k < WS::NB; k += 32) {
+	for (int k = lane; k < WS::NB; k += 32)
 		ws.btab[k] = 0;
-		ws.bcnt[k] = 0;
-	}
 	for (int k = lane; k < WS::NFLAG; k += 32)
 		ws.cflag[k] = 0;
 	if (lane == 0) {
@@ -872,7 +874,7 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 		pb_pair_result &res = ru.r;
 		uint8_t *o_nt = seq_nt ? seq_nt + (size_t) pair * nt_row : nullptr;
 		double *o_p = seq_p ? seq_p + (size_t) pair * seq_stride : nullptr;
-		process_pair<ML>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, s_qoff, res, o_nt, o_p, (int) seq_stride, lane);
+		process_pair<ML>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, s_qoff, s_primer, res, o_nt, o_p, (int) seq_stride, lane);
 		if (lane == 0) {
 			uint4 *dst = reinterpret_cast<uint4 *>(&results[pair]);
 			dst[0] = ru.v[0];
@@ -908,7 +910,7 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 }
 
 template <int ML, bool OVER, int WARPS_PER_BLOCK> constexpr size_t assemble_smem_bytes() {
-	constexpr size_t LUT_BYTES = (2 * PB_NQM * PB_NQM + 2 + (OVER ? 2 * PB_NQ * PB_NQ : 0) + 2 * PB_NQM) * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned) + 512 * sizeof(uint16_t);
+	constexpr size_t LUT_BYTES = (2 * PB_NQM * PB_NQM + 2 + (OVER ? 2 * PB_NQ * PB_NQ : 0) + 2 * PB_NQM) * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned) + 512 * sizeof(uint16_t) + 2 * (PB_MAX_LEN + 2);
 	constexpr size_t LUT_ALIGNED = (LUT_BYTES + 127) & ~(size_t) 127;
 	return LUT_ALIGNED + sizeof(WarpSmem<ML>) * WARPS_PER_BLOCK;
 }
