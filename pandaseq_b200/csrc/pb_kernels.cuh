@@ -192,22 +192,30 @@ __device__ int primer_offset(const uint32_t *nt32, const int8_t *q, int len,
 	for (int base = 0; base < nstart; base += 32) {
 		const int s = min(base + lane, nstart - 1);    /* surplus lanes redo the last start; masked below */
 		double sum = 0.0;
+		int el = TEMPLATE_ORDER ? (len - 1 - s) : s;   /* element holding read position s + x */
 		for (int x0 = 0; x0 < P; x0 += 8) {
-			/* the 8 read positions s+x0 .. s+x0+7 */
-			const int first = TEMPLATE_ORDER ? (len - 1 - (s + x0) - 7) : (s + x0);
-			const unsigned w = nibwin(nt32, first);
+			/* nibbles of the 8 read positions s+x0 .. s+x0+7 (template order: element first+7 is position s+x0) */
+			unsigned w = nibwin(nt32, TEMPLATE_ORDER ? (el - 7) : el);
 			const int xn = min(P - x0, 8);
 #pragma unroll
 			for (int t = 0; t < 8; t++) {
-				if (t < xn) {                          /* warp-uniform */
-					const unsigned pn = primer[x0 + t];
-					if (pn != 15u) {                   /* warp-uniform: N in the primer contributes nothing */
-						const unsigned b = TEMPLATE_ORDER ? (w >> (4 * (7 - t))) : (w >> (4 * t));
-						const int el = TEMPLATE_ORDER ? (first + 7 - t) : (first + t);
-						const unsigned off = qoff[256 + qu[el]] + ((b & pn) ? 0u : (unsigned) (PB_NQM * 8));
-						sum += *reinterpret_cast<const double *>(tab + off);
-					}
+				if (t >= xn)
+					break;                             /* warp-uniform */
+				const unsigned pn = primer[x0 + t];
+				unsigned b;
+				if (TEMPLATE_ORDER) {
+					b = w >> 28;
+					w <<= 4;
+				} else {
+					b = w & 15u;
+					w >>= 4;
 				}
+				unsigned off = qoff[256 + qu[el]];
+				el += TEMPLATE_ORDER ? -1 : 1;
+				if ((b & pn) == 0)
+					off += (unsigned) (PB_NQM * 8);    /* score_err[] follows score[] */
+				if (pn != 15u)                         /* warp-uniform: N in the primer contributes nothing */
+					sum += *reinterpret_cast<const double *>(tab + off);
 			}
 		}
 		/* The reference scans starts in increasing order and keeps the first strictly better one:
