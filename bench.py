@@ -248,6 +248,14 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # DRAM traffic of the kernel from the committed `ncu --set full` capture (bytes per pair x pairs of one launch)
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(str(args.config))
+        if tr:
+            traffic, traffic_src = tr["dram_bytes_per_pair"] * n, tr["source"]
+    except Exception:
+        pass
 
     # ---- counters: the STAT merge ---------------------------------------------------------------
     from pandaseq_b200.shard import dist_merge_counters
@@ -324,7 +332,7 @@ def main():
                        "pairs_per_gpu": n, "l2_policy": f"inputs larger than L2 ({reads.numel() / 1e6:.0f} MB packed per GPU), no flush",
                        "outputs": "32 B result record + merged read (4 bit/base) per pair; per-base log p not requested",
                        "parallelism": f"{world} x independent shards, no data-path collective"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_pair": alg_bytes / n,
                          "kernel": "pb::assemble_kernel", "kernel_ms": kern_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "stat": stat,
