@@ -95,6 +95,7 @@ typedef struct panda_algorithm *PandaAlgorithm;
 typedef const struct panda_algorithm_class *PandaAlgorithmClass;
 typedef struct panda_assembler *PandaAssembler;
 typedef struct panda_log_proxy *PandaLogProxy; /* accepted and ignored: logging is out of scope */
+typedef struct panda_mux *PandaMux;            /* accepted and ignored by panda_run_pool: the mux is out of scope */
 
 /* pandaseq-common.h:335-340, 366-397, 402-403 */
 typedef PandaAlgorithm (*PandaAlgorithmCreate) (const char *args);
@@ -231,6 +232,10 @@ void panda_assembler_set_threshold(PandaAssembler assembler, double threshold); 
 PandaLogProxy panda_assembler_get_logger(PandaAssembler assembler);            /* :261-264 */
 double panda_assembler_get_primer_penalty(PandaAssembler assembler);           /* :399-402 */
 void panda_assembler_set_primer_penalty(PandaAssembler assembler, double threshold); /* :404-410 */
+
+/* pool.c:110-181 (pandaseq-args.h:155-169).  Drains the assembler's source through the device in batches and calls
+ * output() for every assembled pair; consumes the assembler; threads/mux are accepted for signature compatibility. */
+bool panda_run_pool(int threads, PandaAssembler assembler, PandaMux mux, PandaOutputSeq output, void *output_data, PandaDestroy output_destroy);
 
 /* offset.c:103-112.  Runs the device primer scan on one read (batch of one). */
 size_t panda_compute_offset_qual(double threshold, double penalty, bool reverse,

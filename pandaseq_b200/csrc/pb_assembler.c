@@ -457,6 +457,32 @@ const panda_result_seq *panda_assembler_next(PandaAssembler a) {
 	}
 }
 
+/* pool.c:110-181.  The reference fans one assembler out over `threads` workers that pull from a shared PandaMux; here
+ * the one assembler already drains its source in device-sized batches (panda_assembler_next), so `threads` and `mux` only
+ * keep the signature: the mux is an opaque handle this library never creates, and is ignored.  Ownership follows the
+ * reference: the assembler is consumed (unref), output_destroy(output_data) is called at the end.  Returns whether any
+ * pair was read. */
+bool panda_run_pool(int threads, PandaAssembler assembler, PandaMux mux, PandaOutputSeq output, void *output_data, PandaDestroy output_destroy) {
+	const panda_result_seq *result;
+	bool some_seqs;
+	(void) threads;
+	(void) mux;
+	if (assembler == NULL) {
+		if (output_destroy != NULL)
+			output_destroy(output_data);
+		return false;
+	}
+	while ((result = panda_assembler_next(assembler)) != NULL) {
+		if (output != NULL && !output(result, output_data))
+			break;
+	}
+	some_seqs = panda_assembler_get_count(assembler) > 0;
+	panda_assembler_unref(assembler);
+	if (output_destroy != NULL)
+		output_destroy(output_data);
+	return some_seqs;
+}
+
 /* offset.c:103-112 as a batch of one read: an assembler-free entry point.  The read is
  * paired with a 2-base dummy mate and run through the kernel with the needle as forward
  * primer; the forward offset the kernel reports is bestindex-1. */

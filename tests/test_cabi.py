@@ -52,3 +52,14 @@ def test_compute_fails_loudly_without_gpu(built):
     L.panda_assembler_new.restype = ctypes.c_void_p
     L.panda_assembler_new.argtypes = [ctypes.c_void_p] * 4
     assert L.panda_assembler_new(None, None, None, None) is None      # no device, no assembler: there is no CPU path
+
+
+def test_c_demo_compiles_and_links_without_gpu(built, tmp_path):
+    """The drop-in demo builds against the public header alone (it is run in the GPU tests)."""
+    import subprocess
+    exe = str(tmp_path / "dropin_demo")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "dropin_demo.c"), "-L", os.path.join(ROOT, "pandaseq_b200"), "-lpandaseq_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "pandaseq_b200"), "-o", exe], check=True)
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 2          # usage

@@ -1,0 +1,244 @@
+"""The reference-shaped object API (panda_assembler_* / panda_algorithm_*) on the GPU, called through ctypes, and a plain C
+program compiled against include/pandaseq_b200.h: per-pair assemble, pull-source next(), batch call, counters, callbacks."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import datasets
+import oracle_lib
+import pandaseq_b200 as pb
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Qual(C.Structure):
+    _fields_ = [("nt", C.c_char), ("qual", C.c_char)]
+
+
+class Result(C.Structure):
+    _fields_ = [("nt", C.c_char), ("p", C.c_double)]
+
+
+class SeqId(C.Structure):
+    _fields_ = [("instrument", C.c_char * 100), ("run", C.c_char * 100), ("flowcell", C.c_char * 100),
+                ("lane", C.c_int), ("tile", C.c_int), ("x", C.c_int), ("y", C.c_int), ("tag", C.c_char * 50)]
+
+
+class ResultSeq(C.Structure):
+    _fields_ = [("quality", C.c_double), ("degenerates", C.c_size_t), ("name", SeqId), ("sequence", C.POINTER(Result)),
+                ("sequence_length", C.c_size_t), ("forward", C.c_void_p), ("forward_length", C.c_size_t),
+                ("reverse", C.c_void_p), ("reverse_length", C.c_size_t), ("forward_offset", C.c_size_t),
+                ("reverse_offset", C.c_size_t), ("overlap_mismatches", C.c_size_t), ("overlaps_examined", C.c_size_t),
+                ("overlap", C.c_size_t), ("estimated_overlap_probability", C.c_double)]
+
+
+NEXT = C.CFUNCTYPE(C.c_bool, C.POINTER(SeqId), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p)
+OUTPUT = C.CFUNCTYPE(C.c_bool, C.POINTER(ResultSeq), C.c_void_p)
+FAIL = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(SeqId), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def L(built):
+    lib = pb.lib()
+    assert C.sizeof(SeqId) == 368 and C.sizeof(Result) == 16 and C.sizeof(Qual) == 2
+    vp = C.c_void_p
+    lib.panda_assembler_new.restype = vp
+    lib.panda_assembler_new.argtypes = [vp, vp, vp, vp]
+    lib.panda_assembler_assemble.restype = C.POINTER(ResultSeq)
+    lib.panda_assembler_assemble.argtypes = [vp, C.POINTER(SeqId), vp, C.c_size_t, vp, C.c_size_t]
+    lib.panda_assembler_next.restype = C.POINTER(ResultSeq)
+    lib.panda_assembler_next.argtypes = [vp]
+    lib.panda_assembler_assemble_batch.restype = C.c_size_t
+    lib.panda_assembler_assemble_batch.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp]
+    for name in ("count", "ok_count", "low_quality_count", "failed_alignment_count", "bad_read_count", "slow_count",
+                 "no_forward_primer_count", "no_reverse_primer_count"):
+        fn = getattr(lib, "panda_assembler_get_" + name)
+        fn.restype, fn.argtypes = C.c_long, [vp]
+    lib.panda_assembler_get_overlap_count.restype, lib.panda_assembler_get_overlap_count.argtypes = C.c_long, [vp, C.c_size_t]
+    lib.panda_assembler_get_longest_overlap.restype, lib.panda_assembler_get_longest_overlap.argtypes = C.c_size_t, [vp]
+    lib.panda_assembler_get_threshold.restype, lib.panda_assembler_get_threshold.argtypes = C.c_double, [vp]
+    lib.panda_assembler_set_threshold.argtypes = [vp, C.c_double]
+    lib.panda_assembler_set_minimum_overlap.argtypes = [vp, C.c_int]
+    lib.panda_assembler_set_maximum_overlap.argtypes = [vp, C.c_int]
+    lib.panda_assembler_get_minimum_overlap.argtypes = [vp]
+    lib.panda_assembler_set_algorithm.argtypes = [vp, vp]
+    lib.panda_assembler_set_forward_primer.argtypes = [vp, vp, C.c_size_t]
+    lib.panda_assembler_set_reverse_primer.argtypes = [vp, vp, C.c_size_t]
+    lib.panda_assembler_set_forward_trim.argtypes = [vp, C.c_size_t]
+    lib.panda_assembler_get_forward_trim.restype, lib.panda_assembler_get_forward_trim.argtypes = C.c_size_t, [vp]
+    lib.panda_assembler_get_forward_primer.restype, lib.panda_assembler_get_forward_primer.argtypes = vp, [vp, C.POINTER(C.c_size_t)]
+    lib.panda_assembler_copy_configuration.argtypes = [vp, vp]
+    lib.panda_assembler_set_fail_alignment.argtypes = [vp, vp, vp, vp]
+    lib.panda_assembler_unref.argtypes = [vp]
+    lib.panda_algorithm_unref.argtypes = [vp]
+    for name in ("panda_algorithm_pear_new", "panda_algorithm_rdp_mle_new", "panda_algorithm_simple_bayes_new", "panda_algorithm_flash_new"):
+        getattr(lib, name).restype = vp
+    lib.panda_compute_offset_qual.restype = C.c_size_t
+    lib.panda_compute_offset_qual.argtypes = [C.c_double, C.c_double, C.c_bool, vp, C.c_size_t, vp, C.c_size_t]
+    return lib
+
+
+def check_result(res, want, i):
+    r = res.contents
+    assert r.overlap == want["overlap"][i] and r.sequence_length == want["seq_len"][i]
+    assert r.overlap_mismatches == want["mismatches"][i] and r.degenerates == want["degenerates"][i]
+    assert r.overlaps_examined == want["examined"][i]
+    assert r.forward_offset == want["fwd_offset"][i] and r.reverse_offset == want["rev_offset"][i]
+    assert abs(r.quality - want["quality"][i]) <= 1e-6
+    assert abs(r.estimated_overlap_probability - want["est_prob"][i]) <= 1e-6
+    n = r.sequence_length
+    nt = np.array([r.sequence[k].nt[0] for k in range(n)], dtype=np.uint8)
+    p = np.array([r.sequence[k].p for k in range(n)])
+    assert np.array_equal(nt, want["seq_nt"][i, :n])
+    assert np.abs(p - want["seq_p"][i, :n]).max() <= 1e-6
+
+
+def test_assemble_one_pair_at_a_time(L):
+    b = datasets.cfg1(120)
+    want = oracle_lib.assemble("port", pb.make_config("pear"), b)
+    a = L.panda_assembler_new(None, None, None, None)
+    assert a, pb.lib().pb_last_error()
+    algo = L.panda_algorithm_pear_new()
+    L.panda_assembler_set_algorithm(a, algo)
+    L.panda_algorithm_unref(algo)
+    sid = SeqId()
+    for i in range(b.n):
+        f, r = b.pair(i)
+        f, r = np.ascontiguousarray(f), np.ascontiguousarray(r)
+        res = L.panda_assembler_assemble(a, C.byref(sid), f.ctypes.data, len(f), r.ctypes.data, len(r))
+        assert bool(res) == (want["status"][i] == 0)
+        if res:
+            check_result(res, want, i)
+            assert res.contents.forward == f.ctypes.data and res.contents.forward_length == len(f)
+    assert L.panda_assembler_get_count(a) == b.n
+    assert L.panda_assembler_get_ok_count(a) == want["counters"][pb.C_OK]
+    assert L.panda_assembler_get_low_quality_count(a) == want["counters"][pb.C_LOWQ]
+    assert L.panda_assembler_get_failed_alignment_count(a) == want["counters"][pb.C_NOALGN]
+    assert L.panda_assembler_get_slow_count(a) == want["counters"][pb.C_SLOW]
+    assert L.panda_assembler_get_longest_overlap(a) == want["counters"][pb.C_LONGEST]
+    for ov in range(0, 900, 37):
+        assert L.panda_assembler_get_overlap_count(a, ov) == want["counters"][pb.C_OVERLAPS + ov]
+    assert L.panda_assembler_get_overlap_count(a, 900) == -1
+    L.panda_assembler_unref(a)
+
+
+def test_pull_source_next_and_callbacks(L):
+    b = datasets.stress(700)
+    want = oracle_lib.assemble("port", pb.make_config("simple_bayesian", minoverlap=10, threshold=0.7), b)
+    state = {"i": 0, "keep": []}
+
+    def nxt(idp, fp, flp, rp, rlp, _):
+        i = state["i"]
+        if i >= b.n:
+            return False
+        f, r = b.pair(i)
+        f, r = np.ascontiguousarray(f), np.ascontiguousarray(r)
+        state["keep"] = [f, r]                      # valid only until the next call, as the reference's sources are
+        idp.contents.x = i
+        fp[0], flp[0], rp[0], rlp[0] = f.ctypes.data, len(f), r.ctypes.data, len(r)
+        state["i"] = i + 1
+        return True
+
+    failed = []
+    cb_next, cb_fail = NEXT(nxt), FAIL(lambda a, idp, f, fl, r, rl, u: failed.append(idp.contents.x))
+    a = L.panda_assembler_new(C.cast(cb_next, C.c_void_p), None, None, None)
+    L.panda_assembler_set_minimum_overlap(a, 10)
+    L.panda_assembler_set_threshold(a, 0.7)
+    L.panda_assembler_set_fail_alignment(a, C.cast(cb_fail, C.c_void_p), None, None)
+    assert abs(L.panda_assembler_get_threshold(a) - 0.7) < 1e-15 and L.panda_assembler_get_minimum_overlap(a) == 10
+    got = []
+    while True:
+        res = L.panda_assembler_next(a)
+        if not res:
+            break
+        i = res.contents.name.x
+        got.append(i)
+        check_result(res, want, i)
+    assert got == np.nonzero(want["status"] == 0)[0].tolist()        # input order
+    assert failed == np.nonzero(want["status"] == 4)[0].tolist()
+    assert L.panda_assembler_get_count(a) == b.n
+    L.panda_assembler_unref(a)
+
+
+def test_batch_call_with_primers_and_copy_configuration(L):
+    fwd, rev = datasets.primer_codes()
+    b = datasets.primers300(300)
+    want = oracle_lib.assemble("port", pb.make_config("rdp_mle", forward_primer=fwd, reverse_primer=rev), b)
+    proto = L.panda_assembler_new(None, None, None, None)
+    algo = L.panda_algorithm_rdp_mle_new()
+    L.panda_assembler_set_algorithm(proto, algo)
+    L.panda_algorithm_unref(algo)
+    L.panda_assembler_set_forward_trim(proto, 5)
+    L.panda_assembler_set_forward_primer(proto, fwd.ctypes.data, len(fwd))       # a primer clears the trim (assembler_support.c:201-213)
+    L.panda_assembler_set_reverse_primer(proto, rev.ctypes.data, len(rev))
+    assert L.panda_assembler_get_forward_trim(proto) == 0
+    a = L.panda_assembler_new(None, None, None, None)
+    L.panda_assembler_copy_configuration(a, proto)
+    ln = C.c_size_t()
+    assert L.panda_assembler_get_forward_primer(a, C.byref(ln)) and ln.value == len(fwd)
+    fs = [np.ascontiguousarray(b.pair(i)[0]) for i in range(b.n)]
+    rs = [np.ascontiguousarray(b.pair(i)[1]) for i in range(b.n)]
+    fp = (C.c_void_p * b.n)(*[x.ctypes.data for x in fs])
+    rp = (C.c_void_p * b.n)(*[x.ctypes.data for x in rs])
+    fl = (C.c_size_t * b.n)(*[len(x) for x in fs])
+    rl = (C.c_size_t * b.n)(*[len(x) for x in rs])
+    ids = (SeqId * b.n)()
+    for i in range(b.n):
+        ids[i].x = i
+    seen = []
+
+    def out(res, _):
+        i = res.contents.name.x
+        seen.append(i)
+        check_result(res, want, i)
+        return True
+    cb = OUTPUT(out)
+    n_ok = L.panda_assembler_assemble_batch(a, b.n, ids, fp, fl, rp, rl, C.cast(cb, C.c_void_p), None)
+    assert n_ok == int((want["status"] == 0).sum()) and seen == np.nonzero(want["status"] == 0)[0].tolist()
+    assert L.panda_assembler_get_no_forward_primer_count(a) == want["counters"][pb.C_NOFP]
+    L.panda_assembler_unref(a)
+    L.panda_assembler_unref(proto)
+
+
+def test_compute_offset_qual_entry_point(L):
+    fwd, _ = datasets.primer_codes()
+    b = datasets.primers300(40)
+    thr = float(np.log(0.6))
+    for i in range(0, 40, 3):
+        f, r = b.pair(i)
+        for read in (np.ascontiguousarray(f), np.ascontiguousarray(r)):
+            for rv in (False, True):
+                want = oracle_lib.compute_offset("port", thr, 0.0, rv, read, bytes(fwd.tolist()))
+                got = L.panda_compute_offset_qual(thr, 0.0, rv, read.ctypes.data, len(read), fwd.ctypes.data, len(fwd))
+                assert got == want
+
+
+def test_c_program_against_the_header(L, tmp_path):
+    """tests/c/dropin_demo.c: compiled with gcc against include/pandaseq_b200.h, linked with the library, run on the GPU."""
+    exe = str(tmp_path / "dropin_demo")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "dropin_demo.c"),
+                    "-L", os.path.join(ROOT, "pandaseq_b200"), "-lpandaseq_b200", "-Wl,-rpath," + os.path.join(ROOT, "pandaseq_b200"),
+                    "-o", exe], check=True)
+    b = datasets.cfg1(2500)
+    path = str(tmp_path / "pairs.bin")
+    with open(path, "wb") as f:
+        f.write(np.array([b.n, len(b.f_data), len(b.r_data)], dtype=np.uint64).tobytes())
+        f.write(b.f_off.tobytes()); f.write(b.r_off.tobytes()); f.write(b.f_data.tobytes()); f.write(b.r_data.tobytes())
+    for algo in ("simple_bayesian", "rdp_mle"):
+        want = oracle_lib.assemble("port", pb.make_config(algo), b)
+        run = subprocess.run([exe, path, algo], capture_output=True, text=True)
+        assert run.returncode == 0, run.stderr
+        stat = dict(line.split("\t")[1:3] for line in run.stderr.strip().split("\n") if line.startswith("STAT"))
+        assert int(stat["READS"]) == b.n and int(stat["OK"]) == want["counters"][pb.C_OK]
+        assert int(stat["NOALGN"]) == want["counters"][pb.C_NOALGN] and int(stat["LOWQ"]) == want["counters"][pb.C_LOWQ]
+        lines = run.stdout.strip().split("\n")
+        ok = np.nonzero(want["status"] == 0)[0]
+        assert len(lines) == 2 * len(ok)
+        letters = np.frombuffer(b"NACMGRSVTWYHKDBN", dtype=np.uint8)
+        for k, i in enumerate(ok[:200]):
+            assert lines[2 * k].startswith(f">pair{i};overlap={want['overlap'][i]};")
+            assert lines[2 * k + 1] == letters[want["seq_nt"][i, :want["seq_len"][i]]].tobytes().decode()
