@@ -43,7 +43,7 @@ def algorithmic_read_bytes(flen, rlen):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks/throttle reasons sampled every 50 ms while the kernel under test is running."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -52,7 +52,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -217,12 +217,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     ctx.synchronize()
     counters.zero_()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record(stream)
     for k in range(args.steps):
@@ -230,7 +230,18 @@ def main():
         evs[k + 1].record(stream)
     ctx.synchronize()
     barrier()
+    if sampler:
+        # the timed region is ~0.1 s, shorter than nvidia-smi's sampling period can resolve: keep the same kernel running
+        # for ~1 s more (outside the timing, counters restored afterwards) so the clock record is taken under this load
+        saved = counters.clone()
+        t_end = time.perf_counter() + 1.0
+        while time.perf_counter() < t_end:
+            step()
+            ctx.synchronize()
+        counters.copy_(saved)
     clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["note"] = "sampled every 50 ms over warm-up + timed steps + a 1 s continuation of the same launches"
     step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     total_ms = evs[0].elapsed_time(evs[-1])
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)

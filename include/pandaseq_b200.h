@@ -141,24 +141,24 @@ size_t panda_max_len(void);
  * ====================================================================== */
 extern PandaAlgorithmClass *panda_algorithms;           /* algo.c:85, sorted by name */
 extern size_t panda_algorithms_length;                  /* algo.c:86 */
-void panda_algorithm_register(PandaAlgorithmClass clazz);               /* algo.c:95-110 */
-PandaAlgorithm panda_algorithm_new(PandaAlgorithmClass clazz);          /* algo.c:73-83 */
-PandaAlgorithmClass panda_algorithm_class(PandaAlgorithm algo);         /* algo.c:38-41 */
-void *panda_algorithm_data(PandaAlgorithm algo);                        /* algo.c:33-36 */
-double panda_algorithm_quality_compare(PandaAlgorithm algorithm, const panda_qual *a, const panda_qual *b); /* algo.c:26-31 */
-bool panda_algorithm_is_a(PandaAlgorithm algo, PandaAlgorithmClass clazz);  /* algo.c:43-47 */
-PandaAlgorithm panda_algorithm_ref(PandaAlgorithm algo);                /* algo.c:49-59 */
-void panda_algorithm_unref(PandaAlgorithm algo);                        /* algo.c:61-83 */
+void panda_algorithm_register(PandaAlgorithmClass clazz);               /* algo.c:106-120 */
+PandaAlgorithm panda_algorithm_new(PandaAlgorithmClass clazz);          /* algo.c:85-94 */
+PandaAlgorithmClass panda_algorithm_class(PandaAlgorithm algo);         /* algo.c:39-42 */
+void *panda_algorithm_data(PandaAlgorithm algo);                        /* algo.c:34-37 */
+double panda_algorithm_quality_compare(PandaAlgorithm algorithm, const panda_qual *a, const panda_qual *b); /* algo.c:27-32 */
+bool panda_algorithm_is_a(PandaAlgorithm algo, PandaAlgorithmClass clazz);  /* algo.c:44-48 */
+PandaAlgorithm panda_algorithm_ref(PandaAlgorithm algo);                /* algo.c:50-60 */
+void panda_algorithm_unref(PandaAlgorithm algo);                        /* algo.c:62-83 */
 
 extern const struct panda_algorithm_class panda_algorithm_simple_bayes_class; /* algo_simple_bayes.c:100-108 */
 PandaAlgorithm panda_algorithm_simple_bayes_new(void);                  /* algo_simple_bayes.c:110-115 */
-double panda_algorithm_simple_bayes_get_error_estimation(PandaAlgorithm algorithm); /* :117-124 */
-void panda_algorithm_simple_bayes_set_error_estimation(PandaAlgorithm algorithm, double q); /* :126-135 */
+double panda_algorithm_simple_bayes_get_error_estimation(PandaAlgorithm algorithm); /* algo_simple_bayes.c:117-124 */
+void panda_algorithm_simple_bayes_set_error_estimation(PandaAlgorithm algorithm, double q); /* algo_simple_bayes.c:126-135 */
 
-extern const struct panda_algorithm_class panda_algorithm_pear_class;   /* algo_pear.c:89-97 */
-PandaAlgorithm panda_algorithm_pear_new(void);                          /* algo_pear.c:99-104 */
-double panda_algorithm_pear_get_random_base_log_p(PandaAlgorithm algorithm); /* :114-121 */
-void panda_algorithm_pear_set_random_base_log_p(PandaAlgorithm algorithm, double log_p); /* :106-112 */
+extern const struct panda_algorithm_class panda_algorithm_pear_class;   /* algo_pear.c:93-101 */
+PandaAlgorithm panda_algorithm_pear_new(void);                          /* algo_pear.c:103-108 */
+double panda_algorithm_pear_get_random_base_log_p(PandaAlgorithm algorithm); /* algo_pear.c:118-125 */
+void panda_algorithm_pear_set_random_base_log_p(PandaAlgorithm algorithm, double log_p); /* algo_pear.c:110-116 */
 
 extern const struct panda_algorithm_class panda_algorithm_rdp_mle_class; /* algo_rdp_mle.c:84-92 */
 PandaAlgorithm panda_algorithm_rdp_mle_new(void);                        /* algo_rdp_mle.c:94-98 */
@@ -198,40 +198,40 @@ size_t panda_assembler_assemble_batch(PandaAssembler assembler, size_t n, const 
                                       PandaOutputSeq output, void *output_data);
 
 PandaAlgorithm panda_assembler_get_algorithm(PandaAssembler assembler);        /* assembler_support.c:177-180 */
-void panda_assembler_set_algorithm(PandaAssembler assembler, PandaAlgorithm algorithm); /* :182-189 */
-long panda_assembler_get_bad_read_count(PandaAssembler assembler);             /* :191-194 */
-long panda_assembler_get_count(PandaAssembler assembler);                      /* :196-199 */
-void panda_assembler_set_fail_alignment(PandaAssembler assembler, PandaFailAlign handler, void *handler_data, PandaDestroy handler_destroy); /* :215-224 */
-long panda_assembler_get_failed_alignment_count(PandaAssembler assembler);     /* :226-229 */
-panda_nt *panda_assembler_get_forward_primer(PandaAssembler assembler, size_t *length); /* :231-237 */
-void panda_assembler_set_forward_primer(PandaAssembler assembler, panda_nt *sequence, size_t length); /* :201-213 */
-size_t panda_assembler_get_forward_trim(PandaAssembler assembler);             /* :239-242 */
-void panda_assembler_set_forward_trim(PandaAssembler assembler, size_t trim);  /* :244-249 */
-size_t panda_assembler_get_longest_overlap(PandaAssembler assembler);          /* :256-259 */
-long panda_assembler_get_low_quality_count(PandaAssembler assembler);          /* :266-269 */
-int panda_assembler_get_minimum_overlap(PandaAssembler assembler);             /* :271-274 */
-void panda_assembler_set_minimum_overlap(PandaAssembler assembler, int overlap); /* :276-282 */
-int panda_assembler_get_maximum_overlap(PandaAssembler assembler);             /* :284-287 */
-void panda_assembler_set_maximum_overlap(PandaAssembler assembler, int overlap); /* :289-295 */
-const char *panda_assembler_get_name(PandaAssembler assembler);                /* :297-302 */
-void panda_assembler_set_name(PandaAssembler assembler, const char *name);     /* :304-313 */
-long panda_assembler_get_no_forward_primer_count(PandaAssembler assembler);    /* :315-318 */
-long panda_assembler_get_no_reverse_primer_count(PandaAssembler assembler);    /* :320-323 */
-size_t panda_assembler_get_num_kmer(PandaAssembler assembler);                 /* :251-254 */
-long panda_assembler_get_ok_count(PandaAssembler assembler);                   /* :325-328 */
-long panda_assembler_get_overlap_count(PandaAssembler assembler, size_t overlap); /* :330-334 */
-bool panda_assembler_get_primers_after(PandaAssembler assembler);              /* :336-339 */
-void panda_assembler_set_primers_after(PandaAssembler assembler, bool after);  /* :341-345 */
-panda_nt *panda_assembler_get_reverse_primer(PandaAssembler assembler, size_t *length); /* :361-367 */
-void panda_assembler_set_reverse_primer(PandaAssembler assembler, panda_nt *sequence, size_t length); /* :347-359 */
-size_t panda_assembler_get_reverse_trim(PandaAssembler assembler);             /* :369-372 */
-void panda_assembler_set_reverse_trim(PandaAssembler assembler, size_t trim);  /* :374-379 */
-long panda_assembler_get_slow_count(PandaAssembler assembler);                 /* :381-384 */
-double panda_assembler_get_threshold(PandaAssembler assembler);                /* :386-389 */
-void panda_assembler_set_threshold(PandaAssembler assembler, double threshold); /* :391-397 */
-PandaLogProxy panda_assembler_get_logger(PandaAssembler assembler);            /* :261-264 */
-double panda_assembler_get_primer_penalty(PandaAssembler assembler);           /* :399-402 */
-void panda_assembler_set_primer_penalty(PandaAssembler assembler, double threshold); /* :404-410 */
+void panda_assembler_set_algorithm(PandaAssembler assembler, PandaAlgorithm algorithm); /* assembler_support.c:182-189 */
+long panda_assembler_get_bad_read_count(PandaAssembler assembler);             /* assembler_support.c:191-194 */
+long panda_assembler_get_count(PandaAssembler assembler);                      /* assembler_support.c:196-199 */
+void panda_assembler_set_fail_alignment(PandaAssembler assembler, PandaFailAlign handler, void *handler_data, PandaDestroy handler_destroy); /* assembler_support.c:215-224 */
+long panda_assembler_get_failed_alignment_count(PandaAssembler assembler);     /* assembler_support.c:226-229 */
+panda_nt *panda_assembler_get_forward_primer(PandaAssembler assembler, size_t *length); /* assembler_support.c:231-237 */
+void panda_assembler_set_forward_primer(PandaAssembler assembler, panda_nt *sequence, size_t length); /* assembler_support.c:201-213 */
+size_t panda_assembler_get_forward_trim(PandaAssembler assembler);             /* assembler_support.c:239-242 */
+void panda_assembler_set_forward_trim(PandaAssembler assembler, size_t trim);  /* assembler_support.c:244-249 */
+size_t panda_assembler_get_longest_overlap(PandaAssembler assembler);          /* assembler_support.c:256-259 */
+long panda_assembler_get_low_quality_count(PandaAssembler assembler);          /* assembler_support.c:266-269 */
+int panda_assembler_get_minimum_overlap(PandaAssembler assembler);             /* assembler_support.c:271-274 */
+void panda_assembler_set_minimum_overlap(PandaAssembler assembler, int overlap); /* assembler_support.c:276-282 */
+int panda_assembler_get_maximum_overlap(PandaAssembler assembler);             /* assembler_support.c:284-287 */
+void panda_assembler_set_maximum_overlap(PandaAssembler assembler, int overlap); /* assembler_support.c:289-295 */
+const char *panda_assembler_get_name(PandaAssembler assembler);                /* assembler_support.c:297-302 */
+void panda_assembler_set_name(PandaAssembler assembler, const char *name);     /* assembler_support.c:304-313 */
+long panda_assembler_get_no_forward_primer_count(PandaAssembler assembler);    /* assembler_support.c:315-318 */
+long panda_assembler_get_no_reverse_primer_count(PandaAssembler assembler);    /* assembler_support.c:320-323 */
+size_t panda_assembler_get_num_kmer(PandaAssembler assembler);                 /* assembler_support.c:251-254 */
+long panda_assembler_get_ok_count(PandaAssembler assembler);                   /* assembler_support.c:325-328 */
+long panda_assembler_get_overlap_count(PandaAssembler assembler, size_t overlap); /* assembler_support.c:330-334 */
+bool panda_assembler_get_primers_after(PandaAssembler assembler);              /* assembler_support.c:336-339 */
+void panda_assembler_set_primers_after(PandaAssembler assembler, bool after);  /* assembler_support.c:341-345 */
+panda_nt *panda_assembler_get_reverse_primer(PandaAssembler assembler, size_t *length); /* assembler_support.c:361-367 */
+void panda_assembler_set_reverse_primer(PandaAssembler assembler, panda_nt *sequence, size_t length); /* assembler_support.c:347-359 */
+size_t panda_assembler_get_reverse_trim(PandaAssembler assembler);             /* assembler_support.c:369-372 */
+void panda_assembler_set_reverse_trim(PandaAssembler assembler, size_t trim);  /* assembler_support.c:374-379 */
+long panda_assembler_get_slow_count(PandaAssembler assembler);                 /* assembler_support.c:381-384 */
+double panda_assembler_get_threshold(PandaAssembler assembler);                /* assembler_support.c:386-389 */
+void panda_assembler_set_threshold(PandaAssembler assembler, double threshold); /* assembler_support.c:391-397 */
+PandaLogProxy panda_assembler_get_logger(PandaAssembler assembler);            /* assembler_support.c:261-264 */
+double panda_assembler_get_primer_penalty(PandaAssembler assembler);           /* assembler_support.c:399-402 */
+void panda_assembler_set_primer_penalty(PandaAssembler assembler, double threshold); /* assembler_support.c:404-410 */
 
 /* pool.c:110-181 (pandaseq-args.h:155-169).  Drains the assembler's source through the device in batches and calls
  * output() for every assembled pair; consumes the assembler; threads/mux are accepted for signature compatibility. */
@@ -255,7 +255,7 @@ typedef enum {
 	PB_ERR_NOMEM = -5
 } pb_status;
 
-#define PB_MAX_LEN 450  /* == panda_max_len() */
+#define PB_MAX_LEN 450  /* misc.c:38-41 */
 #define PB_PHREDMAX 46
 
 enum pb_algo { PB_SIMPLE_BAYES = 0, PB_PEAR = 1, PB_RDP_MLE = 2, PB_FLASH = 3 };

@@ -93,7 +93,7 @@ static inline int is_degenerate(char nt) {
 }
 
 void po_config_default(po_config *cfg, int algo) {
-	/* assembler_support.c:36-99 defaults; algo_simple_bayes.c:110-115; algo_pear.c:99-104 */
+	/* assembler_support.c:36-99 defaults; algo_simple_bayes.c:110-115; algo_pear.c:103-108 */
 	memset(cfg, 0, sizeof *cfg);
 	cfg->algo = algo;
 	cfg->minoverlap = 2;

@@ -76,7 +76,7 @@ static PandaAlgorithm sb_create(const char *arg) {	/* algo_simple_bayes.c:77-98 
 	return algo;
 }
 
-static PandaAlgorithm pear_create(const char *arg) {	/* algo_pear.c:66-87 */
+static PandaAlgorithm pear_create(const char *arg) {	/* algo_pear.c:70-91 */
 	double p;
 	PandaAlgorithm algo;
 	if (arg == NULL)

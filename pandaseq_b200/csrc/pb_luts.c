@@ -142,7 +142,7 @@ void pb_config_default(pb_config *cfg, int algo) {
 	cfg->threshold = log(0.6);	/* assembler_support.c:76 */
 	cfg->primer_penalty = 0;	/* assembler_support.c:97 */
 	cfg->sb_q = 0.36;		/* algo_simple_bayes.c:113 */
-	cfg->pear_random_base = log(0.25);	/* algo_pear.c:102 */
+	cfg->pear_random_base = log(0.25);	/* algo_pear.c:106 */
 }
 
 void pb_counters_merge(int64_t *dst, const int64_t *src) {
