@@ -241,5 +241,8 @@ class Context:
                "pb_assemble_device")
 
 
+from . import synth  # noqa: E402,F401  (torch is imported lazily by callers that generate data)
+
+
 def tables() -> dict:
     return lib().pb_get_tables().contents.as_dict()

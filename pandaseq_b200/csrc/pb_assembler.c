@@ -15,7 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define NEXT_BATCH 65536	/* pairs pulled from a PandaNextSeq source per launch */
+#define NEXT_BATCH_DEFAULT 65536	/* pairs pulled from a PandaNextSeq source per launch (env PANDASEQ_B200_NEXT_BATCH overrides) */
 #define SEQ_CAP (2 * PB_MAX_LEN + 12)	/* 912: multiple of 16 */
 
 struct panda_assembler {
@@ -56,7 +56,7 @@ struct panda_assembler {
 	pb_pair_result *res;
 	uint8_t *nt;
 	double *p;
-	size_t batch_n, batch_pos;
+	size_t batch_n, batch_pos, next_batch;
 	bool source_dry;
 };
 
@@ -107,6 +107,13 @@ PandaAssembler panda_assembler_new_kmer(PandaNextSeq next, void *next_data, Pand
 	a->num_kmers = num_kmers;
 	a->algo = panda_algorithm_simple_bayes_new();
 	a->result.sequence = a->result_seq;
+	a->next_batch = NEXT_BATCH_DEFAULT;
+	{
+		const char *env = getenv("PANDASEQ_B200_NEXT_BATCH");
+		long v = env ? atol(env) : 0;
+		if (v > 0 && v <= (1L << 24))
+			a->next_batch = (size_t) v;
+	}
 	return a;
 }
 
@@ -423,9 +430,9 @@ const panda_result_seq *panda_assembler_next(PandaAssembler a) {
 		/* refill: the source's arrays are only valid until its next call, so copy as we pull
 		 * (the reference's mux does the same, mux.c:150-157) */
 		size_t n = 0, fb = 0, rb = 0;
-		if (!reserve(a, NEXT_BATCH, (size_t) NEXT_BATCH * 160, (size_t) NEXT_BATCH * 160))
+		if (!reserve(a, a->next_batch, a->next_batch * 160, a->next_batch * 160))
 			return NULL;
-		while (n < NEXT_BATCH) {
+		while (n < a->next_batch) {
 			const panda_qual *f, *r;
 			size_t fl, rl;
 			if (!a->next(&a->ids[n], &f, &fl, &r, &rl, a->next_data)) {

@@ -21,6 +21,7 @@ struct pb_context {
 	pb_config cached_cfg;
 	bool cfg_valid;
 	unsigned long long *d_counters;  /* scratch counters for the host path */
+	pthread_mutex_t lock;            /* one host-path call at a time per context (assemblers share the process-wide one) */
 	/* host-path staging (grown on demand) */
 	struct Slot {
 		size_t cap_pairs, cap_bases, cap_hpairs, cap_hbases, cap_hres;
@@ -73,6 +74,7 @@ extern "C" pb_status pb_context_create(int device, pb_context **out) {
 	if (!ctx)
 		return PB_ERR_NOMEM;
 	ctx->device = device;
+	pthread_mutex_init(&ctx->lock, NULL);
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
 	ctx->sm_count = prop.multiProcessorCount;
@@ -318,12 +320,12 @@ static bool is_pinned(const void *p) {
  * host->device copies and chunk k-1's device->host copies run on the other stream.  Caller buffers that are
  * pinned (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are copied from/to directly; pageable
  * buffers go through the slot's pinned staging area first. */
-extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, size_t n,
+static pb_status assemble_host_locked(pb_context *ctx, const pb_config *cfg, size_t n,
                                       const panda_qual *f_data, const uint64_t *f_off,
                                       const panda_qual *r_data, const uint64_t *r_off,
                                       pb_pair_result *results, uint8_t *seq_nt, double *seq_p,
                                       size_t seq_stride, int64_t *counters) {
-	if (!ctx || !cfg || (!results && n) || (n && (!f_data || !f_off || !r_data || !r_off)) || ((seq_nt || seq_p) && (seq_stride % 16) != 0)) {
+	if (!cfg || (!results && n) || (n && (!f_data || !f_off || !r_data || !r_off)) || ((seq_nt || seq_p) && (seq_stride % 16) != 0)) {
 		pb_set_error("pb_assemble_host: bad argument (seq_stride must be a multiple of 16)");
 		return PB_ERR_ARGUMENT;
 	}
@@ -433,6 +435,21 @@ extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, siz
 		pb_counters_merge(counters, tmp);
 	}
 	return PB_OK;
+}
+
+extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, size_t n,
+                                      const panda_qual *f_data, const uint64_t *f_off,
+                                      const panda_qual *r_data, const uint64_t *r_off,
+                                      pb_pair_result *results, uint8_t *seq_nt, double *seq_p,
+                                      size_t seq_stride, int64_t *counters) {
+	if (!ctx) {
+		pb_set_error("pb_assemble_host: no context");
+		return PB_ERR_ARGUMENT;
+	}
+	pthread_mutex_lock(&ctx->lock);
+	pb_status st = assemble_host_locked(ctx, cfg, n, f_data, f_off, r_data, r_off, results, seq_nt, seq_p, seq_stride, counters);
+	pthread_mutex_unlock(&ctx->lock);
+	return st;
 }
 
 /* process-wide default context for the panda_* object layer */

@@ -1,0 +1,97 @@
+"""BASELINE full size (10 M 2x150 pairs, config 2) on the GPU: properties that do not need the oracle to run 10 M pairs --
+counter identities, run-to-run determinism, shard invariance -- plus exact parity on a random 20 k-pair sample."""
+import numpy as np
+import pytest
+
+import oracle_lib
+import pandaseq_b200 as pb
+from parity import compare
+
+pytestmark = pytest.mark.gpu
+N = 10_000_000
+CHUNK = 1_000_000
+
+
+@pytest.fixture(scope="module")
+def full(built):
+    import torch
+    from pandaseq_b200 import synth
+    ctx = pb.Context(0)
+    parts_r, parts_m, flats, base16, max_len = [], [], [], 0, 0
+    for ci in range(N // CHUNK):
+        rect = synth.generate_config(2, n=CHUNK, device="cuda", chunk_index=ci)
+        f_data, f_off, r_data, r_off = rect.to_flat_tensors()
+        reads, meta, ml, total = ctx.pack_device(f_data, f_off, r_data, r_off)
+        meta[:, 0] += base16
+        base16 += total // 16
+        max_len = max(max_len, ml)
+        parts_r.append(reads[:total])
+        parts_m.append(meta)
+        if ci in (0, 7):       # keep two chunks' raw reads on the host for the sampled oracle comparison
+            flats.append((ci, synth.FlatBatch(f_data.cpu().numpy(), f_off.cpu().numpy().astype(np.uint64),
+                                              r_data.cpu().numpy(), r_off.cpu().numpy().astype(np.uint64))))
+    reads = torch.cat(parts_r + [torch.zeros(16, dtype=torch.uint8, device="cuda")])
+    meta = torch.cat(parts_m)
+    yield ctx, reads, meta, max_len, flats
+    ctx.close()
+
+
+def run(ctx, reads, meta, max_len, lo, hi):
+    import torch
+    n = hi - lo
+    stride = (2 * max_len + 15) & ~15
+    res = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+    nt = torch.zeros((n, stride // 2), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(pb.PB_NCOUNTERS, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.assemble_device(pb.make_config("simple_bayesian"), n, max_len, reads, meta[lo:hi].contiguous(), res, nt, None, stride, cnt)
+    ctx.synchronize()
+    return res, nt, cnt.cpu().numpy()
+
+
+def digest(res, nt):
+    """order-sensitive checksum of the result records and merged reads, computed on the device"""
+    import torch
+    r = res.view(torch.int64)
+    w = torch.arange(1, r.shape[0] + 1, device=r.device, dtype=torch.int64)[:, None]
+    a = int((r * w).sum().item())
+    b = int((nt.view(torch.int64).sum(dim=1) * w[:, 0]).sum().item())
+    return a, b
+
+
+def test_full_size_properties(full):
+    ctx, reads, meta, max_len, flats = full
+    res, nt, cnt = run(ctx, reads, meta, max_len, 0, N)
+    # counter identities (assembler.c:252-348: every pair bumps count and exactly one outcome counter)
+    assert cnt[pb.C_COUNT] == N
+    assert cnt[pb.C_OK] + cnt[pb.C_LOWQ] + cnt[pb.C_NOALGN] + cnt[pb.C_BADR] + cnt[pb.C_NOFP] + cnt[pb.C_NORP] == N
+    assert cnt[pb.C_OVERLAPS:].sum() == cnt[pb.C_OK]
+    assert cnt[pb.C_OK] > 0.999 * N
+    r = res.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel()
+    ok = r["status"] == 0
+    assert int(ok.sum()) == cnt[pb.C_OK] and int(r["slow"].sum()) == cnt[pb.C_SLOW]
+    assert r["overlap"][ok].max() == cnt[pb.C_LONGEST]
+    assert np.array_equal(np.bincount(r["overlap"][ok], minlength=900)[:900], cnt[pb.C_OVERLAPS:pb.C_OVERLAPS + 900])
+    assert ((r["seq_len"][ok].astype(int) + r["overlap"][ok]) == 300).all()          # F - o + R with no primers/trims
+    # determinism
+    res2, nt2, cnt2 = run(ctx, reads, meta, max_len, 0, N)
+    assert digest(res, nt) == digest(res2, nt2) and np.array_equal(cnt, cnt2)
+    # shard invariance: two halves == the whole (what --gpus 2 does, minus the second device)
+    ra, na, ca = run(ctx, reads, meta, max_len, 0, N // 2)
+    rb, nb, cb = run(ctx, reads, meta, max_len, N // 2, N)
+    import torch
+    assert digest(torch.cat([ra, rb]), torch.cat([na, nb])) == digest(res, nt)
+    merged = ca + cb
+    merged[pb.C_LONGEST] = max(ca[pb.C_LONGEST], cb[pb.C_LONGEST])
+    assert np.array_equal(merged, cnt)
+    # exact parity on a sample of the same pairs
+    rng = np.random.default_rng(0)
+    ntc = nt.cpu().numpy()
+    for ci, flat in flats:
+        idx = np.sort(rng.choice(CHUNK, 10_000, replace=False))
+        sub = pb.synth.FlatBatch.from_pairs([(flat.pair(i)[0][:, 0], flat.pair(i)[0][:, 1], flat.pair(i)[1][:, 0], flat.pair(i)[1][:, 1]) for i in idx])
+        want = oracle_lib.assemble("port", pb.make_config("simple_bayesian"), sub)
+        g = ci * CHUNK + idx
+        got = dict(results=r[g], seq_nt=pb.unpack_nt(ntc[g]), seq_p=None, counters=None)
+        rep = compare(got, want, check_counters=False)
+        assert rep["ok"], rep

@@ -126,7 +126,8 @@ def test_assemble_one_pair_at_a_time(L):
     L.panda_assembler_unref(a)
 
 
-def test_pull_source_next_and_callbacks(L):
+def test_pull_source_next_and_callbacks(L, monkeypatch):
+    monkeypatch.setenv("PANDASEQ_B200_NEXT_BATCH", "256")      # 700 pairs -> three device batches behind next()
     b = datasets.stress(700)
     want = oracle_lib.assemble("port", pb.make_config("simple_bayesian", minoverlap=10, threshold=0.7), b)
     state = {"i": 0, "keep": []}
