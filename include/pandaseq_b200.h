@@ -166,6 +166,16 @@ PandaAlgorithm panda_algorithm_rdp_mle_new(void);                        /* algo
 extern const struct panda_algorithm_class panda_algorithm_flash_class;   /* algo_flash.c:91-99 */
 PandaAlgorithm panda_algorithm_flash_new(void);                          /* algo_flash.c:101-104 */
 
+/* the three algorithms outside the north_star's four; same interface, count-based device scorers */
+extern const struct panda_algorithm_class panda_algorithm_ea_util_class; /* algo_ea_util.c:79-87 */
+PandaAlgorithm panda_algorithm_ea_util_new(void);                        /* algo_ea_util.c:89-92 */
+extern const struct panda_algorithm_class panda_algorithm_stitch_class;  /* algo_stitch.c:79-87 */
+PandaAlgorithm panda_algorithm_stitch_new(void);                         /* algo_stitch.c:89-92 */
+extern const struct panda_algorithm_class panda_algorithm_uparse_class;  /* algo_uparse.c:100-108 */
+PandaAlgorithm panda_algorithm_uparse_new(void);                         /* algo_uparse.c:110-115 */
+double panda_algorithm_uparse_get_error_estimation(PandaAlgorithm algorithm); /* algo_uparse.c:117-124 */
+void panda_algorithm_uparse_set_error_estimation(PandaAlgorithm algorithm, double q); /* algo_uparse.c:126-135 */
+
 /* ======================================================================
  * Layer 1b: assembler (pandaseq-assembler.h:37-405, assembler.c, assembler_support.c)
  * ====================================================================== */
@@ -258,7 +268,7 @@ typedef enum {
 #define PB_MAX_LEN 450  /* misc.c:38-41 */
 #define PB_PHREDMAX 46
 
-enum pb_algo { PB_SIMPLE_BAYES = 0, PB_PEAR = 1, PB_RDP_MLE = 2, PB_FLASH = 3 };
+enum pb_algo { PB_SIMPLE_BAYES = 0, PB_PEAR = 1, PB_RDP_MLE = 2, PB_FLASH = 3, PB_EA_UTIL = 4, PB_STITCH = 5, PB_UPARSE = 6 };
 
 /* Why a pair was not emitted, in assemble_seq order (assembler.c:252-348). */
 enum pb_pair_status { PB_PAIR_OK = 0, PB_PAIR_BADR = 1, PB_PAIR_NOFP = 2, PB_PAIR_NORP = 3, PB_PAIR_NOALGN = 4, PB_PAIR_LOWQ = 5 };
@@ -278,7 +288,7 @@ typedef struct {
 	int64_t reverse_primer_length;
 	double threshold;         /* log space */
 	double primer_penalty;
-	double sb_q;              /* simple_bayes error estimation */
+	double sb_q;              /* simple_bayes / uparse error estimation */
 	double pear_random_base;  /* pear: log p of a random base */
 	panda_nt forward_primer[PB_MAX_LEN];
 	panda_nt reverse_primer[PB_MAX_LEN]; /* as the assembler stores it (already complemented) */
@@ -385,6 +395,8 @@ typedef struct {
 	double mismatch_pear[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
 	double mismatch_rdp[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
 	double mismatch_rdp_asm[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
+	double match_uparse[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
+	double mismatch_uparse[PB_PHREDMAX + 1][PB_PHREDMAX + 1];
 	double score[PB_PHREDMAX + 1];
 	double score_err[PB_PHREDMAX + 1];
 } pb_tables;

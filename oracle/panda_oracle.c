@@ -44,6 +44,16 @@ static double f_mismatch_rdp_asm(double p, double q) {
 	return (v == 0) ? DBL_MIN : v;
 }
 
+/* mktable.c:106-131 */
+static double f_match_uparse(double p, double q) {
+	double v = 1 - p * q / (1 - p - q + 4 * p * q / 3);
+	return (v <= 0) ? DBL_MIN : v;
+}
+static double f_mismatch_uparse(double p, double q) {
+	double v = 1 - (p + q / 3) / (p + q - 4 * p * q / 3);
+	return (v <= 0) ? DBL_MIN : v;
+}
+
 static po_tables g_tables;
 static pthread_once_t g_tables_once = PTHREAD_ONCE_INIT;
 
@@ -63,6 +73,8 @@ static void build_tables(void) {
 	fill_matrix(t->mismatch_pear, f_mismatch_pear);
 	fill_matrix(t->mismatch_rdp, f_mismatch_rdp);
 	fill_matrix(t->mismatch_rdp_asm, f_mismatch_rdp_asm);
+	fill_matrix(t->match_uparse, f_match_uparse);
+	fill_matrix(t->mismatch_uparse, f_mismatch_uparse);
 	for (int k = 0; k < PO_NQ; k++) {
 		double p = phred_p(k);
 		/* mktable.c:63-73: p == 1 (PHRED 0) scores -2, otherwise log(1-p); log_output=false. */
@@ -179,6 +191,62 @@ double po_overlap_probability(const po_config *cfg, const po_qual *fwd, size_t f
 			}
 			return prob;
 		}
+	case PO_EA_UTIL:{
+			/* algo_ea_util.c:29-56 */
+			size_t mismatches = 0, real_overlap = 0;
+			for (i = 0; i < overlap; i++) {
+				int fi = (int) (flen + i - overlap);
+				int ri = (int) (rlen - i - 1);
+				if (fi < 0 || ri < 0 || (size_t) fi >= flen || (size_t) ri >= rlen)
+					continue;
+				char f = fwd[fi].nt, r = rev[ri].nt;
+				if (is_n(f) || is_n(r) || (f & r) == 0)
+					mismatches++;
+				real_overlap++;
+			}
+			return log((((double) mismatches) * mismatches + 1) / real_overlap);
+		}
+	case PO_STITCH:{
+			/* algo_stitch.c:28-56: the score is a size_t, so a net-negative score wraps around */
+			size_t score = 0;
+			for (i = 0; i < overlap; i++) {
+				int fi = (int) (flen + i - overlap);
+				int ri = (int) (rlen - i - 1);
+				if (fi < 0 || ri < 0 || (size_t) fi >= flen || (size_t) ri >= rlen)
+					continue;
+				char f = fwd[fi].nt, r = rev[ri].nt;
+				if (is_n(f) || is_n(r))
+					score += 0;
+				else if ((f & r) != 0)
+					score += 1;
+				else
+					score -= 1;
+			}
+			return log(score / (double) (flen + rlen));
+		}
+	case PO_UPARSE:{
+			/* algo_uparse.c:33-66 with the parameters of algo_uparse.c:126-135 */
+			size_t matches = 0, mismatches = 0, unknowns = 0;
+			double q = cfg->sb_q;
+			double pmatch = log(1 - q * q * (1 - 2 * q + 4 * q * q / 3));
+			double pmismatch = log(1 - 4 * q / 3 / (2 * q - 4 * q * q / 3));
+			for (i = 0; i < overlap; i++) {
+				int fi = (int) (flen + i - overlap);
+				int ri = (int) (rlen - i - 1);
+				if (fi < 0 || ri < 0 || (size_t) fi >= flen || (size_t) ri >= rlen)
+					continue;
+				char f = fwd[fi].nt, r = rev[ri].nt;
+				if (is_n(f) || is_n(r))
+					unknowns++;
+				else if ((f & r) != 0)
+					matches++;
+				else
+					mismatches++;
+			}
+			if (overlap >= flen && overlap >= rlen)
+				return (t->qual_nn * unknowns + matches * pmatch + mismatches * pmismatch);
+			return (t->qual_nn * (flen + rlen - 2 * overlap + unknowns) + matches * pmatch + mismatches * pmismatch);
+		}
 	case PO_FLASH:{
 			/* algo_flash.c:30-60: size_t division, so log(0) unless every base mismatches. */
 			size_t mismatches = 0, real_overlap = 0;
@@ -211,6 +279,12 @@ double po_match_probability(const po_config *cfg, int match, char a, char b) {
 			return t->score[clampq(hi)];
 		}
 		return t->mismatch_rdp_asm[clampq(a)][clampq(b)];
+	case PO_EA_UTIL:	/* algo_ea_util.c:58-67: the higher quality, match or not */
+		return t->score[(a > b) ? clampq(a) : clampq(b)];
+	case PO_STITCH:		/* algo_stitch.c:58-66 */
+		return (match ? t->match_sb : t->mismatch_sb)[clampq(a)][clampq(b)];
+	case PO_UPARSE:		/* algo_uparse.c:68-75 */
+		return (match ? t->match_uparse : t->mismatch_uparse)[clampq(a)][clampq(b)];
 	case PO_FLASH:{	/* algo_flash.c:62-80 */
 			int s;
 			if (match) {
@@ -611,7 +685,7 @@ int po_assemble_flat(const po_config *cfg, size_t n,
                      const po_qual *r_data, const uint64_t *r_off,
                      po_flat_out *out, int threads) {
 	if (cfg->num_kmers != 2 || cfg->post_primers != 0 || cfg->minoverlap < 2
-	    || cfg->algo < PO_SIMPLE_BAYES || cfg->algo > PO_FLASH)
+	    || cfg->algo < PO_SIMPLE_BAYES || cfg->algo > PO_UPARSE)
 		return -1;
 	if (threads < 1)
 		threads = 1;

@@ -51,6 +51,16 @@ static PandaAssembler make_assembler(const po_config *cfg) {
 	case PO_FLASH:
 		algo = panda_algorithm_flash_new();
 		break;
+	case PO_EA_UTIL:
+		algo = panda_algorithm_ea_util_new();
+		break;
+	case PO_STITCH:
+		algo = panda_algorithm_stitch_new();
+		break;
+	case PO_UPARSE:
+		algo = panda_algorithm_uparse_new();
+		panda_algorithm_uparse_set_error_estimation(algo, cfg->sb_q);
+		break;
 	}
 	if (algo == NULL) {
 		panda_assembler_unref(a);
@@ -241,6 +251,8 @@ extern const double qual_match_pear[][47];
 extern const double qual_mismatch_pear[][47];
 extern const double qual_mismatch_rdp_mle[][47];
 extern const double qual_mismatch_assembled_rdp_mle[][47];
+extern const double qual_match_uparse[][47];
+extern const double qual_mismatch_uparse[][47];
 extern const double qual_score[47];
 extern const double qual_score_err[47];
 
@@ -252,6 +264,8 @@ void ref_get_tables(po_tables *t) {
 	memcpy(t->mismatch_pear, qual_mismatch_pear, sizeof t->mismatch_pear);
 	memcpy(t->mismatch_rdp, qual_mismatch_rdp_mle, sizeof t->mismatch_rdp);
 	memcpy(t->mismatch_rdp_asm, qual_mismatch_assembled_rdp_mle, sizeof t->mismatch_rdp_asm);
+	memcpy(t->match_uparse, qual_match_uparse, sizeof t->match_uparse);
+	memcpy(t->mismatch_uparse, qual_mismatch_uparse, sizeof t->mismatch_uparse);
 	memcpy(t->score, qual_score, sizeof t->score);
 	memcpy(t->score_err, qual_score_err, sizeof t->score_err);
 }

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libpandaseq_b200.so")
 PB_MAX_LEN = 450
 PB_PHREDMAX = 46
 PB_NCOUNTERS = 16 + 2 * PB_MAX_LEN
-ALGOS = {"simple_bayesian": 0, "pear": 1, "rdp_mle": 2, "flash": 3}
+ALGOS = {"simple_bayesian": 0, "pear": 1, "rdp_mle": 2, "flash": 3, "ea_util": 4, "stitch": 5, "uparse": 6}
 STATUS = {0: "OK", 1: "BADR", 2: "NOFP", 3: "NORP", 4: "NOALGN", 5: "LOWQ"}
 C_COUNT, C_OK, C_LOWQ, C_NOALGN, C_BADR, C_NOFP, C_NORP, C_SLOW, C_LONGEST = range(9)
 C_OVERLAPS = 16
@@ -54,6 +54,7 @@ class PbTables(C.Structure):
         ("match_sb", C.c_double * NQ * NQ), ("mismatch_sb", C.c_double * NQ * NQ),
         ("match_pear", C.c_double * NQ * NQ), ("mismatch_pear", C.c_double * NQ * NQ),
         ("mismatch_rdp", C.c_double * NQ * NQ), ("mismatch_rdp_asm", C.c_double * NQ * NQ),
+        ("match_uparse", C.c_double * NQ * NQ), ("mismatch_uparse", C.c_double * NQ * NQ),
         ("score", C.c_double * NQ), ("score_err", C.c_double * NQ),
     ]
 

@@ -1,4 +1,4 @@
-/* pb_algorithm.c -- PandaAlgorithm objects for the four device-scored algorithms.
+/* pb_algorithm.c -- PandaAlgorithm objects for the device-scored algorithms (the reference's full registry of seven).
  *
  * Keeps the reference's algorithm plug-in surface (pandaseq-algorithm.h:33-228,
  * algo.c:27-133): refcounted instances of a class, private data behind
@@ -46,6 +46,18 @@ static double rdp_match(void *data, bool match, char a, char b) {
 static double flash_match(void *data, bool match, char a, char b) {
 	(void) data;
 	return pb_host_match_probability(PB_FLASH, match, a, b);
+}
+static double ea_util_match(void *data, bool match, char a, char b) {
+	(void) data;
+	return pb_host_match_probability(PB_EA_UTIL, match, a, b);
+}
+static double stitch_match(void *data, bool match, char a, char b) {
+	(void) data;
+	return pb_host_match_probability(PB_STITCH, match, a, b);
+}
+static double uparse_match(void *data, bool match, char a, char b) {
+	(void) data;
+	return pb_host_match_probability(PB_UPARSE, match, a, b);
 }
 
 /* "-A name:argument" parsing, same acceptance rules as the reference's from_string functions. */
@@ -102,6 +114,34 @@ static PandaAlgorithm flash_create(const char *arg) {	/* algo_flash.c:82-89 */
 	return panda_algorithm_flash_new();
 }
 
+static PandaAlgorithm ea_util_create(const char *arg) {	/* algo_ea_util.c:69-77 */
+	if (arg != NULL) {
+		fprintf(stderr, "No arguments allowed: %s\n", arg);
+		return NULL;
+	}
+	return panda_algorithm_ea_util_new();
+}
+
+static PandaAlgorithm stitch_create(const char *arg) {	/* algo_stitch.c:68-77 */
+	if (arg != NULL) {
+		fprintf(stderr, "No arguments allowed: %s\n", arg);
+		return NULL;
+	}
+	return panda_algorithm_stitch_new();
+}
+
+static PandaAlgorithm uparse_create(const char *arg) {	/* algo_uparse.c:77-98 */
+	double q;
+	PandaAlgorithm algo;
+	if (arg == NULL)
+		return panda_algorithm_uparse_new();
+	if (!parse_probability(arg, "Error estimation", &q))
+		return NULL;
+	algo = panda_algorithm_uparse_new();
+	panda_algorithm_uparse_set_error_estimation(algo, q);
+	return algo;
+}
+
 /* qual_nn_simple_bayesian is the literal -1.38629 in every class (table.h via tablebuilder.c:124). */
 #define PB_QUAL_NN (-1.38629)
 
@@ -116,6 +156,16 @@ const struct panda_algorithm_class panda_algorithm_rdp_mle_class = {
 };
 const struct panda_algorithm_class panda_algorithm_flash_class = {
 	0, "flash", flash_create, NULL, overlap_on_device_only, flash_match, PB_QUAL_NN
+};
+
+const struct panda_algorithm_class panda_algorithm_ea_util_class = {
+	0, "ea_util", ea_util_create, NULL, overlap_on_device_only, ea_util_match, PB_QUAL_NN
+};
+const struct panda_algorithm_class panda_algorithm_stitch_class = {
+	0, "stitch", stitch_create, NULL, overlap_on_device_only, stitch_match, PB_QUAL_NN
+};
+const struct panda_algorithm_class panda_algorithm_uparse_class = {
+	sizeof(struct sb_private), "uparse", uparse_create, NULL, overlap_on_device_only, uparse_match, PB_QUAL_NN
 };
 
 /* ---- instances ---------------------------------------------------------- */
@@ -212,6 +262,31 @@ PandaAlgorithm panda_algorithm_flash_new(void) {
 	return panda_algorithm_new(&panda_algorithm_flash_class);
 }
 
+PandaAlgorithm panda_algorithm_ea_util_new(void) {
+	return panda_algorithm_new(&panda_algorithm_ea_util_class);
+}
+
+PandaAlgorithm panda_algorithm_stitch_new(void) {
+	return panda_algorithm_new(&panda_algorithm_stitch_class);
+}
+
+PandaAlgorithm panda_algorithm_uparse_new(void) {
+	PandaAlgorithm a = panda_algorithm_new(&panda_algorithm_uparse_class);
+	panda_algorithm_uparse_set_error_estimation(a, 0.36);
+	return a;
+}
+
+double panda_algorithm_uparse_get_error_estimation(PandaAlgorithm algorithm) {
+	if (!panda_algorithm_is_a(algorithm, &panda_algorithm_uparse_class))
+		return -1;
+	return ((struct sb_private *) panda_algorithm_data(algorithm))->q;
+}
+
+void panda_algorithm_uparse_set_error_estimation(PandaAlgorithm algorithm, double q) {
+	if (q > 0 && q < 1 && panda_algorithm_is_a(algorithm, &panda_algorithm_uparse_class))
+		((struct sb_private *) panda_algorithm_data(algorithm))->q = q;
+}
+
 /* Class identity -> device scorer id + private data.  Unknown classes are refused:
  * a host function pointer cannot run in the kernel and there is no CPU path. */
 int pb_algorithm_fill_config(PandaAlgorithm algo, pb_config *cfg) {
@@ -225,6 +300,13 @@ int pb_algorithm_fill_config(PandaAlgorithm algo, pb_config *cfg) {
 		cfg->algo = PB_RDP_MLE;
 	} else if (panda_algorithm_is_a(algo, &panda_algorithm_flash_class)) {
 		cfg->algo = PB_FLASH;
+	} else if (panda_algorithm_is_a(algo, &panda_algorithm_ea_util_class)) {
+		cfg->algo = PB_EA_UTIL;
+	} else if (panda_algorithm_is_a(algo, &panda_algorithm_stitch_class)) {
+		cfg->algo = PB_STITCH;
+	} else if (panda_algorithm_is_a(algo, &panda_algorithm_uparse_class)) {
+		cfg->algo = PB_UPARSE;
+		cfg->sb_q = ((struct sb_private *) panda_algorithm_data(algo))->q;
 	} else {
 		pb_set_error("algorithm class '%s' has no device scorer", (algo && algo->clazz && algo->clazz->name) ? algo->clazz->name : "?");
 		return -1;
@@ -269,8 +351,11 @@ void panda_algorithm_register(PandaAlgorithmClass clazz) {
 
 __attribute__((constructor))
 static void register_builtin_algorithms(void) {
+	panda_algorithm_register(&panda_algorithm_ea_util_class);
 	panda_algorithm_register(&panda_algorithm_flash_class);
 	panda_algorithm_register(&panda_algorithm_pear_class);
 	panda_algorithm_register(&panda_algorithm_rdp_mle_class);
 	panda_algorithm_register(&panda_algorithm_simple_bayes_class);
+	panda_algorithm_register(&panda_algorithm_stitch_class);
+	panda_algorithm_register(&panda_algorithm_uparse_class);
 }

@@ -673,7 +673,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 				/* overlap_probability for this candidate.  findex = F-ov+i in [0,F), template index i in [0,R) */
 				const int i0 = max(0, ov - F), i1 = min(ov, R);
 				double prob;
-				if (algo == PB_SIMPLE_BAYES || algo == PB_FLASH) {
+				if (algo != PB_PEAR && algo != PB_RDP_MLE) {      /* the count-based scorers */
 					unsigned packed = 0;
 					const int nw = (i1 + 7) >> 3;
 					for (int k0 = 0; k0 < nw; k0 += 32) {
@@ -690,17 +690,26 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 					}
 					packed = __reduce_add_sync(FULL, packed);
 					const int matches = packed & 1023, mism = (packed >> 10) & 1023, unk = packed >> 20;
-					if (algo == PB_SIMPLE_BAYES) {
-						/* algo_simple_bayes.c:61-65: size_t arithmetic inside the parenthesis */
+					if (algo == PB_SIMPLE_BAYES || algo == PB_UPARSE) {
+						/* algo_simple_bayes.c:61-65 / algo_uparse.c:61-65: size_t arithmetic inside the parenthesis
+						 * (sb_pmatch / sb_pmismatch hold the selected algorithm's two constants) */
 						const unsigned long long nn_count = (ov >= F && ov >= R)
 							? (unsigned long long) unk
 							: (unsigned long long) ((long long) F + R - 2 * (long long) ov + unk);
 						prob = qual_nn * (double) nn_count + (double) matches * prm->sb_pmatch;
 						prob = prob + (double) mism * prm->sb_pmismatch;
-					} else {
+					} else if (algo == PB_FLASH) {
 						/* algo_flash.c:59: integer division inside log() */
 						const int real = matches + mism + unk, bad = mism + unk;
 						prob = (real == 0) ? -2.0 : ((bad == real) ? 0.0 : -CUDART_INF);
+					} else if (algo == PB_EA_UTIL) {
+						/* algo_ea_util.c:55: N counts as a mismatch; real_overlap == 0 divides by zero as the reference does */
+						const double bad = (double) (mism + unk);
+						prob = log((bad * bad + 1.0) / (double) (unsigned long long) (matches + mism + unk));
+					} else {
+						/* algo_stitch.c:55: the score is a size_t, a net-negative score wraps */
+						const unsigned long long sc = (unsigned long long) (long long) (matches - mism);
+						prob = log((double) sc / (double) (unsigned long long) (F + R));
 					}
 				} else {
 					double acc = 0.0;

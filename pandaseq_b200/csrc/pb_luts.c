@@ -67,6 +67,17 @@ static double rdp_assembled_diff(double p, double q) {
 	return (v == 0) ? DBL_MIN : v;
 }
 
+/* mktable.c:106-117 */
+static double uparse_same(double p, double q) {
+	double v = 1 - p * q / (1 - p - q + 4 * p * q / 3);
+	return (v <= 0) ? DBL_MIN : v;
+}
+/* mktable.c:119-131 */
+static double uparse_diff(double p, double q) {
+	double v = 1 - (p + q / 3) / (p + q - 4 * p * q / 3);
+	return (v <= 0) ? DBL_MIN : v;
+}
+
 static void tabulate(double dst[PB_NQ][PB_NQ], pair_formula f) {
 	for (int a = 0; a < PB_NQ; a++) {
 		double pa = err_prob(a);
@@ -87,6 +98,8 @@ static void make_tables(void) {
 	tabulate(t->mismatch_pear, pear_diff);
 	tabulate(t->mismatch_rdp, sb_diff);
 	tabulate(t->mismatch_rdp_asm, rdp_assembled_diff);
+	tabulate(t->match_uparse, uparse_same);
+	tabulate(t->mismatch_uparse, uparse_diff);
 	for (int k = 0; k < PB_NQ; k++) {
 		double p = err_prob(k);
 		t->score[k] = six_digits(p == 1 ? -2.0 : log(1.0 - p));	/* mktable.c:63-73 */
@@ -105,9 +118,9 @@ static int clamp_phred(char q) {
 }
 
 /* The per-base posterior each algorithm assigns during reconstruction:
- * algo_simple_bayes.c:68-75, algo_pear.c:61-68, algo_rdp_mle.c:29-41, algo_flash.c:62-80.
+ * algo_simple_bayes.c:68-75, algo_pear.c:61-68, algo_rdp_mle.c:29-41, algo_flash.c:62-80, and the three below.
  * Every one of them is a function of (match, clamp(a), clamp(b)) only, which is what
- * lets the device use one 2x48x48 table for all four. */
+ * lets the device use one 2x48x48 table for all of them. */
 double pb_host_match_probability(int algo, bool match, char a, char b) {
 	const pb_tables *t = pb_get_tables();
 	int qa = clamp_phred(a), qb = clamp_phred(b);
@@ -120,6 +133,12 @@ double pb_host_match_probability(int algo, bool match, char a, char b) {
 		if (match)
 			return t->score[(a >= b) ? qa : qb];
 		return t->mismatch_rdp_asm[qa][qb];
+	case PB_EA_UTIL:	/* algo_ea_util.c:58-67 */
+		return t->score[(a > b) ? qa : qb];
+	case PB_STITCH:		/* algo_stitch.c:58-66 */
+		return match ? t->match_sb[qa][qb] : t->mismatch_sb[qa][qb];
+	case PB_UPARSE:		/* algo_uparse.c:68-75 */
+		return match ? t->match_uparse[qa][qb] : t->mismatch_uparse[qa][qb];
 	case PB_FLASH:
 		if (match)
 			return t->score[(a > b) ? qa : qb];
@@ -158,8 +177,8 @@ void pb_counters_merge(int64_t *dst, const int64_t *src) {
 
 pb_status pb_build_device_params(const pb_config *cfg, pb_device_params *out) {
 	const pb_tables *t = pb_get_tables();
-	if (cfg->algo < PB_SIMPLE_BAYES || cfg->algo > PB_FLASH) {
-		pb_set_error("algorithm %d has no device scorer (only simple_bayesian, pear, rdp_mle, flash)", cfg->algo);
+	if (cfg->algo < PB_SIMPLE_BAYES || cfg->algo > PB_UPARSE) {
+		pb_set_error("algorithm %d has no device scorer", cfg->algo);
 		return PB_ERR_UNSUPPORTED;
 	}
 	if (cfg->num_kmers != 2) {
@@ -189,10 +208,15 @@ pb_status pb_build_device_params(const pb_config *cfg, pb_device_params *out) {
 	out->primer_penalty = cfg->primer_penalty;
 	out->qual_nn = t->qual_nn;
 	out->pear_random_base = cfg->pear_random_base;
-	{			/* algo_simple_bayes.c:126-135 */
+	{
 		double q = cfg->sb_q;
-		out->sb_pmatch = log(0.25 * (1 - 2 * q + q * q));
-		out->sb_pmismatch = log((3 * q - 2 * q * q) / 18.0);
+		if (cfg->algo == PB_UPARSE) {	/* algo_uparse.c:126-135 */
+			out->sb_pmatch = log(1 - q * q * (1 - 2 * q + 4 * q * q / 3));
+			out->sb_pmismatch = log(1 - 4 * q / 3 / (2 * q - 4 * q * q / 3));
+		} else {			/* algo_simple_bayes.c:126-135 */
+			out->sb_pmatch = log(0.25 * (1 - 2 * q + q * q));
+			out->sb_pmismatch = log((3 * q - 2 * q * q) / 18.0);
+		}
 	}
 	for (int k = 0; k < PB_NQ; k++) {
 		out->score[k] = t->score[k];

@@ -28,6 +28,11 @@ CASES = {
     "cfg1_pear": (lambda: datasets.cfg1(600), dict(algo="pear")),
     "cfg1_rdp_mle": (lambda: datasets.cfg1(600), dict(algo="rdp_mle")),
     "cfg1_flash": (lambda: datasets.cfg1(600), dict(algo="flash")),
+    "cfg1_ea_util": (lambda: datasets.cfg1(400), dict(algo="ea_util")),
+    "cfg1_stitch": (lambda: datasets.cfg1(400), dict(algo="stitch")),
+    "cfg1_uparse": (lambda: datasets.cfg1(400), dict(algo="uparse")),
+    "stress_stitch_maxov300": (lambda: datasets.stress(300), dict(algo="stitch", maxoverlap=300)),
+    "edge_cases_ea_util_maxov800": (lambda: datasets.edge_cases(), dict(algo="ea_util", maxoverlap=800)),
     "stress_sb_maxov300": (lambda: datasets.stress(400), dict(algo="simple_bayesian", maxoverlap=300)),
     "stress_pear_trims": (lambda: datasets.stress(400, seed=3), dict(algo="pear", forward_trim=20, reverse_trim=20, maxoverlap=300)),
     "mixed_sb": (lambda: datasets.mixed(400), dict(algo="simple_bayesian")),

@@ -24,14 +24,14 @@ def run_both(ctx, cfg, batch):
     return got, want, compare(got, want)
 
 
-@pytest.mark.parametrize("algo", ["simple_bayesian", "pear", "rdp_mle", "flash"])
+@pytest.mark.parametrize("algo", ["simple_bayesian", "pear", "rdp_mle", "flash", "ea_util", "stitch", "uparse"])
 def test_cfg1_all_algorithms(ctx, algo):
     got, want, rep = run_both(ctx, pb.make_config(algo), datasets.cfg1())
     assert rep["ok"], rep
     assert rep["max_dq"] <= 1e-9 and rep["max_dp"] <= 1e-9
 
 
-@pytest.mark.parametrize("algo", ["simple_bayesian", "pear", "rdp_mle"])
+@pytest.mark.parametrize("algo", ["simple_bayesian", "pear", "rdp_mle", "ea_util", "stitch", "uparse"])
 @pytest.mark.parametrize("maxoverlap", [0, 300])
 def test_read_through_stress(ctx, algo, maxoverlap):
     got, want, rep = run_both(ctx, pb.make_config(algo, maxoverlap=maxoverlap), datasets.stress())
@@ -89,7 +89,7 @@ def test_low_complexity(ctx):
 
 def test_edge_cases(ctx):
     b = datasets.edge_cases()
-    for algo in ("simple_bayesian", "pear", "rdp_mle", "flash"):
+    for algo in ("simple_bayesian", "pear", "rdp_mle", "flash", "ea_util", "stitch", "uparse"):
         for kw in (dict(), dict(maxoverlap=800), dict(minoverlap=10)):
             got, want, rep = run_both(ctx, pb.make_config(algo, **kw), b)
             assert rep["ok"], (algo, kw, rep)
@@ -108,7 +108,7 @@ def test_unsupported_configurations_fail_loudly(ctx):
     with pytest.raises(pb.PandaseqError):
         ctx.assemble_host(pb.make_config("simple_bayesian", post_primers=True), b)
     with pytest.raises(pb.PandaseqError):
-        ctx.assemble_host(pb.make_config(7), b)
+        ctx.assemble_host(pb.make_config(9), b)
 
 
 def test_pinned_host_buffers_take_the_direct_copy_path(ctx):

@@ -40,7 +40,7 @@ def test_registry_sorted_by_name(built):
         _fields_ = [("data_size", C.c_size_t), ("name", C.c_char_p), ("create", C.c_void_p), ("destroy", C.c_void_p),
                     ("overlap", C.c_void_p), ("match", C.c_void_p), ("prob_unpaired", C.c_double)]
     names = [C.cast(arr[i], C.POINTER(Klass)).contents.name.decode() for i in range(n)]
-    assert names == sorted(names) == ["flash", "pear", "rdp_mle", "simple_bayesian"]
+    assert names == sorted(names) == ["ea_util", "flash", "pear", "rdp_mle", "simple_bayesian", "stitch", "uparse"]   # algo.c:125-131
     for i in range(n):
         assert C.cast(arr[i], C.POINTER(Klass)).contents.prob_unpaired == -1.38629
 

@@ -22,7 +22,7 @@ def same(a, r):
     assert np.array_equal(a["seq_p"][ok].view(np.uint64), r["seq_p"][ok].view(np.uint64))
 
 
-@pytest.mark.parametrize("algo", ["simple_bayesian", "pear", "rdp_mle", "flash"])
+@pytest.mark.parametrize("algo", ["simple_bayesian", "pear", "rdp_mle", "flash", "ea_util", "stitch", "uparse"])
 def test_cfg1(built, algo):
     b = datasets.cfg1(4000)
     cfg = pb.make_config(algo)
@@ -64,7 +64,7 @@ def test_primers(built, penalty):
 
 def test_low_complexity_and_edge_cases(built):
     for b in (datasets.low_complexity(), datasets.edge_cases()):
-        for algo in ("simple_bayesian", "pear", "rdp_mle", "flash"):
+        for algo in ("simple_bayesian", "pear", "rdp_mle", "flash", "ea_util", "stitch", "uparse"):
             for kw in (dict(), dict(maxoverlap=800)):
                 cfg = pb.make_config(algo, **kw)
                 same(oracle_lib.assemble("port", cfg, b), oracle_lib.assemble("ref", cfg, b))
