@@ -278,7 +278,7 @@ enum pb_pair_status { PB_PAIR_OK = 0, PB_PAIR_BADR = 1, PB_PAIR_NOFP = 2, PB_PAI
  * flattened into this before every launch. */
 typedef struct {
 	int32_t algo;             /* enum pb_algo */
-	int32_t post_primers;     /* must be 0 (primers-after path: SURVEY.md §8f rank 3, not built yet) */
+	int32_t post_primers;     /* primers_after (-a): locate the primers on the assembled sequence (assembler.c:300-333) */
 	int64_t minoverlap;
 	int64_t maxoverlap;
 	int64_t num_kmers;        /* must be 2 */

@@ -335,6 +335,43 @@ size_t po_compute_offset_qual(double threshold, double penalty, int reverse,
 	return best_index;
 }
 
+/* offset.c:35-38 */
+static double log1mexp(double p) {
+	return (p > 0.69314718055994530942) ? log1p(-exp(-p)) : log(-expm1(-p));
+}
+
+/* offset.c:47-90 with the result_base_score scorer (offset.c:114-133): the haystack is the assembled sequence.
+ * For a log-probability p < 0 the "not p" branch evaluates log(-expm1(-p)) = log(negative) = NaN, so any
+ * mismatching base poisons that start offset; reproduced literally through libm. */
+static size_t compute_offset_result(double threshold, double penalty, int reverse, const char *nt, const double *p,
+                                    size_t hay_len, const char *needle, size_t needle_len) {
+	double ring[PO_MAX_LEN];
+	double best = exp(needle_len * threshold);
+	size_t best_index = 0;
+	if (needle_len > hay_len || needle_len == 0 || needle_len > PO_MAX_LEN)
+		return 0;
+	for (size_t k = 0; k < needle_len; k++)
+		ring[k] = -INFINITY;
+	for (size_t index = 0; index < hay_len; index++) {
+		size_t slot = index % needle_len;
+		double last = exp(ring[slot] / (index + 1)) - index * penalty;
+		if (last > best) {
+			best = last;
+			best_index = index + 1;
+		}
+		ring[slot] = 0;
+		size_t el = reverse ? (hay_len - index - 1) : index;
+		double pr = p[el], notp = log1mexp(pr);
+		for (ptrdiff_t x = (ptrdiff_t) (needle_len > index ? index : needle_len - 1); x >= 0; x--) {
+			if (!is_n(needle[x])) {
+				size_t dst = (index - (size_t) x) % needle_len;
+				ring[dst] += ((nt[el] & needle[x]) != 0) ? pr : notp;
+			}
+		}
+	}
+	return best_index;
+}
+
 /* ------------------------------------------------------------------- align */
 
 typedef struct {
@@ -541,8 +578,7 @@ static int align_pair(const po_config *cfg, uint16_t *table, const po_qual *F, s
 	return 1;
 }
 
-/* assembler.c:252-348 (module hooks and the primers-after block are outside this oracle's scope:
- * post_primers != 0 is refused by po_assemble_flat). */
+/* assembler.c:252-348 (module hooks are host callbacks outside this path). */
 static void assemble_pair(const po_config *cfg, uint16_t *table, const po_qual *F, size_t flen,
                           const po_qual *R, size_t rlen, po_one *out) {
 	size_t fo, ro;
@@ -551,28 +587,32 @@ static void assemble_pair(const po_config *cfg, uint16_t *table, const po_qual *
 		out->status = PO_BADR;
 		return;
 	}
-	if (cfg->forward_primer_length > 0) {
-		fo = po_compute_offset_qual(cfg->threshold, cfg->primer_penalty, 0, F, flen, cfg->forward_primer, (size_t) cfg->forward_primer_length);
-		if (fo == 0) {
-			out->status = PO_NOFP;
-			return;
+	if (!cfg->post_primers) {
+		if (cfg->forward_primer_length > 0) {
+			fo = po_compute_offset_qual(cfg->threshold, cfg->primer_penalty, 0, F, flen, cfg->forward_primer, (size_t) cfg->forward_primer_length);
+			if (fo == 0) {
+				out->status = PO_NOFP;
+				return;
+			}
+			fo--;
+		} else {
+			fo = (size_t) cfg->forward_trim;
 		}
-		fo--;
-	} else {
-		fo = (size_t) cfg->forward_trim;
-	}
-	out->fwd_offset = (int) fo;
-	if (cfg->reverse_primer_length > 0) {
-		ro = po_compute_offset_qual(cfg->threshold, cfg->primer_penalty, 0, R, rlen, cfg->reverse_primer, (size_t) cfg->reverse_primer_length);
-		if (ro == 0) {
-			out->status = PO_NORP;
-			return;
+		out->fwd_offset = (int) fo;
+		if (cfg->reverse_primer_length > 0) {
+			ro = po_compute_offset_qual(cfg->threshold, cfg->primer_penalty, 0, R, rlen, cfg->reverse_primer, (size_t) cfg->reverse_primer_length);
+			if (ro == 0) {
+				out->status = PO_NORP;
+				return;
+			}
+			ro--;
+		} else {
+			ro = (size_t) cfg->reverse_trim;
 		}
-		ro--;
+		out->rev_offset = (int) ro;
 	} else {
-		ro = (size_t) cfg->reverse_trim;
+		fo = ro = 0;		/* assembler.c:285-288 */
 	}
-	out->rev_offset = (int) ro;
 	if ((flen < rlen ? flen : rlen) < (size_t) cfg->minoverlap) {
 		out->status = PO_BADR;
 		return;
@@ -580,6 +620,37 @@ static void assemble_pair(const po_config *cfg, uint16_t *table, const po_qual *
 	if (!align_pair(cfg, table, F, flen, R, rlen, fo, ro, out)) {
 		out->status = PO_NOALGN;
 		return;
+	}
+	if (cfg->post_primers) {	/* assembler.c:300-333 */
+		if (cfg->forward_primer_length > 0) {
+			fo = compute_offset_result(cfg->threshold, cfg->primer_penalty, 0, out->nt, out->p, (size_t) out->seq_len, cfg->forward_primer, (size_t) cfg->forward_primer_length);
+			if (fo == 0) {
+				out->status = PO_NOFP;
+				return;
+			}
+			fo--;
+		} else {
+			fo = (size_t) cfg->forward_trim;
+		}
+		out->fwd_offset = (int) fo;
+		if (cfg->reverse_primer_length > 0) {
+			ro = compute_offset_result(cfg->threshold, cfg->primer_penalty, 1, out->nt, out->p, (size_t) out->seq_len, cfg->reverse_primer, (size_t) cfg->reverse_primer_length);
+			if (ro == 0) {
+				out->status = PO_NORP;
+				return;
+			}
+			ro--;
+		} else {
+			ro = (size_t) cfg->reverse_trim;
+		}
+		out->rev_offset = (int) ro;
+		if ((size_t) out->seq_len <= fo + ro) {
+			out->status = PO_NOFP;	/* sic: assembler.c:324-328 counts this as a missing forward primer */
+			return;
+		}
+		out->seq_len -= (int) (fo + ro);
+		memmove(out->nt, out->nt + fo, (size_t) out->seq_len);
+		memmove(out->p, out->p + fo, (size_t) out->seq_len * sizeof(double));
 	}
 	if (out->quality < cfg->threshold) {
 		out->status = PO_LOWQ;
@@ -684,7 +755,7 @@ int po_assemble_flat(const po_config *cfg, size_t n,
                      const po_qual *f_data, const uint64_t *f_off,
                      const po_qual *r_data, const uint64_t *r_off,
                      po_flat_out *out, int threads) {
-	if (cfg->num_kmers != 2 || cfg->post_primers != 0 || cfg->minoverlap < 2
+	if (cfg->num_kmers != 2 || cfg->minoverlap < 2
 	    || cfg->algo < PO_SIMPLE_BAYES || cfg->algo > PO_UPARSE)
 		return -1;
 	if (threads < 1)

@@ -21,6 +21,8 @@ struct pb_context {
 	pb_config cached_cfg;
 	bool cfg_valid;
 	unsigned long long *d_counters;  /* scratch counters for the host path */
+	uint8_t *d_scratch;              /* per-warp scratch of the primers-after path, allocated on first use */
+	size_t scratch_bytes;
 	pthread_mutex_t lock;            /* one host-path call at a time per context (assemblers share the process-wide one) */
 	/* host-path staging (grown on demand) */
 	struct Slot {
@@ -117,6 +119,7 @@ extern "C" void pb_context_destroy(pb_context *ctx) {
 	cudaFree(ctx->d_params);
 	cudaFreeHost(ctx->h_params);
 	cudaFree(ctx->d_counters);
+	cudaFree(ctx->d_scratch);
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->copy_stream);
 	free(ctx);
@@ -148,7 +151,7 @@ static pb_status upload_params(pb_context *ctx, const pb_config *cfg) {
 template <int ML, bool OVER, int WARPS>
 static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
                                  pb_pair_result *d_results, uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride,
-                                 unsigned long long *d_counters, cudaStream_t stream) {
+                                 unsigned long long *d_counters, cudaStream_t stream, bool post) {
 	auto kern = pb::assemble_kernel<ML, OVER, WARPS>;
 	constexpr size_t smem = pb::assemble_smem_bytes<ML, OVER, WARPS>();
 	static bool configured[16] = { false };
@@ -169,8 +172,21 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 		grid = want;
 	if (grid < 1)
 		grid = 1;
+	uint8_t *scratch = nullptr;
+	if (post) {                  /* primers-after: every resident warp stages its assembled sequence in global scratch */
+		const size_t need = (size_t) grid * WARPS * PB_SCRATCH_STRIDE * 2;      /* x2: the host path runs two streams */
+		if (need > ctx->scratch_bytes) {
+			CUDA_TRY(cudaDeviceSynchronize());
+			cudaFree(ctx->d_scratch);
+			ctx->d_scratch = nullptr;
+			ctx->scratch_bytes = 0;
+			CUDA_TRY(cudaMalloc(&ctx->d_scratch, need));
+			ctx->scratch_bytes = need;
+		}
+		scratch = ctx->d_scratch + (stream == ctx->copy_stream ? need / 2 : 0);
+	}
 	kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p,
-	                                                           (long long) seq_stride, d_counters);
+	                                                           (long long) seq_stride, d_counters, scratch);
 	CUDA_TRY(cudaGetLastError());
 	return PB_OK;
 }
@@ -182,7 +198,7 @@ static pb_status assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n,
 	const bool over = cfg->algo == PB_PEAR || cfg->algo == PB_RDP_MLE;
 	if (max_len <= 0 || max_len > PB_MAX_LEN)
 		max_len = PB_MAX_LEN;
-#define PB_GO(ML, OVER, W) return launch_assemble<ML, OVER, W>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream)
+#define PB_GO(ML, OVER, W) return launch_assemble<ML, OVER, W>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, cfg->post_primers != 0)
 	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */
 	if (max_len <= 160) {
 		if (over) PB_GO(160, true, 24); else PB_GO(160, false, 30);

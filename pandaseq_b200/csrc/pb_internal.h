@@ -37,7 +37,7 @@ typedef struct {
 	int32_t reverse_trim;
 	int32_t forward_primer_length;
 	int32_t reverse_primer_length;
-	int32_t pad0;
+	int32_t post_primers;       /* assembler.c:300-333: locate the primers on the assembled sequence instead of the reads */
 	uint8_t forward_primer[PB_MAX_LEN + 2];
 	uint8_t reverse_primer[PB_MAX_LEN + 2];
 } pb_device_params;
@@ -56,6 +56,9 @@ struct panda_algorithm {
 	void *end;
 };
 int pb_algorithm_fill_config(PandaAlgorithm algo, pb_config *cfg);
+
+/* per-warp global scratch for the primers-after path: 912 f64 log-probabilities + 512 B of 4-bit bases */
+#define PB_SCRATCH_STRIDE (912 * 8 + 512)
 
 /* pb_device.cu */
 pb_status pb_shared_context(pb_context **out);

@@ -244,6 +244,58 @@ __device__ int primer_offset(const uint32_t *nt32, const int8_t *q, int len,
 	return best_index;
 }
 
+/* offset.c:47-90 with the result_base_score scorer (offset.c:114-133), for the primers-after path: the haystack is
+ * the assembled sequence (4-bit bases `snt32`, per-base log p `sp`, both in this warp's global scratch).
+ * For p < 0 the reference's "not p" is log(-expm1(-p)) = NaN, so a start offset with any mismatching base can
+ * never win (NaN > x is false): such starts are dropped, the others sum p in primer order. */
+__device__ int primer_offset_result(const uint32_t *snt32, const double *sp, int len, bool reverse,
+                                    const uint8_t *primer, int P, double threshold, double penalty, int lane) {
+	if (P > len)
+		return 0;
+	double best = (double) P * threshold;
+	if (penalty != 0.0)
+		best = exp(best);
+	int best_index = 0;
+	const int nstart = len - P;
+	const uint8_t *snt = reinterpret_cast<const uint8_t *>(snt32);
+	for (int base = 0; base < nstart; base += 32) {
+		const int s = min(base + lane, nstart - 1);
+		double sum = 0.0;
+		bool dead = false;
+		for (int x = 0; x < P; x++) {
+			const unsigned pn = primer[x];
+			if (pn == 15u)
+				continue;
+			const int el = reverse ? (len - 1 - (s + x)) : (s + x);
+			if (nib(snt, el) & pn)
+				sum += sp[el];
+			else
+				dead = true;
+		}
+		const int index = s + P;
+		double val = sum / (double) (index + 1);
+		if (penalty != 0.0)
+			val = exp(val) - (double) index * penalty;
+		if (dead || base + lane >= nstart)
+			val = -CUDART_INF;
+		int who = s;
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) {
+			const double ov = __shfl_xor_sync(FULL, val, d);
+			const int ow = __shfl_xor_sync(FULL, who, d);
+			if (ov > val || (ov == val && ow < who)) {
+				val = ov;
+				who = ow;
+			}
+		}
+		if (val > best) {
+			best = val;
+			best_index = who + P + 1;
+		}
+	}
+	return best_index;
+}
+
 /* ---- k-mer codes ---------------------------------------------------------------------------------
  * For every position p of a read, the 16-bit code of the 8-mer ending at p (digits of misc.h:41, oldest
  * base in the low bits -- any fixed injective packing will do, both reads use the same one).
@@ -542,7 +594,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
                              const pb_device_params *__restrict__ prm,
                              const double *__restrict__ s_recon, const double *__restrict__ s_over,
                              const double *__restrict__ s_score, const double *__restrict__ s_score_err,
-                             const uint16_t *__restrict__ s_qoff, const uint8_t *__restrict__ s_primer,
+                             const uint16_t *__restrict__ s_qoff, const uint8_t *__restrict__ s_primer, uint8_t *scratch,
                              pb_pair_result &res, uint8_t *out_nt, double *out_p, int out_cap, int lane) {
 	using WS = WarpSmem<ML>;
 	PairView v;
@@ -570,7 +622,12 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 	}
 	const int mo = prm->minoverlap;
 	int fo, ro;
+	const bool post = prm->post_primers != 0;   /* assembler.c:262,285-288: primers are located after assembly instead */
 	/* assembler.c:262-284 (primers before assembly) */
+	if (post) {
+		fo = 0;
+		ro = 0;
+	} else {
 	if (prm->forward_primer_length > 0) {
 		fo = primer_offset<false>(v.fnt32, v.fq, F, s_primer, prm->forward_primer_length,
 		                          prm->threshold, prm->primer_penalty, s_score, s_qoff, lane);
@@ -595,6 +652,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 		ro = prm->reverse_trim;
 	}
 	res.rev_offset = (uint16_t) ro;
+	}
 	/* assembler.c:289-292 */
 	if (min(F, R) < mo) {
 		res.status = PB_PAIR_BADR;
@@ -789,7 +847,12 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 		ra.fnt32 = v.fnt32; ra.rnt32 = v.rnt32; ra.fq = v.fq; ra.rq = v.rq;
 		ra.fo = fo; ra.df = df; ra.dfp = dfp; ra.fend = dfp + nover; ra.seq_len = seq_len;
 		ra.unmasked_f = unmasked_f; ra.lead_r = lead_r; ra.out_nt = out_nt; ra.out_p = out_p; ra.out_cap = out_cap; ra.qoff = s_qoff;
-		if (cliff || anyDeg || out_p != nullptr)
+		if (post) {        /* the whole assembled sequence goes to this warp's scratch first */
+			ra.out_p = reinterpret_cast<double *>(scratch);
+			ra.out_nt = scratch + 912 * 8;
+			ra.out_cap = 912;
+		}
+		if (cliff || anyDeg || ra.out_p != nullptr)
 			qsum = recon_words<true>(ra, s_recon, mism, degen, lane);
 		else
 			qsum = recon_words<false>(ra, s_recon, mism, degen, lane);
@@ -803,6 +866,52 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 	res.seq_len = (uint16_t) seq_len;
 	res.mismatches = (uint16_t) mism;
 	res.degenerates = (uint16_t) degen;
+	if (post) {                                      /* assembler.c:300-333 */
+		__syncwarp();
+		const double *sp = reinterpret_cast<const double *>(scratch);
+		const uint32_t *snt32 = reinterpret_cast<const uint32_t *>(scratch + 912 * 8);
+		int pfo, pro;
+		if (prm->forward_primer_length > 0) {
+			pfo = primer_offset_result(snt32, sp, seq_len, false, s_primer, prm->forward_primer_length, prm->threshold, prm->primer_penalty, lane);
+			if (pfo == 0) {
+				res.status = PB_PAIR_NOFP;
+				return;
+			}
+			pfo--;
+		} else {
+			pfo = prm->forward_trim;
+		}
+		res.fwd_offset = (uint16_t) pfo;
+		if (prm->reverse_primer_length > 0) {
+			pro = primer_offset_result(snt32, sp, seq_len, true, s_primer + PB_MAX_LEN + 2, prm->reverse_primer_length, prm->threshold, prm->primer_penalty, lane);
+			if (pro == 0) {
+				res.status = PB_PAIR_NORP;
+				return;
+			}
+			pro--;
+		} else {
+			pro = prm->reverse_trim;
+		}
+		res.rev_offset = (uint16_t) pro;
+		if (seq_len <= pfo + pro) {
+			res.status = PB_PAIR_NOFP;               /* sic: assembler.c:324-328 */
+			return;
+		}
+		const int newlen = seq_len - pfo - pro;      /* quality, degenerates, mismatches keep their pre-strip values */
+		res.seq_len = (uint16_t) newlen;
+		if (out_nt) {
+			const int nw = (newlen + 7) >> 3;
+			for (int k = lane; k < nw; k += 32)
+				if (8 * k < out_cap)
+					reinterpret_cast<uint32_t *>(out_nt)[k] = nibwin(snt32, pfo + 8 * k) & nibmask(min(newlen - 8 * k, 8));
+		}
+		if (out_p) {
+			for (int k = lane; k < newlen; k += 32)
+				if (k < out_cap)
+					out_p[k] = sp[pfo + k];
+		}
+		__syncwarp();                                /* scratch is reused by this warp's next pair */
+	}
 	if (res.quality < prm->threshold)                /* assembler.c:334-338 */
 		res.status = PB_PAIR_LOWQ;
 }
@@ -812,7 +921,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 assemble_kernel(const pb_device_params *__restrict__ prm, int n,
                 const uint8_t *__restrict__ reads, const pb_pair_meta *__restrict__ meta,
                 pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, double *__restrict__ seq_p,
-                long long seq_stride, unsigned long long *__restrict__ counters) {
+                long long seq_stride, unsigned long long *__restrict__ counters, uint8_t *__restrict__ scratch_all) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	using WS = WarpSmem<ML>;
 	/* block-level: LUTs + counters, then the per-warp areas */
@@ -865,6 +974,7 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 	const int wstride = gridDim.x * WARPS_PER_BLOCK;
 	/* merged read rows: 4 bit per base, seq_stride bases per row */
 	const long long nt_row = seq_stride / 2;
+	uint8_t *scratch = scratch_all ? scratch_all + (size_t) wglobal * PB_SCRATCH_STRIDE : nullptr;
 
 	auto issue = [&](int pair, int stage) {
 		if (lane == 0) {
@@ -891,7 +1001,7 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 		pb_pair_result &res = ru.r;
 		uint8_t *o_nt = seq_nt ? seq_nt + (size_t) pair * nt_row : nullptr;
 		double *o_p = seq_p ? seq_p + (size_t) pair * seq_stride : nullptr;
-		process_pair<ML>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, s_qoff, s_primer, res, o_nt, o_p, (int) seq_stride, lane);
+		process_pair<ML>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, s_qoff, s_primer, scratch, res, o_nt, o_p, (int) seq_stride, lane);
 		if (lane == 0) {
 			uint4 *dst = reinterpret_cast<uint4 *>(&results[pair]);
 			dst[0] = ru.v[0];

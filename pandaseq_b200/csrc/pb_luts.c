@@ -185,10 +185,6 @@ pb_status pb_build_device_params(const pb_config *cfg, pb_device_params *out) {
 		pb_set_error("num_kmers=%ld: the reference's k-mer table indexing (assembler.c:94 vs :99) is only self-consistent for 2", (long) cfg->num_kmers);
 		return PB_ERR_UNSUPPORTED;
 	}
-	if (cfg->post_primers) {
-		pb_set_error("primers_after (-a) is not implemented on the device path yet");
-		return PB_ERR_UNSUPPORTED;
-	}
 	if (cfg->minoverlap < 2 || cfg->minoverlap >= 2 * PB_MAX_LEN || cfg->maxoverlap < 0 || cfg->maxoverlap >= 2 * PB_MAX_LEN
 	    || cfg->forward_primer_length < 0 || cfg->forward_primer_length >= PB_MAX_LEN
 	    || cfg->reverse_primer_length < 0 || cfg->reverse_primer_length >= PB_MAX_LEN
@@ -204,6 +200,7 @@ pb_status pb_build_device_params(const pb_config *cfg, pb_device_params *out) {
 	out->reverse_trim = (int32_t) cfg->reverse_trim;
 	out->forward_primer_length = (int32_t) cfg->forward_primer_length;
 	out->reverse_primer_length = (int32_t) cfg->reverse_primer_length;
+	out->post_primers = cfg->post_primers ? 1 : 0;
 	out->threshold = cfg->threshold;
 	out->primer_penalty = cfg->primer_penalty;
 	out->qual_nn = t->qual_nn;

@@ -39,6 +39,8 @@ CASES = {
     "long250_pear": (lambda: datasets.long250(200), dict(algo="pear")),
     "primers300_rdp": (lambda: datasets.primers300(150), dict(algo="rdp_mle", primers=True)),
     "primers300_rdp_penalty": (lambda: datasets.primers300(150), dict(algo="rdp_mle", primers=True, primer_penalty=0.0005)),
+    "primers300_after_sb": (lambda: datasets.primers300(200), dict(algo="simple_bayesian", primers=True, post_primers=True)),
+    "cfg1_after_trims_pear": (lambda: datasets.cfg1(300), dict(algo="pear", post_primers=True, forward_trim=12, reverse_trim=7)),
     "lowcomplexity_sb": (lambda: datasets.low_complexity(200), dict(algo="simple_bayesian")),
     "edge_cases_sb": (lambda: datasets.edge_cases(), dict(algo="simple_bayesian")),
     "edge_cases_rdp_maxov800": (lambda: datasets.edge_cases(), dict(algo="rdp_mle", maxoverlap=800)),

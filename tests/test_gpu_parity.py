@@ -106,8 +106,6 @@ def test_unsupported_configurations_fail_loudly(ctx):
     with pytest.raises(pb.PandaseqError):
         ctx.assemble_host(pb.make_config("simple_bayesian", num_kmers=3), b)
     with pytest.raises(pb.PandaseqError):
-        ctx.assemble_host(pb.make_config("simple_bayesian", post_primers=True), b)
-    with pytest.raises(pb.PandaseqError):
         ctx.assemble_host(pb.make_config(9), b)
 
 
@@ -158,3 +156,19 @@ def test_device_resident_entry_point(ctx):
                counters=cnt.cpu().numpy())
     rep = compare(got, oracle_lib.assemble("port", cfg, flat))
     assert rep["ok"], rep
+
+
+@pytest.mark.parametrize("algo", ["simple_bayesian", "rdp_mle", "pear"])
+def test_primers_after_assembly(ctx, algo):
+    """-a / primers_after: the primers are located on the assembled sequence (assembler.c:300-333, offset.c:114-133)."""
+    fwd, rev = datasets.primer_codes()
+    cases = [(datasets.primers300(1200), dict(forward_primer=fwd, reverse_primer=rev)),
+             (datasets.primers300(600), dict(forward_primer=fwd, reverse_primer=rev, primer_penalty=0.0005)),
+             (datasets.primers300(600), dict(forward_primer=fwd, reverse_trim=9)),
+             (datasets.cfg1(1500), dict(forward_trim=12, reverse_trim=7)),
+             (datasets.cfg1(800), dict(forward_primer=fwd, reverse_primer=rev)),            # reads without the primers: all NOFP
+             (datasets.stress(1000), dict(forward_primer=fwd[:6], reverse_primer=rev[:5], maxoverlap=300)),
+             (datasets.edge_cases(), dict(forward_primer=fwd[:3], reverse_trim=2))]
+    for batch, kw in cases:
+        got, want, rep = run_both(ctx, pb.make_config(algo, post_primers=True, **kw), batch)
+        assert rep["ok"], (kw.keys(), rep)

@@ -74,3 +74,14 @@ def test_threads_do_not_change_results(built):
     b = datasets.cfg1(3000)
     cfg = pb.make_config("simple_bayesian")
     same(oracle_lib.assemble("port", cfg, b, threads=4), oracle_lib.assemble("ref", cfg, b, threads=3))
+
+
+def test_primers_after(built):
+    fwd, rev = datasets.primer_codes()
+    for b, kw in ((datasets.primers300(600), dict(forward_primer=fwd, reverse_primer=rev)),
+                  (datasets.primers300(300), dict(forward_primer=fwd, reverse_primer=rev, primer_penalty=0.0005)),
+                  (datasets.cfg1(800), dict(forward_trim=12, reverse_trim=7)),
+                  (datasets.stress(800), dict(forward_primer=fwd[:6], reverse_primer=rev[:5], maxoverlap=300))):
+        for algo in ("simple_bayesian", "rdp_mle"):
+            cfg = pb.make_config(algo, post_primers=True, **kw)
+            same(oracle_lib.assemble("port", cfg, b), oracle_lib.assemble("ref", cfg, b))
