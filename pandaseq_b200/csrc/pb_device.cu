@@ -148,11 +148,11 @@ static pb_status upload_params(pb_context *ctx, const pb_config *cfg) {
 	return PB_OK;
 }
 
-template <int ML, bool OVER, int WARPS>
+template <int ML, bool OVER, int WARPS, bool FULLF>
 static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
                                  pb_pair_result *d_results, uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride,
                                  unsigned long long *d_counters, cudaStream_t stream, bool post) {
-	auto kern = pb::assemble_kernel<ML, OVER, WARPS>;
+	auto kern = pb::assemble_kernel<ML, OVER, WARPS, FULLF>;
 	constexpr size_t smem = pb::assemble_smem_bytes<ML, OVER, WARPS>();
 	static bool configured[16] = { false };
 	if (!configured[ctx->device & 15]) {
@@ -198,10 +198,25 @@ static pb_status assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n,
 	const bool over = cfg->algo == PB_PEAR || cfg->algo == PB_RDP_MLE;
 	if (max_len <= 0 || max_len > PB_MAX_LEN)
 		max_len = PB_MAX_LEN;
-#define PB_GO(ML, OVER, W) return launch_assemble<ML, OVER, W>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, cfg->post_primers != 0)
+	/* the full kernel carries the primer scans and the log()-based scorers; everything else runs the lean one */
+	const bool full = cfg->post_primers != 0 || cfg->forward_primer_length > 0 || cfg->reverse_primer_length > 0
+		|| cfg->algo == PB_EA_UTIL || cfg->algo == PB_STITCH;
+#define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, cfg->post_primers != 0); \
+	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false); } while (0)
 	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */
 	if (max_len <= 160) {
-		if (over) PB_GO(160, true, 24); else PB_GO(160, false, 30);
+		if (over) PB_GO(160, true, 24);
+		else {
+			/* 30 warps x 64 registers vs 28 x 72: measured; PANDASEQ_B200_WARPS160 overrides for experiments */
+			static int w160 = -1;
+			if (w160 < 0) {
+				const char *env = getenv("PANDASEQ_B200_WARPS160");
+				w160 = env ? atoi(env) : 30;
+			}
+			if (w160 == 28) PB_GO(160, false, 28);
+			else if (w160 == 24) PB_GO(160, false, 24);
+			else PB_GO(160, false, 30);
+		}
 	} else if (max_len <= 256) {
 		if (over) PB_GO(256, true, 12); else PB_GO(256, false, 16);
 	} else if (max_len <= 320) {

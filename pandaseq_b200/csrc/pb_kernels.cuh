@@ -340,7 +340,7 @@ __device__ __forceinline__ unsigned gen_codes(const uint32_t *nt32, int len, uin
 /* Rare path (a read contains N): bit t of inval[w] is set when the 9 bases ending at 8w+t contain an N
  * or 8w+t < 8 -- the `bad` counter of misc.h:41. */
 template <int NTW>
-__device__ void gen_invalid(const uint32_t *nt32, int len, uint8_t *inval, int lane) {
+__device__ __noinline__ void gen_invalid(const uint32_t *nt32, int len, uint8_t *inval, int lane) {
 	const int nw = (len + 7) >> 3;
 	unsigned carry = 0;
 	for (int w0 = 0; w0 < nw; w0 += 32) {
@@ -589,7 +589,9 @@ __device__ __forceinline__ double recon_words(const ReconArgs &ra, const double 
 	return qsum;
 }
 
-template <int ML>
+/* FULLF = false is the lean instantiation: no primers (before or after assembly) and no log()-based scorers
+ * (ea_util, stitch); the host picks it whenever the configuration allows, which keeps the common kernel small. */
+template <int ML, bool FULLF>
 __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
                              const pb_device_params *__restrict__ prm,
                              const double *__restrict__ s_recon, const double *__restrict__ s_over,
@@ -622,13 +624,13 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 	}
 	const int mo = prm->minoverlap;
 	int fo, ro;
-	const bool post = prm->post_primers != 0;   /* assembler.c:262,285-288: primers are located after assembly instead */
+	const bool post = FULLF && prm->post_primers != 0;   /* assembler.c:262,285-288: primers are located after assembly instead */
 	/* assembler.c:262-284 (primers before assembly) */
 	if (post) {
 		fo = 0;
 		ro = 0;
 	} else {
-	if (prm->forward_primer_length > 0) {
+	if (FULLF && prm->forward_primer_length > 0) {
 		fo = primer_offset<false>(v.fnt32, v.fq, F, s_primer, prm->forward_primer_length,
 		                          prm->threshold, prm->primer_penalty, s_score, s_qoff, lane);
 		if (fo == 0) {
@@ -640,7 +642,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 		fo = prm->forward_trim;
 	}
 	res.fwd_offset = (uint16_t) fo;
-	if (prm->reverse_primer_length > 0) {
+	if (FULLF && prm->reverse_primer_length > 0) {
 		ro = primer_offset<true>(v.rnt32, v.rq, R, s_primer + PB_MAX_LEN + 2, prm->reverse_primer_length,
 		                         prm->threshold, prm->primer_penalty, s_score, s_qoff, lane);
 		if (ro == 0) {
@@ -760,14 +762,16 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 						/* algo_flash.c:59: integer division inside log() */
 						const int real = matches + mism + unk, bad = mism + unk;
 						prob = (real == 0) ? -2.0 : ((bad == real) ? 0.0 : -CUDART_INF);
-					} else if (algo == PB_EA_UTIL) {
+					} else if (FULLF && algo == PB_EA_UTIL) {
 						/* algo_ea_util.c:55: N counts as a mismatch; real_overlap == 0 divides by zero as the reference does */
 						const double bad = (double) (mism + unk);
 						prob = log((bad * bad + 1.0) / (double) (unsigned long long) (matches + mism + unk));
-					} else {
+					} else if (FULLF) {
 						/* algo_stitch.c:55: the score is a size_t, a net-negative score wraps */
 						const unsigned long long sc = (unsigned long long) (long long) (matches - mism);
 						prob = log((double) sc / (double) (unsigned long long) (F + R));
+					} else {
+						prob = -CUDART_INF;      /* not reachable: the host never pairs these scorers with the lean kernel */
 					}
 				} else {
 					double acc = 0.0;
@@ -866,7 +870,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 	res.seq_len = (uint16_t) seq_len;
 	res.mismatches = (uint16_t) mism;
 	res.degenerates = (uint16_t) degen;
-	if (post) {                                      /* assembler.c:300-333 */
+	if (FULLF && post) {                             /* assembler.c:300-333 */
 		__syncwarp();
 		const double *sp = reinterpret_cast<const double *>(scratch);
 		const uint32_t *snt32 = reinterpret_cast<const uint32_t *>(scratch + 912 * 8);
@@ -916,7 +920,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 		res.status = PB_PAIR_LOWQ;
 }
 
-template <int ML, bool OVER, int WARPS_PER_BLOCK>
+template <int ML, bool OVER, int WARPS_PER_BLOCK, bool FULLF>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 assemble_kernel(const pb_device_params *__restrict__ prm, int n,
                 const uint8_t *__restrict__ reads, const pb_pair_meta *__restrict__ meta,
@@ -1001,7 +1005,7 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 		pb_pair_result &res = ru.r;
 		uint8_t *o_nt = seq_nt ? seq_nt + (size_t) pair * nt_row : nullptr;
 		double *o_p = seq_p ? seq_p + (size_t) pair * seq_stride : nullptr;
-		process_pair<ML>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, s_qoff, s_primer, scratch, res, o_nt, o_p, (int) seq_stride, lane);
+		process_pair<ML, FULLF>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, s_qoff, s_primer, scratch, res, o_nt, o_p, (int) seq_stride, lane);
 		if (lane == 0) {
 			uint4 *dst = reinterpret_cast<uint4 *>(&results[pair]);
 			dst[0] = ru.v[0];
