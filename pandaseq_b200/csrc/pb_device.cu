@@ -195,7 +195,7 @@ static pb_status assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n,
                                    const uint8_t *d_reads, const pb_pair_meta *d_meta, pb_pair_result *d_results,
                                    uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride, unsigned long long *d_counters,
                                    cudaStream_t stream) {
-	const bool over = cfg->algo == PB_PEAR || cfg->algo == PB_RDP_MLE;
+	const bool over = cfg->algo == PB_RDP_MLE;      /* pear scores from the reconstruction table, only rdp_mle needs its own */
 	if (max_len <= 0 || max_len > PB_MAX_LEN)
 		max_len = PB_MAX_LEN;
 	/* the full kernel carries the primer scans and the log()-based scorers; everything else runs the lean one */

@@ -16,8 +16,8 @@ extern "C" {
  *  recon[k][a][b]  : per-base log p during reconstruction (assembler.c:162-243), k = bases match;
  *                    a/b = clamped PHRED of the forward/reverse base, or 47 when that read is absent
  *                    (forward-only / reverse-only stretch) or B-cliff masked (assembler.c:176-210).
- *  over[k][a][b]   : per-base term of the overlap score for pear / rdp_mle (algo_pear.c:52-54,
- *                    algo_rdp_mle.c:68-70); unused by simple_bayes / flash.
+ *  over[k][a][b]   : per-base term of the overlap score for rdp_mle (algo_rdp_mle.c:68-70); pear's terms
+ *                    (algo_pear.c:52-54) equal recon[k][a][b] and are read from there.
  */
 typedef struct {
 	double recon[2][PB_NQM][PB_NQM];

@@ -781,13 +781,15 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 						const int qa = clampq(v.fq[fi]);
 						if (algo == PB_PEAR) {
 							/* algo_pear.c:52,54 index the FORWARD qualities with rindex = R-1-i; past the
-							 * end of the forward read that is defined as quality 0. */
+							 * end of the forward read that is defined as quality 0.
+							 * pear's overlap terms are the very matrices its match_probability uses, so they are
+							 * read from the reconstruction table (row stride 48) and need no table of their own. */
 							const int ri = R - 1 - i;
 							const int qb = (ri < F) ? clampq(v.fq[ri]) : 0;
 							if (f == 15u || r == 15u)
 								acc -= prm->pear_random_base;
 							else
-								acc += s_over[(((f & r) ? 1 : 0) * PB_NQ + qa) * PB_NQ + qb];
+								acc += s_recon[(((f & r) ? 1 : 0) * PB_NQM + qa) * PB_NQM + qb];
 						} else {
 							const int qb = clampq(v.rq[i]);
 							acc += s_over[(((f & r) ? 1 : 0) * PB_NQ + qa) * PB_NQ + qb];
