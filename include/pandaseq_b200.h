@@ -271,7 +271,8 @@ typedef enum {
 enum pb_algo { PB_SIMPLE_BAYES = 0, PB_PEAR = 1, PB_RDP_MLE = 2, PB_FLASH = 3, PB_EA_UTIL = 4, PB_STITCH = 5, PB_UPARSE = 6 };
 
 /* Why a pair was not emitted, in assemble_seq order (assembler.c:252-348). */
-enum pb_pair_status { PB_PAIR_OK = 0, PB_PAIR_BADR = 1, PB_PAIR_NOFP = 2, PB_PAIR_NORP = 3, PB_PAIR_NOALGN = 4, PB_PAIR_LOWQ = 5 };
+enum pb_pair_status { PB_PAIR_OK = 0, PB_PAIR_BADR = 1, PB_PAIR_NOFP = 2, PB_PAIR_NORP = 3, PB_PAIR_NOALGN = 4, PB_PAIR_LOWQ = 5,
+                      PB_PAIR_SKIP = 6 /* not a pair: a FASTQ record the reader drops (fastq.c:176) or one past the record that ended the stream; never counted */ };
 
 /* Everything assemble_seq/align read from struct panda_assembler (assembler.h:28-79)
  * plus the algorithm's private data, as one plain struct.  panda_* objects are
@@ -384,6 +385,87 @@ pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, size_t n,
                            const panda_qual *r_data, const uint64_t *r_off,
                            pb_pair_result *results, uint8_t *seq_nt, double *seq_p,
                            size_t seq_stride, int64_t *counters);
+
+/* ======================================================================
+ * Layer 2b: the stages either side of the hot path, on the device
+ *   FASTQ text -> packed records   (fastq.c:44-193, linebuf.c:57-89, seqid.c:136-285, nt.c:48-124)
+ *   assembled pairs -> FASTA/FASTQ text (output.c:85-126, nt.c:126-150, seqid.c:121-128)
+ * ====================================================================== */
+enum pb_tagging { PB_TAG_PRESENT = 0, PB_TAG_ABSENT = 1, PB_TAG_OPTIONAL = 2 };   /* PandaTagging, pandaseq-common.h:165-178 */
+enum pb_idfmt { PB_IDFMT_UNKNOWN = 0, PB_IDFMT_SRA, PB_IDFMT_CASAVA_1_4, PB_IDFMT_CASAVA_1_7, PB_IDFMT_EBI_SRA, PB_IDFMT_CASAVA_CONVERTED }; /* PandaIdFmt, pandaseq-common.h:188-195 */
+/* Why the reader stopped: the PandaCode fastq.c logs before it returns false for good. */
+enum pb_fastq_error {
+	PB_FQ_OK = 0,
+	PB_FQ_ID_PARSE_FAILURE = 1, /* PANDA_CODE_ID_PARSE_FAILURE  fastq.c:126,133 */
+	PB_FQ_NOT_PAIRED = 2,       /* PANDA_CODE_NOT_PAIRED        fastq.c:137 */
+	PB_FQ_PREMATURE_EOF = 3,    /* PANDA_CODE_PREMATURE_EOF     fastq.c:58,69,84 */
+	PB_FQ_BAD_NT = 4,           /* PANDA_CODE_BAD_NT            fastq.c:63 */
+	PB_FQ_READ_TOO_LONG = 5,    /* PANDA_CODE_READ_TOO_LONG     fastq.c:75 */
+	PB_FQ_PARSE_FAILURE = 6,    /* PANDA_CODE_PARSE_FAILURE     fastq.c:78 */
+	PB_FQ_NO_QUALITY_INFO = 7,  /* PANDA_CODE_NO_QUALITY_INFO   fastq.c:95 */
+	PB_FQ_LINE_TOO_LONG = 8     /* a line of 4500 bytes or more: linebuf.c:25,65 returns NULL, the stream just ends */
+};
+#define PB_FQ_LINE_MAX 4500
+
+/* A parsed identifier, 48 bytes: the strings are substrings of the forward header line. */
+typedef struct {
+	uint32_t hdr_off;     /* offset, in the forward text handed to the parser, of the character after '@' */
+	uint16_t hdr_len;     /* length of the header line after that character (CR stripped) */
+	uint8_t fmt;          /* enum pb_idfmt */
+	uint8_t reserved;
+	uint16_t inst_off, inst_len;   /* relative to hdr_off; for the SRA formats the instrument is "%cRR%d" of `sra` */
+	uint16_t run_off, run_len;
+	uint16_t fc_off, fc_len;
+	uint16_t tag_off, tag_len;
+	int32_t lane, tile, x, y;
+	int32_t sra;
+	int32_t mate;         /* what panda_seqid_parse returns (the read direction) */
+} pb_seq_id;
+/* Expand into the reference's 368-byte struct (host helper; `fwd_text` is the text the parser saw). */
+void pb_seq_id_expand(const pb_seq_id *id, const char *fwd_text, panda_seq_identifier *out);
+
+typedef struct {
+	uint64_t records;      /* complete 4-line records present in BOTH texts */
+	uint64_t limit;        /* records before the one that ended the stream (== records when none did) */
+	uint64_t pairs;        /* pairs delivered: limit minus the records with an empty forward read (fastq.c:176) */
+	uint64_t consumed_fwd; /* bytes of each text that belong to records [0, records) */
+	uint64_t consumed_rev;
+	int32_t error;         /* enum pb_fastq_error of record `limit`, PB_FQ_OK when the data simply ran out */
+	int32_t max_read_len;  /* longest read among the records (selects the assemble kernel's class) */
+	uint32_t stride16;     /* packed records are laid out at a fixed stride of 16*stride16 bytes */
+	uint32_t reserved;
+} pb_fastq_info;
+
+/* pb_fastq_parse_device: every pointer is a DEVICE pointer, the call returns after the (small) pb_fastq_info came
+ * back.  d_fwd/d_rev: FASTQ text (16-byte aligned).  Record i of the result is FASTQ record i: d_meta[i].flen ==
+ * 0xFFFF marks a record that is not a pair (pb_assemble_device gives it PB_PAIR_SKIP and does not count it); assemble
+ * records [0, info.limit).  d_reads must hold records * pb_record_bytes(PB_MAX_LEN, PB_MAX_LEN) bytes unless the caller knows better
+ * (info.stride16 tells what was used), d_meta / d_ids `max_records` entries.  Text that does not end on a record
+ * boundary is the caller's to resubmit (consumed_*). */
+pb_status pb_fastq_parse_device(pb_context *ctx, const char *d_fwd, size_t fwd_bytes, const char *d_rev, size_t rev_bytes,
+                                int qualmin, int policy, size_t max_records,
+                                uint8_t *d_reads, size_t reads_capacity, pb_pair_meta *d_meta, pb_seq_id *d_ids, pb_fastq_info *info);
+
+enum pb_out_format { PB_OUT_FASTA = 0, PB_OUT_FASTQ = 1 };   /* panda_output_fasta / panda_output_fastq */
+/* pb_format_device: text of every PB_PAIR_OK record, in record order, written to d_text (capacity bytes); FASTQ needs
+ * d_seq_p.  d_fwd is the forward text the ids point into.  *text_bytes receives the length (a larger value than
+ * capacity means nothing was written: call again with enough room). */
+pb_status pb_format_device(pb_context *ctx, int format, size_t n, const pb_pair_result *d_results, const uint8_t *d_seq_nt,
+                           const double *d_seq_p, size_t seq_stride, const pb_seq_id *d_ids, const char *d_fwd,
+                           char *d_text, size_t capacity, size_t *text_bytes);
+
+/* The whole chain with HOST buffers: two FASTQ texts in, assembled FASTA/FASTQ text out; H2D copies, parse, assemble,
+ * format and the D2H copy happen inside, in chunks on two streams.  `final` != 0: the texts are complete files (a
+ * trailing partial record is an error); == 0: the caller resubmits what consumed_* leaves.  out_text may be NULL to
+ * only count.  counters (PB_NCOUNTERS, accumulated) as pb_assemble_host. */
+typedef struct {
+	uint64_t records, pairs, consumed_fwd, consumed_rev, out_bytes;
+	int32_t error;         /* enum pb_fastq_error */
+	int32_t reserved;
+} pb_stream_info;
+pb_status pb_fastq_assemble_host(pb_context *ctx, const pb_config *cfg, int qualmin, int policy, int out_format,
+                                 const char *fwd, size_t fwd_bytes, const char *rev, size_t rev_bytes, int final,
+                                 char *out_text, size_t out_capacity, int64_t *counters, pb_stream_info *info);
 
 /* The LUTs the kernels use (regenerated with the reference's formulas and "%g"
  * rounding, mktable.c:23-155 + tablebuilder.c:73-183), exposed for the table parity test. */

@@ -10,6 +10,7 @@
  * per-pair "INFO BESTOLP" formatting stays out of the timing.
  */
 #include <math.h>
+#include <stdio.h>
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -274,4 +275,161 @@ void ref_get_tables(po_tables *t) {
 size_t ref_compute_offset_qual(double threshold, double penalty, int reverse,
                                const po_qual *hay, size_t hay_len, const char *needle, size_t needle_len) {
 	return panda_compute_offset_qual(threshold, penalty, reverse != 0, (const panda_qual *) hay, hay_len, (const panda_nt *) needle, needle_len);
+}
+
+/* ---- the stages either side of the hot path, through the reference's own entry points ---------- */
+typedef struct {
+	const char *data;
+	size_t len, pos, max_read;
+} mem_src;
+
+static bool mem_read(char *buffer, size_t buffer_length, size_t *read, void *user) {
+	mem_src *m = user;
+	size_t n = m->len - m->pos;
+	if (n > buffer_length)
+		n = buffer_length;
+	if (m->max_read && n > m->max_read)
+		n = m->max_read;
+	memcpy(buffer, m->data + m->pos, n);
+	m->pos += n;
+	*read = n;
+	return true;
+}
+
+typedef struct {
+	char text[1 << 16];
+	size_t len;
+} log_sink;
+
+static void sink_write(const char *buffer, size_t buffer_length, void *user) {
+	log_sink *s = user;
+	if (s->len + buffer_length >= sizeof s->text)
+		buffer_length = sizeof s->text - 1 - s->len;
+	memcpy(s->text + s->len, buffer, buffer_length);
+	s->len += buffer_length;
+	s->text[s->len] = '\0';
+}
+
+static int code_from_log(const char *text) {
+	/* the LAST "ERR\t<code>" line decides (fastq.c logs exactly one before it stops) */
+	static const struct { const char *name; int code; } map[] = {
+		{ "ERR\tBADID", PO_FQ_ID_PARSE_FAILURE }, { "ERR\tNOTPAIRED", PO_FQ_NOT_PAIRED }, { "ERR\tEOF", PO_FQ_PREMATURE_EOF },
+		{ "ERR\tBADNT", PO_FQ_BAD_NT }, { "ERR\tREADLEN", PO_FQ_READ_TOO_LONG }, { "ERR\tBADSEQ", PO_FQ_PARSE_FAILURE },
+		{ "ERR\tNOQUAL", PO_FQ_NO_QUALITY_INFO },
+	};
+	int code = PO_FQ_OK;
+	const char *best = NULL;
+	for (size_t k = 0; k < sizeof map / sizeof map[0]; k++) {
+		const char *p = text, *last = NULL;
+		while ((p = strstr(p, map[k].name)) != NULL) {
+			last = p;
+			p++;
+		}
+		if (last != NULL && (best == NULL || last > best)) {
+			best = last;
+			code = map[k].code;
+		}
+	}
+	return code;
+}
+
+/* panda_create_fastq_reader (fastq.c:205-237) over two in-memory files; `max_read` > 0 caps what one
+ * PandaBufferRead call returns, to exercise linebuf refills. */
+int ref_fastq_parse(const char *fwd, size_t fwd_len, const char *rev, size_t rev_len, int qualmin, int policy,
+                    size_t max_pairs, po_fastq_out *out, size_t max_read) {
+	mem_src sf = { fwd, fwd_len, 0, max_read }, sr = { rev, rev_len, 0, max_read };
+	log_sink *sink = calloc(1, sizeof(log_sink));
+	PandaLogProxy logger = panda_log_proxy_new(panda_writer_new(sink_write, sink, NULL));
+	void *next_data = NULL;
+	PandaDestroy next_destroy = NULL;
+	PandaNextSeq next;
+	size_t n = 0;
+	uint64_t fo = 0, ro = 0;
+	panda_debug_flags = PANDA_DEBUG_FILE;
+	next = panda_create_fastq_reader(mem_read, &sf, NULL, mem_read, &sr, NULL, logger, (unsigned char) qualmin, (PandaTagging) policy,
+	                                 NULL, NULL, NULL, &next_data, &next_destroy);
+	if (out->f_off) out->f_off[0] = 0;
+	if (out->r_off) out->r_off[0] = 0;
+	while (n < max_pairs) {
+		panda_seq_identifier id;
+		const panda_qual *f, *r;
+		size_t fl, rl;
+		memset(&id, 0, sizeof id);
+		if (!next(&id, &f, &fl, &r, &rl, next_data))
+			break;
+		if (out->ids) memcpy(&out->ids[n], &id, sizeof id);
+		if (out->f_data) memcpy(out->f_data + fo, f, fl * sizeof(panda_qual));
+		if (out->r_data) memcpy(out->r_data + ro, r, rl * sizeof(panda_qual));
+		fo += fl;
+		ro += rl;
+		n++;
+		if (out->f_off) out->f_off[n] = fo;
+		if (out->r_off) out->r_off[n] = ro;
+	}
+	out->n = n;
+	out->records = 0;      /* not observable through the reference's API */
+	/* the writer hands its buffer over when the last reference goes away */
+	if (next_destroy)
+		next_destroy(next_data);
+	panda_log_proxy_unref(logger);
+	panda_debug_flags = 0;
+	out->error = code_from_log(sink->text);
+	free(sink);
+	return 0;
+}
+
+int ref_seqid_parse(po_seq_identifier *id, const char *input, int policy, int *format) {
+	PandaIdFmt fmt = PANDA_IDFMT_UNKNOWN;
+	int rc = panda_seqid_parse_fail((panda_seq_identifier *) id, input, (PandaTagging) policy, &fmt, NULL);
+	if (format)
+		*format = (int) fmt;
+	return rc;
+}
+
+char ref_result_phred(double p) {
+	panda_result r;
+	r.nt = 1;
+	r.p = p;
+	return panda_result_phred(&r);
+}
+
+typedef struct {
+	char *dst;
+	size_t len;
+} text_sink;
+
+static void text_write(const char *buffer, size_t buffer_length, void *user) {
+	text_sink *s = user;
+	memcpy(s->dst + s->len, buffer, buffer_length);
+	s->len += buffer_length;
+}
+
+/* panda_output_fasta / panda_output_fastq (output.c:85-126) through a PandaWriter into memory */
+size_t ref_format_flat(char *dst, int fastq, size_t n, const po_seq_identifier *ids, const uint8_t *status,
+                       const double *quality, const int32_t *seq_len, const uint8_t *seq_nt, const double *seq_p,
+                       int64_t seq_stride) {
+	text_sink sink = { dst, 0 };
+	PandaWriter w = panda_writer_new(text_write, &sink, NULL);
+	panda_result *seq = calloc(2 * PO_MAX_LEN + 1, sizeof(panda_result));
+	for (size_t i = 0; i < n; i++) {
+		panda_result_seq rs;
+		if (status[i] != PO_OK)
+			continue;
+		memset(&rs, 0, sizeof rs);
+		rs.quality = quality[i];
+		memcpy(&rs.name, &ids[i], sizeof rs.name);
+		rs.sequence = seq;
+		rs.sequence_length = (size_t) seq_len[i];
+		for (size_t k = 0; k < rs.sequence_length; k++) {
+			seq[k].nt = (panda_nt) seq_nt[i * (size_t) seq_stride + k];
+			seq[k].p = seq_p ? seq_p[i * (size_t) seq_stride + k] : 0.0;
+		}
+		if (fastq)
+			panda_output_fastq(&rs, w);
+		else
+			panda_output_fasta(&rs, w);
+	}
+	panda_writer_unref(w);
+	free(seq);
+	return sink.len;
 }

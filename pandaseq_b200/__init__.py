@@ -23,7 +23,10 @@ PB_MAX_LEN = 450
 PB_PHREDMAX = 46
 PB_NCOUNTERS = 16 + 2 * PB_MAX_LEN
 ALGOS = {"simple_bayesian": 0, "pear": 1, "rdp_mle": 2, "flash": 3, "ea_util": 4, "stitch": 5, "uparse": 6}
-STATUS = {0: "OK", 1: "BADR", 2: "NOFP", 3: "NORP", 4: "NOALGN", 5: "LOWQ"}
+STATUS = {0: "OK", 1: "BADR", 2: "NOFP", 3: "NORP", 4: "NOALGN", 5: "LOWQ", 6: "SKIP"}
+FQ_ERRORS = {0: "OK", 1: "BADID", 2: "NOTPAIRED", 3: "EOF", 4: "BADNT", 5: "READLEN", 6: "BADSEQ", 7: "NOQUAL", 8: "LINELEN"}
+TAG_PRESENT, TAG_ABSENT, TAG_OPTIONAL = 0, 1, 2
+OUT_FASTA, OUT_FASTQ = 0, 1
 C_COUNT, C_OK, C_LOWQ, C_NOALGN, C_BADR, C_NOFP, C_NORP, C_SLOW, C_LONGEST = range(9)
 C_OVERLAPS = 16
 
@@ -71,6 +74,25 @@ PAIR_RESULT_DTYPE = np.dtype([
     ("degenerates", "<u2"), ("examined", "<u2"), ("fwd_offset", "<u2"), ("rev_offset", "<u2"),
     ("quality", "<f8"), ("est_prob", "<f8")])
 assert PAIR_RESULT_DTYPE.itemsize == 32 and PAIR_META_DTYPE.itemsize == 8
+SEQ_ID_DTYPE = np.dtype([("hdr_off", "<u4"), ("hdr_len", "<u2"), ("fmt", "u1"), ("reserved", "u1"),
+                         ("inst_off", "<u2"), ("inst_len", "<u2"), ("run_off", "<u2"), ("run_len", "<u2"),
+                         ("fc_off", "<u2"), ("fc_len", "<u2"), ("tag_off", "<u2"), ("tag_len", "<u2"),
+                         ("lane", "<i4"), ("tile", "<i4"), ("x", "<i4"), ("y", "<i4"), ("sra", "<i4"), ("mate", "<i4")])
+assert SEQ_ID_DTYPE.itemsize == 48
+PANDA_SEQID_DTYPE = np.dtype([("instrument", "S100"), ("run", "S100"), ("flowcell", "S100"), ("lane", "<i4"), ("tile", "<i4"),
+                              ("x", "<i4"), ("y", "<i4"), ("tag", "S50"), ("_pad", "V2")])      # pandaseq-common.h:235-247
+assert PANDA_SEQID_DTYPE.itemsize == 368
+
+
+class PbFastqInfo(C.Structure):
+    _fields_ = [("records", C.c_uint64), ("limit", C.c_uint64), ("pairs", C.c_uint64), ("consumed_fwd", C.c_uint64),
+                ("consumed_rev", C.c_uint64), ("error", C.c_int32), ("max_read_len", C.c_int32), ("stride16", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class PbStreamInfo(C.Structure):
+    _fields_ = [("records", C.c_uint64), ("pairs", C.c_uint64), ("consumed_fwd", C.c_uint64), ("consumed_rev", C.c_uint64),
+                ("out_bytes", C.c_uint64), ("error", C.c_int32), ("reserved", C.c_int32)]
 
 
 def make_config(algo="simple_bayesian", *, threshold=0.6, minoverlap=2, maxoverlap=0, forward_primer=None,
@@ -134,6 +156,13 @@ def lib() -> C.CDLL:
     L.pb_assemble_host.argtypes = [vp, C.POINTER(PbConfig), sz, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.pb_assemble_host.restype = i32
     L.pb_counters_merge.argtypes = [vp, vp]
+    L.pb_fastq_parse_device.argtypes = [vp, vp, sz, vp, sz, i32, i32, sz, vp, sz, vp, vp, C.POINTER(PbFastqInfo)]
+    L.pb_fastq_parse_device.restype = i32
+    L.pb_format_device.argtypes = [vp, i32, sz, vp, vp, vp, sz, vp, vp, vp, sz, C.POINTER(sz)]
+    L.pb_format_device.restype = i32
+    L.pb_fastq_assemble_host.argtypes = [vp, C.POINTER(PbConfig), i32, i32, i32, vp, sz, vp, sz, i32, vp, sz, vp, C.POINTER(PbStreamInfo)]
+    L.pb_fastq_assemble_host.restype = i32
+    L.pb_seq_id_expand.argtypes = [vp, vp, vp]
     L.panda_max_len.restype = sz
     _lib = L
     return L
@@ -240,6 +269,74 @@ class Context:
                                         results.data_ptr(), seq_nt.data_ptr() if seq_nt is not None else None,
                                         seq_p.data_ptr() if seq_p is not None else None, int(seq_stride), counters.data_ptr()),
                "pb_assemble_device")
+
+
+    # ---- FASTQ text in, FASTA/FASTQ text out -------------------------------------------------------
+    def fastq_parse_device(self, fwd, rev, *, qualmin=33, policy=TAG_PRESENT, max_records=None):
+        """fwd/rev: uint8 torch CUDA tensors holding FASTQ text.  Returns dict(info, reads, meta, ids) -- torch CUDA
+        tensors (meta: (max_records, 2) int32 view of pb_pair_meta; ids: (max_records, 48) uint8) and the info dict."""
+        import torch
+        dev = fwd.device
+        if max_records is None:
+            max_records = int(min(fwd.numel(), rev.numel()) // 7 + 1)       # "@\n\n+\n\n" is the shortest record
+        cap = max(max_records, 1) * int(record_bytes(PB_MAX_LEN, PB_MAX_LEN))
+        reads = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        meta = torch.zeros((max(max_records, 1), 2), dtype=torch.int32, device=dev)
+        ids = torch.zeros((max(max_records, 1), 48), dtype=torch.uint8, device=dev)
+        info = PbFastqInfo()
+        self._sync_from_torch()
+        _check(lib().pb_fastq_parse_device(self._h, fwd.data_ptr(), fwd.numel(), rev.data_ptr(), rev.numel(), int(qualmin), int(policy),
+                                           int(max_records), reads.data_ptr(), reads.numel(), meta.data_ptr(), ids.data_ptr(),
+                                           C.byref(info)), "pb_fastq_parse_device")
+        d = {k: getattr(info, k) for k, _ in PbFastqInfo._fields_}
+        return dict(info=d, reads=reads, meta=meta, ids=ids)
+
+    def format_device(self, fmt, n, results, seq_nt, seq_p, seq_stride, ids, fwd, capacity=None):
+        """-> bytes of the FASTA/FASTQ text of records [0, n) (torch CUDA tensors in, text copied back)."""
+        import torch
+        self._sync_from_torch()
+        total = C.c_size_t(0)
+        args = lambda t, cap: (self._h, int(fmt), int(n), results.data_ptr(), seq_nt.data_ptr(), seq_p.data_ptr() if seq_p is not None else None,
+                               int(seq_stride), ids.data_ptr(), fwd.data_ptr(), t, cap, C.byref(total))
+        _check(lib().pb_format_device(*args(None, 0)), "pb_format_device (length)")
+        text = torch.zeros(max(int(total.value), 1), dtype=torch.uint8, device=fwd.device)
+        _check(lib().pb_format_device(*args(text.data_ptr(), text.numel())), "pb_format_device")
+        return bytes(text[:int(total.value)].cpu().numpy())
+
+    def fastq_assemble_host(self, cfg: PbConfig, fwd, rev, *, qualmin=33, policy=TAG_PRESENT, out_format=OUT_FASTA, final=True,
+                            out=None, out_capacity=None):
+        """fwd/rev: bytes or uint8 numpy arrays / pinned torch tensors with FASTQ text.  Returns (text bytes or None, info dict,
+        counters).  `out`: optional preallocated uint8 buffer (numpy or pinned torch) receiving the text."""
+        def ptr_len(x):
+            if isinstance(x, (bytes, bytearray)):
+                a = np.frombuffer(x, dtype=np.uint8)
+                return a, a.ctypes.data, a.size
+            if isinstance(x, np.ndarray):
+                return x, x.ctypes.data, x.size
+            return x, x.data_ptr(), x.numel()
+        fk, fp, fl = ptr_len(fwd)
+        rk, rp, rl = ptr_len(rev)
+        own = out is None
+        if own:
+            out = np.zeros(int(out_capacity if out_capacity is not None else fl + rl + 1024), dtype=np.uint8)
+        ok, op, ol = ptr_len(out)
+        counters = np.zeros(PB_NCOUNTERS, dtype=np.int64)
+        info = PbStreamInfo()
+        _check(lib().pb_fastq_assemble_host(self._h, C.byref(cfg), int(qualmin), int(policy), int(out_format), fp, fl, rp, rl, int(bool(final)),
+                                            op, ol, _np_ptr(counters), C.byref(info)), "pb_fastq_assemble_host")
+        d = {k: getattr(info, k) for k, _ in PbStreamInfo._fields_}
+        text = bytes(out[:d["out_bytes"]]) if own else None
+        return text, d, counters
+
+
+def expand_ids(ids: np.ndarray, fwd_text: bytes) -> np.ndarray:
+    """pb_seq_id records (SEQ_ID_DTYPE) -> panda_seq_identifier records (PANDA_SEQID_DTYPE), via pb_seq_id_expand"""
+    ids = np.ascontiguousarray(ids)
+    out = np.zeros(len(ids), dtype=PANDA_SEQID_DTYPE)
+    buf = C.create_string_buffer(fwd_text, len(fwd_text) + 1)
+    for i in range(len(ids)):
+        lib().pb_seq_id_expand(ids[i:i + 1].ctypes.data, C.cast(buf, C.c_void_p), out[i:i + 1].ctypes.data)
+    return out
 
 
 from . import synth  # noqa: E402,F401  (torch is imported lazily by callers that generate data)

@@ -1,0 +1,59 @@
+/* pb_ctx.h -- the device context shared by pb_device.cu (assembly) and pb_io.cu (FASTQ in / text out). */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pb_internal.h"
+
+struct pb_io_state;
+
+struct pb_context {
+	int device;
+	int sm_count;
+	cudaStream_t stream;
+	cudaStream_t copy_stream;
+	pb_device_params *d_params;      /* in HBM */
+	pb_device_params *h_params;      /* pinned mirror */
+	pb_config cached_cfg;
+	bool cfg_valid;
+	unsigned long long *d_counters;  /* scratch counters for the host path */
+	uint8_t *d_scratch;              /* per-warp scratch of the primers-after path, allocated on first use */
+	size_t scratch_bytes;
+	pthread_mutex_t lock;            /* one host-path call at a time per context (assemblers share the process-wide one) */
+	/* host-path staging (grown on demand) */
+	struct Slot {
+		size_t cap_pairs, cap_bases, cap_hpairs, cap_hbases, cap_hres;
+		uint8_t *h_f, *h_r;              /* pinned AoS */
+		unsigned long long *h_foff, *h_roff;
+		uint32_t *h_recoff;
+		uint8_t *d_f, *d_r;
+		unsigned long long *d_foff, *d_roff;
+		uint32_t *d_recoff;
+		uint8_t *d_reads;
+		size_t cap_reads;
+		pb_pair_meta *d_meta;
+		pb_pair_result *d_res, *h_res;
+		uint8_t *d_nt, *h_nt;
+		double *d_p, *h_p;
+		size_t cap_nt, cap_p, cap_dnt, cap_dp;
+		cudaEvent_t done;
+	} slot[2];
+	pb_io_state *io;                 /* buffers of the FASTQ / text stages, allocated on first use (pb_io.cu) */
+};
+
+#define CUDA_TRY(expr)                                                                         \
+	do {                                                                                       \
+		cudaError_t e_ = (expr);                                                               \
+		if (e_ != cudaSuccess) {                                                               \
+			pb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+			return PB_ERR_CUDA;                                                                \
+		}                                                                                      \
+	} while (0)
+
+
+pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int max_len,
+                               const uint8_t *d_reads, const pb_pair_meta *d_meta, pb_pair_result *d_results,
+                               uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride, unsigned long long *d_counters,
+                               cudaStream_t stream);
+pb_status pb_upload_params(pb_context *ctx, const pb_config *cfg);
+bool pb_is_pinned(const void *p);
+void pb_io_release(pb_context *ctx);

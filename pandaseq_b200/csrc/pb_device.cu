@@ -11,47 +11,7 @@
 #include <string.h>
 #include "pb_kernels.cuh"
 
-struct pb_context {
-	int device;
-	int sm_count;
-	cudaStream_t stream;
-	cudaStream_t copy_stream;
-	pb_device_params *d_params;      /* in HBM */
-	pb_device_params *h_params;      /* pinned mirror */
-	pb_config cached_cfg;
-	bool cfg_valid;
-	unsigned long long *d_counters;  /* scratch counters for the host path */
-	uint8_t *d_scratch;              /* per-warp scratch of the primers-after path, allocated on first use */
-	size_t scratch_bytes;
-	pthread_mutex_t lock;            /* one host-path call at a time per context (assemblers share the process-wide one) */
-	/* host-path staging (grown on demand) */
-	struct Slot {
-		size_t cap_pairs, cap_bases, cap_hpairs, cap_hbases, cap_hres;
-		uint8_t *h_f, *h_r;              /* pinned AoS */
-		unsigned long long *h_foff, *h_roff;
-		uint32_t *h_recoff;
-		uint8_t *d_f, *d_r;
-		unsigned long long *d_foff, *d_roff;
-		uint32_t *d_recoff;
-		uint8_t *d_reads;
-		size_t cap_reads;
-		pb_pair_meta *d_meta;
-		pb_pair_result *d_res, *h_res;
-		uint8_t *d_nt, *h_nt;
-		double *d_p, *h_p;
-		size_t cap_nt, cap_p, cap_dnt, cap_dp;
-		cudaEvent_t done;
-	} slot[2];
-};
-
-#define CUDA_TRY(expr)                                                                         \
-	do {                                                                                       \
-		cudaError_t e_ = (expr);                                                               \
-		if (e_ != cudaSuccess) {                                                               \
-			pb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-			return PB_ERR_CUDA;                                                                \
-		}                                                                                      \
-	} while (0)
+#include "pb_ctx.h"
 
 extern "C" int pb_device_count(void) {
 	int n = 0;
@@ -120,6 +80,7 @@ extern "C" void pb_context_destroy(pb_context *ctx) {
 	cudaFreeHost(ctx->h_params);
 	cudaFree(ctx->d_counters);
 	cudaFree(ctx->d_scratch);
+	pb_io_release(ctx);
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->copy_stream);
 	free(ctx);
@@ -134,7 +95,7 @@ extern "C" pb_status pb_synchronize(pb_context *ctx) {
 	return PB_OK;
 }
 
-static pb_status upload_params(pb_context *ctx, const pb_config *cfg) {
+pb_status pb_upload_params(pb_context *ctx, const pb_config *cfg) {
 	if (ctx->cfg_valid && memcmp(&ctx->cached_cfg, cfg, sizeof *cfg) == 0)
 		return PB_OK;
 	/* the pinned mirror may still be in flight from the previous upload */
@@ -191,7 +152,7 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 	return PB_OK;
 }
 
-static pb_status assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int max_len,
+pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int max_len,
                                    const uint8_t *d_reads, const pb_pair_meta *d_meta, pb_pair_result *d_results,
                                    uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride, unsigned long long *d_counters,
                                    cudaStream_t stream) {
@@ -236,12 +197,12 @@ extern "C" pb_status pb_assemble_device(pb_context *ctx, const pb_config *cfg, s
 		return PB_ERR_ARGUMENT;
 	}
 	CUDA_TRY(cudaSetDevice(ctx->device));
-	pb_status st = upload_params(ctx, cfg);
+	pb_status st = pb_upload_params(ctx, cfg);
 	if (st != PB_OK)
 		return st;
 	if (n == 0)
 		return PB_OK;
-	return assemble_dispatch(ctx, cfg, (int) n, max_read_len, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride,
+	return pb_assemble_dispatch(ctx, cfg, (int) n, max_read_len, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride,
 	                         (unsigned long long *) d_counters, ctx->stream);
 }
 
@@ -336,7 +297,7 @@ static pb_status ensure_slot(pb_context::Slot &s, size_t pairs, size_t fbases, s
 	return PB_OK;
 }
 
-static bool is_pinned(const void *p) {
+bool pb_is_pinned(const void *p) {
 	if (!p)
 		return false;
 	cudaPointerAttributes attr;
@@ -361,15 +322,15 @@ static pb_status assemble_host_locked(pb_context *ctx, const pb_config *cfg, siz
 		return PB_ERR_ARGUMENT;
 	}
 	CUDA_TRY(cudaSetDevice(ctx->device));
-	pb_status st = upload_params(ctx, cfg);
+	pb_status st = pb_upload_params(ctx, cfg);
 	if (st != PB_OK)
 		return st;
 	if (n == 0)
 		return PB_OK;
 	CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, PB_NCOUNTERS * sizeof(unsigned long long), ctx->stream));
 	CUDA_TRY(cudaStreamSynchronize(ctx->stream));      /* parameters + zeroed counters visible to both streams */
-	const bool pin_in = is_pinned(f_data) && is_pinned(r_data) && is_pinned(f_off) && is_pinned(r_off);
-	const bool pin_res = is_pinned(results), pin_nt = is_pinned(seq_nt), pin_p = is_pinned(seq_p);
+	const bool pin_in = pb_is_pinned(f_data) && pb_is_pinned(r_data) && pb_is_pinned(f_off) && pb_is_pinned(r_off);
+	const bool pin_res = pb_is_pinned(results), pin_nt = pb_is_pinned(seq_nt), pin_p = pb_is_pinned(seq_p);
 	const size_t CHUNK = n > (1u << 21) ? (1u << 20) : (n + 1) / 2 + 1;       /* at least two chunks so the slots overlap */
 	const size_t nt_row = seq_stride / 2;
 	struct Pending { bool live; size_t begin, count; } pend[2] = { { false, 0, 0 }, { false, 0, 0 } };
@@ -438,7 +399,7 @@ static pb_status assemble_host_locked(pb_context *ctx, const pb_config *cfg, siz
 			pb::pack_kernel<<<blocks, threads, 0, stream>>>((int) count, s.d_f, s.d_foff, fb, s.d_r, s.d_roff, rb, s.d_recoff, s.d_reads, s.d_meta);
 			CUDA_TRY(cudaGetLastError());
 		}
-		st = assemble_dispatch(ctx, cfg, (int) count, (int) max_len, s.d_reads, s.d_meta, s.d_res,
+		st = pb_assemble_dispatch(ctx, cfg, (int) count, (int) max_len, s.d_reads, s.d_meta, s.d_res,
 		                       seq_nt ? s.d_nt : nullptr, seq_p ? s.d_p : nullptr, seq_stride, ctx->d_counters, stream);
 		if (st != PB_OK)
 			return st;

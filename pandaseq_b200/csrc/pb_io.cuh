@@ -1,0 +1,822 @@
+/* pb_io.cuh -- sm_100a kernels for the two stages either side of the assembly kernel.
+ *
+ *   FASTQ text -> packed records (the reference's fastq.c:44-193 reader over linebuf.c:57-89 lines, identifiers by
+ *   seqid.c:136-285, letters by nt.c:48-124):
+ *     nl_count / nl_scan / nl_write   line index: position of every '\n' of both texts (HBM-bound byte scan)
+ *     fq_geometry                     record count, bytes consumed, longest read, record stride
+ *     fq_ids                          one THREAD per record: both header lines parsed, compared (fastq.c:121-139)
+ *     fq_reads                        one WARP per record: letters -> 4-bit codes (reverse read complemented and laid
+ *                                     out in template order), quality characters -> PHRED with fastq.c:44's clamp,
+ *                                     the '+' line and length checks, straight into the assemble kernel's layout
+ *     fq_finish                       first failing record (the reader stops there), pairs delivered
+ *   assembled pairs -> FASTA/FASTQ text (output.c:85-126):
+ *     fmt_length / (scan) / fmt_write
+ *
+ * All of it is byte/integer work bounded by HBM bandwidth; nothing here is a contraction.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pb_internal.h"
+
+namespace pbio {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int NL_THREADS = 256;
+constexpr int NL_BYTES_PER_THREAD = 32;
+constexpr int NL_TILE = NL_THREADS * NL_BYTES_PER_THREAD;    /* 8 KB of text per CTA */
+constexpr uint64_t NO_ERROR_KEY = ~0ull;
+
+struct TextView {
+	const uint8_t *text;
+	unsigned long long bytes;
+	uint32_t *nl;               /* newline positions */
+	unsigned nl_cap;
+	uint32_t *block_cnt;        /* per-tile newline counts, then their exclusive scan */
+	unsigned nblocks;
+};
+
+/* Device-resident state of one parse (written by the kernels, copied back once). */
+struct ParseState {
+	unsigned nl_total[2];       /* newlines in the forward / reverse text */
+	unsigned records;
+	unsigned max_len[2];        /* longest sequence line of the records, clamped to PB_MAX_LEN */
+	unsigned stride16;
+	unsigned long long consumed[2];
+	unsigned long long err_key; /* min over failing records of (record << 8 | stage << 4 | code) */
+	unsigned long long limit;
+	unsigned long long pairs;
+	int error;
+	int nl_overflow;
+};
+
+/* 32 bytes of text -> bit b set iff byte b is '\n' (bytes past `valid` ignored) */
+__device__ __forceinline__ unsigned newline_mask(const uint8_t *p, long long valid) {
+	unsigned mask = 0;
+	if (valid >= 32) {
+		const uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1];
+		const unsigned w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			const unsigned eq = __vcmpeq4(w[k], 0x0A0A0A0Au) & 0x01010101u;        /* bit 8j set iff byte j matches */
+			mask |= (((eq * 0x01020408u) >> 24) & 15u) << (4 * k);             /* gather the four flags: byte j -> bit j */
+		}
+	} else {
+		for (int k = 0; k < valid; k++)
+			if (p[k] == '\n')
+				mask |= 1u << k;
+	}
+	return mask;
+}
+
+__global__ void __launch_bounds__(NL_THREADS) nl_count(TextView tf, TextView tr) {
+	const TextView &t = blockIdx.y ? tr : tf;
+	if (blockIdx.x >= t.nblocks)
+		return;
+	const long long base = (long long) blockIdx.x * NL_TILE + (long long) threadIdx.x * NL_BYTES_PER_THREAD;
+	const long long valid = (long long) t.bytes - base;
+	int c = valid > 0 ? __popc(newline_mask(t.text + base, valid)) : 0;
+	c = __reduce_add_sync(FULL, c);
+	__shared__ int wsum[NL_THREADS / 32];
+	if ((threadIdx.x & 31) == 0)
+		wsum[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int s = 0;
+		for (int k = 0; k < NL_THREADS / 32; k++)
+			s += wsum[k];
+		t.block_cnt[blockIdx.x] = (uint32_t) s;
+	}
+}
+
+/* exclusive scan of block_cnt in place, one CTA per text; total -> st->nl_total[] */
+__global__ void __launch_bounds__(1024) nl_scan(TextView tf, TextView tr, ParseState *st) {
+	const TextView &t = blockIdx.x ? tr : tf;
+	__shared__ unsigned part[1024];
+	const unsigned per = (t.nblocks + 1023) / 1024;
+	const unsigned lo = min(threadIdx.x * per, t.nblocks), hi = min(lo + per, t.nblocks);
+	unsigned s = 0;
+	for (unsigned k = lo; k < hi; k++)
+		s += t.block_cnt[k];
+	part[threadIdx.x] = s;
+	__syncthreads();
+	for (int d = 1; d < 1024; d <<= 1) {             /* Hillis-Steele over the 1024 partial sums */
+		unsigned v = threadIdx.x >= (unsigned) d ? part[threadIdx.x - d] : 0u;
+		__syncthreads();
+		part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	unsigned run = part[threadIdx.x] - s;
+	for (unsigned k = lo; k < hi; k++) {
+		const unsigned c = t.block_cnt[k];
+		t.block_cnt[k] = run;
+		run += c;
+	}
+	if (threadIdx.x == 1023) {
+		st->nl_total[blockIdx.x] = part[1023];
+		if (part[1023] > t.nl_cap)
+			st->nl_overflow = 1;
+	}
+}
+
+__global__ void __launch_bounds__(NL_THREADS) nl_write(TextView tf, TextView tr) {
+	const TextView &t = blockIdx.y ? tr : tf;
+	if (blockIdx.x >= t.nblocks)
+		return;
+	const long long base = (long long) blockIdx.x * NL_TILE + (long long) threadIdx.x * NL_BYTES_PER_THREAD;
+	const long long valid = (long long) t.bytes - base;
+	unsigned mask = valid > 0 ? newline_mask(t.text + base, valid) : 0u;
+	const int c = __popc(mask);
+	int incl = c;                                    /* inclusive scan inside the warp, then across the 8 warps */
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int v = __shfl_up_sync(FULL, incl, d);
+		if ((int) (threadIdx.x & 31) >= d)
+			incl += v;
+	}
+	__shared__ int wsum[NL_THREADS / 32];
+	if ((threadIdx.x & 31) == 31)
+		wsum[threadIdx.x >> 5] = incl;
+	__syncthreads();
+	int before = incl - c;
+	for (int k = 0; k < (int) (threadIdx.x >> 5); k++)
+		before += wsum[k];
+	unsigned slot = t.block_cnt[blockIdx.x] + (unsigned) before;
+	while (mask) {
+		const int b = __ffs(mask) - 1;
+		mask &= mask - 1;
+		if (slot < t.nl_cap)
+			t.nl[slot] = (uint32_t) (base + b);
+		slot++;
+	}
+}
+
+/* ---- lines --------------------------------------------------------------------------------------------------- */
+struct Line {
+	const uint8_t *p;
+	int len;            /* CR stripped (linebuf.c:82-85) */
+	int raw;            /* bytes up to the '\n' */
+};
+__device__ __forceinline__ Line get_line(const TextView &t, unsigned k) {
+	const unsigned s = k ? t.nl[k - 1] + 1u : 0u, e = t.nl[k];
+	Line l;
+	l.p = t.text + s;
+	l.raw = (int) (e - s);
+	l.len = l.raw;
+	if (l.len > 0 && l.p[l.len - 1] == '\r')
+		l.len--;
+	return l;
+}
+
+__global__ void fq_geometry(TextView tf, TextView tr, ParseState *st, unsigned max_records) {
+	/* launched after nl_write with a grid-stride over the records: longest sequence line */
+	const unsigned nf = min(st->nl_total[0], tf.nl_cap), nr = min(st->nl_total[1], tr.nl_cap);
+	const unsigned records = min(min(nf, nr) / 4, max_records);
+	unsigned mf = 0, mr = 0;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < records; i += gridDim.x * blockDim.x) {
+		mf = max(mf, (unsigned) get_line(tf, 4 * i + 1).len);
+		mr = max(mr, (unsigned) get_line(tr, 4 * i + 1).len);
+	}
+	mf = __reduce_max_sync(FULL, mf);
+	mr = __reduce_max_sync(FULL, mr);
+	if ((threadIdx.x & 31) == 0) {
+		if (mf) atomicMax(&st->max_len[0], min(mf, (unsigned) PB_MAX_LEN));
+		if (mr) atomicMax(&st->max_len[1], min(mr, (unsigned) PB_MAX_LEN));
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		st->records = records;
+		st->consumed[0] = records ? (unsigned long long) tf.nl[4 * records - 1] + 1ull : 0ull;
+		st->consumed[1] = records ? (unsigned long long) tr.nl[4 * records - 1] + 1ull : 0ull;
+	}
+}
+
+__global__ void fq_stride(ParseState *st) {
+	const unsigned f = st->max_len[0], r = st->max_len[1];
+	const unsigned b = ((f + 7) / 8) * 4 + ((r + 7) / 8) * 4 + ((f + 3) / 4) * 4 + ((r + 3) / 4) * 4;
+	st->stride16 = (b + 15) / 16;
+}
+
+/* ---- identifiers: seqid.c:136-285, one thread per record -------------------------------------------------------- */
+struct Cursor {
+	const uint8_t *s;
+	int pos, len;
+	__device__ __forceinline__ int cur() const { return pos < len ? (int) s[pos] : 0; }    /* 0 = end of the C string */
+};
+__device__ __forceinline__ bool is_delim(int c) {
+	return c == 0 || c == ':' || c == '#' || c == '/' || c == ' ';
+}
+struct IdFields {
+	int inst_off, inst_len, run_off, run_len, fc_off, fc_len, tag_off, tag_len;
+	int lane, tile, x, y, sra, fmt;
+};
+__device__ __forceinline__ bool take_str(Cursor &c, int &off, int &len, int cap) {
+	if (c.cur() == 0)
+		return false;
+	off = c.pos;
+	while (!is_delim(c.cur()))
+		c.pos++;
+	len = c.pos - off;
+	return len <= cap;       /* a field of 101 characters overruns the reference's struct member (seqid.c:153); refused */
+}
+__device__ __forceinline__ bool take_int(Cursor &c, int &value) {
+	if (c.cur() == 0)
+		return false;
+	unsigned v = 0;
+	while (!is_delim(c.cur())) {
+		const int ch = c.cur();
+		if (ch < '0' || ch > '9')
+			return false;
+		v = 10u * v + (unsigned) (ch - '0');
+		c.pos++;
+	}
+	value = (int) v;
+	return true;
+}
+__device__ __forceinline__ bool take_sra_int(Cursor &c, int &value) {
+	unsigned v = 0;
+	for (int ch = c.cur(); ch != 0 && ch != '.' && ch != ' '; ch = c.cur()) {
+		if (ch < '0' || ch > '9')
+			return false;
+		v = 10u * v + (unsigned) (ch - '0');
+		c.pos++;
+	}
+	value = (int) v;
+	return true;
+}
+__device__ __forceinline__ bool push(Cursor &c) {
+	if (c.cur() == 0)
+		return false;
+	c.pos++;
+	return true;
+}
+__device__ __forceinline__ bool take_tag(Cursor &c, int &off, int &len) {
+	off = c.pos;
+	while (!is_delim(c.cur()))
+		c.pos++;
+	len = c.pos - off;
+	return len <= PANDA_TAG_LEN;
+}
+__device__ __forceinline__ bool tag_policy_ok(int tag_len, int policy) {
+	if (policy == PB_TAG_OPTIONAL)
+		return true;
+	return policy == (tag_len == 0 ? PB_TAG_ABSENT : PB_TAG_PRESENT);
+}
+
+/* returns the direction (0 = failure).  hdr/len: the header line after its first character, ended by a NUL if it has one */
+__device__ int parse_id(const uint8_t *hdr, int len, int policy, IdFields &f) {
+	Cursor c = { hdr, 0, len };
+	for (int k = 0; k < len; k++)
+		if (hdr[k] == 0) {
+			c.len = k;
+			break;
+		}
+	len = c.len;
+	f.inst_off = f.inst_len = f.run_off = f.run_len = f.fc_off = f.fc_len = f.tag_off = f.tag_len = 0;
+	f.lane = f.tile = f.x = f.y = f.sra = 0;
+	int v;
+	if (len > 3 && (hdr[0] == 'E' || hdr[0] == 'S') && hdr[1] == 'R' && hdr[2] == 'R') {
+		f.fmt = hdr[0] == 'S' ? PB_IDFMT_SRA : PB_IDFMT_EBI_SRA;
+		c.pos = 3;
+		if (!take_sra_int(c, v) || !push(c))
+			return 0;
+		f.sra = v;
+		if (!take_sra_int(c, v) || !push(c))
+			return 0;
+		f.lane = v;
+		if (!push(c))
+			return 0;
+		return 1;
+	}
+	bool slash = false;
+	for (int k = 0; k < len; k++)
+		slash |= hdr[k] == '/';
+	if (slash) {
+		int colons = 0;
+		for (int k = 0; k < len && hdr[k] != '#'; k++)
+			colons += hdr[k] == ':';
+		if (colons == 6) {
+			f.fmt = PB_IDFMT_CASAVA_CONVERTED;
+			if (!take_str(c, f.inst_off, f.inst_len, 100) || !push(c)) return 0;
+			if (!take_str(c, f.run_off, f.run_len, 100) || !push(c)) return 0;
+			if (!take_str(c, f.fc_off, f.fc_len, 100) || !push(c)) return 0;
+		} else {
+			f.fmt = PB_IDFMT_CASAVA_1_4;
+			if (!take_str(c, f.inst_off, f.inst_len, 100) || !push(c)) return 0;
+		}
+		if (!take_int(c, f.lane) || !push(c)) return 0;
+		if (!take_int(c, f.tile) || !push(c)) return 0;
+		if (!take_int(c, f.x) || !push(c)) return 0;
+		if (!take_int(c, f.y) || !push(c)) return 0;
+		if (hdr[c.pos - 1] == '#') {
+			if (!take_tag(c, f.tag_off, f.tag_len) || !push(c))
+				return 0;
+		}
+		if (!tag_policy_ok(f.tag_len, policy))
+			return 0;
+		if (!take_int(c, v))
+			return 0;
+		return v;
+	}
+	f.fmt = PB_IDFMT_CASAVA_1_7;
+	int mate, skip_off, skip_len;
+	if (!take_str(c, f.inst_off, f.inst_len, 100) || !push(c)) return 0;
+	if (!take_str(c, f.run_off, f.run_len, 100) || !push(c)) return 0;
+	if (!take_str(c, f.fc_off, f.fc_len, 100) || !push(c)) return 0;
+	if (!take_int(c, f.lane) || !push(c)) return 0;
+	if (!take_int(c, f.tile) || !push(c)) return 0;
+	if (!take_int(c, f.x) || !push(c)) return 0;
+	if (!take_int(c, f.y) || !push(c)) return 0;
+	if (!take_int(c, mate) || !push(c)) return 0;
+	if (!take_str(c, skip_off, skip_len, 1 << 20) || !push(c)) return 0;
+	if (!take_int(c, v) || !push(c)) return 0;
+	if (!take_tag(c, f.tag_off, f.tag_len))
+		return 0;
+	if (!tag_policy_ok(f.tag_len, policy))
+		return 0;
+	return mate;
+}
+
+__device__ __forceinline__ bool same_str(const uint8_t *a, int aoff, int alen, const uint8_t *b, int boff, int blen) {
+	if (alen != blen)
+		return false;
+	for (int k = 0; k < alen; k++)
+		if (a[aoff + k] != b[boff + k])
+			return false;
+	return true;
+}
+
+__device__ __forceinline__ void report(ParseState *st, unsigned record, int stage, int code) {
+	atomicMin(&st->err_key, ((unsigned long long) record << 8) | ((unsigned long long) stage << 4) | (unsigned long long) code);
+}
+
+__global__ void fq_ids(TextView tf, TextView tr, ParseState *st, int policy, pb_seq_id *ids) {
+	const unsigned records = st->records;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < records; i += gridDim.x * blockDim.x) {
+		const Line hf = get_line(tf, 4 * i), hr = get_line(tr, 4 * i);
+		IdFields f, r;
+		pb_seq_id out;
+		memset(&out, 0, sizeof out);
+		/* fastq.c:125 hands the parser `line + 1` without looking at the first character */
+		const int fdir = (hf.raw < PB_FQ_LINE_MAX && hf.len > 0) ? parse_id(hf.p + 1, hf.len - 1, policy, f) : 0;
+		if (fdir == 0) {
+			report(st, i, 0, hf.raw >= PB_FQ_LINE_MAX ? PB_FQ_LINE_TOO_LONG : PB_FQ_ID_PARSE_FAILURE);
+		} else {
+			const int rdir = (hr.raw < PB_FQ_LINE_MAX && hr.len > 0) ? parse_id(hr.p + 1, hr.len - 1, policy, r) : 0;
+			if (rdir == 0) {
+				report(st, i, 1, hr.raw >= PB_FQ_LINE_MAX ? PB_FQ_LINE_TOO_LONG : PB_FQ_ID_PARSE_FAILURE);
+			} else {
+				const uint8_t *a = hf.p + 1, *b = hr.p + 1;
+				/* panda_seqid_equal (seqid.c:95-99); the SRA instrument is "%cRR%d": same letter (fmt) and number */
+				bool eq = f.lane == r.lane && f.tile == r.tile && f.x == r.x && f.y == r.y && f.sra == r.sra
+					&& ((f.fmt == PB_IDFMT_SRA || f.fmt == PB_IDFMT_EBI_SRA) == (r.fmt == PB_IDFMT_SRA || r.fmt == PB_IDFMT_EBI_SRA))
+					&& ((f.fmt != PB_IDFMT_SRA && f.fmt != PB_IDFMT_EBI_SRA) || f.fmt == r.fmt)
+					&& same_str(a, f.inst_off, f.inst_len, b, r.inst_off, r.inst_len)
+					&& same_str(a, f.run_off, f.run_len, b, r.run_off, r.run_len)
+					&& same_str(a, f.fc_off, f.fc_len, b, r.fc_off, r.fc_len)
+					&& same_str(a, f.tag_off, min(f.tag_len, PANDA_TAG_LEN), b, r.tag_off, min(r.tag_len, PANDA_TAG_LEN));
+				const bool directional = f.fmt != PB_IDFMT_SRA && f.fmt != PB_IDFMT_EBI_SRA;      /* seqid.c:43-46 */
+				if (!eq || (directional && rdir == fdir))
+					report(st, i, 2, PB_FQ_NOT_PAIRED);
+			}
+			out.hdr_off = (uint32_t) (hf.p + 1 - tf.text);
+			out.hdr_len = (uint16_t) (hf.len - 1);
+			out.fmt = (uint8_t) f.fmt;
+			out.inst_off = (uint16_t) f.inst_off; out.inst_len = (uint16_t) f.inst_len;
+			out.run_off = (uint16_t) f.run_off; out.run_len = (uint16_t) f.run_len;
+			out.fc_off = (uint16_t) f.fc_off; out.fc_len = (uint16_t) f.fc_len;
+			out.tag_off = (uint16_t) f.tag_off; out.tag_len = (uint16_t) f.tag_len;
+			out.lane = f.lane; out.tile = f.tile; out.x = f.x; out.y = f.y; out.sra = f.sra; out.mate = fdir;
+		}
+		if (ids) {
+			const uint4 *src = reinterpret_cast<const uint4 *>(&out);
+			uint4 *dst = reinterpret_cast<uint4 *>(&ids[i]);
+			dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+		}
+	}
+}
+
+/* ---- reads: fastq.c:44-102, one warp per record --------------------------------------------------------------- */
+/* nt.c:48-118: letter & 0x1F -> 4-bit code, two codes per byte of a 64-bit constant pair */
+__device__ __forceinline__ unsigned letter_code(unsigned ch, bool complement) {
+	/* index (ch & 31):  0 1  2 3  4 5 6 7  8 9 10 11 12 13 14 15 | 16 17 18 19 20 21 22 23 24 25 26..31 */
+	/* iupac_forward:    0 1 14 2 13 0 0 4 11 0  0 12  0  3 15  0 |  0  0  5  6  8  8  7  9 15 10  0      */
+	const unsigned idx = ch & 31u;
+	const unsigned long long tab = idx < 16u ? 0x0F30C00B400D2E10ull : 0x000000AF97886500ull;   /* nibble k = code of index k */
+	unsigned v = (unsigned) ((tab >> (4u * (idx & 15u))) & 15ull);
+	if (complement)
+		v = __brev(v) >> 28;                /* A<->T, C<->G: the four bits reversed (nt.c:27-44, 85-118) */
+	return v;
+}
+
+__device__ __forceinline__ int to_index(int ch, int qualmin) {      /* fastq.c:44, on a signed char */
+	if (ch < qualmin)
+		return 0;
+	return (ch > qualmin + PB_PHREDMAX ? PB_PHREDMAX : ch) - qualmin;
+}
+
+/* Validate one read (lines 1..3 of its record) in the reference's order; returns PB_FQ_OK or the code. */
+__device__ int check_read(const Line &seq, const Line &plus, const Line &qual, bool complement, int &len, int lane) {
+	if (seq.raw >= PB_FQ_LINE_MAX)
+		return PB_FQ_LINE_TOO_LONG;
+	len = min(seq.len, PB_MAX_LEN);
+	bool bad = false;
+	for (int k = lane; k < len; k += 32)
+		bad |= letter_code(seq.p[k], complement) == 0u;
+	if (__any_sync(FULL, bad))
+		return PB_FQ_BAD_NT;
+	if (plus.raw >= PB_FQ_LINE_MAX)
+		return PB_FQ_LINE_TOO_LONG;
+	const int first = plus.len > 0 ? (int) plus.p[0] : 0;
+	if (first != '+')
+		return letter_code((unsigned) first, complement) != 0u ? PB_FQ_READ_TOO_LONG : PB_FQ_PARSE_FAILURE;
+	if (qual.raw >= PB_FQ_LINE_MAX)
+		return PB_FQ_LINE_TOO_LONG;
+	if (qual.len != len)
+		return PB_FQ_NO_QUALITY_INFO;
+	/* a NUL ends the reference's C string early; such input is refused here */
+	bool nul = false;
+	for (int k = lane; k < len; k += 32)
+		nul |= qual.p[k] == 0;
+	if (__any_sync(FULL, nul))
+		return PB_FQ_NO_QUALITY_INFO;
+	return PB_FQ_OK;
+}
+
+/* element j of the packed read = read position j (forward) or len-1-j (reverse: template order) */
+__device__ __forceinline__ void pack_read(const Line &seq, const Line &qual, int len, bool reverse, int qualmin,
+                                          uint8_t *nt_out, int nt_bytes, uint8_t *q_out, int q_bytes, int lane) {
+	for (int j0 = 0; j0 < nt_bytes * 2; j0 += 32) {
+		const int j = j0 + lane;
+		unsigned code = 0;
+		if (j < len)
+			code = letter_code(seq.p[reverse ? len - 1 - j : j], reverse);
+		const unsigned hi = __shfl_down_sync(FULL, code, 1);
+		if ((lane & 1) == 0 && j < nt_bytes * 2)
+			nt_out[j >> 1] = (uint8_t) (code | (hi << 4));
+	}
+	for (int j = lane; j < q_bytes; j += 32) {
+		int q = 0;
+		if (j < len)
+			q = to_index((int) (signed char) qual.p[reverse ? len - 1 - j : j], qualmin);
+		q_out[j] = (uint8_t) q;
+	}
+}
+
+__global__ void __launch_bounds__(256) fq_reads(TextView tf, TextView tr, ParseState *st, int qualmin,
+                                                uint8_t *reads, unsigned long long reads_cap, pb_pair_meta *meta) {
+	const int lane = threadIdx.x & 31;
+	const unsigned records = st->records;
+	const unsigned stride16 = st->stride16;
+	const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+	for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < records; i += warps) {
+		const Line fs = get_line(tf, 4 * i + 1), fp = get_line(tf, 4 * i + 2), fq = get_line(tf, 4 * i + 3);
+		const Line rs = get_line(tr, 4 * i + 1), rp = get_line(tr, 4 * i + 2), rq = get_line(tr, 4 * i + 3);
+		int F = 0, R = 0;
+		int code = check_read(fs, fp, fq, false, F, lane);
+		int stage = 3;
+		if (code == PB_FQ_OK) {
+			code = check_read(rs, rp, rq, true, R, lane);
+			stage = 4;
+		}
+		pb_pair_meta m;
+		m.off16 = i * stride16;
+		m.flen = 0xFFFF;
+		m.rlen = 0;
+		const unsigned long long rec_at = (unsigned long long) i * stride16 * 16ull;
+		if (code != PB_FQ_OK) {
+			if (lane == 0)
+				report(st, i, stage, code);
+		} else if (F > 0 && rec_at + (unsigned long long) stride16 * 16ull <= reads_cap) {     /* fastq.c:176: an empty forward read is dropped */
+			uint8_t *rec = reads + rec_at;
+			const int fwb = ((F + 7) / 8) * 4, rwb = ((R + 7) / 8) * 4, fqb = ((F + 3) / 4) * 4, rqb = ((R + 3) / 4) * 4;
+			pack_read(fs, fq, F, false, qualmin, rec, fwb, rec + fwb + rwb, fqb, lane);
+			pack_read(rs, rq, R, true, qualmin, rec + fwb, rwb, rec + fwb + rwb + fqb, rqb, lane);
+			const int used = fwb + rwb + fqb + rqb, total = (used + 15) & ~15;
+			for (int k = used + lane; k < total; k += 32)
+				rec[k] = 0;
+			m.flen = (uint16_t) F;
+			m.rlen = (uint16_t) R;
+		}
+		if (lane == 0)
+			meta[i] = m;
+	}
+}
+
+__global__ void fq_finish(ParseState *st, const pb_pair_meta *meta) {
+	/* single CTA: the record that ended the stream, and the pairs delivered before it */
+	__shared__ unsigned long long s_limit;
+	__shared__ unsigned s_skipped;
+	if (threadIdx.x == 0) {
+		const unsigned long long key = st->err_key;
+		s_limit = key == NO_ERROR_KEY ? (unsigned long long) st->records : (key >> 8);
+		st->error = key == NO_ERROR_KEY ? PB_FQ_OK : (int) (key & 15ull);
+		s_skipped = 0;
+	}
+	__syncthreads();
+	unsigned skipped = 0;
+	for (unsigned long long i = threadIdx.x; i < s_limit; i += blockDim.x)
+		skipped += meta[i].flen == 0xFFFF;
+	skipped = __reduce_add_sync(FULL, skipped);
+	if ((threadIdx.x & 31) == 0 && skipped)
+		atomicAdd(&s_skipped, skipped);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		st->limit = s_limit;
+		st->pairs = s_limit - s_skipped;
+	}
+}
+
+/* ---- output: output.c:85-126 -------------------------------------------------------------------------------- */
+__device__ __forceinline__ int int_chars(int v) {          /* strlen of "%d" */
+	unsigned u = v < 0 ? 0u - (unsigned) v : (unsigned) v;
+	int n = v < 0 ? 2 : 1;
+	while (u >= 10u) {
+		u /= 10u;
+		n++;
+	}
+	return n;
+}
+__device__ __forceinline__ int put_int(char *dst, int v) {
+	const int n = int_chars(v);
+	unsigned u = v < 0 ? 0u - (unsigned) v : (unsigned) v;
+	for (int k = n - 1; k >= (v < 0 ? 1 : 0); k--) {
+		dst[k] = (char) ('0' + u % 10u);
+		u /= 10u;
+	}
+	if (v < 0)
+		dst[0] = '-';
+	return n;
+}
+/* round(v * 10^6) to nearest, ties to even, on the exact binary value -- what printf("%f") prints; v >= 0 finite */
+__device__ __forceinline__ unsigned long long scaled_micro(double v) {
+	const unsigned long long bits = (unsigned long long) __double_as_longlong(v);
+	int e = (int) ((bits >> 52) & 0x7FFull);
+	unsigned long long m = bits & ((1ull << 52) - 1ull);
+	if (e == 0)
+		e = 1;
+	else
+		m |= 1ull << 52;
+	const int sh = 1075 - e;                     /* v = m / 2^sh */
+	unsigned __int128 N = (unsigned __int128) m * 1000000u;
+	if (sh <= 0)
+		return (unsigned long long) (N << (-sh));   /* v < 2^63 / 10^6 assumed: exp(quality) <= 1 */
+	if (sh > 100)
+		return 0ull;
+	const unsigned __int128 q = N >> sh, rem = N & ((((unsigned __int128) 1) << sh) - 1), half = ((unsigned __int128) 1) << (sh - 1);
+	unsigned long long out = (unsigned long long) q;
+	if (rem > half || (rem == half && (out & 1ull)))
+		out++;
+	return out;
+}
+__device__ __forceinline__ int f6_chars(unsigned long long micro) {
+	unsigned long long ip = micro / 1000000ull;
+	int n = 8;                                  /* "d.dddddd" */
+	while (ip >= 10ull) {
+		ip /= 10ull;
+		n++;
+	}
+	return n;
+}
+__device__ __forceinline__ int put_f6(char *dst, unsigned long long micro) {
+	const int n = f6_chars(micro);
+	unsigned long long ip = micro / 1000000ull;
+	unsigned fr = (unsigned) (micro % 1000000ull);
+	for (int k = n - 1; k > n - 7; k--) {
+		dst[k] = (char) ('0' + fr % 10u);
+		fr /= 10u;
+	}
+	dst[n - 7] = '.';
+	for (int k = n - 8; k >= 0; k--) {
+		dst[k] = (char) ('0' + ip % 10ull);
+		ip /= 10ull;
+	}
+	return n;
+}
+__device__ __forceinline__ int sra_chars(int v) { return 3 + int_chars(v); }
+
+/* nt.c:126-150 */
+__device__ __forceinline__ int result_phred(double p, const double *score) {
+	int lower = 0, upper = PB_PHREDMAX;
+	if (p <= score[0])
+		return 1;
+	while (lower < upper) {
+		const int mid = lower + (upper - lower) / 2;
+		const double s = score[mid];
+		if (s == p)
+			return mid;
+		if (mid == lower)
+			return lower;
+		if (s > p)
+			upper = mid;
+		else if (s < p)
+			lower = mid + 1;
+	}
+	return lower;
+}
+
+__device__ __forceinline__ bool emitted(const pb_pair_result &r) {
+	return r.status == PB_PAIR_OK && r.seq_len > 0;        /* output.c:88,108 */
+}
+
+/* header text length: "%s:%s:%s:%d:%d:%d:%d:%s" (seqid.c:121-128) + ";%f" */
+__device__ __forceinline__ int header_chars(const pb_seq_id &id, unsigned long long micro) {
+	const bool sra = id.fmt == PB_IDFMT_SRA || id.fmt == PB_IDFMT_EBI_SRA;
+	return 1 + (sra ? sra_chars(id.sra) : (int) id.inst_len) + 1 + id.run_len + 1 + id.fc_len + 1 + int_chars(id.lane) + 1 + int_chars(id.tile)
+		+ 1 + int_chars(id.x) + 1 + int_chars(id.y) + 1 + min((int) id.tag_len, PANDA_TAG_LEN) + 1 + f6_chars(micro) + 1;
+}
+
+__global__ void fmt_length(int n, int fastq, const pb_pair_result *__restrict__ res, const pb_seq_id *__restrict__ ids,
+                           uint32_t *__restrict__ len_out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const pb_pair_result r = res[i];
+	unsigned len = 0;
+	if (emitted(r)) {
+		const pb_seq_id id = ids[i];
+		len = (unsigned) header_chars(id, scaled_micro(exp(r.quality))) + r.seq_len + 1u;
+		if (fastq)
+			len += 2u + r.seq_len + 1u;
+	}
+	len_out[i] = len;
+}
+
+/* generic exclusive scan of n u32 (in place) with a 64-bit total: per-tile sums, scan of the sums, apply */
+constexpr int SCAN_TILE = 2048;
+__global__ void __launch_bounds__(256) scan_tile_sums(int n, const uint32_t *__restrict__ v, unsigned long long *__restrict__ tile_sum) {
+	const int base = blockIdx.x * SCAN_TILE;
+	unsigned long long s = 0;
+	for (int k = threadIdx.x; k < SCAN_TILE && base + k < n; k += 256)
+		s += v[base + k];
+	__shared__ unsigned long long sh[256];
+	sh[threadIdx.x] = s;
+	__syncthreads();
+	for (int d = 128; d > 0; d >>= 1) {
+		if ((int) threadIdx.x < d)
+			sh[threadIdx.x] += sh[threadIdx.x + d];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+		tile_sum[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(1024) scan_tiles(int ntiles, unsigned long long *tile_sum, unsigned long long *total) {
+	__shared__ unsigned long long part[1024];
+	const int per = (ntiles + 1023) / 1024;
+	const int lo = min((int) threadIdx.x * per, ntiles), hi = min(lo + per, ntiles);
+	unsigned long long s = 0;
+	for (int k = lo; k < hi; k++)
+		s += tile_sum[k];
+	part[threadIdx.x] = s;
+	__syncthreads();
+	for (int d = 1; d < 1024; d <<= 1) {
+		unsigned long long v = (int) threadIdx.x >= d ? part[threadIdx.x - d] : 0ull;
+		__syncthreads();
+		part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	unsigned long long run = part[threadIdx.x] - s;
+	for (int k = lo; k < hi; k++) {
+		const unsigned long long c = tile_sum[k];
+		tile_sum[k] = run;
+		run += c;
+	}
+	if (threadIdx.x == 1023)
+		*total = part[1023];
+}
+
+/* off[i] = exclusive prefix of v[0..i) */
+__global__ void __launch_bounds__(256) scan_apply(int n, const uint32_t *__restrict__ v, const unsigned long long *__restrict__ tile_off,
+                                                  unsigned long long *__restrict__ off) {
+	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+	unsigned e[8];
+	unsigned long long s = 0;
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		e[k] = base + k < n ? v[base + k] : 0u;
+		s += e[k];
+	}
+	unsigned long long incl = s;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const unsigned long long t = __shfl_up_sync(FULL, incl, d);
+		if ((int) (threadIdx.x & 31) >= d)
+			incl += t;
+	}
+	__shared__ unsigned long long wsum[8];
+	if ((threadIdx.x & 31) == 31)
+		wsum[threadIdx.x >> 5] = incl;
+	__syncthreads();
+	unsigned long long run = tile_off[blockIdx.x] + incl - s;
+	for (int k = 0; k < (int) (threadIdx.x >> 5); k++)
+		run += wsum[k];
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		if (base + k < n)
+			off[base + k] = run;
+		run += e[k];
+	}
+}
+
+/* one warp per record */
+__global__ void __launch_bounds__(256) fmt_write(int n, int fastq, const pb_pair_result *__restrict__ res,
+                                                 const uint8_t *__restrict__ seq_nt, const double *__restrict__ seq_p, long long seq_stride,
+                                                 const pb_seq_id *__restrict__ ids, const uint8_t *__restrict__ fwd_text,
+                                                 const uint32_t *__restrict__ len_in, const unsigned long long *__restrict__ rec_off,
+                                                 const double *__restrict__ score, char *__restrict__ text, unsigned long long capacity) {
+	__shared__ char hdr_s[8][448];
+	__shared__ double s_score[PB_NQ];
+	for (int k = threadIdx.x; k < PB_NQ; k += blockDim.x)
+		s_score[k] = score[k];
+	__syncthreads();
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (i >= n)
+		return;
+	const unsigned mylen = len_in[i];
+	if (mylen == 0)
+		return;
+	const unsigned long long off = rec_off[i];
+	if (off + mylen > capacity)
+		return;
+	const pb_pair_result r = res[i];
+	const pb_seq_id id = ids[i];
+	char *h = hdr_s[w];
+	int hl = 0;
+	const uint8_t *src = fwd_text + id.hdr_off;
+	const bool sra = id.fmt == PB_IDFMT_SRA || id.fmt == PB_IDFMT_EBI_SRA;
+	if (lane == 0) {
+		/* the numeric pieces and separators; the strings are copied by the whole warp below */
+		int p = 0;
+		h[p++] = fastq ? '@' : '>';
+		if (sra) {
+			h[p++] = id.fmt == PB_IDFMT_SRA ? 'S' : 'E';
+			h[p++] = 'R';
+			h[p++] = 'R';
+			p += put_int(h + p, id.sra);
+		} else {
+			p += id.inst_len;
+		}
+		h[p++] = ':';
+		p += id.run_len;
+		h[p++] = ':';
+		p += id.fc_len;
+		h[p++] = ':';
+		p += put_int(h + p, id.lane);
+		h[p++] = ':';
+		p += put_int(h + p, id.tile);
+		h[p++] = ':';
+		p += put_int(h + p, id.x);
+		h[p++] = ':';
+		p += put_int(h + p, id.y);
+		h[p++] = ':';
+		p += min((int) id.tag_len, PANDA_TAG_LEN);
+		h[p++] = ';';
+		p += put_f6(h + p, scaled_micro(exp(r.quality)));
+		h[p++] = '\n';
+		hl = p;
+	}
+	hl = __shfl_sync(FULL, hl, 0);
+	{
+		int p = 1;
+		if (!sra)
+			for (int k = lane; k < id.inst_len; k += 32)
+				h[p + k] = (char) src[id.inst_off + k];
+		p += (sra ? sra_chars(id.sra) : (int) id.inst_len) + 1;
+		for (int k = lane; k < id.run_len; k += 32)
+			h[p + k] = (char) src[id.run_off + k];
+		p += id.run_len + 1;
+		for (int k = lane; k < id.fc_len; k += 32)
+			h[p + k] = (char) src[id.fc_off + k];
+		p += id.fc_len + 1 + int_chars(id.lane) + 1 + int_chars(id.tile) + 1 + int_chars(id.x) + 1 + int_chars(id.y) + 1;
+		for (int k = lane; k < min((int) id.tag_len, PANDA_TAG_LEN); k += 32)
+			h[p + k] = (char) src[id.tag_off + k];
+	}
+	__syncwarp();
+	char *dst = text + off;
+	for (int k = lane; k < hl; k += 32)
+		dst[k] = h[k];
+	dst += hl;
+	const uint8_t *nt = seq_nt + (size_t) i * (size_t) (seq_stride / 2);
+	const int L = r.seq_len;
+	for (int k = lane; k < L; k += 32) {
+		const unsigned c = (nt[k >> 1] >> ((k & 1) * 4)) & 15u;
+		dst[k] = "NACMGRSVTWYHKDBN"[c];                 /* nt.c:25 */
+	}
+	if (lane == 0)
+		dst[L] = '\n';
+	if (fastq) {
+		dst += L + 1;
+		if (lane == 0) {
+			dst[0] = '+';
+			dst[1] = '\n';
+		}
+		dst += 2;
+		const double *p = seq_p + (size_t) i * (size_t) seq_stride;
+		for (int k = lane; k < L; k += 32)
+			dst[k] = (char) (33 + result_phred(p[k], s_score));
+		if (lane == 0)
+			dst[L] = '\n';
+	}
+}
+
+}  // namespace pbio

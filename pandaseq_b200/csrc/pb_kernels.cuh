@@ -986,7 +986,7 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 		if (lane == 0) {
 			pb_pair_meta m = meta[pair];
 			ws.meta[stage] = m;
-			unsigned bytes = record_bytes(m.flen, m.rlen);
+			unsigned bytes = m.flen == 0xFFFFu ? 0u : record_bytes(m.flen, m.rlen);     /* 0xFFFF: not a pair (FASTQ reader) */
 			mbar_expect_tx(&ws.bar[stage], bytes);
 			if (bytes)
 				bulk_g2s(ws.stage[stage], reads + (size_t) m.off16 * 16, bytes, &ws.bar[stage]);
@@ -1005,6 +1005,18 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 		const pb_pair_meta m = ws.meta[stage];
 		union { pb_pair_result r; uint4 v[2]; } ru;
 		pb_pair_result &res = ru.r;
+		if (m.flen == 0xFFFFu) {       /* a record the FASTQ reader drops (fastq.c:176): no result, no counter */
+			if (lane == 0) {
+				ru.v[0] = make_uint4(0, 0, 0, 0);
+				ru.v[1] = make_uint4(0, 0, 0, 0);
+				res.status = PB_PAIR_SKIP;
+				uint4 *dst = reinterpret_cast<uint4 *>(&results[pair]);
+				dst[0] = ru.v[0];
+				dst[1] = ru.v[1];
+			}
+			__syncwarp();
+			continue;
+		}
 		uint8_t *o_nt = seq_nt ? seq_nt + (size_t) pair * nt_row : nullptr;
 		double *o_p = seq_p ? seq_p + (size_t) pair * seq_stride : nullptr;
 		process_pair<ML, FULLF>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, s_qoff, s_primer, scratch, res, o_nt, o_p, (int) seq_stride, lane);

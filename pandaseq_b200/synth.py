@@ -215,3 +215,67 @@ def generate_config(cfg_id: int, n: int | None = None, device="cpu", n_rate=0.0,
     return generate(n if n is not None else c["n"], rl=c["rl"], tmpl=c.get("tmpl") or (0, 0), seed=c["seed"], device=device,
                     mixed=c.get("mixed", False), primers=c.get("primers", False), n_rate=n_rate, btail_rate=btail_rate,
                     chunk_index=chunk_index)
+
+
+# ---- FASTQ text of a batch (what fastq.c parses; SURVEY.md §8d header format) -------------------------
+_LETTERS = np.frombuffer(b"NACMGRSVTWYHKDBN", dtype=np.uint8)        # nt.c:25
+_COMP4 = np.array([((c & 1) << 3) | ((c & 2) << 1) | ((c & 4) >> 1) | ((c & 8) >> 3) for c in range(16)], dtype=np.uint8)
+
+
+def fastq_text(data, off, mate: int, *, complement: bool, qual_offset=33, seed=7, crlf=False):
+    """FASTQ text (uint8 torch tensor, same device as `data`) of flat reads: data (N,2) uint8 (nt, qual), off (n+1).
+    Headers are CASAVA 1.7, fixed width: ``@M01271:10:000000000-A3WGH:1:<tile 4d>:<x 5d>:<y 5d> <mate>:N:0:1``; tile/x/y
+    are a deterministic function of (seed, pair index), identical for both mates.  complement=True writes the letter of the
+    complementary base, i.e. what the sequencer reports for a reverse read that the API holds complemented (fastq.c:154)."""
+    data = torch.as_tensor(data)
+    dev = data.device
+    off = torch.as_tensor(np.asarray(off).astype(np.int64) if not torch.is_tensor(off) else off).to(dev).to(torch.int64)
+    n = off.numel() - 1
+    lens = off[1:] - off[:-1]
+    idx = torch.arange(n, device=dev, dtype=torch.int64)
+    h = (idx * 2654435761 + seed * 40503) & 0x7FFFFFFF
+    tile = 1101 + (h % 1019)
+    x = 10000 + ((h // 1019) % 20000)
+    y = 10000 + ((idx * 7919 + seed) % 20000)
+    prefix = torch.tensor(list(b"@M01271:10:000000000-A3WGH:1:"), dtype=torch.uint8, device=dev)
+    suffix = torch.tensor(list(b" %d:N:0:1" % mate), dtype=torch.uint8, device=dev)
+
+    def digits(v, w):
+        return torch.stack([(v // (10 ** (w - 1 - k))) % 10 + 48 for k in range(w)], dim=1).to(torch.uint8)
+
+    colon = torch.full((n, 1), 58, dtype=torch.uint8, device=dev)
+    hdr = torch.cat([prefix[None, :].expand(n, -1), digits(tile, 4), colon, digits(x, 5), colon, digits(y, 5),
+                     suffix[None, :].expand(n, -1)], dim=1)
+    hw = hdr.shape[1]
+    eol = 2 if crlf else 1
+    rec_len = hw + eol + lens + eol + 1 + eol + lens + eol
+    rec_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    rec_off[1:] = torch.cumsum(rec_len, 0)
+    total = int(rec_off[-1].item())
+    out = torch.full((total,), 10, dtype=torch.uint8, device=dev)          # every byte not written below is '\n'
+    start = rec_off[:-1]
+    pos = start[:, None] + torch.arange(hw, device=dev)[None, :]
+    out[pos.reshape(-1)] = hdr.reshape(-1)
+    nt = data[:, 0].to(torch.int64) & 15
+    if complement:
+        nt = torch.from_numpy(_COMP4).to(dev)[nt].to(torch.int64)
+    letters = torch.from_numpy(_LETTERS.copy()).to(dev)[nt]
+    quals = (data[:, 1].to(torch.int16) + qual_offset).to(torch.uint8)
+    rec = torch.repeat_interleave(idx, lens)
+    k = torch.arange(data.shape[0], device=dev, dtype=torch.int64) - off[:-1][rec]
+    seq_pos = start[rec] + hw + eol + k
+    out[seq_pos] = letters
+    plus_pos = start + hw + eol + lens + eol
+    out[plus_pos] = 43
+    out[seq_pos + lens[rec] + eol + 1 + eol] = quals
+    if crlf:
+        for p in (start + hw, start + hw + eol + lens, plus_pos + 1, start + rec_len - eol):
+            out[p] = 13
+    return out
+
+
+def fastq_pair(batch: "FlatBatch", device="cpu", **kw):
+    """(forward text, reverse text) uint8 tensors for a FlatBatch"""
+    f = fastq_text(torch.from_numpy(np.ascontiguousarray(batch.f_data)).to(device), batch.f_off, 1, complement=False, **kw)
+    r = fastq_text(torch.from_numpy(np.ascontiguousarray(batch.r_data)).to(device), batch.r_off, 2, complement=True, **kw)
+    return f, r

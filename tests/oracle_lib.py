@@ -88,3 +88,81 @@ def tables(which: str) -> dict:
     L.ref_get_tables.argtypes = [C.POINTER(PbTables)]
     L.ref_get_tables(C.byref(t))
     return t.as_dict()
+
+
+# ---- the stages either side of the hot path: FASTQ text in, FASTA/FASTQ text out ---------------------------
+SEQID_DTYPE = np.dtype([("instrument", "S100"), ("run", "S100"), ("flowcell", "S100"), ("lane", "<i4"), ("tile", "<i4"),
+                        ("x", "<i4"), ("y", "<i4"), ("tag", "S50"), ("_pad", "V2")])
+assert SEQID_DTYPE.itemsize == 368
+FQ_ERRORS = {0: "OK", 1: "BADID", 2: "NOTPAIRED", 3: "EOF", 4: "BADNT", 5: "READLEN", 6: "BADSEQ", 7: "NOQUAL"}
+TAG_PRESENT, TAG_ABSENT, TAG_OPTIONAL = 0, 1, 2
+
+
+class FastqOut(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("records", C.c_size_t), ("error", C.c_int), ("ids", C.c_void_p), ("f_data", C.c_void_p),
+                ("f_off", C.c_void_p), ("r_data", C.c_void_p), ("r_off", C.c_void_p)]
+
+
+def _io(which):
+    L = _get(which)[0]
+    pre = "po" if which == "port" else "ref"
+    return L, pre
+
+
+def fastq_parse(which: str, fwd: bytes, rev: bytes, *, qualmin=33, policy=TAG_PRESENT, max_pairs=None, max_read=0):
+    """-> dict(n, error, ids (SEQID_DTYPE), batch (FlatBatch), records)"""
+    from pandaseq_b200.synth import FlatBatch
+    L, pre = _io(which)
+    fn = getattr(L, pre + "_fastq_parse")
+    fn.restype = C.c_int
+    if max_pairs is None:
+        max_pairs = fwd.count(b"\n") // 4 + 1
+    cap = max_pairs * PB_MAX_LEN
+    ids = np.zeros(max_pairs, dtype=SEQID_DTYPE)
+    f_data, r_data = np.zeros((cap, 2), np.uint8), np.zeros((cap, 2), np.uint8)
+    f_off, r_off = np.zeros(max_pairs + 1, np.uint64), np.zeros(max_pairs + 1, np.uint64)
+    out = FastqOut(0, 0, 0, ids.ctypes.data, f_data.ctypes.data, f_off.ctypes.data, r_data.ctypes.data, r_off.ctypes.data)
+    args = [C.c_char_p(fwd), C.c_size_t(len(fwd)), C.c_char_p(rev), C.c_size_t(len(rev)), C.c_int(qualmin), C.c_int(policy),
+            C.c_size_t(max_pairs), C.byref(out)]
+    if which != "port":
+        args.append(C.c_size_t(max_read))
+    fn(*args)
+    n = int(out.n)
+    batch = FlatBatch(f_data[:int(f_off[n])].copy(), f_off[:n + 1].copy(), r_data[:int(r_off[n])].copy(), r_off[:n + 1].copy())
+    return dict(n=n, error=int(out.error), ids=ids[:n].copy(), batch=batch, records=int(out.records))
+
+
+def seqid_parse(which: str, text: bytes, policy=TAG_PRESENT):
+    L, pre = _io(which)
+    fn = getattr(L, pre + "_seqid_parse")
+    fn.restype = C.c_int
+    ident = np.zeros(1, dtype=SEQID_DTYPE)
+    fmt = C.c_int(0)
+    rc = fn(C.c_void_p(ident.ctypes.data), C.c_char_p(text), C.c_int(policy), C.byref(fmt))
+    return int(rc), int(fmt.value), ident[0]
+
+
+def result_phred(which: str, p: float) -> int:
+    L, pre = _io(which)
+    fn = getattr(L, pre + "_result_phred")
+    fn.restype = C.c_char
+    fn.argtypes = [C.c_double]
+    return fn(float(p))[0]
+
+
+def format_flat(which: str, fastq: bool, ids, status, quality, seq_len, seq_nt, seq_p, seq_stride) -> bytes:
+    L, pre = _io(which)
+    fn = getattr(L, pre + "_format_flat")
+    fn.restype = C.c_size_t
+    n = len(status)
+    ids = np.ascontiguousarray(ids)
+    status = np.ascontiguousarray(status, dtype=np.uint8)
+    quality = np.ascontiguousarray(quality, dtype=np.float64)
+    seq_len = np.ascontiguousarray(seq_len, dtype=np.int32)
+    seq_nt = np.ascontiguousarray(seq_nt, dtype=np.uint8)
+    seq_p = None if seq_p is None else np.ascontiguousarray(seq_p, dtype=np.float64)
+    dst = np.zeros(n * (2 * (2 * PB_MAX_LEN) + 512) + 16, dtype=np.uint8)
+    total = fn(C.c_void_p(dst.ctypes.data), C.c_int(int(fastq)), C.c_size_t(n), C.c_void_p(ids.ctypes.data), C.c_void_p(status.ctypes.data),
+               C.c_void_p(quality.ctypes.data), C.c_void_p(seq_len.ctypes.data), C.c_void_p(seq_nt.ctypes.data),
+               C.c_void_p(seq_p.ctypes.data) if seq_p is not None else None, C.c_int64(seq_stride))
+    return dst[:total].tobytes()
