@@ -144,6 +144,139 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def text_path(args):
+    """--path text: the chain FASTQ text -> parse -> assemble -> FASTA text (pb_fastq_assemble_host, pinned host buffers),
+    its three device stages timed separately on resident text, and the reference's own CLI on a bounded sample."""
+    import torch
+    import pandaseq_b200 as pb
+    from pandaseq_b200 import synth
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    c, kw = workload(args.config)
+    cfg = pb.make_config(c["algo"], **kw)
+    n = args.pairs if args.pairs is not None else 4_000_000
+    ctx = pb.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle, device=dev)
+    ftxt, rtxt = [], []
+    for ci, start in enumerate(range(0, n, GEN_CHUNK)):
+        cnt = min(GEN_CHUNK, n - start)
+        rect = synth.generate_config(args.config, n=cnt, device=dev, chunk_index=ci)
+        f_data, f_off, r_data, r_off = rect.to_flat_tensors()
+        ftxt.append(synth.fastq_text(f_data, f_off, 1, complement=False, seed=7 + ci))
+        rtxt.append(synth.fastq_text(r_data, r_off, 2, complement=True, seed=7 + ci))
+        del rect, f_data, r_data
+    # ---- device-resident stages on the first 1 M pairs (one chunk of the chain) -------------------------
+    df, dr = ftxt[0], rtxt[0]
+    n1 = min(n, GEN_CHUNK)
+    import ctypes as C
+    stage_ms = {"parse": [], "assemble": [], "format": []}
+    parsed = ctx.fastq_parse_device(df, dr, max_records=n1 + 16)
+    info = parsed["info"]
+    lim = int(info["limit"])
+    stride = (2 * int(info["max_read_len"]) + 15) & ~15
+    results = torch.empty((lim, 32), dtype=torch.uint8, device=dev)
+    nt = torch.empty((lim, stride // 2), dtype=torch.uint8, device=dev)
+    counters = torch.zeros(pb.PB_NCOUNTERS, dtype=torch.int64, device=dev)
+    text_dev = torch.empty(int(df.numel()), dtype=torch.uint8, device=dev)
+    total = C.c_size_t(0)
+    L = pb.lib()
+    for it in range(args.warmup + args.steps):
+        # parse and format return after a small device->host read, so the host clock around the call is the stage time
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        parsed = ctx.fastq_parse_device(df, dr, max_records=n1 + 16)
+        t_parse = (time.perf_counter() - t0) * 1e3
+        e1, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e1.record(stream)
+        ctx.assemble_device(cfg, lim, int(info["max_read_len"]), parsed["reads"], parsed["meta"], results, nt, None, stride, counters)
+        e2.record(stream)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        rc = L.pb_format_device(ctx._h, pb.OUT_FASTA, lim, results.data_ptr(), nt.data_ptr(), None, stride, parsed["ids"].data_ptr(),
+                                df.data_ptr(), text_dev.data_ptr(), text_dev.numel(), C.byref(total))
+        t_fmt = (time.perf_counter() - t0) * 1e3
+        if rc != 0:
+            raise RuntimeError(L.pb_last_error().decode())
+        if it >= args.warmup:
+            stage_ms["parse"].append(t_parse)
+            stage_ms["assemble"].append(e1.elapsed_time(e2))
+            stage_ms["format"].append(t_fmt)
+    del results, nt, text_dev
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    text_bytes = int(df.numel() + dr.numel())
+    rec_bytes = int(parsed["info"]["stride16"]) * 16 * n1
+    parse_alg = text_bytes + rec_bytes + (48 + 8) * n1
+    parse_ms = float(np.median(stage_ms["parse"]))
+    # ---- the chain with pinned host buffers ---------------------------------------------------------------------
+    hf = torch.cat(ftxt).cpu().pin_memory()
+    hr = torch.cat(rtxt).cpu().pin_memory()
+    del ftxt, rtxt, df, dr
+    out = torch.zeros(hf.numel() + hr.numel(), dtype=torch.uint8).pin_memory()
+    infos = None
+    for _ in range(max(1, min(args.warmup, 2))):
+        _, infos, cnt = ctx.fastq_assemble_host(cfg, hf, hr, out=out)
+    torch.cuda.synchronize(dev)
+    ksteps = max(1, min(args.steps, 3))
+    sampler = ClockSampler(local)
+    t0 = time.perf_counter()
+    for _ in range(ksteps):
+        _, infos, cnt = ctx.fastq_assemble_host(cfg, hf, hr, out=out)
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert infos["pairs"] == n and infos["error"] == 0, infos
+    value = n * ksteps / dt / 1e6
+    # ---- the reference's CLI on a bounded sample of the same text -------------------------------------------------
+    cpu = None
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "pandaseq")
+    if not args.no_cpu and os.path.exists(ref_bin):
+        import tempfile
+        sample = min(n, 400_000)
+        fb = bytes(hf.numpy()).split(b"\n", 4 * sample)
+        rb = bytes(hr.numpy()).split(b"\n", 4 * sample)
+        with tempfile.TemporaryDirectory() as td:
+            pf_, pr_ = os.path.join(td, "f.fastq"), os.path.join(td, "r.fastq")
+            open(pf_, "wb").write(b"\n".join(fb[:4 * sample]) + b"\n")
+            open(pr_, "wb").write(b"\n".join(rb[:4 * sample]) + b"\n")
+            cores = os.cpu_count() or 1
+            best = None
+            for threads in sorted({1, min(cores, 8), min(cores, 32)}):
+                t0 = time.perf_counter()
+                subprocess.run([ref_bin, "-f", pf_, "-r", pr_, "-A", c["algo"], "-T", str(threads), "-w", os.devnull, "-g", os.devnull],
+                               check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                rate = sample / (time.perf_counter() - t0) / 1e6
+                if best is None or rate > best[0]:
+                    best = (rate, threads)
+            cpu = {"value": best[0], "unit": "Mpairs/s", "cores": best[1], "kind": "reference",
+                   "sample": f"the reference's own CLI (oracle/_ref/pandaseq -f -r -T {best[1]} -w /dev/null) on the first {sample} pairs of the same "
+                             "FASTQ text; best of -T 1/8/32 (it is parser-bound behind a mutex and does not scale)"}
+    line = {
+        "metric": "read-pairs/s (Mpairs/s), FASTQ text in -> assembled FASTA text out", "value": value, "unit": "Mpairs/s", "n_gpus": 1,
+        "steps": ksteps, "warmup": min(args.warmup, 2), "ms_per_step": dt / ksteps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8 text -> u8/f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE config {args.config} as FASTQ text: {n} pairs, {c['algo']}, CASAVA 1.7 headers, PHRED+33; "
+                               "pinned host text in, pinned host FASTA text out (pb_fastq_assemble_host)",
+                   "pairs": n, "l2_policy": "inputs larger than L2, streamed in 96 MB windows"},
+        "e2e": {"value": value, "unit": "Mpairs/s", "h2d_bytes_per_step": int(hf.numel() + hr.numel()), "d2h_bytes_per_step": int(infos["out_bytes"])},
+        "stages_resident": {"pairs": n1, "parse_ms": parse_ms, "assemble_ms": float(np.median(stage_ms["assemble"])),
+                            "format_ms": float(np.median(stage_ms["format"])),
+                            "note": "one 1 M-pair chunk with its text resident in HBM; parse = line index + identifiers + reads + finish "
+                                    "(host wall clock around pb_fastq_parse_device, which returns after its 64-byte info came back)"},
+        "roofline": {"bound": "hbm", "kernel": "pbio::nl_count+nl_write+fq_ids+fq_reads (FASTQ parse)", "achieved": parse_alg / (parse_ms / 1e3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": parse_alg / (parse_ms / 1e3) / 1e9 / peak, "traffic": None,
+                     "algorithmic_bytes": parse_alg, "note": "text read once + packed records, identifiers and metadata written once"},
+        "cpu_baseline": cpu, "gpu_launches": None, "clocks": clocks,
+        "stat": {"count": int(cnt[pb.C_COUNT]), "ok": int(cnt[pb.C_OK]), "out_bytes": int(infos["out_bytes"])},
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -152,11 +285,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU (default: the config's, capped at 10 M per GPU)")
+    ap.add_argument("--path", default="pairs", choices=["pairs", "text"],
+                    help="pairs: the BASELINE metric on panda_qual pairs (default); text: FASTQ text in -> FASTA text out (SURVEY.md 8f rank 1+2)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.path == "text":
+        text_path(args)
         return
 
     import torch

@@ -166,22 +166,21 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false); } while (0)
 	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */
 	if (max_len <= 160) {
-		if (over) PB_GO(160, true, 24);
+		if (over) PB_GO(160, true, 23);
 		else {
 			/* 30 warps x 64 registers vs 28 x 72: measured; PANDASEQ_B200_WARPS160 overrides for experiments */
 			static int w160 = -1;
 			if (w160 < 0) {
 				const char *env = getenv("PANDASEQ_B200_WARPS160");
-				w160 = env ? atoi(env) : 30;
+				w160 = env ? atoi(env) : 28;
 			}
-			if (w160 == 28) PB_GO(160, false, 28);
-			else if (w160 == 24) PB_GO(160, false, 24);
-			else PB_GO(160, false, 30);
+			if (w160 == 24) PB_GO(160, false, 24);
+			else PB_GO(160, false, 28);
 		}
 	} else if (max_len <= 256) {
-		if (over) PB_GO(256, true, 12); else PB_GO(256, false, 16);
+		if (over) PB_GO(256, true, 12); else PB_GO(256, false, 15);
 	} else if (max_len <= 320) {
-		if (over) PB_GO(320, true, 12); else PB_GO(320, false, 15);
+		if (over) PB_GO(320, true, 12); else PB_GO(320, false, 14);
 	} else {
 		if (over) PB_GO(456, true, 6); else PB_GO(456, false, 8);
 	}

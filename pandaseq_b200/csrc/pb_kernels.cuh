@@ -56,6 +56,7 @@ template <int ML> struct WarpSmem {
 	static constexpr int NFLAG = ((2 * ML + 15) & ~15) + 16;
 	alignas(128) uint8_t stage[NSTAGE][STAGE_BYTES];
 	alignas(16) uint64_t btab[NB];
+	alignas(16) uint32_t bcnt[NB / 8];                       /* entries per bucket, 4 bits each */
 	alignas(16) uint16_t code_f[CODEN];
 	alignas(16) uint16_t code_r[CODEN];
 	alignas(16) uint8_t inval_f[(NTW + 19) & ~15];           /* bit t of byte w: k-mer ending at 8w+t is invalid */
@@ -372,39 +373,27 @@ __device__ __forceinline__ void seed_candidates(WarpSmem<ML> &ws, int F, int R, 
 	constexpr unsigned IDXMASK = WS::NB - 1;
 	constexpr unsigned PLIM = (1u << WS::PBITS) - 1u;
 	uint16_t *bt16 = reinterpret_cast<uint16_t *>(ws.btab);
-	const unsigned lt = lanemask_lt();
 	unsigned ovf = 0;
-	/* K1: forward 8-mers into the bucket table, in position order.  Two rounds are prepared together so the
-	 * second round's match.any is in flight while the first round's bucket counters are updated. */
-	for (int p0 = 8 + lane; p0 - lane < F; p0 += 64) {
-		unsigned code[2], idx[2], grp[2];
-		bool live[2];
-#pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const int p = p0 + 32 * h;
-			live[h] = p < F;
-			if (HASN)
-				live[h] = live[h] && ((ws.inval_f[p >> 3] >> (p & 7)) & 1u) == 0;
-			code[h] = ws.code_f[p];
-			idx[h] = code[h] & IDXMASK;
-			grp[h] = __match_any_sync(FULL, live[h] ? idx[h] : (WS::NB + lane));
-		}
-#pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const int p = p0 + 32 * h;
-			/* entries fill a bucket from slot 0 upwards, so the count is the number of non-zero halfwords */
-			const uint2 b = *reinterpret_cast<const uint2 *>(&ws.btab[idx[h]]);
-			const unsigned cnt = b.y ? ((b.y >> 16) ? 4u : 3u) : (b.x ? ((b.x >> 16) ? 2u : 1u) : 0u);
-			__syncwarp();
-			const unsigned slot = cnt + __popc(grp[h] & lt);
-			const unsigned entry = ((code[h] >> WS::IDXBITS) << WS::PBITS) | (unsigned) p;
-			if (live[h] && slot < 4u)
-				bt16[idx[h] * 4 + slot] = (uint16_t) entry;
-			ovf |= (live[h] && slot >= 4u) ? 1u : 0u;
-			__syncwarp();
+	/* K1: forward 8-mers into the bucket table.  A lane claims its slot with one shared-memory atomic on the bucket's
+	 * 4-bit counter; the order of the entries inside a bucket is whatever the atomics made it, which is why the probe
+	 * below takes the two LOWEST matching positions (= the reference's "first two", assembler.c:93-100). */
+	for (int p = 8 + lane; p - lane < F; p += 32) {
+		bool live = p < F;
+		if (HASN)
+			live = live && ((ws.inval_f[p >> 3] >> (p & 7)) & 1u) == 0;
+		const unsigned code = ws.code_f[p];
+		const unsigned idx = code & IDXMASK;
+		if (live) {
+			const unsigned sh = 4u * (idx & 7u);
+			const unsigned slot = (atomicAdd(&ws.bcnt[idx >> 3], 1u << sh) >> sh) & 15u;
+			if (slot < 4u)
+				bt16[idx * 4 + slot] = (uint16_t) (((code >> WS::IDXBITS) << WS::PBITS) | (unsigned) p);
+			else
+				ovf = 1u;      /* a 5th entry; counters past this point may carry into their neighbours, nobody reads them */
 		}
 	}
 	const bool overflow = __any_sync(FULL, ovf != 0);
+	__syncwarp();
 	const int cbase = F - mo;                  /* overlap - mo = cbase - p + e */
 	if (!overflow) {
 		/* K2: reverse 8-mers probe one bucket each (assembler.c:104-110); byte flags = BIT_LIST_SET */
@@ -417,13 +406,14 @@ __device__ __forceinline__ void seed_candidates(WarpSmem<ML> &ws, int F, int R, 
 			const unsigned tagsh = (code >> WS::IDXBITS) << WS::PBITS;
 			const uint2 b = *reinterpret_cast<const uint2 *>(&ws.btab[code & IDXMASK]);
 			/* entry ^ tagsh is the stored position iff the tags agree (positions are >= 8, empty entries are 0) */
-			const unsigned x0 = (b.x & 0xFFFFu) ^ tagsh, x1 = (b.x >> 16) ^ tagsh;
-			const unsigned x2 = (b.y & 0xFFFFu) ^ tagsh, x3 = (b.y >> 16) ^ tagsh;
-			unsigned m1 = 0x7FFFu, m2 = 0x7FFFu;      /* entries are in position order: first two that match */
-			if (x3 - 1u < PLIM) { m1 = x3; }
-			if (x2 - 1u < PLIM) { m2 = m1; m1 = x2; }
-			if (x1 - 1u < PLIM) { m2 = m1; m1 = x1; }
-			if (x0 - 1u < PLIM) { m2 = m1; m1 = x0; }
+			unsigned x0 = (b.x & 0xFFFFu) ^ tagsh, x1 = (b.x >> 16) ^ tagsh;
+			unsigned x2 = (b.y & 0xFFFFu) ^ tagsh, x3 = (b.y >> 16) ^ tagsh;
+			if (x0 - 1u >= PLIM) x0 = 0x7FFFu;
+			if (x1 - 1u >= PLIM) x1 = 0x7FFFu;
+			if (x2 - 1u >= PLIM) x2 = 0x7FFFu;
+			if (x3 - 1u >= PLIM) x3 = 0x7FFFu;
+			const unsigned lo01 = min(x0, x1), hi01 = max(x0, x1), lo23 = min(x2, x3), hi23 = max(x2, x3);
+			const unsigned m1 = min(lo01, lo23), m2 = min(max(lo01, lo23), min(hi01, hi23));
 			const unsigned c = live ? (unsigned) (cbase + e) : 0u;   /* dead lanes: index underflows, no flag */
 			const unsigned i1 = c - m1, i2 = c - m2;
 			if (i1 < (unsigned) nbits)
@@ -438,8 +428,15 @@ __device__ __forceinline__ void seed_candidates(WarpSmem<ML> &ws, int F, int R, 
 #pragma unroll
 		for (int k = 0; k < WS::NB * 8 / 16 / 32; k++)
 			t4[k * 32 + lane] = z;
+		uint4 *c4 = reinterpret_cast<uint4 *>(ws.bcnt);
+#pragma unroll
+		for (int k = 0; k < (WS::NB / 8 * 4 + 511) / 512; k++)
+			if (k * 32 + lane < WS::NB / 8 / 4)
+				c4[k * 32 + lane] = z;
 		return;
 	}
+	for (int k = lane; k < WS::NB / 8; k += 32)
+		ws.bcnt[k] = 0;
 	/* Exact open-addressing path for pairs whose k-mers crowd a bucket (low-complexity reads): every
 	 * (code, position) is stored; the probe walks the whole chain and keeps the two lowest positions. */
 	constexpr unsigned SMASK = WS::SLOTS - 1;
@@ -967,6 +964,8 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 	WS &ws = wsall[warp];
 	for (int k = lane; k < WS::NB; k += 32)
 		ws.btab[k] = 0;
+	for (int k = lane; k < WS::NB / 8; k += 32)
+		ws.bcnt[k] = 0;
 	for (int k = lane; k < WS::NFLAG; k += 32)
 		ws.cflag[k] = 0;
 	if (lane == 0) {
