@@ -184,3 +184,38 @@ def test_fastq_assemble_pinned_large(ctx):
     sf, sr = (bytes(t.numpy()) for t in synth.fastq_pair(sub))
     _, _, want = _oracle_chain(sf, sr, cfg, False)
     assert text.startswith(want)
+
+
+# ---- against the golden vectors generated from the compiled reference (tests/golden/make_golden_io.py) -----------------
+import test_io_golden as gold  # noqa: E402
+
+
+@pytest.mark.parametrize("name", [str(n) for n in gold.FQ["names"]])
+def test_parse_golden(ctx, name):
+    f, r, kw = gold.golden_case(name)
+    got = device_parse(ctx, f, r, **kw)
+    if name in TAIL_CASES:
+        got["error"] = int(gold.FQ[f"{name}.error"])        # simplified rule for a truncated last record: data compared, code not
+    gold.check_against_golden(name, got)
+
+
+@pytest.mark.parametrize("fastq", [False, True])
+def test_format_golden(ctx, fastq):
+    """reference results in, text out: only the formatter is under test (identifiers come from the device parse of the same text)"""
+    FM = gold.FM
+    f, r = bytes(FM["fwd"]), bytes(FM["rev"])
+    got = device_parse(ctx, f, r)
+    n, width = len(FM["status"]), FM["seq_nt"].shape[1]
+    stride = (width + 15) & ~15
+    res = np.zeros(n, dtype=pb.PAIR_RESULT_DTYPE)
+    res["status"], res["quality"], res["seq_len"] = FM["status"], FM["quality"], FM["seq_len"]
+    nt = np.zeros((n, stride), np.uint8)
+    nt[:, :width] = FM["seq_nt"]
+    packed = (nt[:, 0::2] | (nt[:, 1::2] << 4)).astype(np.uint8)
+    p = np.zeros((n, stride), np.float64)
+    p[:, :width] = FM["seq_p"]
+    cfg = pb.make_config("simple_bayesian")
+    ctx.assemble_host(cfg, synth.generate_config(1, n=4).to_flat())       # uploads the configuration (qual_score table)
+    text = ctx.format_device(int(fastq), n, torch.from_numpy(res.view(np.uint8).reshape(n, 32)).cuda(), torch.from_numpy(packed).cuda(),
+                             torch.from_numpy(p).cuda(), stride, got["raw"]["ids"], got["text"][0])
+    assert text == bytes(FM["fastq" if fastq else "fasta"])
