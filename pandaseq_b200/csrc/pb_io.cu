@@ -159,8 +159,10 @@ static pb_status parse_launch(pb_context *ctx, IoSlot &s, cudaStream_t st, const
 		const int grid = ctx->sm_count * 8;
 		pbio::fq_geometry<<<grid, 256, 0, st>>>(tv[0], tv[1], s.d_state, (unsigned) max_records);
 		pbio::fq_stride<<<1, 1, 0, st>>>(s.d_state);
-		pbio::fq_ids<<<grid, 128, 0, st>>>(tv[0], tv[1], s.d_state, policy, d_ids);
-		pbio::fq_reads<<<grid, 256, 0, st>>>(tv[0], tv[1], s.d_state, qualmin, d_reads, (unsigned long long) reads_cap, d_meta);
+		pbio::fq_ids<<<ctx->sm_count * 6, pbio::ID_THREADS, 0, st>>>(tv[0], tv[1], s.d_state, policy, d_ids);
+		pbio::fq_reads<5><<<ctx->sm_count * 16, 128, 0, st>>>(tv[0], tv[1], s.d_state, qualmin, d_reads, (unsigned long long) reads_cap, d_meta);
+		pbio::fq_reads<10><<<ctx->sm_count * 10, 128, 0, st>>>(tv[0], tv[1], s.d_state, qualmin, d_reads, (unsigned long long) reads_cap, d_meta);
+		pbio::fq_reads<15><<<ctx->sm_count * 6, 128, 0, st>>>(tv[0], tv[1], s.d_state, qualmin, d_reads, (unsigned long long) reads_cap, d_meta);
 		pbio::fq_finish<<<1, 1024, 0, st>>>(s.d_state, d_meta);
 		CUDA_TRY(cudaGetLastError());
 	}

@@ -265,11 +265,19 @@ __device__ __forceinline__ bool tag_policy_ok(int tag_len, int policy) {
 /* returns the direction (0 = failure).  hdr/len: the header line after its first character, ended by a NUL if it has one */
 __device__ int parse_id(const uint8_t *hdr, int len, int policy, IdFields &f) {
 	Cursor c = { hdr, 0, len };
-	for (int k = 0; k < len; k++)
-		if (hdr[k] == 0) {
+	/* one pass: where the C string ends, whether it holds a '/', and the ':' before the first '#' (seqid.c:170-178) */
+	bool slash = false, hashed = false;
+	int colons = 0;
+	for (int k = 0; k < len; k++) {
+		const int ch = hdr[k];
+		if (ch == 0) {
 			c.len = k;
 			break;
 		}
+		slash |= ch == '/';
+		hashed |= ch == '#';
+		colons += (ch == ':' && !hashed) ? 1 : 0;
+	}
 	len = c.len;
 	f.inst_off = f.inst_len = f.run_off = f.run_len = f.fc_off = f.fc_len = f.tag_off = f.tag_len = 0;
 	f.lane = f.tile = f.x = f.y = f.sra = 0;
@@ -287,13 +295,7 @@ __device__ int parse_id(const uint8_t *hdr, int len, int policy, IdFields &f) {
 			return 0;
 		return 1;
 	}
-	bool slash = false;
-	for (int k = 0; k < len; k++)
-		slash |= hdr[k] == '/';
 	if (slash) {
-		int colons = 0;
-		for (int k = 0; k < len && hdr[k] != '#'; k++)
-			colons += hdr[k] == ':';
 		if (colons == 6) {
 			f.fmt = PB_IDFMT_CASAVA_CONVERTED;
 			if (!take_str(c, f.inst_off, f.inst_len, 100) || !push(c)) return 0;
@@ -349,23 +351,81 @@ __device__ __forceinline__ void report(ParseState *st, unsigned record, int stag
 	atomicMin(&st->err_key, ((unsigned long long) record << 8) | ((unsigned long long) stage << 4) | (unsigned long long) code);
 }
 
-__global__ void fq_ids(TextView tf, TextView tr, ParseState *st, int policy, pb_seq_id *ids) {
+/* One thread parses one record's two header lines.  The lines of a CTA's 128 records are first copied into shared
+ * memory by whole warps (coalesced), so the character-at-a-time parser never waits on HBM; a header longer than
+ * ID_STAGE characters is parsed in place. */
+constexpr int ID_THREADS = 128;
+constexpr int ID_STAGE = 124;                      /* characters staged per header (after the first character) */
+constexpr int ID_ROW = 132;                        /* row stride in bytes: 33 words, so the threads of a warp hit different banks */
+
+__global__ void __launch_bounds__(ID_THREADS) fq_ids(TextView tf, TextView tr, ParseState *st, int policy, pb_seq_id *ids) {
+	__shared__ __align__(16) uint8_t stage[2][ID_THREADS][ID_ROW];
+	__shared__ unsigned s_start[2][ID_THREADS];
+	__shared__ int s_len[2][ID_THREADS], s_raw[2][ID_THREADS];
 	const unsigned records = st->records;
-	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < records; i += gridDim.x * blockDim.x) {
-		const Line hf = get_line(tf, 4 * i), hr = get_line(tr, 4 * i);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (unsigned base = blockIdx.x * ID_THREADS; base < records; base += gridDim.x * ID_THREADS) {
+		const unsigned i = base + threadIdx.x;
+		__syncthreads();                           /* the previous round's rows are no longer read */
+		if (i < records) {
+#pragma unroll
+			for (int f = 0; f < 2; f++) {
+				const Line h = get_line(f ? tr : tf, 4 * i);
+				s_start[f][threadIdx.x] = (unsigned) (h.p - (f ? tr.text : tf.text));
+				s_len[f][threadIdx.x] = h.len;
+				s_raw[f][threadIdx.x] = h.raw;
+			}
+		}
+		__syncthreads();
+		/* warp w copies the headers of records 32w .. 32w+31: one coalesced 132-byte row of aligned words per header, four
+		 * records' loads in flight at a time; the parser reads its row at the header's offset inside the first word */
+		for (int r0 = 0; r0 < 32; r0 += 4) {
+			uint32_t w[4][2], w32[4][2];
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+#pragma unroll
+				for (int f = 0; f < 2; f++) {
+					const int slot = warp * 32 + r0 + u;
+					w[u][f] = w32[u][f] = 0;
+					if (base + slot < records && s_len[f][slot] > 0) {
+						const TextView &t = f ? tr : tf;
+						const unsigned long long first = ((unsigned long long) s_start[f][slot] + 1ull) & ~3ull;
+						const uint32_t *src = reinterpret_cast<const uint32_t *>(t.text + first);
+						if (first + 4ull * lane + 4ull <= t.bytes)
+							w[u][f] = src[lane];
+						if (lane == 0 && first + 132ull <= t.bytes)
+							w32[u][f] = src[32];
+					}
+				}
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+#pragma unroll
+				for (int f = 0; f < 2; f++) {
+					uint32_t *row = reinterpret_cast<uint32_t *>(stage[f][warp * 32 + r0 + u]);
+					row[lane] = w[u][f];
+					if (lane == 0)
+						row[32] = w32[u][f];
+				}
+		}
+		__syncthreads();
+		if (i >= records)
+			continue;
 		IdFields f, r;
 		pb_seq_id out;
 		memset(&out, 0, sizeof out);
+		const int flen = s_len[0][threadIdx.x], rlen = s_len[1][threadIdx.x], fraw = s_raw[0][threadIdx.x], rraw = s_raw[1][threadIdx.x];
+		const uint8_t *gf = tf.text + s_start[0][threadIdx.x] + 1, *gr = tr.text + s_start[1][threadIdx.x] + 1;
+		const uint8_t *a = flen - 1 <= ID_STAGE ? stage[0][threadIdx.x] + ((s_start[0][threadIdx.x] + 1u) & 3u) : gf;
+		const uint8_t *b = rlen - 1 <= ID_STAGE ? stage[1][threadIdx.x] + ((s_start[1][threadIdx.x] + 1u) & 3u) : gr;
 		/* fastq.c:125 hands the parser `line + 1` without looking at the first character */
-		const int fdir = (hf.raw < PB_FQ_LINE_MAX && hf.len > 0) ? parse_id(hf.p + 1, hf.len - 1, policy, f) : 0;
+		const int fdir = (fraw < PB_FQ_LINE_MAX && flen > 0) ? parse_id(a, flen - 1, policy, f) : 0;
 		if (fdir == 0) {
-			report(st, i, 0, hf.raw >= PB_FQ_LINE_MAX ? PB_FQ_LINE_TOO_LONG : PB_FQ_ID_PARSE_FAILURE);
+			report(st, i, 0, fraw >= PB_FQ_LINE_MAX ? PB_FQ_LINE_TOO_LONG : PB_FQ_ID_PARSE_FAILURE);
 		} else {
-			const int rdir = (hr.raw < PB_FQ_LINE_MAX && hr.len > 0) ? parse_id(hr.p + 1, hr.len - 1, policy, r) : 0;
+			const int rdir = (rraw < PB_FQ_LINE_MAX && rlen > 0) ? parse_id(b, rlen - 1, policy, r) : 0;
 			if (rdir == 0) {
-				report(st, i, 1, hr.raw >= PB_FQ_LINE_MAX ? PB_FQ_LINE_TOO_LONG : PB_FQ_ID_PARSE_FAILURE);
+				report(st, i, 1, rraw >= PB_FQ_LINE_MAX ? PB_FQ_LINE_TOO_LONG : PB_FQ_ID_PARSE_FAILURE);
 			} else {
-				const uint8_t *a = hf.p + 1, *b = hr.p + 1;
 				/* panda_seqid_equal (seqid.c:95-99); the SRA instrument is "%cRR%d": same letter (fmt) and number */
 				bool eq = f.lane == r.lane && f.tile == r.tile && f.x == r.x && f.y == r.y && f.sra == r.sra
 					&& ((f.fmt == PB_IDFMT_SRA || f.fmt == PB_IDFMT_EBI_SRA) == (r.fmt == PB_IDFMT_SRA || r.fmt == PB_IDFMT_EBI_SRA))
@@ -378,8 +438,8 @@ __global__ void fq_ids(TextView tf, TextView tr, ParseState *st, int policy, pb_
 				if (!eq || (directional && rdir == fdir))
 					report(st, i, 2, PB_FQ_NOT_PAIRED);
 			}
-			out.hdr_off = (uint32_t) (hf.p + 1 - tf.text);
-			out.hdr_len = (uint16_t) (hf.len - 1);
+			out.hdr_off = (uint32_t) (gf - tf.text);
+			out.hdr_len = (uint16_t) (flen - 1);
 			out.fmt = (uint8_t) f.fmt;
 			out.inst_off = (uint16_t) f.inst_off; out.inst_len = (uint16_t) f.inst_len;
 			out.run_off = (uint16_t) f.run_off; out.run_len = (uint16_t) f.run_len;
@@ -414,92 +474,158 @@ __device__ __forceinline__ int to_index(int ch, int qualmin) {      /* fastq.c:4
 	return (ch > qualmin + PB_PHREDMAX ? PB_PHREDMAX : ch) - qualmin;
 }
 
-/* Validate one read (lines 1..3 of its record) in the reference's order; returns PB_FQ_OK or the code. */
-__device__ int check_read(const Line &seq, const Line &plus, const Line &qual, bool complement, int &len, int lane) {
-	if (seq.raw >= PB_FQ_LINE_MAX)
-		return PB_FQ_LINE_TOO_LONG;
-	len = min(seq.len, PB_MAX_LEN);
-	bool bad = false;
-	for (int k = lane; k < len; k += 32)
-		bad |= letter_code(seq.p[k], complement) == 0u;
-	if (__any_sync(FULL, bad))
-		return PB_FQ_BAD_NT;
-	if (plus.raw >= PB_FQ_LINE_MAX)
-		return PB_FQ_LINE_TOO_LONG;
-	const int first = plus.len > 0 ? (int) plus.p[0] : 0;
-	if (first != '+')
-		return letter_code((unsigned) first, complement) != 0u ? PB_FQ_READ_TOO_LONG : PB_FQ_PARSE_FAILURE;
-	if (qual.raw >= PB_FQ_LINE_MAX)
-		return PB_FQ_LINE_TOO_LONG;
-	if (qual.len != len)
-		return PB_FQ_NO_QUALITY_INFO;
-	/* a NUL ends the reference's C string early; such input is refused here */
-	bool nul = false;
-	for (int k = lane; k < len; k += 32)
-		nul |= qual.p[k] == 0;
-	if (__any_sync(FULL, nul))
-		return PB_FQ_NO_QUALITY_INFO;
-	return PB_FQ_OK;
+/* One record with every byte of its two reads held in registers: NI characters per lane and line.  The line index,
+ * the CR / '+' probes and the characters are each fetched in ONE batch of independent loads. */
+template <int NI>
+__device__ __forceinline__ void reads_record(const TextView &tf, const TextView &tr, ParseState *st, int qualmin, unsigned i, unsigned stride16,
+                                             uint8_t *reads, unsigned long long reads_cap, pb_pair_meta *meta, int lane,
+                                             const uint8_t *__restrict__ lut) {
+	/* lanes 0..4: forward newline positions 4i-1 .. 4i+3; lanes 8..12: the reverse ones */
+	const bool rev_lane = lane >= 8;
+	const int kk = (lane & 7);
+	unsigned pos = 0;
+	if (kk < 5 && lane < 13) {
+		const TextView &t = rev_lane ? tr : tf;
+		const long long q = (long long) 4 * i - 1 + kk;
+		pos = q < 0 ? 0xFFFFFFFFu : t.nl[q];
+	}
+	/* line k of the record (1 = sequence, 2 = '+', 3 = quality) of file f: start = pos[f][k-1]+1, end = pos[f][k] */
+	unsigned ls[2][3], le[2][3];
+#pragma unroll
+	for (int f = 0; f < 2; f++)
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			ls[f][k] = __shfl_sync(FULL, pos, 8 * f + k + 1) + 1u;
+			le[f][k] = __shfl_sync(FULL, pos, 8 * f + k + 2);
+		}
+	/* one probe per line: its last byte (CR?) and, for the '+' line, its first byte */
+	unsigned last = 0, first = 0;
+	if (lane < 6) {
+		const int f = lane / 3, k = lane % 3;
+		const uint8_t *text = f ? tr.text : tf.text;
+		unsigned s0 = 0, e0 = 0;
+#pragma unroll
+		for (int ff = 0; ff < 2; ff++)
+#pragma unroll
+			for (int k2 = 0; k2 < 3; k2++)
+				if (ff == f && k2 == k) {
+					s0 = ls[ff][k2];
+					e0 = le[ff][k2];
+				}
+		if (e0 > s0) {
+			last = text[e0 - 1];
+			first = text[s0];
+		}
+	}
+	int raw[2][3], len[2][3];
+#pragma unroll
+	for (int f = 0; f < 2; f++)
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			raw[f][k] = (int) (le[f][k] - ls[f][k]);
+			const unsigned lb = __shfl_sync(FULL, last, 3 * f + k);
+			len[f][k] = raw[f][k] - ((raw[f][k] > 0 && lb == '\r') ? 1 : 0);
+		}
+	const unsigned plus_f = __shfl_sync(FULL, first, 1), plus_r = __shfl_sync(FULL, first, 4);
+	const int F = min(len[0][0], PB_MAX_LEN), R = min(len[1][0], PB_MAX_LEN);
+	/* every character this lane is responsible for: element j = j0 + 32 n of the packed read (template order for the
+	 * reverse read: element j is read position R-1-j) */
+	unsigned cs[2][NI], cq[2][NI];
+	const uint8_t *fs = tf.text + ls[0][0], *fq = tf.text + ls[0][2], *rs = tr.text + ls[1][0], *rq = tr.text + ls[1][2];
+	const bool qual_ok_f = len[0][2] == F, qual_ok_r = len[1][2] == R;
+#pragma unroll
+	for (int n = 0; n < NI; n++) {
+		const int j = lane + 32 * n;
+		cs[0][n] = j < F ? fs[j] : 'A';
+		cq[0][n] = (j < F && qual_ok_f) ? fq[j] : 1;
+		cs[1][n] = j < R ? rs[R - 1 - j] : 'A';
+		cq[1][n] = (j < R && qual_ok_r) ? rq[R - 1 - j] : 1;
+	}
+	/* letters -> 4-bit codes, once (lut[0..31] = iupac_forward, lut[32..63] = iupac_reverse, nt.c:48-118) */
+#pragma unroll
+	for (int n = 0; n < NI; n++) {
+		cs[0][n] = lut[cs[0][n] & 31u];
+		cs[1][n] = lut[32u + (cs[1][n] & 31u)];
+	}
+	/* checks, in the reference's order (fastq.c:57-99), forward read first */
+	int code = PB_FQ_OK, stage = 3;
+#pragma unroll
+	for (int f = 0; f < 2 && code == PB_FQ_OK; f++) {
+		stage = 3 + f;
+		bool bad = false, nul = false;
+#pragma unroll
+		for (int n = 0; n < NI; n++) {
+			bad |= cs[f][n] == 0u;
+			nul |= cq[f][n] == 0u;
+		}
+		const unsigned plus = f ? plus_r : plus_f;
+		if (raw[f][0] >= PB_FQ_LINE_MAX)
+			code = PB_FQ_LINE_TOO_LONG;
+		else if (__any_sync(FULL, bad))
+			code = PB_FQ_BAD_NT;
+		else if (raw[f][1] >= PB_FQ_LINE_MAX)
+			code = PB_FQ_LINE_TOO_LONG;
+		else if (len[f][1] == 0 || plus != '+')
+			code = letter_code(len[f][1] == 0 ? 0u : plus, f == 1) != 0u ? PB_FQ_READ_TOO_LONG : PB_FQ_PARSE_FAILURE;
+		else if (raw[f][2] >= PB_FQ_LINE_MAX)
+			code = PB_FQ_LINE_TOO_LONG;
+		else if (len[f][2] != (f ? R : F) || __any_sync(FULL, nul))
+			code = PB_FQ_NO_QUALITY_INFO;
+	}
+	pb_pair_meta m;
+	m.off16 = i * stride16;
+	m.flen = 0xFFFF;
+	m.rlen = 0;
+	const unsigned long long rec_at = (unsigned long long) i * stride16 * 16ull;
+	if (code != PB_FQ_OK) {
+		if (lane == 0)
+			report(st, i, stage, code);
+	} else if (F > 0 && rec_at + (unsigned long long) stride16 * 16ull <= reads_cap) {     /* fastq.c:176: an empty forward read is dropped */
+		uint8_t *rec = reads + rec_at;
+		const int fwb = ((F + 7) / 8) * 4, rwb = ((R + 7) / 8) * 4, fqb = ((F + 3) / 4) * 4, rqb = ((R + 3) / 4) * 4;
+		uint8_t *nt_out[2] = { rec, rec + fwb }, *q_out[2] = { rec + fwb + rwb, rec + fwb + rwb + fqb };
+		const int ntb[2] = { fwb, rwb }, qb[2] = { fqb, rqb }, ln[2] = { F, R };
+#pragma unroll
+		for (int f = 0; f < 2; f++)
+#pragma unroll
+			for (int n = 0; n < NI; n++) {
+				const int j = lane + 32 * n;
+				const unsigned c = j < ln[f] ? cs[f][n] : 0u;
+				const unsigned hi = __shfl_down_sync(FULL, c, 1);
+				if ((lane & 1) == 0 && j < 2 * ntb[f])
+					nt_out[f][j >> 1] = (uint8_t) (c | (hi << 4));
+				if (j < qb[f])
+					q_out[f][j] = (uint8_t) (j < ln[f] ? to_index((int) (signed char) cq[f][n], qualmin) : 0);
+			}
+		const int used = fwb + rwb + fqb + rqb, total = (used + 15) & ~15;
+		for (int k = used + lane; k < total; k += 32)
+			rec[k] = 0;
+		m.flen = (uint16_t) F;
+		m.rlen = (uint16_t) R;
+	}
+	if (lane == 0)
+		meta[i] = m;
 }
 
-/* element j of the packed read = read position j (forward) or len-1-j (reverse: template order) */
-__device__ __forceinline__ void pack_read(const Line &seq, const Line &qual, int len, bool reverse, int qualmin,
-                                          uint8_t *nt_out, int nt_bytes, uint8_t *q_out, int q_bytes, int lane) {
-	for (int j0 = 0; j0 < nt_bytes * 2; j0 += 32) {
-		const int j = j0 + lane;
-		unsigned code = 0;
-		if (j < len)
-			code = letter_code(seq.p[reverse ? len - 1 - j : j], reverse);
-		const unsigned hi = __shfl_down_sync(FULL, code, 1);
-		if ((lane & 1) == 0 && j < nt_bytes * 2)
-			nt_out[j >> 1] = (uint8_t) (code | (hi << 4));
-	}
-	for (int j = lane; j < q_bytes; j += 32) {
-		int q = 0;
-		if (j < len)
-			q = to_index((int) (signed char) qual.p[reverse ? len - 1 - j : j], qualmin);
-		q_out[j] = (uint8_t) q;
-	}
-}
-
-__global__ void __launch_bounds__(256) fq_reads(TextView tf, TextView tr, ParseState *st, int qualmin,
-                                                uint8_t *reads, unsigned long long reads_cap, pb_pair_meta *meta) {
+/* NI = characters per lane and line; the host launches the three instantiations back to back and the two whose
+ * length class does not match the chunk return at once (the longest read is known only on the device). */
+template <int NI>
+__global__ void __launch_bounds__(128, (NI <= 5 ? 8 : (NI <= 10 ? 5 : 3))) fq_reads(TextView tf, TextView tr, ParseState *st, int qualmin,
+                                                                                   uint8_t *reads, unsigned long long reads_cap, pb_pair_meta *meta) {
+	const unsigned longest = max(st->max_len[0], st->max_len[1]);
+	const int want = longest <= 160 ? 5 : (longest <= 320 ? 10 : 15);
+	if (want != NI)
+		return;
+	__shared__ uint8_t lut[64];
+	if (threadIdx.x < 64)
+		lut[threadIdx.x] = (uint8_t) letter_code(threadIdx.x & 31u, threadIdx.x >= 32);
+	__syncthreads();
 	const int lane = threadIdx.x & 31;
 	const unsigned records = st->records;
 	const unsigned stride16 = st->stride16;
 	const unsigned warps = (gridDim.x * blockDim.x) >> 5;
-	for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < records; i += warps) {
-		const Line fs = get_line(tf, 4 * i + 1), fp = get_line(tf, 4 * i + 2), fq = get_line(tf, 4 * i + 3);
-		const Line rs = get_line(tr, 4 * i + 1), rp = get_line(tr, 4 * i + 2), rq = get_line(tr, 4 * i + 3);
-		int F = 0, R = 0;
-		int code = check_read(fs, fp, fq, false, F, lane);
-		int stage = 3;
-		if (code == PB_FQ_OK) {
-			code = check_read(rs, rp, rq, true, R, lane);
-			stage = 4;
-		}
-		pb_pair_meta m;
-		m.off16 = i * stride16;
-		m.flen = 0xFFFF;
-		m.rlen = 0;
-		const unsigned long long rec_at = (unsigned long long) i * stride16 * 16ull;
-		if (code != PB_FQ_OK) {
-			if (lane == 0)
-				report(st, i, stage, code);
-		} else if (F > 0 && rec_at + (unsigned long long) stride16 * 16ull <= reads_cap) {     /* fastq.c:176: an empty forward read is dropped */
-			uint8_t *rec = reads + rec_at;
-			const int fwb = ((F + 7) / 8) * 4, rwb = ((R + 7) / 8) * 4, fqb = ((F + 3) / 4) * 4, rqb = ((R + 3) / 4) * 4;
-			pack_read(fs, fq, F, false, qualmin, rec, fwb, rec + fwb + rwb, fqb, lane);
-			pack_read(rs, rq, R, true, qualmin, rec + fwb, rwb, rec + fwb + rwb + fqb, rqb, lane);
-			const int used = fwb + rwb + fqb + rqb, total = (used + 15) & ~15;
-			for (int k = used + lane; k < total; k += 32)
-				rec[k] = 0;
-			m.flen = (uint16_t) F;
-			m.rlen = (uint16_t) R;
-		}
-		if (lane == 0)
-			meta[i] = m;
-	}
+	for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < records; i += warps)
+		reads_record<NI>(tf, tr, st, qualmin, i, stride16, reads, reads_cap, meta, lane, lut);
 }
 
 __global__ void fq_finish(ParseState *st, const pb_pair_meta *meta) {
@@ -569,8 +695,10 @@ __device__ __forceinline__ unsigned long long scaled_micro(double v) {
 	return out;
 }
 __device__ __forceinline__ int f6_chars(unsigned long long micro) {
+	if (micro < 10000000ull)                    /* exp(quality) <= 1: always this branch in practice */
+		return 8;                               /* "d.dddddd" */
 	unsigned long long ip = micro / 1000000ull;
-	int n = 8;                                  /* "d.dddddd" */
+	int n = 8;
 	while (ip >= 10ull) {
 		ip /= 10ull;
 		n++;
@@ -578,6 +706,17 @@ __device__ __forceinline__ int f6_chars(unsigned long long micro) {
 	return n;
 }
 __device__ __forceinline__ int put_f6(char *dst, unsigned long long micro) {
+	if (micro < 10000000ull) {                  /* 32-bit arithmetic: 64-bit division is a subroutine on the GPU */
+		unsigned v = (unsigned) micro;
+#pragma unroll
+		for (int k = 7; k > 1; k--) {
+			dst[k] = (char) ('0' + v % 10u);
+			v /= 10u;
+		}
+		dst[1] = '.';
+		dst[0] = (char) ('0' + v);
+		return 8;
+	}
 	const int n = f6_chars(micro);
 	unsigned long long ip = micro / 1000000ull;
 	unsigned fr = (unsigned) (micro % 1000000ull);
@@ -723,12 +862,11 @@ __global__ void __launch_bounds__(256) fmt_write(int n, int fastq, const pb_pair
                                                  const pb_seq_id *__restrict__ ids, const uint8_t *__restrict__ fwd_text,
                                                  const uint32_t *__restrict__ len_in, const unsigned long long *__restrict__ rec_off,
                                                  const double *__restrict__ score, char *__restrict__ text, unsigned long long capacity) {
-	__shared__ char hdr_s[8][448];
 	__shared__ double s_score[PB_NQ];
 	for (int k = threadIdx.x; k < PB_NQ; k += blockDim.x)
 		s_score[k] = score[k];
 	__syncthreads();
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
 	const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (i >= n)
 		return;
@@ -740,67 +878,52 @@ __global__ void __launch_bounds__(256) fmt_write(int n, int fastq, const pb_pair
 		return;
 	const pb_pair_result r = res[i];
 	const pb_seq_id id = ids[i];
-	char *h = hdr_s[w];
-	int hl = 0;
 	const uint8_t *src = fwd_text + id.hdr_off;
 	const bool sra = id.fmt == PB_IDFMT_SRA || id.fmt == PB_IDFMT_EBI_SRA;
-	if (lane == 0) {
-		/* the numeric pieces and separators; the strings are copied by the whole warp below */
-		int p = 0;
-		h[p++] = fastq ? '@' : '>';
-		if (sra) {
-			h[p++] = id.fmt == PB_IDFMT_SRA ? 'S' : 'E';
-			h[p++] = 'R';
-			h[p++] = 'R';
-			p += put_int(h + p, id.sra);
-		} else {
-			p += id.inst_len;
-		}
-		h[p++] = ':';
-		p += id.run_len;
-		h[p++] = ':';
-		p += id.fc_len;
-		h[p++] = ':';
-		p += put_int(h + p, id.lane);
-		h[p++] = ':';
-		p += put_int(h + p, id.tile);
-		h[p++] = ':';
-		p += put_int(h + p, id.x);
-		h[p++] = ':';
-		p += put_int(h + p, id.y);
-		h[p++] = ':';
-		p += min((int) id.tag_len, PANDA_TAG_LEN);
-		h[p++] = ';';
-		p += put_f6(h + p, scaled_micro(exp(r.quality)));
-		h[p++] = '\n';
-		hl = p;
-	}
-	hl = __shfl_sync(FULL, hl, 0);
-	{
-		int p = 1;
-		if (!sra)
-			for (int k = lane; k < id.inst_len; k += 32)
-				h[p + k] = (char) src[id.inst_off + k];
-		p += (sra ? sra_chars(id.sra) : (int) id.inst_len) + 1;
-		for (int k = lane; k < id.run_len; k += 32)
-			h[p + k] = (char) src[id.run_off + k];
-		p += id.run_len + 1;
-		for (int k = lane; k < id.fc_len; k += 32)
-			h[p + k] = (char) src[id.fc_off + k];
-		p += id.fc_len + 1 + int_chars(id.lane) + 1 + int_chars(id.tile) + 1 + int_chars(id.x) + 1 + int_chars(id.y) + 1;
-		for (int k = lane; k < min((int) id.tag_len, PANDA_TAG_LEN); k += 32)
-			h[p + k] = (char) src[id.tag_off + k];
-	}
-	__syncwarp();
+	/* where every piece of "%s:%s:%s:%d:%d:%d:%d:%s;%f\n" goes (all lanes compute the same layout) */
+	const unsigned long long micro = scaled_micro(exp(r.quality));
+	const int l_inst = sra ? sra_chars(id.sra) : (int) id.inst_len, l_tag = min((int) id.tag_len, PANDA_TAG_LEN);
+	const int p_inst = 1, p_run = p_inst + l_inst + 1, p_fc = p_run + id.run_len + 1, p_lane = p_fc + id.fc_len + 1;
+	const int p_tile = p_lane + int_chars(id.lane) + 1, p_x = p_tile + int_chars(id.tile) + 1, p_y = p_x + int_chars(id.x) + 1;
+	const int p_tag = p_y + int_chars(id.y) + 1, p_q = p_tag + l_tag + 1, hl = p_q + f6_chars(micro) + 1;
 	char *dst = text + off;
-	for (int k = lane; k < hl; k += 32)
-		dst[k] = h[k];
+	if (lane < 10) {                    /* the punctuation, one character per lane */
+		const int at[10] = { 0, p_run - 1, p_fc - 1, p_lane - 1, p_tile - 1, p_x - 1, p_y - 1, p_tag - 1, p_q - 1, hl - 1 };
+		int where = 0;
+#pragma unroll
+		for (int k = 0; k < 10; k++)
+			if (lane == k)
+				where = at[k];
+		dst[where] = lane == 0 ? (fastq ? '@' : '>') : (lane == 8 ? ';' : (lane == 9 ? '\n' : ':'));
+	} else if (lane < 14) {             /* the four integers */
+		const int v = lane == 10 ? id.lane : (lane == 11 ? id.tile : (lane == 12 ? id.x : id.y));
+		const int at = lane == 10 ? p_lane : (lane == 11 ? p_tile : (lane == 12 ? p_x : p_y));
+		put_int(dst + at, v);
+	} else if (lane == 14) {
+		put_f6(dst + p_q, micro);
+	} else if (lane == 15 && sra) {
+		dst[p_inst] = id.fmt == PB_IDFMT_SRA ? 'S' : 'E';
+		dst[p_inst + 1] = 'R';
+		dst[p_inst + 2] = 'R';
+		put_int(dst + p_inst + 3, id.sra);
+	}
+	if (!sra)
+		for (int k = lane; k < id.inst_len; k += 32)
+			dst[p_inst + k] = (char) src[id.inst_off + k];
+	for (int k = lane; k < id.run_len; k += 32)
+		dst[p_run + k] = (char) src[id.run_off + k];
+	for (int k = lane; k < id.fc_len; k += 32)
+		dst[p_fc + k] = (char) src[id.fc_off + k];
+	for (int k = lane; k < l_tag; k += 32)
+		dst[p_tag + k] = (char) src[id.tag_off + k];
 	dst += hl;
 	const uint8_t *nt = seq_nt + (size_t) i * (size_t) (seq_stride / 2);
 	const int L = r.seq_len;
+#pragma unroll 4
 	for (int k = lane; k < L; k += 32) {
 		const unsigned c = (nt[k >> 1] >> ((k & 1) * 4)) & 15u;
-		dst[k] = "NACMGRSVTWYHKDBN"[c];                 /* nt.c:25 */
+		/* nt.c:25 "NACMGRSVTWYHKDBN", eight letters per 64-bit constant */
+		dst[k] = (char) (((c < 8u ? 0x565352474d43414eull : 0x4e42444b48595754ull) >> (8u * (c & 7u))) & 0xFFull);
 	}
 	if (lane == 0)
 		dst[L] = '\n';
@@ -812,6 +935,7 @@ __global__ void __launch_bounds__(256) fmt_write(int n, int fastq, const pb_pair
 		}
 		dst += 2;
 		const double *p = seq_p + (size_t) i * (size_t) seq_stride;
+#pragma unroll 4
 		for (int k = lane; k < L; k += 32)
 			dst[k] = (char) (33 + result_phred(p[k], s_score));
 		if (lane == 0)
