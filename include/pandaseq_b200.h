@@ -274,6 +274,13 @@ enum pb_algo { PB_SIMPLE_BAYES = 0, PB_PEAR = 1, PB_RDP_MLE = 2, PB_FLASH = 3, P
 enum pb_pair_status { PB_PAIR_OK = 0, PB_PAIR_BADR = 1, PB_PAIR_NOFP = 2, PB_PAIR_NORP = 3, PB_PAIR_NOALGN = 4, PB_PAIR_LOWQ = 5,
                       PB_PAIR_SKIP = 6 /* not a pair: a FASTQ record the reader drops (fastq.c:176) or one past the record that ended the stream; never counted */ };
 
+/* One check on an assembled pair (see pb_config.filters). */
+struct pb_filter {
+	int32_t kind;         /* enum pb_filter_kind */
+	int32_t ivalue;
+	double dvalue;
+};
+
 /* Everything assemble_seq/align read from struct panda_assembler (assembler.h:28-79)
  * plus the algorithm's private data, as one plain struct.  panda_* objects are
  * flattened into this before every launch. */
@@ -293,7 +300,31 @@ typedef struct {
 	double pear_random_base;  /* pear: log p of a random base */
 	panda_nt forward_primer[PB_MAX_LEN];
 	panda_nt reverse_primer[PB_MAX_LEN]; /* as the assembler stores it (already complemented) */
+	/* Overhang trimmer in front of the assembler (hang.c:39-72, panda_trim_overhangs): the two sequences as that function
+	 * receives them (args_hang.c:105-107: the reverse one already complemented); 0 length = off.  A pair whose overhang
+	 * sequence is not found is dropped before it reaches the assembler (PB_PAIR_SKIP) unless hang_skip is set. */
+	int64_t hang_forward_length;
+	int64_t hang_reverse_length;
+	int32_t hang_skip;
+	int32_t nfilters;
+	double hang_threshold;    /* passed to panda_compute_offset_qual as is (log space) */
+	panda_nt hang_forward[PB_MAX_LEN];
+	panda_nt hang_reverse[PB_MAX_LEN];
+	/* Filters on the assembled pair, in module order (module.c:124-137): the first one that fails rejects the pair
+	 * (status PB_PAIR_FILTERED + its index, counter PB_C_REJECTED + its index). */
+	struct pb_filter filters[7];
 } pb_config;
+#define PB_MAX_FILTERS 7
+enum pb_filter_kind {
+	PB_FILTER_NONE = 0,
+	PB_FILTER_NO_N = 1,            /* -N: degenerates == 0                          args_assembler.c:106-115 */
+	PB_FILTER_SHORT = 2,           /* -l n: sequence_length >= n                    args_assembler.c:233-239 */
+	PB_FILTER_LONG = 3,            /* -L n: sequence_length <= n                    args_assembler.c:268-275 */
+	PB_FILTER_MIN_OVERLAPBITS = 4, /* min_overlapbits:bits  bits*ln2 <= estimated_overlap_probability, bits >= 0  plugin_min_overlapbits.c:17-50 */
+	PB_FILTER_MISS_THE_POINT = 5,  /* completely_miss_the_point:n  overlap_mismatches <= n   plugin_completely_miss_the_point.c:9-16 */
+	PB_FILTER_MIN_PHRED = 6        /* min_phred:v  every base's panda_result_phred >= v      plugin_min_phred.c:8-22 */
+};
+#define PB_PAIR_FILTERED 8
 
 void pb_config_default(pb_config *cfg, int algo);
 
@@ -302,6 +333,7 @@ void pb_config_default(pb_config *cfg, int algo);
 enum {
 	PB_C_COUNT = 0, PB_C_OK, PB_C_LOWQ, PB_C_NOALGN, PB_C_BADR, PB_C_NOFP, PB_C_NORP, PB_C_SLOW,
 	PB_C_LONGEST,
+	PB_C_REJECTED = 9,     /* [9 .. 15]: pairs rejected by filter 0 .. 6 (the reference's per-module `rejected`, module.c:133) */
 	PB_C_OVERLAPS = 16,
 	PB_NCOUNTERS = 16 + 2 * PB_MAX_LEN
 };

@@ -661,6 +661,60 @@ static void assemble_pair(const po_config *cfg, uint16_t *table, const po_qual *
 
 /* ------------------------------------------------------------ batch driver */
 
+/* hang.c:39-72 with the reversed copies of hang.c:103-106.  Returns 0 when the pair is dropped. */
+static int trim_overhangs(const po_config *cfg, const po_qual *F, size_t *flen, const po_qual *R, size_t *rlen) {
+	char rev[PO_MAX_LEN];
+	if (cfg->hang_forward_length > 0) {
+		size_t n = (size_t) cfg->hang_forward_length, off;
+		for (size_t k = 0; k < n; k++)
+			rev[n - k - 1] = cfg->hang_forward[k];
+		off = po_compute_offset_qual(cfg->hang_threshold, 0, 1, F, *flen, rev, n);
+		if (off == 0) {
+			if (!cfg->hang_skip)
+				return 0;
+		} else {
+			*flen -= off - 1;
+		}
+	}
+	if (cfg->hang_reverse_length > 0) {
+		size_t n = (size_t) cfg->hang_reverse_length, off;
+		for (size_t k = 0; k < n; k++)
+			rev[n - k - 1] = cfg->hang_reverse[k];
+		off = po_compute_offset_qual(cfg->hang_threshold, 0, 1, R, *rlen, rev, n);
+		if (off == 0) {
+			if (!cfg->hang_skip)
+				return 0;
+		} else {
+			*rlen -= off - 1;
+		}
+	}
+	return 1;
+}
+
+/* args_assembler.c:106-115,233-239,268-275; plugin_min_overlapbits.c:17-23; plugin_completely_miss_the_point.c:9-16;
+ * plugin_min_phred.c:8-22.  Returns the index of the first check that fails, -1 if all pass. */
+static int first_failing_filter(const po_config *cfg, const po_one *one) {
+	for (int k = 0; k < cfg->nfilters && k < 7; k++) {
+		const struct po_filter *f = &cfg->filters[k];
+		int pass = 1;
+		switch (f->kind) {
+		case PO_FILTER_NO_N: pass = one->degenerates == 0; break;
+		case PO_FILTER_SHORT: pass = (size_t) one->seq_len >= (size_t) f->ivalue; break;
+		case PO_FILTER_LONG: pass = (size_t) one->seq_len <= (size_t) f->ivalue; break;
+		case PO_FILTER_MIN_OVERLAPBITS: pass = f->dvalue * M_LN2 <= one->est_prob; break;	/* the plugin takes bits and compares nats */
+		case PO_FILTER_MISS_THE_POINT: pass = (size_t) one->mismatches <= (size_t) f->ivalue; break;
+		case PO_FILTER_MIN_PHRED:
+			for (int it = 0; it < one->seq_len && pass; it++)
+				if (po_result_phred(one->p[it]) < f->ivalue)
+					pass = 0;
+			break;
+		}
+		if (!pass)
+			return k;
+	}
+	return -1;
+}
+
 typedef struct {
 	const po_config *cfg;
 	size_t begin, end;
@@ -696,12 +750,36 @@ static void *run_job(void *arg) {
 			job->failed = 1;
 			break;
 		}
+		/* hang.c:39-72: the overhang trimmer sits between the reader and the assembler */
+		if (!trim_overhangs(job->cfg, F, &flen, R, &rlen)) {
+			if (o->status) o->status[i] = PO_SKIP;
+			if (o->slow) o->slow[i] = 0;
+			if (o->overlap) o->overlap[i] = 0;
+			if (o->seq_len) o->seq_len[i] = 0;
+			if (o->mismatches) o->mismatches[i] = 0;
+			if (o->degenerates) o->degenerates[i] = 0;
+			if (o->examined) o->examined[i] = 0;
+			if (o->fwd_offset) o->fwd_offset[i] = 0;
+			if (o->rev_offset) o->rev_offset[i] = 0;
+			if (o->quality) o->quality[i] = 0;
+			if (o->est_prob) o->est_prob[i] = 0;
+			if (o->seq_nt) memset(o->seq_nt + i * (size_t) o->seq_stride, 0, (size_t) o->seq_stride);
+			if (o->seq_p) memset(o->seq_p + i * (size_t) o->seq_stride, 0, (size_t) o->seq_stride * sizeof(double));
+			continue;
+		}
 		if (job->cfg->algo == PO_PEAR) {
 			memset(fpad, 0, sizeof fpad);
 			memcpy(fpad, F, flen * sizeof(po_qual));
 			F = fpad;
 		}
 		assemble_pair(job->cfg, table, F, flen, R, rlen, one);
+		if (one->status == PO_OK) {	/* module_checkseq, module.c:124-137: the first failing check rejects */
+			int k = first_failing_filter(job->cfg, one);
+			if (k >= 0) {
+				one->status = PO_FILTERED + k;
+				job->counters[PO_C_REJECTED + k]++;
+			}
+		}
 		job->counters[PO_C_COUNT]++;
 		if (one->slow)
 			job->counters[PO_C_SLOW]++;
@@ -720,7 +798,7 @@ static void *run_job(void *arg) {
 		}
 		if (o->status) o->status[i] = (uint8_t) one->status;
 		if (o->slow) o->slow[i] = (uint8_t) one->slow;
-		int emitted = (one->status == PO_OK || one->status == PO_LOWQ);
+		int emitted = (one->status == PO_OK || one->status == PO_LOWQ || one->status >= PO_FILTERED);
 		if (o->overlap) o->overlap[i] = emitted ? one->overlap : 0;
 		if (o->seq_len) o->seq_len[i] = emitted ? one->seq_len : 0;
 		if (o->mismatches) o->mismatches[i] = emitted ? one->mismatches : 0;

@@ -30,6 +30,28 @@ typedef struct {
 	int failed;
 } ref_job;
 
+bool no_n_check(PandaLogProxy logger, const panda_result_seq *sequence, void *user_data);      /* args_assembler.c:106 */
+bool short_check(PandaLogProxy logger, const panda_result_seq *sequence, void *user_data);     /* args_assembler.c:233 */
+bool long_check(PandaLogProxy logger, const panda_result_seq *sequence, void *user_data);      /* args_assembler.c:268 */
+#define OPENER(name) bool name##_LTX_opener(PandaLogProxy logger, const char *args, PandaPreCheck *precheck, PandaCheck *check, void **user_data, PandaDestroy *destroy)
+OPENER(min_overlapbits);
+OPENER(completely_miss_the_point);
+OPENER(min_phred);
+
+typedef struct {
+	long rejected[8];
+	int n;
+} reject_counts;
+
+static bool count_rejected(PandaAssembler assembler, PandaModule module, size_t rejected, void *data) {
+	reject_counts *rc = data;
+	(void) assembler;
+	(void) module;
+	if (rc->n < 8)
+		rc->rejected[rc->n++] = (long) rejected;
+	return true;
+}
+
 static PandaAssembler make_assembler(const po_config *cfg) {
 	PandaLogProxy logger = panda_log_proxy_new(panda_writer_new_null());
 	PandaAssembler a = panda_assembler_new_kmer(NULL, NULL, NULL, logger, (size_t) cfg->num_kmers);
@@ -98,6 +120,46 @@ static PandaAssembler make_assembler(const po_config *cfg) {
 		panda_assembler_set_reverse_primer(a, (panda_nt *) cfg->reverse_primer, (size_t) cfg->reverse_primer_length);
 	else
 		panda_assembler_set_reverse_trim(a, (size_t) cfg->reverse_trim);
+	/* module_checkseq (module.c:124-137) with the reference's own check functions: the three built into the library
+	 * (args_assembler.c) and three plugins compiled into this harness from their sources (oracle/Makefile) */
+	PandaLogProxy quiet = panda_log_proxy_new(panda_writer_new_null());
+	for (int k = 0; k < cfg->nfilters && k < 7; k++) {
+		const struct po_filter *f = &cfg->filters[k];
+		PandaModule m = NULL;
+		char args[64];
+		PandaPreCheck precheck = NULL;
+		PandaCheck check = NULL;
+		void *user = NULL;
+		PandaDestroy destroy = NULL;
+		switch (f->kind) {
+		case PO_FILTER_NO_N: m = panda_module_new("N", no_n_check, NULL, NULL, NULL); break;
+		case PO_FILTER_SHORT: m = panda_module_new("SHORT", short_check, NULL, (void *) (size_t) f->ivalue, NULL); break;
+		case PO_FILTER_LONG: m = panda_module_new("LONG", long_check, NULL, (void *) (size_t) f->ivalue, NULL); break;
+		case PO_FILTER_MIN_OVERLAPBITS:
+			snprintf(args, sizeof args, "%.17g", f->dvalue);
+			if (min_overlapbits_LTX_opener(quiet, args, &precheck, &check, &user, &destroy))
+				m = panda_module_new("min_overlapbits", check, precheck, user, destroy);
+			break;
+		case PO_FILTER_MISS_THE_POINT:
+			snprintf(args, sizeof args, "%d", f->ivalue);
+			if (completely_miss_the_point_LTX_opener(quiet, args, &precheck, &check, &user, &destroy))
+				m = panda_module_new("completely_miss_the_point", check, precheck, user, destroy);
+			break;
+		case PO_FILTER_MIN_PHRED:
+			snprintf(args, sizeof args, "%d", f->ivalue);
+			if (min_phred_LTX_opener(quiet, args, &precheck, &check, &user, &destroy))
+				m = panda_module_new("min_phred", check, precheck, user, destroy);
+			break;
+		}
+		if (m == NULL) {
+			panda_log_proxy_unref(quiet);
+			panda_assembler_unref(a);
+			return NULL;
+		}
+		panda_assembler_add_module(a, m);
+		panda_module_unref(m);
+	}
+	panda_log_proxy_unref(quiet);
 	return a;
 }
 
@@ -114,28 +176,38 @@ double ref_effective_threshold(const po_config *cfg) {
 	return t;
 }
 
-static void *run_job(void *arg) {
-	ref_job *job = arg;
+static void blank_row(po_flat_out *o, size_t i, int status) {
+	if (o->status) o->status[i] = (uint8_t) status;
+	if (o->slow) o->slow[i] = 0;
+	if (o->overlap) o->overlap[i] = 0;
+	if (o->seq_len) o->seq_len[i] = 0;
+	if (o->mismatches) o->mismatches[i] = 0;
+	if (o->degenerates) o->degenerates[i] = 0;
+	if (o->examined) o->examined[i] = 0;
+	if (o->fwd_offset) o->fwd_offset[i] = 0;
+	if (o->rev_offset) o->rev_offset[i] = 0;
+	if (o->quality) o->quality[i] = 0;
+	if (o->est_prob) o->est_prob[i] = 0;
+	if (o->seq_nt) memset(o->seq_nt + i * (size_t) o->seq_stride, 0, (size_t) o->seq_stride);
+	if (o->seq_p) memset(o->seq_p + i * (size_t) o->seq_stride, 0, (size_t) o->seq_stride * sizeof(double));
+}
+
+static void process_one(ref_job *job, PandaAssembler a, size_t i, const panda_qual *F, size_t flen, const panda_qual *R, size_t rlen) {
 	po_flat_out *o = job->out;
-	PandaAssembler a = make_assembler(job->cfg);
 	panda_seq_identifier id;
 	panda_qual fpad[PO_MAX_LEN];
-	memset(job->counters, 0, sizeof job->counters);
+	reject_counts before, after;
 	memset(&id, 0, sizeof id);
-	if (a == NULL) {
-		job->failed = 1;
-		return NULL;
-	}
-	for (size_t i = job->begin; i < job->end; i++) {
-		size_t flen = job->f_off[i + 1] - job->f_off[i];
-		size_t rlen = job->r_off[i + 1] - job->r_off[i];
-		const panda_qual *F = (const panda_qual *) (job->f_data + job->f_off[i]);
-		const panda_qual *R = (const panda_qual *) (job->r_data + job->r_off[i]);
+	memset(&before, 0, sizeof before);
+	memset(&after, 0, sizeof after);
+	{
 		long slow_before = panda_assembler_get_slow_count(a);
 		long lowq_before = panda_assembler_get_low_quality_count(a);
 		long badr_before = panda_assembler_get_bad_read_count(a);
 		long nofp_before = panda_assembler_get_no_forward_primer_count(a);
 		long norp_before = panda_assembler_get_no_reverse_primer_count(a);
+		long noalgn_before = panda_assembler_get_failed_alignment_count(a);
+		panda_assembler_foreach_module(a, count_rejected, &before);
 		if (job->cfg->algo == PO_PEAR) {
 			/* algo_pear.c:52,54 read forward[rindex]; pin the out-of-range case to zeros. */
 			memset(fpad, 0, sizeof fpad);
@@ -154,8 +226,15 @@ static void *run_job(void *arg) {
 			status = PO_NOFP;
 		else if (panda_assembler_get_no_reverse_primer_count(a) != norp_before)
 			status = PO_NORP;
-		else
+		else if (panda_assembler_get_failed_alignment_count(a) != noalgn_before)
 			status = PO_NOALGN;
+		else {
+			status = PO_NOALGN;
+			panda_assembler_foreach_module(a, count_rejected, &after);
+			for (int k = 0; k < after.n; k++)
+				if (after.rejected[k] != before.rejected[k])
+					status = PO_FILTERED + k;
+		}
 		if (o->status) o->status[i] = (uint8_t) status;
 		if (o->slow) o->slow[i] = (uint8_t) (panda_assembler_get_slow_count(a) != slow_before);
 		/* On LOWQ the reference returns NULL but has filled its result; that object is
@@ -185,6 +264,65 @@ static void *run_job(void *arg) {
 					dst[k] = res->sequence[k].p;
 		}
 	}
+}
+
+/* the pairs of a job as a PandaNextSeq, so that the reference's own panda_trim_overhangs can sit on top (hang.c:82-113) */
+typedef struct {
+	ref_job *job;
+	size_t cur;
+} pair_source;
+
+static bool pair_source_next(panda_seq_identifier *id, const panda_qual **forward, size_t *forward_length,
+                             const panda_qual **reverse, size_t *reverse_length, void *user) {
+	pair_source *src = user;
+	ref_job *job = src->job;
+	if (src->cur >= job->end)
+		return false;
+	size_t i = src->cur++;
+	memset(id, 0, sizeof *id);
+	*forward = (const panda_qual *) (job->f_data + job->f_off[i]);
+	*forward_length = job->f_off[i + 1] - job->f_off[i];
+	*reverse = (const panda_qual *) (job->r_data + job->r_off[i]);
+	*reverse_length = job->r_off[i + 1] - job->r_off[i];
+	return true;
+}
+
+static void *run_job(void *arg) {
+	ref_job *job = arg;
+	PandaAssembler a = make_assembler(job->cfg);
+	memset(job->counters, 0, sizeof job->counters);
+	if (a == NULL) {
+		job->failed = 1;
+		return NULL;
+	}
+	if (job->cfg->hang_forward_length > 0 || job->cfg->hang_reverse_length > 0) {
+		pair_source src = { job, job->begin };
+		void *next_data = NULL;
+		PandaDestroy next_destroy = NULL;
+		PandaLogProxy logger = panda_log_proxy_new(panda_writer_new_null());
+		PandaNextSeq next = panda_trim_overhangs(pair_source_next, &src, NULL, logger, (panda_nt *) job->cfg->hang_forward,
+		                                         (size_t) job->cfg->hang_forward_length, (panda_nt *) job->cfg->hang_reverse,
+		                                         (size_t) job->cfg->hang_reverse_length, job->cfg->hang_skip != 0, job->cfg->hang_threshold,
+		                                         &next_data, &next_destroy);
+		for (;;) {
+			panda_seq_identifier id;
+			const panda_qual *F, *R;
+			size_t flen, rlen, before = src.cur;
+			bool more = next(&id, &F, &flen, &R, &rlen, next_data);
+			size_t upto = more ? src.cur - 1 : job->end;
+			for (size_t i = before; i < upto; i++)
+				blank_row(job->out, i, PO_SKIP);       /* dropped by the trimmer: the assembler never sees them */
+			if (!more)
+				break;
+			process_one(job, a, src.cur - 1, F, flen, R, rlen);
+		}
+		next_destroy(next_data);
+		panda_log_proxy_unref(logger);
+	} else {
+		for (size_t i = job->begin; i < job->end; i++)
+			process_one(job, a, i, (const panda_qual *) (job->f_data + job->f_off[i]), job->f_off[i + 1] - job->f_off[i],
+			            (const panda_qual *) (job->r_data + job->r_off[i]), job->r_off[i + 1] - job->r_off[i]);
+	}
 	job->counters[PO_C_COUNT] = panda_assembler_get_count(a);
 	job->counters[PO_C_OK] = panda_assembler_get_ok_count(a);
 	job->counters[PO_C_LOWQ] = panda_assembler_get_low_quality_count(a);
@@ -194,6 +332,13 @@ static void *run_job(void *arg) {
 	job->counters[PO_C_NORP] = panda_assembler_get_no_reverse_primer_count(a);
 	job->counters[PO_C_SLOW] = panda_assembler_get_slow_count(a);
 	job->counters[PO_C_LONGEST] = (int64_t) panda_assembler_get_longest_overlap(a);
+	{
+		reject_counts rc;
+		memset(&rc, 0, sizeof rc);
+		panda_assembler_foreach_module(a, count_rejected, &rc);
+		for (int k = 0; k < rc.n && k < 7; k++)
+			job->counters[PO_C_REJECTED + k] = rc.rejected[k];
+	}
 	for (size_t k = 0; k < 2 * PO_MAX_LEN; k++)
 		job->counters[PO_C_OVERLAPS + k] = panda_assembler_get_overlap_count(a, k);
 	panda_assembler_unref(a);

@@ -35,6 +35,15 @@ class PandaseqError(RuntimeError):
     pass
 
 
+class PbFilter(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ivalue", C.c_int32), ("dvalue", C.c_double)]
+
+
+FILTERS = {"no_n": 1, "short": 2, "long": 3, "min_overlapbits": 4, "completely_miss_the_point": 5, "min_phred": 6}
+STATUS_FILTERED = 8
+C_REJECTED = 9
+
+
 class PbConfig(C.Structure):
     """mirror of pb_config (and, by construction, of oracle/panda_oracle.h po_config)"""
     _fields_ = [
@@ -45,6 +54,10 @@ class PbConfig(C.Structure):
         ("threshold", C.c_double), ("primer_penalty", C.c_double),
         ("sb_q", C.c_double), ("pear_random_base", C.c_double),
         ("forward_primer", C.c_char * PB_MAX_LEN), ("reverse_primer", C.c_char * PB_MAX_LEN),
+        ("hang_forward_length", C.c_int64), ("hang_reverse_length", C.c_int64), ("hang_skip", C.c_int32), ("nfilters", C.c_int32),
+        ("hang_threshold", C.c_double),
+        ("hang_forward", C.c_char * PB_MAX_LEN), ("hang_reverse", C.c_char * PB_MAX_LEN),
+        ("filters", PbFilter * 7),
     ]
 
 
@@ -97,7 +110,8 @@ class PbStreamInfo(C.Structure):
 
 def make_config(algo="simple_bayesian", *, threshold=0.6, minoverlap=2, maxoverlap=0, forward_primer=None,
                 reverse_primer=None, forward_trim=0, reverse_trim=0, primer_penalty=0.0, sb_q=0.36,
-                pear_random_base=None, post_primers=False, num_kmers=2) -> PbConfig:
+                pear_random_base=None, post_primers=False, num_kmers=2, hang_forward=None, hang_reverse=None, hang_skip=False,
+                hang_threshold=None, filters=()) -> PbConfig:
     """Flat assembler configuration.  Primers are sequences of panda_nt codes *as the assembler
     stores them* (the reverse primer already complemented, args_assembler.c:222)."""
     cfg = PbConfig()
@@ -120,6 +134,25 @@ def make_config(algo="simple_bayesian", *, threshold=0.6, minoverlap=2, maxoverl
         C.memmove(C.byref(cfg, PbConfig.reverse_primer.offset), rp, len(rp))
     else:
         cfg.reverse_trim = int(reverse_trim)
+    # overhang trimmer: panda_nt codes as panda_trim_overhangs receives them (the reverse one already complemented)
+    if hang_forward is not None and len(hang_forward):
+        hf = bytes(int(x) & 0xFF for x in hang_forward)
+        cfg.hang_forward_length = len(hf)
+        C.memmove(C.byref(cfg, PbConfig.hang_forward.offset), hf, len(hf))
+    if hang_reverse is not None and len(hang_reverse):
+        hr = bytes(int(x) & 0xFF for x in hang_reverse)
+        cfg.hang_reverse_length = len(hr)
+        C.memmove(C.byref(cfg, PbConfig.hang_reverse.offset), hr, len(hr))
+    cfg.hang_skip = int(bool(hang_skip))
+    cfg.hang_threshold = cfg.threshold if hang_threshold is None else float(hang_threshold)
+    # filters: sequence of (name, value) in module order, e.g. [("no_n", 0), ("short", 100), ("min_overlapbits", -20.0)]
+    cfg.nfilters = len(filters)
+    for k, (name, value) in enumerate(filters):
+        cfg.filters[k].kind = FILTERS[name]
+        if name == "min_overlapbits":
+            cfg.filters[k].dvalue = float(value)
+        else:
+            cfg.filters[k].ivalue = int(value)
     return cfg
 
 

@@ -160,9 +160,14 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 	if (max_len <= 0 || max_len > PB_MAX_LEN)
 		max_len = PB_MAX_LEN;
 	/* the full kernel carries the primer scans and the log()-based scorers; everything else runs the lean one */
-	const bool full = cfg->post_primers != 0 || cfg->forward_primer_length > 0 || cfg->reverse_primer_length > 0
-		|| cfg->algo == PB_EA_UTIL || cfg->algo == PB_STITCH;
-#define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, cfg->post_primers != 0); \
+	const bool full0 = cfg->post_primers != 0 || cfg->forward_primer_length > 0 || cfg->reverse_primer_length > 0
+		|| cfg->algo == PB_EA_UTIL || cfg->algo == PB_STITCH || cfg->hang_forward_length > 0 || cfg->hang_reverse_length > 0;
+	bool stage_seq = cfg->post_primers != 0;
+	for (int k = 0; k < cfg->nfilters && k < PB_MAX_FILTERS; k++)
+		if (cfg->filters[k].kind == PB_FILTER_MIN_PHRED)
+			stage_seq = true;
+	const bool full = full0 || stage_seq;
+#define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq); \
 	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false); } while (0)
 	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */
 	if (max_len <= 160) {

@@ -40,6 +40,17 @@ typedef struct {
 	int32_t post_primers;       /* assembler.c:300-333: locate the primers on the assembled sequence instead of the reads */
 	uint8_t forward_primer[PB_MAX_LEN + 2];
 	uint8_t reverse_primer[PB_MAX_LEN + 2];
+	/* overhang trimmer: the two sequences REVERSED, as hang.c:103-106 stores them for its end-first scans */
+	int32_t hang_forward_length;
+	int32_t hang_reverse_length;
+	int32_t hang_skip;
+	int32_t nfilters;
+	int32_t need_stage;         /* a filter reads the per-base log p (min_phred): the sequence is staged as for primers-after */
+	int32_t pad0;
+	double hang_threshold;
+	uint8_t hang_forward[PB_MAX_LEN + 2];
+	uint8_t hang_reverse[PB_MAX_LEN + 2];
+	struct pb_filter filters[PB_MAX_FILTERS];
 } pb_device_params;
 
 /* pb_luts.c */

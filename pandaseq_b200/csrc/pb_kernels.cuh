@@ -588,8 +588,89 @@ __device__ __forceinline__ double recon_words(const ReconArgs &ra, const double 
 
 /* FULLF = false is the lean instantiation: no primers (before or after assembly) and no log()-based scorers
  * (ea_util, stitch); the host picks it whenever the configuration allows, which keeps the common kernel small. */
+/* hang.c:39-72: the overhang trimmer, applied to the staged record in place.  The forward read keeps a prefix; the
+ * reverse read keeps a prefix in READ order, i.e. a suffix of its template-order copy, which is moved to the front.
+ * Returns false when the pair is dropped (sequence not found and hang_skip unset). */
+template <int ML>
+__device__ bool trim_overhangs(uint8_t *rec, int F0, int R0, int &F, int &R, const pb_device_params *__restrict__ prm,
+                               const double *__restrict__ s_score, const uint16_t *__restrict__ s_qoff, int lane) {
+	const int fwb = ((F0 + 7) / 8) * 4, rwb = ((R0 + 7) / 8) * 4;
+	uint32_t *fnt32 = reinterpret_cast<uint32_t *>(rec), *rnt32 = reinterpret_cast<uint32_t *>(rec + fwb);
+	int8_t *fq = reinterpret_cast<int8_t *>(rec + fwb + rwb), *rq = fq + ((F0 + 3) / 4) * 4;
+	F = F0;
+	R = R0;
+	if (prm->hang_forward_length > 0) {
+		/* index i of the scan is read position F-1-i: the "template order" form of primer_offset */
+		const int off = primer_offset<true>(fnt32, fq, F0, prm->hang_forward, prm->hang_forward_length, prm->hang_threshold, 0.0, s_score, s_qoff, lane);
+		if (off == 0) {
+			if (!prm->hang_skip)
+				return false;
+		} else {
+			F = F0 - (off - 1);
+		}
+	}
+	if (prm->hang_reverse_length > 0) {
+		/* the reverse read is stored in template order: scan index i (read position R-1-i) is element i */
+		const int off = primer_offset<false>(rnt32, rq, R0, prm->hang_reverse, prm->hang_reverse_length, prm->hang_threshold, 0.0, s_score, s_qoff, lane);
+		if (off == 0) {
+			if (!prm->hang_skip)
+				return false;
+		} else {
+			R = R0 - (off - 1);
+		}
+	}
+	__syncwarp();
+	if (F < F0) {        /* bases past the new end must read as padding */
+		const int w = F >> 3;
+		if (lane == 0) {
+			fnt32[w] &= nibmask(F & 7);
+			if (w + 1 < fwb / 4)
+				fnt32[w + 1] = 0;
+		}
+	}
+	if (R < R0) {
+		const int d = R0 - R, nw = (R + 7) >> 3, nq = (R + 3) >> 2;
+		uint32_t nt_new[(ML + 7) / 8 / 32 + 1], q_new[(ML + 3) / 4 / 32 + 1];
+		const uint32_t *rq32 = reinterpret_cast<const uint32_t *>(rq);
+#pragma unroll
+		for (int k = 0; k < (ML + 7) / 8 / 32 + 1; k++) {
+			const int w = k * 32 + lane;
+			nt_new[k] = w < nw ? (nibwin(rnt32, 8 * w + d) & nibmask(min(R - 8 * w, 8))) : 0u;
+		}
+#pragma unroll
+		for (int k = 0; k < (ML + 3) / 4 / 32 + 1; k++) {
+			const int w = k * 32 + lane;
+			unsigned v = 0;
+			if (w < nq) {
+				const int b = 4 * w + d;
+				v = __funnelshift_r(rq32[b >> 2], rq32[(b >> 2) + 1], (b & 3) * 8);
+				const int keep = min(R - 4 * w, 4);
+				if (keep < 4)
+					v &= (1u << (8 * keep)) - 1u;
+			}
+			q_new[k] = v;
+		}
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < (ML + 7) / 8 / 32 + 1; k++) {
+			const int w = k * 32 + lane;
+			if (w < rwb / 4)
+				rnt32[w] = nt_new[k];
+		}
+		uint32_t *rq32w = reinterpret_cast<uint32_t *>(rq);
+#pragma unroll
+		for (int k = 0; k < (ML + 3) / 4 / 32 + 1; k++) {
+			const int w = k * 32 + lane;
+			if (w < ((R0 + 3) >> 2))
+				rq32w[w] = q_new[k];
+		}
+	}
+	__syncwarp();
+	return true;
+}
+
 template <int ML, bool FULLF>
-__device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
+__device__ void process_pair(WarpSmem<ML> &ws, uint8_t *rec, int F, int R,
                              const pb_device_params *__restrict__ prm,
                              const double *__restrict__ s_recon, const double *__restrict__ s_over,
                              const double *__restrict__ s_score, const double *__restrict__ s_score_err,
@@ -597,8 +678,6 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
                              pb_pair_result &res, uint8_t *out_nt, double *out_p, int out_cap, int lane) {
 	using WS = WarpSmem<ML>;
 	PairView v;
-	v.F = F;
-	v.R = R;
 	const int fwb = ((F + 7) / 8) * 4, rwb = ((R + 7) / 8) * 4;
 	v.fnt = rec;
 	v.rnt = rec + fwb;
@@ -606,6 +685,22 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 	v.rnt32 = reinterpret_cast<const uint32_t *>(v.rnt);
 	v.fq = (const int8_t *) (rec + fwb + rwb);
 	v.rq = v.fq + ((F + 3) / 4) * 4;
+	if (FULLF && (prm->hang_forward_length > 0 || prm->hang_reverse_length > 0)) {
+		int Ft, Rt;
+		if (!trim_overhangs<ML>(rec, F, R, Ft, Rt, prm, s_score, s_qoff, lane)) {
+			res.status = PB_PAIR_SKIP;         /* the reader drops the pair: the assembler never sees it */
+			res.slow = 0;
+			res.overlap = res.seq_len = res.mismatches = res.degenerates = res.examined = 0;
+			res.fwd_offset = res.rev_offset = 0;
+			res.quality = 0.0;
+			res.est_prob = 0.0;
+			return;
+		}
+		F = Ft;
+		R = Rt;
+	}
+	v.F = F;
+	v.R = R;
 
 	res.status = PB_PAIR_OK;
 	res.slow = 0;
@@ -622,6 +717,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 	const int mo = prm->minoverlap;
 	int fo, ro;
 	const bool post = FULLF && prm->post_primers != 0;   /* assembler.c:262,285-288: primers are located after assembly instead */
+	const bool staged = FULLF && (post || prm->need_stage != 0);   /* the assembled sequence goes through this warp's scratch */
 	/* assembler.c:262-284 (primers before assembly) */
 	if (post) {
 		fo = 0;
@@ -850,7 +946,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 		ra.fnt32 = v.fnt32; ra.rnt32 = v.rnt32; ra.fq = v.fq; ra.rq = v.rq;
 		ra.fo = fo; ra.df = df; ra.dfp = dfp; ra.fend = dfp + nover; ra.seq_len = seq_len;
 		ra.unmasked_f = unmasked_f; ra.lead_r = lead_r; ra.out_nt = out_nt; ra.out_p = out_p; ra.out_cap = out_cap; ra.qoff = s_qoff;
-		if (post) {        /* the whole assembled sequence goes to this warp's scratch first */
+		if (staged) {      /* the whole assembled sequence goes to this warp's scratch first */
 			ra.out_p = reinterpret_cast<double *>(scratch);
 			ra.out_nt = scratch + 912 * 8;
 			ra.out_cap = 912;
@@ -869,12 +965,15 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 	res.seq_len = (uint16_t) seq_len;
 	res.mismatches = (uint16_t) mism;
 	res.degenerates = (uint16_t) degen;
-	if (FULLF && post) {                             /* assembler.c:300-333 */
+	int min_phred = 127;
+	if (FULLF && staged) {                           /* assembler.c:300-333 */
 		__syncwarp();
 		const double *sp = reinterpret_cast<const double *>(scratch);
 		const uint32_t *snt32 = reinterpret_cast<const uint32_t *>(scratch + 912 * 8);
-		int pfo, pro;
-		if (prm->forward_primer_length > 0) {
+		int pfo = 0, pro = 0;
+		if (!post) {
+			/* staged only because a filter reads the per-base log p: nothing is stripped */
+		} else if (prm->forward_primer_length > 0) {
 			pfo = primer_offset_result(snt32, sp, seq_len, false, s_primer, prm->forward_primer_length, prm->threshold, prm->primer_penalty, lane);
 			if (pfo == 0) {
 				res.status = PB_PAIR_NOFP;
@@ -884,8 +983,10 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 		} else {
 			pfo = prm->forward_trim;
 		}
-		res.fwd_offset = (uint16_t) pfo;
-		if (prm->reverse_primer_length > 0) {
+		if (post)
+			res.fwd_offset = (uint16_t) pfo;
+		if (!post) {
+		} else if (prm->reverse_primer_length > 0) {
 			pro = primer_offset_result(snt32, sp, seq_len, true, s_primer + PB_MAX_LEN + 2, prm->reverse_primer_length, prm->threshold, prm->primer_penalty, lane);
 			if (pro == 0) {
 				res.status = PB_PAIR_NORP;
@@ -895,8 +996,9 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 		} else {
 			pro = prm->reverse_trim;
 		}
-		res.rev_offset = (uint16_t) pro;
-		if (seq_len <= pfo + pro) {
+		if (post)
+			res.rev_offset = (uint16_t) pro;
+		if (post && seq_len <= pfo + pro) {
 			res.status = PB_PAIR_NOFP;               /* sic: assembler.c:324-328 */
 			return;
 		}
@@ -913,10 +1015,60 @@ __device__ void process_pair(WarpSmem<ML> &ws, const uint8_t *rec, int F, int R,
 				if (k < out_cap)
 					out_p[k] = sp[pfo + k];
 		}
+		if (prm->need_stage) {                       /* plugin_min_phred.c:15-20 over what is emitted */
+			int mp = 127;
+			for (int k = lane; k < newlen; k += 32) {
+				/* nt.c:126-150 */
+				const double p = sp[pfo + k];
+				int lower = 0, upper = PB_PHREDMAX, ph = -1;
+				if (p <= s_score[0])
+					ph = 1;
+				while (ph < 0 && lower < upper) {
+					const int mid = lower + (upper - lower) / 2;
+					const double sc = s_score[mid];
+					if (sc == p)
+						ph = mid;
+					else if (mid == lower)
+						ph = lower;
+					else if (sc > p)
+						upper = mid;
+					else
+						lower = mid + 1;
+				}
+				if (ph < 0)
+					ph = lower;
+				mp = min(mp, ph);
+			}
+			min_phred = __reduce_min_sync(FULL, mp);
+		}
 		__syncwarp();                                /* scratch is reused by this warp's next pair */
 	}
-	if (res.quality < prm->threshold)                /* assembler.c:334-338 */
+	if (res.quality < prm->threshold) {              /* assembler.c:334-338 */
 		res.status = PB_PAIR_LOWQ;
+		return;
+	}
+	/* module_checkseq (module.c:124-137): the first failing check rejects the pair */
+	const int nf = prm->nfilters;
+	for (int k = 0; k < nf; k++) {
+		const int kind = prm->filters[k].kind, iv = prm->filters[k].ivalue;
+		bool pass = true;
+		if (kind == PB_FILTER_NO_N)
+			pass = res.degenerates == 0;
+		else if (kind == PB_FILTER_SHORT)
+			pass = (int) res.seq_len >= iv;
+		else if (kind == PB_FILTER_LONG)
+			pass = (int) res.seq_len <= iv;
+		else if (kind == PB_FILTER_MIN_OVERLAPBITS)
+			pass = prm->filters[k].dvalue * 0.693147180559945309417232121458 <= res.est_prob;     /* bits -> nats, M_LN2 */
+		else if (kind == PB_FILTER_MISS_THE_POINT)
+			pass = (int) res.mismatches <= iv;
+		else if (kind == PB_FILTER_MIN_PHRED)
+			pass = min_phred >= iv;
+		if (!pass) {
+			res.status = (uint8_t) (PB_PAIR_FILTERED + k);
+			return;
+		}
+	}
 }
 
 template <int ML, bool OVER, int WARPS_PER_BLOCK, bool FULLF>
@@ -1023,7 +1175,8 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 			uint4 *dst = reinterpret_cast<uint4 *>(&results[pair]);
 			dst[0] = ru.v[0];
 			dst[1] = ru.v[1];
-			atomicAdd(&s_cnt[PB_C_COUNT], 1u);
+			if (res.status != PB_PAIR_SKIP)
+				atomicAdd(&s_cnt[PB_C_COUNT], 1u);
 			if (res.slow)
 				atomicAdd(&s_cnt[PB_C_SLOW], 1u);
 			switch (res.status) {
@@ -1037,6 +1190,8 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 			case PB_PAIR_BADR: atomicAdd(&s_cnt[PB_C_BADR], 1u); break;
 			case PB_PAIR_NOFP: atomicAdd(&s_cnt[PB_C_NOFP], 1u); break;
 			case PB_PAIR_NORP: atomicAdd(&s_cnt[PB_C_NORP], 1u); break;
+			case PB_PAIR_SKIP: break;
+			default: atomicAdd(&s_cnt[PB_C_REJECTED + res.status - PB_PAIR_FILTERED], 1u); break;
 			}
 		}
 		__syncwarp();      /* every lane is done with this stage before it is refilled */

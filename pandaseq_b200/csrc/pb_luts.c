@@ -192,7 +192,34 @@ pb_status pb_build_device_params(const pb_config *cfg, pb_device_params *out) {
 		pb_set_error("configuration outside the ranges the reference's setters allow");
 		return PB_ERR_ARGUMENT;
 	}
+	if (cfg->hang_forward_length < 0 || cfg->hang_forward_length >= PB_MAX_LEN || cfg->hang_reverse_length < 0
+	    || cfg->hang_reverse_length >= PB_MAX_LEN || cfg->nfilters < 0 || cfg->nfilters > PB_MAX_FILTERS) {
+		pb_set_error("overhang sequences must be shorter than %d, at most %d filters", PB_MAX_LEN, PB_MAX_FILTERS);
+		return PB_ERR_ARGUMENT;
+	}
+	for (int k = 0; k < cfg->nfilters; k++) {
+		const struct pb_filter *f = &cfg->filters[k];
+		if (f->kind < PB_FILTER_NO_N || f->kind > PB_FILTER_MIN_PHRED || (f->kind == PB_FILTER_MIN_OVERLAPBITS && !(f->dvalue >= 0))
+		    || (f->kind != PB_FILTER_MIN_OVERLAPBITS && f->ivalue < 0)) {
+			pb_set_error("filter %d: unknown kind or value out of range", k);
+			return PB_ERR_ARGUMENT;
+		}
+	}
 	memset(out, 0, sizeof *out);
+	out->hang_forward_length = (int32_t) cfg->hang_forward_length;
+	out->hang_reverse_length = (int32_t) cfg->hang_reverse_length;
+	out->hang_skip = cfg->hang_skip ? 1 : 0;
+	out->hang_threshold = cfg->hang_threshold;
+	for (int k = 0; k < cfg->hang_forward_length; k++)      /* hang.c:103-104 */
+		out->hang_forward[cfg->hang_forward_length - k - 1] = (uint8_t) cfg->hang_forward[k] & 15;
+	for (int k = 0; k < cfg->hang_reverse_length; k++)      /* hang.c:105-106 */
+		out->hang_reverse[cfg->hang_reverse_length - k - 1] = (uint8_t) cfg->hang_reverse[k] & 15;
+	out->nfilters = cfg->nfilters;
+	for (int k = 0; k < cfg->nfilters; k++) {
+		out->filters[k] = cfg->filters[k];
+		if (cfg->filters[k].kind == PB_FILTER_MIN_PHRED)
+			out->need_stage = 1;
+	}
 	out->algo = cfg->algo;
 	out->minoverlap = (int32_t) cfg->minoverlap;
 	out->maxoverlap = (int32_t) cfg->maxoverlap;

@@ -107,3 +107,28 @@ def edge_cases():
         t = rng.integers(0, 4, size=L + L // 2)
         pairs.append((1 << t[:L], q(L), 1 << t[::-1][:L], q(L)))
     return synth.FlatBatch.from_pairs(pairs)
+
+
+def overhang(n=2000, seed=21):
+    """Amplicons shorter than the reads (inserts 60-200 nt between the two 17-nt primers, 2x150 reads): most reads run
+    through the far primer into unrelated sequence -- what the overhang trimmer (hang.c) cuts off."""
+    return synth.generate(n, rl=(150, 150), tmpl=(60, 200), seed=seed, primers=True, n_rate=0.002, btail_rate=0.05).to_flat()
+
+
+def overhang_codes():
+    """(-P, -Q) sequences as panda_trim_overhangs receives them (args_hang.c:105-107): what follows the insert in the forward
+    read, and -- complemented at parse time -- what follows it in the reverse read."""
+    fwd = synth.encode(synth.revcomp(synth.REV_PRIMER))
+    rev = synth.encode("".join(synth._COMP[c] for c in synth.revcomp(synth.FWD_PRIMER)))
+    return fwd, rev
+
+
+FILTER_SETS = [
+    [("no_n", 0)],
+    [("short", 200), ("long", 240)],
+    [("long", 230), ("no_n", 0), ("short", 190)],
+    [("min_overlapbits", 120.0)],
+    [("completely_miss_the_point", 1)],
+    [("min_phred", 12)],
+    [("min_phred", 4), ("completely_miss_the_point", 3), ("min_overlapbits", 100.5), ("no_n", 0), ("short", 185), ("long", 270)],
+]

@@ -44,6 +44,10 @@ CASES = {
     "lowcomplexity_sb": (lambda: datasets.low_complexity(200), dict(algo="simple_bayesian")),
     "edge_cases_sb": (lambda: datasets.edge_cases(), dict(algo="simple_bayesian")),
     "edge_cases_rdp_maxov800": (lambda: datasets.edge_cases(), dict(algo="rdp_mle", maxoverlap=800)),
+    "cfg1_filters_rdp": (lambda: datasets.cfg1(300), dict(algo="rdp_mle", filters=datasets.FILTER_SETS[-1])),
+    "cfg1_filters_sb": (lambda: datasets.cfg1(300), dict(algo="simple_bayesian", filters=[("long", 230), ("no_n", 0), ("short", 190), ("min_phred", 8)])),
+    "overhang_sb": (lambda: datasets.overhang(300), dict(algo="simple_bayesian", hang=True)),
+    "overhang_strict_pear_filters": (lambda: datasets.overhang(300, seed=4), dict(algo="pear", hang=True, hang_threshold=-0.0003, filters=[("short", 80)])),
 }
 
 
@@ -53,6 +57,9 @@ def build_config(spec):
     if kw.pop("primers", False):
         fwd, rev = datasets.primer_codes()
         kw.update(forward_primer=fwd, reverse_primer=rev)
+    if kw.pop("hang", False):
+        hf, hr = datasets.overhang_codes()
+        kw.update(hang_forward=hf, hang_reverse=hr)
     return pb.make_config(algo, **kw)
 
 

@@ -27,7 +27,7 @@ def compare(got: dict, want: dict, *, emitted_only_ok=False, check_counters=True
     if emitted_only_ok:
         rows = want["status"] == 0
     else:
-        rows = (want["status"] == 0) | (want["status"] == 5)
+        rows = (want["status"] == 0) | (want["status"] == 5) | (want["status"] >= 8)       # OK, LOWQ, rejected by a filter
     rows &= res["status"] == want["status"]
     for k in INT_FIELDS:
         if k == "examined" and not emitted_only_ok:

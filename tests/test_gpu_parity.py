@@ -172,3 +172,48 @@ def test_primers_after_assembly(ctx, algo):
     for batch, kw in cases:
         got, want, rep = run_both(ctx, pb.make_config(algo, post_primers=True, **kw), batch)
         assert rep["ok"], (kw.keys(), rep)
+
+
+# ---- the stages SURVEY.md 8f ranks 3 and 4: overhang trimmer (hang.c) and filters on the assembled pair (module.c) ----
+@pytest.mark.parametrize("filters", datasets.FILTER_SETS)
+@pytest.mark.parametrize("algo", ["simple_bayesian", "rdp_mle"])
+def test_filters(ctx, filters, algo):
+    got, want, rep = run_both(ctx, pb.make_config(algo, filters=filters), datasets.cfg1(3000))
+    assert rep["ok"], rep
+    assert (got["results"]["status"] >= 8).sum() == want["counters"][pb.C_REJECTED:pb.C_REJECTED + 7].sum()
+
+
+def test_filters_after_primer_strip(ctx):
+    fwd, rev = datasets.primer_codes()
+    cfg = pb.make_config("simple_bayesian", forward_primer=fwd, reverse_primer=rev, post_primers=True,
+                         filters=[("short", 440), ("min_phred", 3), ("long", 480)])
+    got, want, rep = run_both(ctx, cfg, datasets.primers300(600))
+    assert rep["ok"], rep
+
+
+@pytest.mark.parametrize("skip", [False, True])
+@pytest.mark.parametrize("which", ["both", "forward", "reverse"])
+@pytest.mark.parametrize("algo", ["simple_bayesian", "pear", "rdp_mle"])
+def test_overhang_trimmer(ctx, skip, which, algo):
+    hf, hr = datasets.overhang_codes()
+    kw = dict(hang_forward=hf if which != "reverse" else None, hang_reverse=hr if which != "forward" else None, hang_skip=skip)
+    got, want, rep = run_both(ctx, pb.make_config(algo, **kw), datasets.overhang(2000))
+    assert rep["ok"], rep
+
+
+def test_overhang_strict_threshold_drops_pairs(ctx):
+    hf, hr = datasets.overhang_codes()
+    b = datasets.overhang(2000, seed=4)
+    cfg = pb.make_config("simple_bayesian", hang_forward=hf, hang_reverse=hr, hang_threshold=np.log(0.9997), filters=[("short", 80), ("no_n", 0)])
+    got, want, rep = run_both(ctx, cfg, b)
+    assert rep["ok"], rep
+    dropped = (got["results"]["status"] == 6).sum()
+    assert 0 < dropped < b.n and got["counters"][pb.C_COUNT] == b.n - dropped
+
+
+def test_overhang_mixed_lengths_and_long_reads(ctx):
+    """the trimmer on the other read-length classes (the reverse read's suffix move depends on the class)"""
+    hf, hr = datasets.overhang_codes()
+    for b in (datasets.mixed(1500), datasets.long250(600), datasets.primers300(400)):
+        got, want, rep = run_both(ctx, pb.make_config("simple_bayesian", hang_forward=hf[:9], hang_reverse=hr[:9]), b)
+        assert rep["ok"], rep
