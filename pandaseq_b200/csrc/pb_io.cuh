@@ -198,9 +198,10 @@ __global__ void fq_stride(ParseState *st) {
 
 /* ---- identifiers: seqid.c:136-285, one thread per record -------------------------------------------------------- */
 struct Cursor {
-	const uint8_t *s;
+	const uint8_t *s;       /* the header as a C string: a NUL (or the end of the line, `len`) ends it */
 	int pos, len;
-	__device__ __forceinline__ int cur() const { return pos < len ? (int) s[pos] : 0; }    /* 0 = end of the C string */
+	bool terminated;        /* s[len] == 0: no bounds test needed */
+	__device__ __forceinline__ int cur() const { return (terminated || pos < len) ? (int) s[pos] : 0; }
 };
 __device__ __forceinline__ bool is_delim(int c) {
 	return c == 0 || c == ':' || c == '#' || c == '/' || c == ' ';
@@ -263,8 +264,8 @@ __device__ __forceinline__ bool tag_policy_ok(int tag_len, int policy) {
 }
 
 /* returns the direction (0 = failure).  hdr/len: the header line after its first character, ended by a NUL if it has one */
-__device__ int parse_id(const uint8_t *hdr, int len, int policy, IdFields &f) {
-	Cursor c = { hdr, 0, len };
+__device__ int parse_id(const uint8_t *hdr, int len, int policy, IdFields &f, bool terminated) {
+	Cursor c = { hdr, 0, len, terminated };
 	/* one pass: where the C string ends, whether it holds a '/', and the ':' before the first '#' (seqid.c:170-178) */
 	bool slash = false, hashed = false;
 	int colons = 0;
@@ -418,11 +419,16 @@ __global__ void __launch_bounds__(ID_THREADS) fq_ids(TextView tf, TextView tr, P
 		const uint8_t *a = flen - 1 <= ID_STAGE ? stage[0][threadIdx.x] + ((s_start[0][threadIdx.x] + 1u) & 3u) : gf;
 		const uint8_t *b = rlen - 1 <= ID_STAGE ? stage[1][threadIdx.x] + ((s_start[1][threadIdx.x] + 1u) & 3u) : gr;
 		/* fastq.c:125 hands the parser `line + 1` without looking at the first character */
-		const int fdir = (fraw < PB_FQ_LINE_MAX && flen > 0) ? parse_id(a, flen - 1, policy, f) : 0;
+		const bool fterm = flen - 1 <= ID_STAGE, rterm = rlen - 1 <= ID_STAGE;
+		if (fterm && flen > 0)
+			const_cast<uint8_t *>(a)[flen - 1] = 0;
+		if (rterm && rlen > 0)
+			const_cast<uint8_t *>(b)[rlen - 1] = 0;
+		const int fdir = (fraw < PB_FQ_LINE_MAX && flen > 0) ? parse_id(a, flen - 1, policy, f, fterm) : 0;
 		if (fdir == 0) {
 			report(st, i, 0, fraw >= PB_FQ_LINE_MAX ? PB_FQ_LINE_TOO_LONG : PB_FQ_ID_PARSE_FAILURE);
 		} else {
-			const int rdir = (rraw < PB_FQ_LINE_MAX && rlen > 0) ? parse_id(b, rlen - 1, policy, r) : 0;
+			const int rdir = (rraw < PB_FQ_LINE_MAX && rlen > 0) ? parse_id(b, rlen - 1, policy, r, rterm) : 0;
 			if (rdir == 0) {
 				report(st, i, 1, rraw >= PB_FQ_LINE_MAX ? PB_FQ_LINE_TOO_LONG : PB_FQ_ID_PARSE_FAILURE);
 			} else {
@@ -654,16 +660,11 @@ __global__ void fq_finish(ParseState *st, const pb_pair_meta *meta) {
 
 /* ---- output: output.c:85-126 -------------------------------------------------------------------------------- */
 __device__ __forceinline__ int int_chars(int v) {          /* strlen of "%d" */
-	unsigned u = v < 0 ? 0u - (unsigned) v : (unsigned) v;
-	int n = v < 0 ? 2 : 1;
-	while (u >= 10u) {
-		u /= 10u;
-		n++;
-	}
-	return n;
+	const unsigned u = v < 0 ? 0u - (unsigned) v : (unsigned) v;
+	return (v < 0 ? 2 : 1) + (u >= 10u) + (u >= 100u) + (u >= 1000u) + (u >= 10000u) + (u >= 100000u) + (u >= 1000000u)
+		+ (u >= 10000000u) + (u >= 100000000u) + (u >= 1000000000u);
 }
-__device__ __forceinline__ int put_int(char *dst, int v) {
-	const int n = int_chars(v);
+__device__ __forceinline__ int put_int(char *dst, int v, int n) {      /* n = int_chars(v) */
 	unsigned u = v < 0 ? 0u - (unsigned) v : (unsigned) v;
 	for (int k = n - 1; k >= (v < 0 ? 1 : 0); k--) {
 		dst[k] = (char) ('0' + u % 10u);
@@ -884,8 +885,9 @@ __global__ void __launch_bounds__(256) fmt_write(int n, int fastq, const pb_pair
 	const unsigned long long micro = scaled_micro(exp(r.quality));
 	const int l_inst = sra ? sra_chars(id.sra) : (int) id.inst_len, l_tag = min((int) id.tag_len, PANDA_TAG_LEN);
 	const int p_inst = 1, p_run = p_inst + l_inst + 1, p_fc = p_run + id.run_len + 1, p_lane = p_fc + id.fc_len + 1;
-	const int p_tile = p_lane + int_chars(id.lane) + 1, p_x = p_tile + int_chars(id.tile) + 1, p_y = p_x + int_chars(id.x) + 1;
-	const int p_tag = p_y + int_chars(id.y) + 1, p_q = p_tag + l_tag + 1, hl = p_q + f6_chars(micro) + 1;
+	const int l_lane = int_chars(id.lane), l_tile = int_chars(id.tile), l_x = int_chars(id.x), l_y = int_chars(id.y);
+	const int p_tile = p_lane + l_lane + 1, p_x = p_tile + l_tile + 1, p_y = p_x + l_x + 1;
+	const int p_tag = p_y + l_y + 1, p_q = p_tag + l_tag + 1, hl = p_q + f6_chars(micro) + 1;
 	char *dst = text + off;
 	if (lane < 10) {                    /* the punctuation, one character per lane */
 		const int at[10] = { 0, p_run - 1, p_fc - 1, p_lane - 1, p_tile - 1, p_x - 1, p_y - 1, p_tag - 1, p_q - 1, hl - 1 };
@@ -898,32 +900,52 @@ __global__ void __launch_bounds__(256) fmt_write(int n, int fastq, const pb_pair
 	} else if (lane < 14) {             /* the four integers */
 		const int v = lane == 10 ? id.lane : (lane == 11 ? id.tile : (lane == 12 ? id.x : id.y));
 		const int at = lane == 10 ? p_lane : (lane == 11 ? p_tile : (lane == 12 ? p_x : p_y));
-		put_int(dst + at, v);
+		put_int(dst + at, v, lane == 10 ? l_lane : (lane == 11 ? l_tile : (lane == 12 ? l_x : l_y)));
 	} else if (lane == 14) {
 		put_f6(dst + p_q, micro);
 	} else if (lane == 15 && sra) {
 		dst[p_inst] = id.fmt == PB_IDFMT_SRA ? 'S' : 'E';
 		dst[p_inst + 1] = 'R';
 		dst[p_inst + 2] = 'R';
-		put_int(dst + p_inst + 3, id.sra);
+		put_int(dst + p_inst + 3, id.sra, l_inst - 3);
 	}
-	if (!sra)
-		for (int k = lane; k < id.inst_len; k += 32)
-			dst[p_inst + k] = (char) src[id.inst_off + k];
-	for (int k = lane; k < id.run_len; k += 32)
-		dst[p_run + k] = (char) src[id.run_off + k];
-	for (int k = lane; k < id.fc_len; k += 32)
-		dst[p_fc + k] = (char) src[id.fc_off + k];
+	if (!sra && id.run_off == id.inst_off + id.inst_len + 1 && id.fc_off == id.run_off + id.run_len + 1) {
+		/* "instrument:run:flowcell" stand next to each other in the header: one copy, the two separators are rewritten as ':' below */
+		const int n = id.inst_len + 1 + id.run_len + 1 + id.fc_len;
+		for (int k = lane; k < n; k += 32) {
+			const bool sep = k == id.inst_len || k == id.inst_len + 1 + id.run_len;
+			dst[p_inst + k] = sep ? ':' : (char) src[id.inst_off + k];
+		}
+	} else {
+		if (!sra)
+			for (int k = lane; k < id.inst_len; k += 32)
+				dst[p_inst + k] = (char) src[id.inst_off + k];
+		for (int k = lane; k < id.run_len; k += 32)
+			dst[p_run + k] = (char) src[id.run_off + k];
+		for (int k = lane; k < id.fc_len; k += 32)
+			dst[p_fc + k] = (char) src[id.fc_off + k];
+	}
 	for (int k = lane; k < l_tag; k += 32)
 		dst[p_tag + k] = (char) src[id.tag_off + k];
 	dst += hl;
 	const uint8_t *nt = seq_nt + (size_t) i * (size_t) (seq_stride / 2);
 	const int L = r.seq_len;
-#pragma unroll 4
-	for (int k = lane; k < L; k += 32) {
-		const unsigned c = (nt[k >> 1] >> ((k & 1) * 4)) & 15u;
-		/* nt.c:25 "NACMGRSVTWYHKDBN", eight letters per 64-bit constant */
-		dst[k] = (char) (((c < 8u ? 0x565352474d43414eull : 0x4e42444b48595754ull) >> (8u * (c & 7u))) & 0xFFull);
+	{
+		/* nt.c:25 "NACMGRSVTWYHKDBN": a byte-permute picks the letter of a 3-bit index out of a register pair */
+		const uint32_t *nt32 = reinterpret_cast<const uint32_t *>(nt);
+		const int nw = (L + 7) >> 3;
+		for (int w = lane; w < nw; w += 32) {
+			unsigned x = nt32[w];
+			const int n = min(L - 8 * w, 8);
+#pragma unroll
+			for (int t = 0; t < 8; t++) {
+				const unsigned c = x & 15u;
+				x >>= 4;
+				const unsigned lo = __byte_perm(0x4D43414Eu, 0x56535247u, c & 7u), hi = __byte_perm(0x48595754u, 0x4E42444Bu, c & 7u);
+				if (t < n)
+					dst[8 * w + t] = (char) ((c & 8u) ? hi : lo);
+			}
+		}
 	}
 	if (lane == 0)
 		dst[L] = '\n';
