@@ -178,6 +178,8 @@ def lib() -> C.CDLL:
     L.pb_context_stream.restype = vp
     L.pb_synchronize.argtypes = [vp]
     L.pb_synchronize.restype = i32
+    L.pb_lanes_stats.argtypes = [vp, vp, vp]
+    L.pb_lanes_stats.restype = i32
     L.pb_config_default.argtypes = [C.POINTER(PbConfig), i32]
     L.pb_get_tables.restype = C.POINTER(PbTables)
     L.pb_layout_host.argtypes = [sz, vp, vp, vp]
@@ -249,6 +251,12 @@ class Context:
 
     def synchronize(self):
         _check(lib().pb_synchronize(self._h), "pb_synchronize")
+
+    def lanes_stats(self):
+        """(pairs launched on the lane-per-pair kernel, pairs it handed to the general kernel) since the context was created."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().pb_lanes_stats(self._h, C.byref(a), C.byref(b)), "pb_lanes_stats")
+        return int(a.value), int(b.value)
 
     # ---- host-buffer (e2e) path ----------------------------------------------------
     def assemble_host(self, cfg: PbConfig, batch, *, want_nt=True, want_p=False, seq_stride=None):

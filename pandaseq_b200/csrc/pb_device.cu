@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "pb_kernels.cuh"
+#include "pb_lanes.cuh"
 
 #include "pb_ctx.h"
 
@@ -50,6 +51,8 @@ extern "C" pb_status pb_context_create(int device, pb_context **out) {
 	CUDA_TRY(cudaMalloc(&ctx->d_params, sizeof(pb_device_params)));
 	CUDA_TRY(cudaMallocHost(&ctx->h_params, sizeof(pb_device_params)));
 	CUDA_TRY(cudaMalloc(&ctx->d_counters, PB_NCOUNTERS * sizeof(unsigned long long)));
+	CUDA_TRY(cudaMalloc(&ctx->d_defer_total, sizeof(unsigned long long)));
+	CUDA_TRY(cudaMemset(ctx->d_defer_total, 0, sizeof(unsigned long long)));
 	for (int s = 0; s < 2; s++)
 		CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot[s].done, cudaEventDisableTiming));
 	*out = ctx;
@@ -80,6 +83,9 @@ extern "C" void pb_context_destroy(pb_context *ctx) {
 	cudaFreeHost(ctx->h_params);
 	cudaFree(ctx->d_counters);
 	cudaFree(ctx->d_scratch);
+	cudaFree(ctx->d_defer[0]);
+	cudaFree(ctx->d_defer[1]);
+	cudaFree(ctx->d_defer_total);
 	pb_io_release(ctx);
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->copy_stream);
@@ -104,6 +110,14 @@ pb_status pb_upload_params(pb_context *ctx, const pb_config *cfg) {
 	if (st != PB_OK)
 		return st;
 	CUDA_TRY(cudaMemcpyAsync(ctx->d_params, ctx->h_params, sizeof(pb_device_params), cudaMemcpyHostToDevice, ctx->stream));
+	ctx->recon_symmetric = true;
+	for (int m = 0; m < 2 && ctx->recon_symmetric; m++)
+		for (int a = 0; a < PB_NQM && ctx->recon_symmetric; a++)
+			for (int b = 0; b < a; b++)
+				if (memcmp(&ctx->h_params->recon[m][a][b], &ctx->h_params->recon[m][b][a], sizeof(double)) != 0) {
+					ctx->recon_symmetric = false;
+					break;
+				}
 	ctx->cached_cfg = *cfg;
 	ctx->cfg_valid = true;
 	return PB_OK;
@@ -112,7 +126,8 @@ pb_status pb_upload_params(pb_context *ctx, const pb_config *cfg) {
 template <int ML, bool OVER, int WARPS, bool FULLF>
 static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
                                  pb_pair_result *d_results, uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride,
-                                 unsigned long long *d_counters, cudaStream_t stream, bool post) {
+                                 unsigned long long *d_counters, cudaStream_t stream, bool post,
+                                 const int *d_list = nullptr, const int *d_list_n = nullptr) {
 	auto kern = pb::assemble_kernel<ML, OVER, WARPS, FULLF>;
 	constexpr size_t smem = pb::assemble_smem_bytes<ML, OVER, WARPS>();
 	static bool configured[16] = { false };
@@ -147,9 +162,47 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 		scratch = ctx->d_scratch + (stream == ctx->copy_stream ? need / 2 : 0);
 	}
 	kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p,
-	                                                           (long long) seq_stride, d_counters, scratch);
+	                                                           (long long) seq_stride, d_counters, scratch, d_list, d_list_n);
 	CUDA_TRY(cudaGetLastError());
 	return PB_OK;
+}
+
+/* The lane-per-pair kernel (pb_lanes.cuh) over the whole batch, then the general kernel over the pairs it deferred. */
+template <int ML, int WARPS, int GW>
+static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
+                              pb_pair_result *d_results, uint8_t *d_seq_nt, size_t seq_stride,
+                              unsigned long long *d_counters, cudaStream_t stream) {
+	auto kern = pbl::assemble_lanes_kernel<ML, WARPS>;
+	constexpr size_t smem = pbl::lanes_smem_bytes<ML, WARPS>();
+	static bool configured[16] = { false };
+	if (!configured[ctx->device & 15]) {
+		CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		configured[ctx->device & 15] = true;
+	}
+	const int si = stream == ctx->copy_stream ? 1 : 0;
+	if ((size_t) n + 4 > ctx->defer_cap[si]) {
+		CUDA_TRY(cudaDeviceSynchronize());
+		cudaFree(ctx->d_defer[si]);
+		ctx->d_defer[si] = nullptr;
+		ctx->defer_cap[si] = 0;
+		const size_t cap = (size_t) n + (size_t) n / 4 + 64;
+		CUDA_TRY(cudaMalloc(&ctx->d_defer[si], cap * sizeof(int)));
+		ctx->defer_cap[si] = cap;
+	}
+	int *d_count = ctx->d_defer[si], *d_list = ctx->d_defer[si] + 4;
+	CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+	const long long nbatch = ((long long) n + 31) / 32;
+	long long grid = ((long long) nbatch + WARPS - 1) / WARPS;
+	if (grid > ctx->sm_count)
+		grid = ctx->sm_count;
+	if (grid < 1)
+		grid = 1;
+	kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_results, d_seq_nt, (long long) seq_stride,
+	                                                      d_counters, d_list, d_count, ctx->d_defer_total);
+	CUDA_TRY(cudaGetLastError());
+	ctx->lanes_pairs += (unsigned long long) n;
+	return launch_assemble<ML, false, GW, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, nullptr, seq_stride, d_counters, stream, false,
+	                                             d_list, d_count);
 }
 
 pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int max_len,
@@ -167,6 +220,15 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 		if (cfg->filters[k].kind == PB_FILTER_MIN_PHRED)
 			stage_seq = true;
 	const bool full = full0 || stage_seq;
+	/* the common case goes lane-per-pair (pb_lanes.cuh); PANDASEQ_B200_LANES=0 keeps everything on the general kernel */
+	static int lanes_on = -1;
+	if (lanes_on < 0) {
+		const char *env = getenv("PANDASEQ_B200_LANES");
+		lanes_on = (env && atoi(env) == 0) ? 0 : 1;
+	}
+	if (lanes_on && !full && !d_seq_p && max_len <= 160 && ctx->recon_symmetric && cfg->forward_trim == 0 && cfg->reverse_trim == 0
+	    && (cfg->algo == PB_SIMPLE_BAYES || cfg->algo == PB_UPARSE || cfg->algo == PB_FLASH) && ((uintptr_t) d_seq_nt % 8) == 0)
+		return launch_lanes<160, 4, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
 #define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq); \
 	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false); } while (0)
 	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */
@@ -227,6 +289,20 @@ extern "C" pb_status pb_pack_device(pb_context *ctx, size_t n,
 	                                                      (const uint8_t *) d_r_data, (const unsigned long long *) d_r_off, 0ull,
 	                                                      d_rec_off16, d_reads, d_meta);
 	CUDA_TRY(cudaGetLastError());
+	return PB_OK;
+}
+
+extern "C" pb_status pb_lanes_stats(pb_context *ctx, uint64_t *lanes_pairs, uint64_t *deferred_pairs) {
+	if (!ctx || !lanes_pairs || !deferred_pairs) {
+		pb_set_error("pb_lanes_stats: bad argument");
+		return PB_ERR_ARGUMENT;
+	}
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	CUDA_TRY(cudaDeviceSynchronize());
+	unsigned long long d = 0;
+	CUDA_TRY(cudaMemcpy(&d, ctx->d_defer_total, sizeof d, cudaMemcpyDeviceToHost));
+	*lanes_pairs = ctx->lanes_pairs;
+	*deferred_pairs = d;
 	return PB_OK;
 }
 

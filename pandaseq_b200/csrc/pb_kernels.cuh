@@ -1076,9 +1076,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 assemble_kernel(const pb_device_params *__restrict__ prm, int n,
                 const uint8_t *__restrict__ reads, const pb_pair_meta *__restrict__ meta,
                 pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, double *__restrict__ seq_p,
-                long long seq_stride, unsigned long long *__restrict__ counters, uint8_t *__restrict__ scratch_all) {
+                long long seq_stride, unsigned long long *__restrict__ counters, uint8_t *__restrict__ scratch_all,
+                const int *__restrict__ list, const int *__restrict__ list_n) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	using WS = WarpSmem<ML>;
+	/* list mode: assemble pairs list[0 .. *list_n) -- the ones the lane-per-pair kernel (pb_lanes.cuh) deferred */
+	if (list)
+		n = *list_n;
 	/* block-level: LUTs + counters, then the per-warp areas */
 	constexpr int OVER_N = OVER ? 2 * PB_NQ * PB_NQ : 0;
 	double *s_recon = reinterpret_cast<double *>(smem_raw);
@@ -1133,9 +1137,9 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 	const long long nt_row = seq_stride / 2;
 	uint8_t *scratch = scratch_all ? scratch_all + (size_t) wglobal * PB_SCRATCH_STRIDE : nullptr;
 
-	auto issue = [&](int pair, int stage) {
+	auto issue = [&](int k, int stage) {
 		if (lane == 0) {
-			pb_pair_meta m = meta[pair];
+			pb_pair_meta m = meta[list ? list[k] : k];
 			ws.meta[stage] = m;
 			unsigned bytes = m.flen == 0xFFFFu ? 0u : record_bytes(m.flen, m.rlen);     /* 0xFFFF: not a pair (FASTQ reader) */
 			mbar_expect_tx(&ws.bar[stage], bytes);
@@ -1144,14 +1148,15 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 		}
 	};
 
-	int pair = wglobal;
-	if (pair < n)
-		issue(pair, 0);
-	for (int it = 0; pair < n; it++, pair += wstride) {
+	int item = wglobal;
+	if (item < n)
+		issue(item, 0);
+	for (int it = 0; item < n; it++, item += wstride) {
 		const int stage = it & 1;
-		const int next = pair + wstride;
+		const int next = item + wstride;
 		if (next < n)
 			issue(next, stage ^ 1);
+		const int pair = list ? list[item] : item;
 		mbar_wait(&ws.bar[stage], (it >> 1) & 1);
 		const pb_pair_meta m = ws.meta[stage];
 		union { pb_pair_result r; uint4 v[2]; } ru;

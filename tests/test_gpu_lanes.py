@@ -1,0 +1,158 @@
+"""GPU parity of the lane-per-pair kernel (pb_lanes.cuh) and of its hand-over to the general kernel.
+
+Configurations without per-base log p, primers or trims and with reads <= 160 nt are dispatched to the lane-per-pair
+kernel; pairs it does not cover (N or IUPAC codes, qualities outside 0..46, no seed, tiny reads) are appended to a
+deferral list and assembled by the general kernel in a second launch.  Either way the result must equal the oracle's:
+integer fields and merged bases bit-exact, quality / overlap score within 1e-6 (the lane kernel adds in the reference's
+order, so its quality is in fact identical)."""
+import numpy as np
+import pytest
+
+import datasets
+import oracle_lib
+import pandaseq_b200 as pb
+from pandaseq_b200 import synth
+from parity import compare
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = pb.Context(0)
+    yield c
+    c.close()
+
+
+def run_lanes(ctx, cfg, batch, *, expect_lanes=True, seq_stride=None):
+    before = ctx.lanes_stats()
+    got = ctx.assemble_host(cfg, batch, want_nt=True, want_p=False, seq_stride=seq_stride)
+    after = ctx.lanes_stats()
+    want = oracle_lib.assemble("port", cfg, batch)
+    rep = compare(got, want)
+    rep["lanes_pairs"] = after[0] - before[0]
+    rep["deferred"] = after[1] - before[1]
+    if expect_lanes is True:
+        assert rep["lanes_pairs"] == batch.n, rep
+    elif expect_lanes is False:
+        assert rep["lanes_pairs"] == 0, rep
+    return got, want, rep
+
+
+def clean(n, seed=1, tmpl=(180, 280), rl=(150, 150)):
+    """A/C/G/T only, qualities 2..41: what the lane-per-pair kernel keeps for itself."""
+    return synth.generate(n, rl=rl, tmpl=tmpl, seed=seed).to_flat()
+
+
+@pytest.mark.parametrize("algo", ["simple_bayesian", "uparse", "flash"])
+def test_clean_pairs_stay_on_the_lane_kernel(ctx, algo):
+    b = clean(20_000, seed=101)
+    got, want, rep = run_lanes(ctx, pb.make_config(algo), b)
+    assert rep["ok"], rep
+    assert rep["deferred"] <= b.n // 500, rep         # only the pairs without any seed (SLOW) are handed on
+    assert rep["max_dq"] == 0.0 and rep["max_dp"] == 0.0, rep
+
+
+@pytest.mark.parametrize("algo", ["simple_bayesian", "uparse", "flash"])
+def test_cfg1_with_n_and_b_tails(ctx, algo):
+    # 0.1 % N and 5 % '#' tails: about a quarter of the pairs carry an N and are handed to the general kernel
+    got, want, rep = run_lanes(ctx, pb.make_config(algo), datasets.cfg1())
+    assert rep["ok"], rep
+    assert 0 < rep["deferred"] < rep["n"], rep
+
+
+@pytest.mark.parametrize("maxoverlap", [0, 140, 300])
+def test_read_through_stress(ctx, maxoverlap):
+    # inserts shorter than the reads: no seed inside the bitset (SLOW), overlaps longer than a read when maxoverlap allows
+    got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian", maxoverlap=maxoverlap), datasets.stress())
+    assert rep["ok"], rep
+
+
+def test_b_tails_without_n(ctx):
+    b = synth.generate(8000, rl=(150, 150), tmpl=(160, 290), seed=31, btail_rate=0.5).to_flat()
+    got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian"), b)
+    assert rep["ok"], rep
+    assert rep["deferred"] <= b.n // 100, rep
+    assert rep["max_dq"] == 0.0, rep
+
+
+def test_short_and_unequal_reads(ctx):
+    rng = np.random.default_rng(5)
+    pairs = []
+    for i in range(3000):
+        F, R = int(rng.integers(16, 161)), int(rng.integers(16, 161))
+        L = int(rng.integers(max(F, R), F + R - 1))
+        t = rng.integers(0, 4, size=L)
+        f, r = t[:F].copy(), t[::-1][:R].copy()
+        for arr in (f, r):
+            m = rng.random(len(arr)) < 0.02
+            arr[m] = (arr[m] + rng.integers(1, 4, size=int(m.sum()))) & 3
+        pairs.append((1 << f, rng.integers(0, 47, size=F), 1 << r, rng.integers(0, 47, size=R)))
+    b = synth.FlatBatch.from_pairs(pairs)
+    got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian"), b)
+    assert rep["ok"], rep
+    assert rep["max_dq"] == 0.0, rep
+
+
+def test_thresholds_minoverlap_and_error_estimate(ctx):
+    b = clean(6000, seed=9, tmpl=(152, 296))
+    for kw in (dict(threshold=0.9), dict(threshold=0.3, minoverlap=30), dict(minoverlap=140, maxoverlap=145), dict(sb_q=0.1),
+               dict(maxoverlap=100), dict(minoverlap=149)):
+        got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian", **kw), b)
+        assert rep["ok"], (kw, rep)
+
+
+def test_low_complexity(ctx):
+    # homopolymers and short tandem repeats: the same code at many positions, long probe chains, many candidates
+    got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian"), datasets.low_complexity())
+    assert rep["ok"], rep
+
+
+def test_edge_cases_mix_of_classes(ctx):
+    # reads of every size next to each other: the chunk holding the 450-nt reads goes to the general kernel as a whole
+    got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian"), datasets.edge_cases(), expect_lanes=None)
+    assert rep["ok"], rep
+
+
+def test_edge_cases_up_to_160(ctx):
+    full = datasets.edge_cases()
+    fl, rl = full.lengths()
+    keep = [i for i in range(full.n) if fl[i] <= 160 and rl[i] <= 160]
+    pairs = []
+    for i in keep:
+        f, r = full.pair(i)
+        pairs.append((f[:, 0], f[:, 1], r[:, 0], r[:, 1]))
+    b = synth.FlatBatch.from_pairs(pairs)
+    got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian"), b)
+    assert rep["ok"], rep
+    got, want, rep = run_lanes(ctx, pb.make_config("flash"), b)
+    assert rep["ok"], rep
+
+
+@pytest.mark.parametrize("filters", [f for f in datasets.FILTER_SETS if not any(k == "min_phred" for k, _ in f)])
+def test_filters_on_the_result_record(ctx, filters):
+    b = datasets.cfg1(4000)
+    cfg = pb.make_config("simple_bayesian", filters=filters)
+    got, want, rep = run_lanes(ctx, cfg, b)
+    assert rep["ok"], rep
+
+
+def test_row_capacity_smaller_than_the_sequence(ctx):
+    b = clean(2000, seed=12)
+    got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian"), b, seq_stride=208)
+    res = got["results"]
+    assert (res["status"] == want["status"]).all() and (res["seq_len"] == want["seq_len"]).all()
+    w = 208
+    sl = np.minimum(want["seq_len"], w)
+    ok = want["status"] == 0
+    mask = (np.arange(w)[None, :] < sl[:, None]) & ok[:, None]
+    assert not ((got["seq_nt"][:, :w] != want["seq_nt"][:, :w]) & mask).any()
+
+
+def test_trims_and_per_base_p_use_the_general_kernel(ctx):
+    b = clean(1000, seed=13)
+    run_lanes(ctx, pb.make_config("simple_bayesian", forward_trim=5), b, expect_lanes=False)
+    before = ctx.lanes_stats()
+    ctx.assemble_host(pb.make_config("simple_bayesian"), b, want_nt=True, want_p=True)
+    assert ctx.lanes_stats()[0] == before[0]
+    run_lanes(ctx, pb.make_config("pear"), b, expect_lanes=False)
