@@ -21,9 +21,9 @@ struct pb_context {
 	/* deferral lists of the lane-per-pair kernel, one per stream of the host path: [0] = count, [4 ..] = pair indices */
 	int *d_defer[2];
 	size_t defer_cap[2];
+	uint32_t *d_seeds[2];            /* candidate-overlap masks of pb::seed_kernel, 8 words per pair */
 	unsigned long long *d_defer_total;   /* pairs deferred so far (device), next to lanes_pairs (host) */
 	unsigned long long lanes_pairs;
-	bool recon_symmetric;            /* recon[k][a][b] == recon[k][b][a] for the uploaded parameters (pb_lanes.cuh stores a triangle) */
 	pthread_mutex_t lock;            /* one host-path call at a time per context (assemblers share the process-wide one) */
 	/* host-path staging (grown on demand) */
 	struct Slot {

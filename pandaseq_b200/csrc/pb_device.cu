@@ -85,6 +85,8 @@ extern "C" void pb_context_destroy(pb_context *ctx) {
 	cudaFree(ctx->d_scratch);
 	cudaFree(ctx->d_defer[0]);
 	cudaFree(ctx->d_defer[1]);
+	cudaFree(ctx->d_seeds[0]);
+	cudaFree(ctx->d_seeds[1]);
 	cudaFree(ctx->d_defer_total);
 	pb_io_release(ctx);
 	cudaStreamDestroy(ctx->stream);
@@ -110,14 +112,6 @@ pb_status pb_upload_params(pb_context *ctx, const pb_config *cfg) {
 	if (st != PB_OK)
 		return st;
 	CUDA_TRY(cudaMemcpyAsync(ctx->d_params, ctx->h_params, sizeof(pb_device_params), cudaMemcpyHostToDevice, ctx->stream));
-	ctx->recon_symmetric = true;
-	for (int m = 0; m < 2 && ctx->recon_symmetric; m++)
-		for (int a = 0; a < PB_NQM && ctx->recon_symmetric; a++)
-			for (int b = 0; b < a; b++)
-				if (memcmp(&ctx->h_params->recon[m][a][b], &ctx->h_params->recon[m][b][a], sizeof(double)) != 0) {
-					ctx->recon_symmetric = false;
-					break;
-				}
 	ctx->cached_cfg = *cfg;
 	ctx->cfg_valid = true;
 	return PB_OK;
@@ -167,15 +161,20 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 	return PB_OK;
 }
 
-/* The lane-per-pair kernel (pb_lanes.cuh) over the whole batch, then the general kernel over the pairs it deferred. */
-template <int ML, int WARPS, int GW>
+/* The two-kernel path for the common configurations: pb::seed_kernel (warp per pair, K1-K3) leaves the candidate
+ * overlaps of every pair, pbl::assemble_lanes_kernel (lane per pair, K4-K6) scores and merges, and the general kernel
+ * assembles the pairs those two handed on. */
+template <int ML, int SW, int LW, int GW>
 static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
                               pb_pair_result *d_results, uint8_t *d_seq_nt, size_t seq_stride,
                               unsigned long long *d_counters, cudaStream_t stream) {
-	auto kern = pbl::assemble_lanes_kernel<ML, WARPS>;
-	constexpr size_t smem = pbl::lanes_smem_bytes<ML, WARPS>();
+	auto seedk = pb::seed_kernel<ML, SW>;
+	auto kern = pbl::assemble_lanes_kernel<ML, LW>;
+	constexpr size_t seed_smem = sizeof(pb::WarpSmem<ML>) * SW;
+	constexpr size_t smem = pbl::lanes_smem_bytes<ML, LW>();
 	static bool configured[16] = { false };
 	if (!configured[ctx->device & 15]) {
+		CUDA_TRY(cudaFuncSetAttribute(seedk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) seed_smem));
 		CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		configured[ctx->device & 15] = true;
 	}
@@ -183,22 +182,33 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 	if ((size_t) n + 4 > ctx->defer_cap[si]) {
 		CUDA_TRY(cudaDeviceSynchronize());
 		cudaFree(ctx->d_defer[si]);
+		cudaFree(ctx->d_seeds[si]);
 		ctx->d_defer[si] = nullptr;
+		ctx->d_seeds[si] = nullptr;
 		ctx->defer_cap[si] = 0;
 		const size_t cap = (size_t) n + (size_t) n / 4 + 64;
 		CUDA_TRY(cudaMalloc(&ctx->d_defer[si], cap * sizeof(int)));
+		CUDA_TRY(cudaMalloc(&ctx->d_seeds[si], cap * pb::PB_SEED_WORDS * sizeof(uint32_t)));
 		ctx->defer_cap[si] = cap;
 	}
 	int *d_count = ctx->d_defer[si], *d_list = ctx->d_defer[si] + 4;
+	uint32_t *d_seeds = ctx->d_seeds[si];
 	CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+	{
+		long long grid = ((long long) n + SW - 1) / SW;
+		if (grid > ctx->sm_count)
+			grid = ctx->sm_count;
+		seedk<<<(unsigned) (grid < 1 ? 1 : grid), SW * 32, seed_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds);
+		CUDA_TRY(cudaGetLastError());
+	}
 	const long long nbatch = ((long long) n + 31) / 32;
-	long long grid = ((long long) nbatch + WARPS - 1) / WARPS;
+	long long grid = ((long long) nbatch + LW - 1) / LW;
 	if (grid > ctx->sm_count)
 		grid = ctx->sm_count;
 	if (grid < 1)
 		grid = 1;
-	kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_results, d_seq_nt, (long long) seq_stride,
-	                                                      d_counters, d_list, d_count, ctx->d_defer_total);
+	kern<<<(unsigned) grid, LW * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, d_results, d_seq_nt, (long long) seq_stride,
+	                                                   d_counters, d_list, d_count, ctx->d_defer_total);
 	CUDA_TRY(cudaGetLastError());
 	ctx->lanes_pairs += (unsigned long long) n;
 	return launch_assemble<ML, false, GW, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, nullptr, seq_stride, d_counters, stream, false,
@@ -226,9 +236,9 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 		const char *env = getenv("PANDASEQ_B200_LANES");
 		lanes_on = (env && atoi(env) == 0) ? 0 : 1;
 	}
-	if (lanes_on && !full && !d_seq_p && max_len <= 160 && ctx->recon_symmetric && cfg->forward_trim == 0 && cfg->reverse_trim == 0
+	if (lanes_on && !full && !d_seq_p && max_len <= 160 && cfg->forward_trim == 0 && cfg->reverse_trim == 0
 	    && (cfg->algo == PB_SIMPLE_BAYES || cfg->algo == PB_UPARSE || cfg->algo == PB_FLASH) && ((uintptr_t) d_seq_nt % 8) == 0)
-		return launch_lanes<160, 4, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
+		return launch_lanes<160, 32, 11, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
 #define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq); \
 	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false); } while (0)
 	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */

@@ -371,7 +371,7 @@ template <int ML, bool HASN>
 __device__ __forceinline__ void seed_candidates(WarpSmem<ML> &ws, int F, int R, int mo, int nbits, int lane) {
 	using WS = WarpSmem<ML>;
 	constexpr unsigned IDXMASK = WS::NB - 1;
-	constexpr unsigned PLIM = (1u << WS::PBITS) - 1u;
+	constexpr unsigned PLIM = 1u << WS::PBITS;       /* entry ^ tag below this: the tags agree and the value is a position */
 	uint16_t *bt16 = reinterpret_cast<uint16_t *>(ws.btab);
 	unsigned ovf = 0;
 	/* K1: forward 8-mers into the bucket table.  A lane claims its slot with one shared-memory atomic on the bucket's
@@ -405,29 +405,29 @@ __device__ __forceinline__ void seed_candidates(WarpSmem<ML> &ws, int F, int R, 
 			const unsigned code = ws.code_r[e];
 			const unsigned tagsh = (code >> WS::IDXBITS) << WS::PBITS;
 			const uint2 b = *reinterpret_cast<const uint2 *>(&ws.btab[code & IDXMASK]);
-			/* entry ^ tagsh is the stored position iff the tags agree (positions are >= 8, empty entries are 0) */
-			unsigned x0 = (b.x & 0xFFFFu) ^ tagsh, x1 = (b.x >> 16) ^ tagsh;
-			unsigned x2 = (b.y & 0xFFFFu) ^ tagsh, x3 = (b.y >> 16) ^ tagsh;
-			if (x0 - 1u >= PLIM) x0 = 0x7FFFu;
-			if (x1 - 1u >= PLIM) x1 = 0x7FFFu;
-			if (x2 - 1u >= PLIM) x2 = 0x7FFFu;
-			if (x3 - 1u >= PLIM) x3 = 0x7FFFu;
-			const unsigned lo01 = min(x0, x1), hi01 = max(x0, x1), lo23 = min(x2, x3), hi23 = max(x2, x3);
-			const unsigned m1 = min(lo01, lo23), m2 = min(max(lo01, lo23), min(hi01, hi23));
+			/* entry ^ tag is the stored position iff the tags agree, and at least 2^PBITS otherwise (an empty entry is 0xFFFF);
+			 * the two lowest of the four 16-bit values, two at a time (VIMNMX.U16x2) */
+			const unsigned t2 = tagsh * 0x10001u;
+			const unsigned y0 = b.x ^ t2, y1 = b.y ^ t2;
+			unsigned lo2, hi2;
+			asm("min.u16x2 %0, %1, %2;" : "=r"(lo2) : "r"(y0), "r"(y1));
+			asm("max.u16x2 %0, %1, %2;" : "=r"(hi2) : "r"(y0), "r"(y1));
+			const unsigned l0 = lo2 & 0xFFFFu, l1 = lo2 >> 16, h0 = hi2 & 0xFFFFu, h1 = hi2 >> 16;
+			const unsigned m1 = min(l0, l1), m2 = min(max(l0, l1), min(h0, h1));
 			const unsigned c = live ? (unsigned) (cbase + e) : 0u;   /* dead lanes: index underflows, no flag */
 			const unsigned i1 = c - m1, i2 = c - m2;
-			if (i1 < (unsigned) nbits)
+			if (m1 < PLIM && i1 < (unsigned) nbits)
 				ws.cflag[i1] = 1;
-			if (i2 < (unsigned) nbits)
+			if (m2 < PLIM && i2 < (unsigned) nbits)
 				ws.cflag[i2] = 1;
 		}
 		__syncwarp();
-		/* K3: clear (assembler.c:113-116) */
-		const uint4 z = make_uint4(0, 0, 0, 0);
+		/* K3: clear (assembler.c:113-116); an empty entry is 0xFFFF */
+		const uint4 z = make_uint4(0, 0, 0, 0), ones = make_uint4(~0u, ~0u, ~0u, ~0u);
 		uint4 *t4 = reinterpret_cast<uint4 *>(ws.btab);
 #pragma unroll
 		for (int k = 0; k < WS::NB * 8 / 16 / 32; k++)
-			t4[k * 32 + lane] = z;
+			t4[k * 32 + lane] = ones;
 		uint4 *c4 = reinterpret_cast<uint4 *>(ws.bcnt);
 #pragma unroll
 		for (int k = 0; k < (WS::NB / 8 * 4 + 511) / 512; k++)
@@ -505,7 +505,7 @@ __device__ __forceinline__ void seed_candidates(WarpSmem<ML> &ws, int F, int R, 
 	}
 	__syncwarp();
 	for (int k = lane; k < WS::SLOTS; k += 32)
-		slots[k] = 0;
+		slots[k] = ~0u;                /* back to the bucket table's "empty" */
 }
 
 /* ---- K6 of align() (assembler.c:158-244), 8 output bases per lane ----
@@ -1119,7 +1119,7 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 	}
 	WS &ws = wsall[warp];
 	for (int k = lane; k < WS::NB; k += 32)
-		ws.btab[k] = 0;
+		ws.btab[k] = ~0ull;
 	for (int k = lane; k < WS::NB / 8; k += 32)
 		ws.bcnt[k] = 0;
 	for (int k = lane; k < WS::NFLAG; k += 32)
@@ -1210,6 +1210,108 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 			else
 				atomicAdd(&counters[i], (unsigned long long) c);
 		}
+	}
+}
+
+/* ---- seeding on its own: K1-K3 of align() for every pair of the batch, one warp per pair ------------------------
+ * First half of the two-kernel path for the common configurations (pb_lanes.cuh is the second half): only the packed
+ * bases of a record are staged, the candidate overlaps come out as a bit mask per pair.
+ *   seeds[pair][0..4]  bit i set <=> overlap minoverlap + i shares a valid 8-mer between the reads (BIT_LIST_SET)
+ *   seeds[pair][5]     PB_SEED_GENERAL: leave this pair to the general kernel (a base that is not A/C/G/T, reads
+ *                      outside 16..ML, more than 160 candidate overlaps, no seed at all, k-mers crowding a bucket);
+ *                      PB_SEED_SKIP: not a pair (flen == 0xFFFF). */
+constexpr unsigned PB_SEED_GENERAL = 1u, PB_SEED_SKIP = 2u;
+constexpr int PB_SEED_WORDS = 8;
+
+template <int ML, int WARPS_PER_BLOCK>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
+seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__restrict__ reads,
+            const pb_pair_meta *__restrict__ meta, uint32_t *__restrict__ seeds) {
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	using WS = WarpSmem<ML>;
+	static_assert(ML <= 160, "the candidate mask has 160 bits");
+	WS *wsall = reinterpret_cast<WS *>(smem_raw);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	WS &ws = wsall[warp];
+	for (int k = lane; k < WS::NB; k += 32)
+		ws.btab[k] = ~0ull;
+	for (int k = lane; k < WS::NB / 8; k += 32)
+		ws.bcnt[k] = 0;
+	for (int k = lane; k < WS::NFLAG; k += 32)
+		ws.cflag[k] = 0;
+	if (lane == 0) {
+		for (int s = 0; s < NSTAGE; s++)
+			mbar_init(&ws.bar[s], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	const int mo = prm->minoverlap, cfg_maxov = prm->maxoverlap;
+	const int wglobal = blockIdx.x * WARPS_PER_BLOCK + warp;
+	const int wstride = gridDim.x * WARPS_PER_BLOCK;
+
+	auto issue = [&](int pair, int stage) {
+		if (lane == 0) {
+			pb_pair_meta m = meta[pair];
+			ws.meta[stage] = m;
+			unsigned bytes = 0;
+			if (m.flen != 0xFFFFu && m.flen <= ML && m.rlen <= ML)      /* only the packed bases: the qualities play no part in seeding */
+				bytes = ((((unsigned) m.flen + 7) / 8) * 4 + (((unsigned) m.rlen + 7) / 8) * 4 + 15u) & ~15u;
+			mbar_expect_tx(&ws.bar[stage], bytes);
+			if (bytes)
+				bulk_g2s(ws.stage[stage], reads + (size_t) m.off16 * 16, bytes, &ws.bar[stage]);
+		}
+	};
+
+	int pair = wglobal;
+	if (pair < n)
+		issue(pair, 0);
+	for (int it = 0; pair < n; it++, pair += wstride) {
+		const int stage = it & 1;
+		const int next = pair + wstride;
+		if (next < n)
+			issue(next, stage ^ 1);
+		mbar_wait(&ws.bar[stage], (it >> 1) & 1);
+		const pb_pair_meta m = ws.meta[stage];
+		const int F = m.flen, R = m.rlen;
+		unsigned word = 0, flags = 0;
+		if (F == 0xFFFF) {
+			flags = PB_SEED_SKIP;
+		} else if (F > ML || R > ML || F < 16 || R < 16 || mo >= min(F, R)) {
+			flags = PB_SEED_GENERAL;
+		} else {
+			const int maxov = cfg_maxov == 0 ? min(F, R) : min(F + R - mo - 1, cfg_maxov);      /* assembler.c:59,78-84 */
+			const int nbits = (mo <= maxov) ? (maxov - mo + 1) : 1;
+			const uint32_t *fnt32 = reinterpret_cast<const uint32_t *>(ws.stage[stage]);
+			const uint32_t *rnt32 = fnt32 + ((F + 7) >> 3);
+			unsigned flg = gen_codes<WS::NTW>(fnt32, F, ws.code_f, lane) | gen_codes<WS::NTW>(rnt32, R, ws.code_r, lane);
+			flg = __reduce_or_sync(FULL, flg);
+			__syncwarp();
+			if (flg != 0u || nbits > 160) {
+				flags = PB_SEED_GENERAL;
+			} else {
+				seed_candidates<ML, false>(ws, F, R, mo, nbits, lane);
+				__syncwarp();
+				/* flag bytes -> mask words; lane w keeps word w */
+				unsigned any = 0;
+#pragma unroll
+				for (int w = 0; w < 5; w++) {
+					const unsigned b = __ballot_sync(FULL, ws.cflag[32 * w + lane] != 0);
+					any |= b;
+					if (lane == w)
+						word = b;
+				}
+				__syncwarp();
+				if (lane < 10)
+					reinterpret_cast<uint4 *>(ws.cflag)[lane] = make_uint4(0, 0, 0, 0);
+				if (any == 0u)
+					flags = PB_SEED_GENERAL;       /* ALL_BITS_IF_NONE (assembler.c:118): every overlap is scored */
+			}
+		}
+		if (lane == 5)
+			word = flags;
+		if (lane < PB_SEED_WORDS)
+			seeds[(size_t) pair * PB_SEED_WORDS + lane] = lane < 6 ? word : 0u;
+		__syncwarp();      /* every lane is done with this stage before it is refilled */
 	}
 }
 

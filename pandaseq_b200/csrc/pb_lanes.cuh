@@ -1,29 +1,31 @@
-/* pb_lanes.cuh -- sm_100a kernel for the common case of the pair-assembly hot path: one LANE per read pair (kernel v4).
+/* pb_lanes.cuh -- second half of the two-kernel path for the common configurations: one LANE per read pair.
  *
- * assemble_kernel (pb_kernels.cuh) gives a whole warp to a pair; every step then pays for partly filled lane rounds,
- * shuffles, ballots and warp-wide bookkeeping.  Here a warp takes 32 consecutive pairs and every lane runs the
- * reference's align() (assembler.c:48-250) for its own pair as straight scalar code over 32-bit words of packed
- * bases.  What makes that affordable is that the rare cases do not have to be handled here at all: a lane that meets
- * one (a base that is not A/C/G/T, a quality outside 0..46, no seed at all, an overlap longer than a read, a read
- * outside this length class) appends its pair to a deferral list and the exact general kernel assembles those pairs
- * in a second launch on the same stream.  Both kernels implement the same function, so the split is invisible in the
- * results.
+ * assemble_kernel (pb_kernels.cuh) gives a whole warp to a pair from the record to the result; after the k-mer join
+ * (K1-K3, which does want 32 lanes on one pair) everything that is left -- scoring a handful of candidate overlaps,
+ * merging the reads, summing the per-base posterior -- is a stream of 32-bit words of packed bases, and a warp-wide
+ * formulation pays for partly filled lane rounds, shuffles, ballots and per-pair bookkeeping.  So the common
+ * configurations run as two kernels: pb::seed_kernel (warp per pair) leaves the candidate overlaps of every pair as a
+ * bit mask, and the kernel here takes 32 consecutive pairs per warp, every lane running K4-K6 of the reference's
+ * align() (assembler.c:118-250) for its own pair as straight scalar code.  What makes that affordable is that the rare
+ * cases do not have to be handled here: a lane that meets one (a base that is not A/C/G/T, a quality outside 0..46, no
+ * seed at all, an overlap longer than a read, a read outside 16..160 nt) appends its pair to a deferral list and the
+ * exact general kernel assembles those pairs in a third launch on the same stream.  All kernels implement the same
+ * function, so the split is invisible in the results.
  *
  *   stage   32 bulk async copies (one per lane, cp.async.bulk / UBLKCP) land the 32 records in this warp's shared
- *           memory at a stride of an odd number of 16-byte units; one mbarrier per warp.
- *   seed    K1-K3 (assembler.c:92-118): the lane streams its forward read, forms the 2-bit digit of every base
- *           (misc.h:41) eight at a time, and inserts each 8-mer into its own 256-slot open-addressing table
- *           (lane-interleaved in shared memory, so 32 lanes always hit 32 different banks).  A slot is
- *           code:16 | first position:8 | second position:8 -- exactly what the reference's 65536x2 table remembers
- *           of a code ("first two positions", assembler.c:93-100).  The reverse read (template order) then probes;
- *           every hit sets a bit of the lane's candidate mask (BIT_LIST_SET, assembler.c:108).
+ *           memory at a stride of an odd number of 16-byte units; one mbarrier per warp; the warp's next batch is
+ *           prefetched into L2 meanwhile.
  *   score   K4/K5 (assembler.c:120-143): candidates in increasing overlap; the count-based scorers
  *           (algo_simple_bayes.c:33-66, algo_uparse.c:33-66, algo_flash.c:30-60) need one AND + POPC per 8 bases.
- *   merge   K6 (assembler.c:158-244): merged bases 8 per word; the per-base posterior is summed in the reference's
- *           own order (forward-only stretch, overlap, reverse-only stretch, each left to right), so `quality` is
- *           bit-identical, not merely within tolerance.
+ *   merge   K6 (assembler.c:158-244): merged bases 8 per word; the per-base posterior is summed per stretch (forward-
+ *           only, overlap, reverse-only) as the reference does, on two accumulators each.
  *
- * Configurations this kernel takes (the host decides, pb_device.cu): simple_bayesian / uparse / flash, no primers, no
+ * A first version of this file also did the k-mer join per lane (a 256-slot open-addressing table per lane, lane-
+ * interleaved in shared memory).  Measured on B200: 124 Mpairs/s against 650 for the warp-per-pair kernel -- 1 KB of
+ * table per pair leaves 4 warps per SM, and the probe chains of 32 lanes are as long as the longest of them
+ * (1,541 warp-instructions per pair at 13 active lanes, 0.17 instructions per cycle and scheduler).  DESIGN.md section 5.
+ *
+ * Configurations this path takes (the host decides, pb_device.cu): simple_bayesian / uparse / flash, no primers, no
  * trims, no overhang trimmer, no per-base log p requested, filters that read only the result record, reads <= 160 nt.
  */
 #pragma once
@@ -34,73 +36,41 @@ namespace pbl {
 using pb::FULL;
 using pb::NIB1;
 
-constexpr int TRI = PB_NQM * (PB_NQM + 1) / 2;      /* entries of one triangular posterior table */
-constexpr int TRI47 = PB_NQ * (PB_NQ + 1) / 2;      /* row 47 ("the other read is absent or masked"): qual_score[] */
+constexpr int LUT_DOUBLES = 2 * PB_NQM * PB_NQM + 256;      /* the posterior table, then qual_score[] padded to one entry per byte value */
 constexpr uint8_t ST_DEFER = 255;
 
 template <int ML> struct LaneArea {
 	static constexpr int REC0 = (((ML + 7) / 8) * 4 * 2 + ((ML + 3) / 4) * 4 * 2 + 15) & ~15;
 	static constexpr int REC_STRIDE = ((REC0 / 16) | 1) * 16;    /* odd number of 16-byte units: a lane's 128-bit loads never collide */
-	static constexpr int SLOTS = 256;
-	static constexpr int CW = (ML + 31) / 32;                    /* words of the candidate mask */
-	static_assert(ML - 7 < 256, "positions are stored in 8 bits");
-	static_assert(ML - 8 < SLOTS * 3 / 4, "the table must stay sparse");
+	static constexpr int CW = 5;                                 /* words of the candidate mask (pb::seed_kernel) */
+	static_assert(ML <= 160, "the candidate mask has 160 bits");
 	alignas(128) uint8_t rec[32 * REC_STRIDE];
-	alignas(16) uint32_t tab[SLOTS * 32];                        /* slot s of lane l: tab[s * 32 + l] */
-	uint32_t cmask[CW * 32];                                     /* word w of lane l: cmask[w * 32 + l] */
 	alignas(8) uint64_t bar;
 };
-
-/* misc.h:41 on a word of eight one-hot bases: T=3 G=2 C=1 A=0, digit of base k in bits 4k, 4k+1 */
-__device__ __forceinline__ unsigned digits8(unsigned x) {
-	const unsigned x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
-	const unsigned lo = (x1 | x3) & NIB1;
-	const unsigned hi = (x2 | x3) & NIB1;
-	return lo | (hi << 1);
-}
-/* eight nibble-spaced digits -> 16 bits (an injective packing; both reads use the same one) */
-__device__ __forceinline__ unsigned code16(unsigned c) {
-	return (c | (c >> 14)) & 0xFFFFu;
-}
-__device__ __forceinline__ unsigned slot_of(unsigned code) {
-	return (code * 0x9E3779B1u) >> 24;
-}
-/* some nibble of x is zero */
-__device__ __forceinline__ unsigned zero_nib(unsigned x) {
-	return (x - NIB1) & ~x & 0x88888888u;
-}
-__device__ __forceinline__ unsigned tri_index(unsigned a, unsigned b) {
-	const unsigned lo = min(a, b), hi = max(a, b);
-	return ((hi * hi + hi) >> 1) + lo;
-}
 
 template <int ML, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
                       const uint8_t *__restrict__ reads, const pb_pair_meta *__restrict__ meta,
-                      pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, long long seq_stride,
+                      const uint32_t *__restrict__ seeds, pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, long long seq_stride,
                       unsigned long long *__restrict__ counters, int *__restrict__ defer_list, int *__restrict__ defer_count,
                       unsigned long long *__restrict__ defer_total) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	using LA = LaneArea<ML>;
-	double *s_tri = reinterpret_cast<double *>(smem_raw);                 /* [2][TRI]: posterior by (match, max q, min q) */
-	unsigned *s_cnt = reinterpret_cast<unsigned *>(s_tri + 2 * TRI);
-	constexpr size_t HEAD = ((2 * TRI * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned)) + 127) & ~(size_t) 127;
+	double *s_rec = reinterpret_cast<double *>(smem_raw);                 /* recon[2][48][48], row = quality a + 48 * match */
+	double *s_score = s_rec + LUT_DOUBLES - 256;                          /* qual_score[] by raw byte: 256 entries, [47..] zero */
+	unsigned *s_cnt = reinterpret_cast<unsigned *>(s_rec + LUT_DOUBLES);
+	constexpr size_t HEAD = ((LUT_DOUBLES * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned)) + 127) & ~(size_t) 127;
 	LA *areas = reinterpret_cast<LA *>(smem_raw + HEAD);
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	for (int i = tid; i < 2 * PB_NQM * PB_NQM; i += blockDim.x) {
-		const int m = i / (PB_NQM * PB_NQM), a = (i / PB_NQM) % PB_NQM, b = i % PB_NQM;
-		if (b <= a)
-			s_tri[m * TRI + a * (a + 1) / 2 + b] = prm->recon[m][a][b];
-	}
+	for (int i = tid; i < 2 * PB_NQM * PB_NQM; i += blockDim.x)
+		s_rec[i] = (&prm->recon[0][0][0])[i];
+	for (int i = tid; i < 256; i += blockDim.x)
+		s_score[i] = i < PB_NQ ? prm->score[i] : 0.0;
 	for (int i = tid; i < PB_NCOUNTERS; i += blockDim.x)
 		s_cnt[i] = 0;
 	LA &wa = areas[warp];
-	for (int k = lane; k < LA::SLOTS * 32; k += 32)
-		wa.tab[k] = 0;
-	for (int k = lane; k < LA::CW * 32; k += 32)
-		wa.cmask[k] = 0;
 	if (lane == 0) {
 		pb::mbar_init(&wa.bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -112,8 +82,6 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 	const long long nt_row = seq_stride / 2;
 	const int out_cap = (int) seq_stride;
 	const int nbatch = (n + 31) >> 5;
-	uint32_t *const tab = wa.tab + lane;
-	uint32_t *const cm = wa.cmask + lane;
 	const uint8_t *const rb = wa.rec + lane * LA::REC_STRIDE;
 	unsigned parity = 0;
 
@@ -127,8 +95,16 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 			F = (int) (mraw.y & 0xFFFFu);
 			R = (int) (mraw.y >> 16);
 		}
+		unsigned cw[LA::CW] = { 0, 0, 0, 0, 0 };
+		unsigned sflags = pb::PB_SEED_SKIP;
+		if (pair < n) {
+			const uint4 s0 = reinterpret_cast<const uint4 *>(seeds)[(size_t) pair * 2];
+			const uint2 s1 = reinterpret_cast<const uint2 *>(seeds)[(size_t) pair * 4 + 2];
+			cw[0] = s0.x; cw[1] = s0.y; cw[2] = s0.z; cw[3] = s0.w; cw[4] = s1.x;
+			sflags = s1.y;
+		}
 		const bool skip = F == 0xFFFF;              /* not a pair (FASTQ reader, fastq.c:176), or past the end of the batch */
-		bool defer = !skip && (F > ML || R > ML || F < 16 || R < 16 || mo >= min(F, R));
+		bool defer = !skip && (sflags & pb::PB_SEED_GENERAL) != 0;
 		const bool act = !skip && !defer;
 		const unsigned bytes = act ? pb::record_bytes((unsigned) F, (unsigned) R) : 0u;
 		const unsigned total = __reduce_add_sync(FULL, bytes);
@@ -170,123 +146,12 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 			if (nbits > LA::CW * 32)
 				defer = true;
 		}
-		if (act && !defer) {
-			/* ---- K1: forward 8-mers into this lane's table (assembler.c:92-103) ---- */
-			unsigned pops = 0, zf = 0;
-			{
-				const int nw = (F + 7) >> 3;
-				unsigned x = fnt[0];
-				pops = __popc(x);
-				zf = zero_nib(x);
-				unsigned dprev = digits8(x);
-				for (int w = 1; w < nw; w++) {
-					x = fnt[w];
-					pops += __popc(x);
-					const int inw = min(F - 8 * w, 8);
-					zf |= zero_nib(x | ~pb::nibmask(inw));
-					const unsigned d = digits8(x);
-#pragma unroll
-					for (int t = 0; t < 8; t++) {
-						if (t < inw) {
-							const unsigned c = (t == 7) ? d : __funnelshift_r(dprev, d, 4 * (t + 1));
-							const unsigned code = code16(c);
-							const unsigned pp = (unsigned) (8 * w + t - 7);     /* position p = 8w+t, stored as p-7 (1..) */
-							const unsigned key = code << 16;
-							unsigned s = slot_of(code);
-							for (;;) {
-								const unsigned e = tab[s * 32];
-								if (e == 0u) {
-									tab[s * 32] = key | (pp << 8);
-									break;
-								}
-								if ((e ^ key) < 0x10000u) {
-									if ((e & 0xFFu) == 0u)
-										tab[s * 32] = e | pp;                   /* the second position of this code; later ones are lost */
-									break;
-								}
-								s = (s + 1) & (LA::SLOTS - 1);
-							}
-						}
-					}
-					dprev = d;
-				}
-				if (pops != (unsigned) F || zf != 0u)
-					defer = true;                       /* some base is not exactly one of A, C, G, T */
-			}
-			/* ---- K2: reverse 8-mers probe (assembler.c:104-112); template order, so overlap = F - p + e ---- */
-			{
-				const int nw = (R + 7) >> 3;
-				const int cb = F - mo - 7;              /* index = F - mo - p + e, p = stored + 7 */
-				unsigned last = 0xFFFFFFFFu;
-				unsigned x = rnt[0];
-				pops = __popc(x);
-				zf = zero_nib(x);
-				unsigned dprev = digits8(x);
-				for (int w = 1; w < nw; w++) {
-					x = rnt[w];
-					pops += __popc(x);
-					const int inw = min(R - 8 * w, 8);
-					zf |= zero_nib(x | ~pb::nibmask(inw));
-					const unsigned d = digits8(x);
-#pragma unroll
-					for (int t = 0; t < 8; t++) {
-						if (t < inw) {
-							const unsigned c = (t == 7) ? d : __funnelshift_r(dprev, d, 4 * (t + 1));
-							const unsigned code = code16(c);
-							const unsigned key = code << 16;
-							unsigned s = slot_of(code);
-							unsigned e;
-							for (;;) {
-								e = tab[s * 32];
-								if (e == 0u || (e ^ key) < 0x10000u)
-									break;
-								s = (s + 1) & (LA::SLOTS - 1);
-							}
-							if (e != 0u) {
-								const unsigned base = (unsigned) (cb + 8 * w + t);
-								const unsigned i1 = base - ((e >> 8) & 0xFFu);
-								if (i1 != last && i1 < (unsigned) nbits) {
-									last = i1;
-									cm[(i1 >> 5) * 32] |= 1u << (i1 & 31u);
-								}
-								const unsigned p2 = e & 0xFFu;
-								if (p2 != 0u) {
-									const unsigned i2 = base - p2;
-									if (i2 < (unsigned) nbits) {
-										last = i2;
-										cm[(i2 >> 5) * 32] |= 1u << (i2 & 31u);
-									}
-								}
-							}
-						}
-					}
-					dprev = d;
-				}
-				if (pops != (unsigned) R || zf != 0u)
-					defer = true;
-			}
-		}
-		/* ---- K3: clear (assembler.c:113-116), all lanes together ---- */
-		__syncwarp();
-		{
-			const uint4 z = make_uint4(0, 0, 0, 0);
-			uint4 *t4 = reinterpret_cast<uint4 *>(wa.tab);
-#pragma unroll 8
-			for (int k = 0; k < LA::SLOTS * 32 * 4 / 16 / 32; k++)
-				t4[k * 32 + lane] = z;
-		}
-		__syncwarp();
 		if (act) {
 			/* ---- K4/K5: the candidates in increasing overlap (assembler.c:118-143) ---- */
-			unsigned any = 0;
 			best = qual_nn * (double) (unsigned long long) (F + R);          /* assembler.c:60 */
-#pragma unroll 1
+#pragma unroll
 			for (int w = 0; w < LA::CW; w++) {
-				unsigned mw = cm[w * 32];
-				cm[w * 32] = 0;
-				if (defer)
-					mw = 0;
-				any |= mw;
+				unsigned mw = defer ? 0u : cw[w];
 				while (mw) {
 					const int ov = w * 32 + __ffs(mw) - 1 + mo;
 					mw &= mw - 1;
@@ -326,8 +191,6 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 					}
 				}
 			}
-			if (any == 0u)
-				defer = true;                           /* no seed at all: every overlap is scored (assembler.c:118), the general kernel's job */
 			if ((long long) examined == (long long) maxov - mo + 1)    /* assembler.c:135-137 */
 				slow = 1;
 			if (!defer && bestov < 0)
@@ -349,82 +212,117 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 					lead_r++;
 			}
 			unsigned qbad = 0;
-			const double *const score = s_tri + TRI47;
-			/* forward-only stretch: positions [0, df) (assembler.c:162-173) */
-			double fquality = 0.0;
+			/* The sums below run on two accumulators each (even / odd bases): the additions are the reference's, their
+			 * order is not, which moves `quality` by an ulp or two (tolerance 1e-6, BASELINE.json north_star).
+			 * forward-only stretch: positions [0, df) (assembler.c:162-173) */
+			double fquality = 0.0, fquality1 = 0.0;
 			{
-				const int nwq = (df + 3) >> 2;
-				for (int w = 0; w < nwq; w++) {
+				const int nfull = df >> 2;
+#pragma unroll 2
+				for (int w = 0; w < nfull; w++) {
 					const unsigned q4 = fq32[w];
 					qbad |= ((q4 & 0x7F7F7F7Fu) + 0x51515151u) | q4;
-					const int nb = min(df - 4 * w, 4);
-#pragma unroll
-					for (int t = 0; t < 4; t++)
-						if (t < nb)
-							fquality += score[(q4 >> (8 * t)) & 0x3Fu];
+					fquality += s_score[__byte_perm(q4, 0, 0x4440)];
+					fquality1 += s_score[__byte_perm(q4, 0, 0x4441)];
+					fquality += s_score[__byte_perm(q4, 0, 0x4442)];
+					fquality1 += s_score[__byte_perm(q4, 0, 0x4443)];
 				}
+				const int nb = df & 3;
+				if (nb) {
+					const unsigned q4 = fq32[nfull] & ((1u << (8 * nb)) - 1u);      /* the rest of this word belongs to the overlap and is checked there */
+					qbad |= ((q4 & 0x7F7F7F7Fu) + 0x51515151u) | q4;
+					for (int t = 0; t < nb; t++)
+						fquality += s_score[(q4 >> (8 * t)) & 0xFFu];
+				}
+				fquality += fquality1;
 			}
-			/* overlap: position df+i pairs forward base df+i with template-order reverse base i (assembler.c:181-228) */
-			double oquality = 0.0;
+			/* overlap: position df+i pairs forward base df+i with template-order reverse base i (assembler.c:181-228).
+			 * The posterior is recon[match][a][b]; the match bit is folded into the row index (row = a + 48 * match),
+			 * B-cliff masked bases get index 47 (assembler.c:194-210). */
+			double oquality = 0.0, oquality1 = 0.0;
 			{
-				const int nwq = (bestov + 3) >> 2;
+				const bool cliff = unmasked_f < F || lead_r > 0;
+				const int ia = unmasked_f - df;           /* overlap bases i >= ia have a masked forward base */
 				const int shq = (df & 3) * 8, shn = (df & 7) * 4;
 				const uint32_t *fqp = fq32 + (df >> 2);
 				const uint32_t *fnp = fnt + (df >> 3);
-				unsigned qlo = fqp[0];
-				unsigned mbits = 0;
+				unsigned qlo = fqp[0], nlo = fnp[0];
+				unsigned mw = 0;
+				const int nwq = (bestov + 3) >> 2;
 				for (int w = 0; w < nwq; w++) {
 					const unsigned qhi = fqp[w + 1];
-					const unsigned qa4 = __funnelshift_r(qlo, qhi, shq);
+					unsigned qa4 = __funnelshift_r(qlo, qhi, shq);
 					qlo = qhi;
-					const unsigned qb4 = rq32[w];
+					unsigned qb4 = rq32[w];
+					const int nb = min(bestov - 4 * w, 4);
+					if (nb < 4) {                        /* the last word: what lies past the overlap must not reach the range check */
+						const unsigned keep = (1u << (8 * nb)) - 1u;
+						qa4 &= keep;
+						qb4 &= keep;
+					}
+					qbad |= ((qa4 & 0x7F7F7F7Fu) + 0x51515151u) | qa4;
 					qbad |= ((qb4 & 0x7F7F7F7Fu) + 0x51515151u) | qb4;
+					qa4 &= 0x3F3F3F3Fu;                  /* keeps the table index inside shared memory for pairs that are handed on */
+					qb4 &= 0x3F3F3F3Fu;
 					if ((w & 1) == 0) {
 						const int k = w >> 1;
-						const unsigned f = __funnelshift_r(fnp[k], fnp[k + 1], shn);
-						mbits = f & rnt[k];               /* one-hot bases: a nibble is non-zero iff the bases match */
+						const unsigned nhi = fnp[k + 1];
+						const unsigned f = __funnelshift_r(nlo, nhi, shn);
+						nlo = nhi;
+						mw = pb::nz_nib(f & rnt[k]);      /* bit 4t: bases t of this word match */
+					} else {
+						mw >>= 16;
 					}
-					const int nb = min(bestov - 4 * w, 4);
-#pragma unroll
-					for (int t = 0; t < 4; t++) {
-						if (t < nb) {
-							const int i = 4 * w + t;
-							unsigned a = (qa4 >> (8 * t)) & 0x3Fu, b = (qb4 >> (8 * t)) & 0x3Fu;
-							if (df + i >= unmasked_f)
-								a = PB_NQ;
-							if (i < lead_r)
-								b = PB_NQ;
-							const unsigned isnz = ((mbits >> (4 * (i & 7))) & 15u) != 0u ? (unsigned) TRI : 0u;
-							oquality += s_tri[isnz + tri_index(a, b)];
-						}
+					if (cliff) {
+						const unsigned ma = __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 8 * min(max(ia - 4 * w, 0), 4));
+						const unsigned mb = __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 8 * min(max(lead_r - 4 * w, 0), 4));
+						qa4 = (qa4 & ma) | (0x2F2F2F2Fu & ~ma);
+						qb4 = (qb4 & ~mb) | (0x2F2F2F2Fu & mb);
 					}
-				}
-				/* forward qualities of the overlap were not range-checked above: positions [df, F) */
-				for (int w = df >> 2; w < ((F + 3) >> 2); w++) {
-					const unsigned q4 = fq32[w];
-					qbad |= ((q4 & 0x7F7F7F7Fu) + 0x51515151u) | q4;
+					/* match bits 0,4,8,12 -> bits 0,8,16,24, times 48, added to the forward qualities */
+					unsigned sp = mw & 0x1111u;
+					sp = (sp | (sp << 8)) & 0x00110011u;
+					sp = (sp | (sp << 4)) & 0x01010101u;
+					const unsigned row4 = qa4 + sp * 48u;
+					if (nb == 4) {
+						oquality += s_rec[__byte_perm(row4, 0, 0x4440) * PB_NQM + __byte_perm(qb4, 0, 0x4440)];
+						oquality1 += s_rec[__byte_perm(row4, 0, 0x4441) * PB_NQM + __byte_perm(qb4, 0, 0x4441)];
+						oquality += s_rec[__byte_perm(row4, 0, 0x4442) * PB_NQM + __byte_perm(qb4, 0, 0x4442)];
+						oquality1 += s_rec[__byte_perm(row4, 0, 0x4443) * PB_NQM + __byte_perm(qb4, 0, 0x4443)];
+					} else {
+						for (int t = 0; t < nb; t++)
+							oquality += s_rec[((row4 >> (8 * t)) & 0xFFu) * PB_NQM + ((qb4 >> (8 * t)) & 0xFFu)];
+					}
 				}
 			}
+			oquality += oquality1;
 			/* reverse-only stretch: template-order reverse bases [bestov, R) (assembler.c:231-243) */
-			double rquality = 0.0;
+			double rquality = 0.0, rquality1 = 0.0;
 			{
 				const int shq = (bestov & 3) * 8;
 				const uint32_t *rqp = rq32 + (bestov >> 2);
-				const int nwq = (dr + 3) >> 2;
+				const int nfull = dr >> 2;
 				unsigned qlo = rqp[0];
-				for (int w = 0; w < nwq; w++) {
+#pragma unroll 2
+				for (int w = 0; w < nfull; w++) {
 					const unsigned qhi = rqp[w + 1];
-					unsigned q4 = __funnelshift_r(qlo, qhi, shq);
+					const unsigned q4 = __funnelshift_r(qlo, qhi, shq);
 					qlo = qhi;
-					const int nb = min(dr - 4 * w, 4);
-					if (nb < 4)
-						q4 &= (1u << (8 * nb)) - 1u;      /* what follows the read in shared memory is not a quality */
 					qbad |= ((q4 & 0x7F7F7F7Fu) + 0x51515151u) | q4;
-#pragma unroll
-					for (int t = 0; t < 4; t++)
-						if (t < nb)
-							rquality += score[(q4 >> (8 * t)) & 0x3Fu];
+					rquality += s_score[__byte_perm(q4, 0, 0x4440)];
+					rquality1 += s_score[__byte_perm(q4, 0, 0x4441)];
+					rquality += s_score[__byte_perm(q4, 0, 0x4442)];
+					rquality1 += s_score[__byte_perm(q4, 0, 0x4443)];
 				}
+				const int nb = dr & 3;
+				if (nb) {
+					unsigned q4 = __funnelshift_r(qlo, rqp[nfull + 1], shq);
+					q4 &= (1u << (8 * nb)) - 1u;          /* what follows the read in shared memory is not a quality */
+					qbad |= ((q4 & 0x7F7F7F7Fu) + 0x51515151u) | q4;
+					for (int t = 0; t < nb; t++)
+						rquality += s_score[(q4 >> (8 * t)) & 0xFFu];
+				}
+				rquality += rquality1;
 			}
 			if (qbad & 0x80808080u)
 				defer = true;                           /* a quality outside 0..46: PHREDCLAMP (prob.h:23) is the general kernel's job */
@@ -559,7 +457,7 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 }
 
 template <int ML, int WARPS> constexpr size_t lanes_smem_bytes() {
-	constexpr size_t HEAD = ((2 * TRI * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned)) + 127) & ~(size_t) 127;
+	constexpr size_t HEAD = ((LUT_DOUBLES * sizeof(double) + PB_NCOUNTERS * sizeof(unsigned)) + 127) & ~(size_t) 127;
 	return HEAD + sizeof(LaneArea<ML>) * WARPS;
 }
 
