@@ -387,9 +387,44 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = n * world * args.steps / (total_ms / 1e3) / 1e6
-    # the step is one launch of the assemble kernel: its average duration is the kernel duration
+    # the step is the library's kernels back to back on one stream: its average duration is their summed duration
     kern_ms = float(np.mean(step_ms))
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+    # which kernels a step launches and how long each runs: three more steps, outside the timed region, with the library's
+    # own events around every kernel (pb_set_timing / pb_last_timing)
+    saved = counters.clone()
+    ctx.set_timing(True)
+    kt = []
+    for _ in range(3):
+        step()
+        kt.append(ctx.last_timing())
+    ctx.set_timing(False)
+    ctx.synchronize()
+    counters.copy_(saved)
+    kind = kt[-1][0]
+    kms = [float(np.mean([t[1][k] for t in kt])) for k in range(3)]
+    fl0 = int(meta[0, 1].item()) & 0xFFFF
+    rl0 = (int(meta[0, 1].item()) >> 16) & 0xFFFF
+    if kind == 2:
+        # algorithmic bytes per pair of each kernel: seeding reads the packed bases + metadata and writes a 32-byte mask record;
+        # the lane kernel reads the whole record, the metadata and the mask record and writes the result + the merged read
+        seed_b = ((fl0 + 1) // 2 + (rl0 + 1) // 2 + 8)
+        kernels = [
+            {"name": "pb::seed_kernel (K1-K3: k-mer join, one warp per pair)", "ms": kms[0], "launches_per_step": 1,
+             "algorithmic_read_bytes_per_pair": seed_b, "achieved_gbs": seed_b * n / (kms[0] / 1e3) / 1e9},
+            {"name": "pbl::assemble_lanes_kernel (K4-K6: score + merge, one lane per pair)", "ms": kms[1], "launches_per_step": 1,
+             "algorithmic_read_bytes_per_pair": alg_bytes / n + 32, "achieved_gbs": (alg_bytes + 32 * n) / (kms[1] / 1e3) / 1e9},
+            {"name": "pb::assemble_kernel, list mode (the pairs the two kernels above hand on)", "ms": kms[2], "launches_per_step": 1},
+        ]
+        kernel_name = "pb::seed_kernel + pbl::assemble_lanes_kernel + pb::assemble_kernel<list> (one step; the read bytes of the path over their summed duration)"
+        launches_per_step = 3
+    else:
+        kernels = [{"name": "pb::assemble_kernel", "ms": kms[2], "launches_per_step": 1}]
+        kernel_name = "pb::assemble_kernel"
+        launches_per_step = 1
+    for k in kernels:
+        if "achieved_gbs" in k:
+            k["frac_of_peak"] = None      # filled in below, once the peak is known
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -397,6 +432,9 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    for k in kernels:
+        if "achieved_gbs" in k:
+            k["frac_of_peak"] = k["achieved_gbs"] / peak
     # DRAM traffic of the kernel from the committed `ncu --set full` capture (bytes per pair x pairs of one launch)
     traffic, traffic_src = None, None
     try:
@@ -483,8 +521,8 @@ def main():
                        "parallelism": f"{world} x independent shards, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_pair": alg_bytes / n,
-                         "kernel": "pb::assemble_kernel", "kernel_ms": kern_ms},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "stat": stat,
+                         "kernel": kernel_name, "kernel_ms": kern_ms, "kernels": kernels},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks, "stat": stat,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

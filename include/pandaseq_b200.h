@@ -408,6 +408,13 @@ pb_status pb_synchronize(pb_context *ctx);
  * A/C/G/T, a quality outside 0..46, no seed, ...) to the general warp-per-pair kernel.  This reports, since the context was
  * created, how many pairs were launched that way and how many of them were handed on.  Synchronises the device. */
 pb_status pb_lanes_stats(pb_context *ctx, uint64_t *lanes_pairs, uint64_t *deferred_pairs);
+/* Measurement.  With timing on, pb_assemble_device records CUDA events around its kernels on the context's stream;
+ * pb_last_timing waits for the last call and returns their durations in milliseconds:
+ *   kind 1: the general kernel alone, ms[2];
+ *   kind 2: the two-kernel path -- ms[0] seeding (pb::seed_kernel), ms[1] lane-per-pair score + merge, ms[2] the general
+ *           kernel over the pairs handed on;   kind 0: nothing recorded. */
+pb_status pb_set_timing(pb_context *ctx, int on);
+pb_status pb_last_timing(pb_context *ctx, int *kind, float ms[3]);
 
 /* Host helpers for the layout (pure integer bookkeeping, no compute on reads). */
 /* fills rec_off16[n] and returns total packed bytes */

@@ -180,6 +180,10 @@ def lib() -> C.CDLL:
     L.pb_synchronize.restype = i32
     L.pb_lanes_stats.argtypes = [vp, vp, vp]
     L.pb_lanes_stats.restype = i32
+    L.pb_set_timing.argtypes = [vp, i32]
+    L.pb_set_timing.restype = i32
+    L.pb_last_timing.argtypes = [vp, vp, vp]
+    L.pb_last_timing.restype = i32
     L.pb_config_default.argtypes = [C.POINTER(PbConfig), i32]
     L.pb_get_tables.restype = C.POINTER(PbTables)
     L.pb_layout_host.argtypes = [sz, vp, vp, vp]
@@ -257,6 +261,16 @@ class Context:
         a, b = C.c_uint64(0), C.c_uint64(0)
         _check(lib().pb_lanes_stats(self._h, C.byref(a), C.byref(b)), "pb_lanes_stats")
         return int(a.value), int(b.value)
+
+    def set_timing(self, on: bool):
+        _check(lib().pb_set_timing(self._h, 1 if on else 0), "pb_set_timing")
+
+    def last_timing(self):
+        """(kind, [seed ms, lanes ms, general ms]) of the last assemble_device call made with timing on."""
+        kind = C.c_int(0)
+        ms = (C.c_float * 3)()
+        _check(lib().pb_last_timing(self._h, C.byref(kind), ms), "pb_last_timing")
+        return int(kind.value), [float(x) for x in ms]
 
     # ---- host-buffer (e2e) path ----------------------------------------------------
     def assemble_host(self, cfg: PbConfig, batch, *, want_nt=True, want_p=False, seq_stride=None):

@@ -24,6 +24,10 @@ struct pb_context {
 	uint32_t *d_seeds[2];            /* candidate-overlap masks of pb::seed_kernel, 8 words per pair */
 	unsigned long long *d_defer_total;   /* pairs deferred so far (device), next to lanes_pairs (host) */
 	unsigned long long lanes_pairs;
+	/* pb_set_timing / pb_last_timing: events around the kernels of the last pb_assemble_device call */
+	bool timing;
+	int timing_kind;                 /* 0 = nothing recorded, 1 = general kernel alone, 2 = seed + lanes + general(list) */
+	cudaEvent_t tev[4];
 	pthread_mutex_t lock;            /* one host-path call at a time per context (assemblers share the process-wide one) */
 	/* host-path staging (grown on demand) */
 	struct Slot {

@@ -51,6 +51,8 @@ extern "C" pb_status pb_context_create(int device, pb_context **out) {
 	CUDA_TRY(cudaMalloc(&ctx->d_params, sizeof(pb_device_params)));
 	CUDA_TRY(cudaMallocHost(&ctx->h_params, sizeof(pb_device_params)));
 	CUDA_TRY(cudaMalloc(&ctx->d_counters, PB_NCOUNTERS * sizeof(unsigned long long)));
+	for (int k = 0; k < 4; k++)
+		CUDA_TRY(cudaEventCreate(&ctx->tev[k]));
 	CUDA_TRY(cudaMalloc(&ctx->d_defer_total, sizeof(unsigned long long)));
 	CUDA_TRY(cudaMemset(ctx->d_defer_total, 0, sizeof(unsigned long long)));
 	for (int s = 0; s < 2; s++)
@@ -88,6 +90,8 @@ extern "C" void pb_context_destroy(pb_context *ctx) {
 	cudaFree(ctx->d_seeds[0]);
 	cudaFree(ctx->d_seeds[1]);
 	cudaFree(ctx->d_defer_total);
+	for (int k = 0; k < 4; k++)
+		cudaEventDestroy(ctx->tev[k]);
 	pb_io_release(ctx);
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->copy_stream);
@@ -155,9 +159,16 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 		}
 		scratch = ctx->d_scratch + (stream == ctx->copy_stream ? need / 2 : 0);
 	}
+	const bool timed = ctx->timing && stream == ctx->stream;
+	if (timed && !d_list)
+		CUDA_TRY(cudaEventRecord(ctx->tev[0], stream));
 	kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p,
 	                                                           (long long) seq_stride, d_counters, scratch, d_list, d_list_n);
 	CUDA_TRY(cudaGetLastError());
+	if (timed) {
+		CUDA_TRY(cudaEventRecord(ctx->tev[3], stream));
+		ctx->timing_kind = d_list ? 2 : 1;
+	}
 	return PB_OK;
 }
 
@@ -194,6 +205,9 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 	int *d_count = ctx->d_defer[si], *d_list = ctx->d_defer[si] + 4;
 	uint32_t *d_seeds = ctx->d_seeds[si];
 	CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+	const bool timed = ctx->timing && stream == ctx->stream;
+	if (timed)
+		CUDA_TRY(cudaEventRecord(ctx->tev[0], stream));
 	{
 		long long grid = ((long long) n + SW - 1) / SW;
 		if (grid > ctx->sm_count)
@@ -201,6 +215,8 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 		seedk<<<(unsigned) (grid < 1 ? 1 : grid), SW * 32, seed_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds);
 		CUDA_TRY(cudaGetLastError());
 	}
+	if (timed)
+		CUDA_TRY(cudaEventRecord(ctx->tev[1], stream));
 	const long long nbatch = ((long long) n + 31) / 32;
 	long long grid = ((long long) nbatch + LW - 1) / LW;
 	if (grid > ctx->sm_count)
@@ -210,6 +226,8 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 	kern<<<(unsigned) grid, LW * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, d_results, d_seq_nt, (long long) seq_stride,
 	                                                   d_counters, d_list, d_count, ctx->d_defer_total);
 	CUDA_TRY(cudaGetLastError());
+	if (timed)
+		CUDA_TRY(cudaEventRecord(ctx->tev[2], stream));
 	ctx->lanes_pairs += (unsigned long long) n;
 	return launch_assemble<ML, false, GW, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, nullptr, seq_stride, d_counters, stream, false,
 	                                             d_list, d_count);
@@ -313,6 +331,37 @@ extern "C" pb_status pb_lanes_stats(pb_context *ctx, uint64_t *lanes_pairs, uint
 	CUDA_TRY(cudaMemcpy(&d, ctx->d_defer_total, sizeof d, cudaMemcpyDeviceToHost));
 	*lanes_pairs = ctx->lanes_pairs;
 	*deferred_pairs = d;
+	return PB_OK;
+}
+
+extern "C" pb_status pb_set_timing(pb_context *ctx, int on) {
+	if (!ctx) {
+		pb_set_error("pb_set_timing: no context");
+		return PB_ERR_ARGUMENT;
+	}
+	ctx->timing = on != 0;
+	ctx->timing_kind = 0;
+	return PB_OK;
+}
+
+extern "C" pb_status pb_last_timing(pb_context *ctx, int *kind, float ms[3]) {
+	if (!ctx || !kind || !ms) {
+		pb_set_error("pb_last_timing: bad argument");
+		return PB_ERR_ARGUMENT;
+	}
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	ms[0] = ms[1] = ms[2] = 0.0f;
+	*kind = ctx->timing_kind;
+	if (ctx->timing_kind == 0)
+		return PB_OK;
+	CUDA_TRY(cudaEventSynchronize(ctx->tev[3]));
+	if (ctx->timing_kind == 1) {
+		CUDA_TRY(cudaEventElapsedTime(&ms[2], ctx->tev[0], ctx->tev[3]));
+	} else {
+		CUDA_TRY(cudaEventElapsedTime(&ms[0], ctx->tev[0], ctx->tev[1]));
+		CUDA_TRY(cudaEventElapsedTime(&ms[1], ctx->tev[1], ctx->tev[2]));
+		CUDA_TRY(cudaEventElapsedTime(&ms[2], ctx->tev[2], ctx->tev[3]));
+	}
 	return PB_OK;
 }
 
