@@ -89,6 +89,10 @@ extern "C" void pb_context_destroy(pb_context *ctx) {
 	cudaFree(ctx->d_defer[1]);
 	cudaFree(ctx->d_seeds[0]);
 	cudaFree(ctx->d_seeds[1]);
+	cudaFree(ctx->d_order[0]);
+	cudaFree(ctx->d_order[1]);
+	cudaFree(ctx->d_bins[0]);
+	cudaFree(ctx->d_bins[1]);
 	cudaFree(ctx->d_defer_total);
 	for (int k = 0; k < 4; k++)
 		cudaEventDestroy(ctx->tev[k]);
@@ -175,14 +179,14 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 /* The two-kernel path for the common configurations: pb::seed_kernel (warp per pair, K1-K3) leaves the candidate
  * overlaps of every pair, pbl::assemble_lanes_kernel (lane per pair, K4-K6) scores and merges, and the general kernel
  * assembles the pairs those two handed on. */
-template <int ML, int SW, int LW, int GW>
+template <int ML, int LML, int SW, int LW, int GW>
 static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
                               pb_pair_result *d_results, uint8_t *d_seq_nt, size_t seq_stride,
                               unsigned long long *d_counters, cudaStream_t stream) {
 	auto seedk = pb::seed_kernel<ML, SW>;
-	auto kern = pbl::assemble_lanes_kernel<ML, LW>;
+	auto kern = pbl::assemble_lanes_kernel<LML, LW>;      /* LML <= ML: the length class that sizes the lane kernel's record slots */
 	constexpr size_t seed_smem = sizeof(pb::WarpSmem<ML>) * SW;
-	constexpr size_t smem = pbl::lanes_smem_bytes<ML, LW>();
+	constexpr size_t smem = pbl::lanes_smem_bytes<LML, LW>();
 	static bool configured[16] = { false };
 	if (!configured[ctx->device & 15]) {
 		CUDA_TRY(cudaFuncSetAttribute(seedk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) seed_smem));
@@ -194,17 +198,23 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 		CUDA_TRY(cudaDeviceSynchronize());
 		cudaFree(ctx->d_defer[si]);
 		cudaFree(ctx->d_seeds[si]);
+		cudaFree(ctx->d_order[si]);
 		ctx->d_defer[si] = nullptr;
 		ctx->d_seeds[si] = nullptr;
+		ctx->d_order[si] = nullptr;
 		ctx->defer_cap[si] = 0;
 		const size_t cap = (size_t) n + (size_t) n / 4 + 64;
 		CUDA_TRY(cudaMalloc(&ctx->d_defer[si], cap * sizeof(int)));
 		CUDA_TRY(cudaMalloc(&ctx->d_seeds[si], cap * pb::PB_SEED_WORDS * sizeof(uint32_t)));
+		CUDA_TRY(cudaMalloc(&ctx->d_order[si], cap * sizeof(int)));
+		if (!ctx->d_bins[si])
+			CUDA_TRY(cudaMalloc(&ctx->d_bins[si], 2 * pb::PB_SEED_BINS * sizeof(unsigned)));
 		ctx->defer_cap[si] = cap;
 	}
 	int *d_count = ctx->d_defer[si], *d_list = ctx->d_defer[si] + 4;
 	uint32_t *d_seeds = ctx->d_seeds[si];
 	CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+	CUDA_TRY(cudaMemsetAsync(ctx->d_bins[si], 0, 2 * pb::PB_SEED_BINS * sizeof(unsigned), stream));
 	const bool timed = ctx->timing && stream == ctx->stream;
 	if (timed)
 		CUDA_TRY(cudaEventRecord(ctx->tev[0], stream));
@@ -212,7 +222,9 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 		long long grid = ((long long) n + SW - 1) / SW;
 		if (grid > ctx->sm_count)
 			grid = ctx->sm_count;
-		seedk<<<(unsigned) (grid < 1 ? 1 : grid), SW * 32, seed_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds);
+		seedk<<<(unsigned) (grid < 1 ? 1 : grid), SW * 32, seed_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si]);
+		CUDA_TRY(cudaGetLastError());
+		pb::bin_order_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(n, d_seeds, ctx->d_bins[si], ctx->d_order[si]);
 		CUDA_TRY(cudaGetLastError());
 	}
 	if (timed)
@@ -223,7 +235,7 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 		grid = ctx->sm_count;
 	if (grid < 1)
 		grid = 1;
-	kern<<<(unsigned) grid, LW * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, d_results, d_seq_nt, (long long) seq_stride,
+	kern<<<(unsigned) grid, LW * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_order[si], d_results, d_seq_nt, (long long) seq_stride,
 	                                                   d_counters, d_list, d_count, ctx->d_defer_total);
 	CUDA_TRY(cudaGetLastError());
 	if (timed)
@@ -256,7 +268,12 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 	}
 	if (lanes_on && !full && !d_seq_p && max_len <= 160 && cfg->forward_trim == 0 && cfg->reverse_trim == 0
 	    && (cfg->algo == PB_SIMPLE_BAYES || cfg->algo == PB_UPARSE || cfg->algo == PB_FLASH) && ((uintptr_t) d_seq_nt % 8) == 0)
-		return launch_lanes<160, 32, 11, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
+	{
+		/* reads up to 152 nt (2x150 included) leave room for a 12th warp of the lane kernel */
+		if (max_len <= 152)
+			return launch_lanes<160, 152, 32, 12, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
+		return launch_lanes<160, 160, 32, 11, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
+	}
 #define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq); \
 	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false); } while (0)
 	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */

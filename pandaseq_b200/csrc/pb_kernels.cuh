@@ -1222,16 +1222,23 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
  *                      PB_SEED_SKIP: not a pair (flen == 0xFFFF). */
 constexpr unsigned PB_SEED_GENERAL = 1u, PB_SEED_SKIP = 2u;
 constexpr int PB_SEED_WORDS = 8;
+/*   seeds[pair][6]     bin of the pair: (lowest candidate overlap - minoverlap) / 16, or PB_SEED_BINS - 1 for the pairs that
+ *                      carry a flag.  bin_order_kernel lists the pairs bin by bin, so that the 32 pairs a warp of the lane-per-
+ *                      pair kernel takes have overlaps within 16 bases of each other and its loops end together. */
+constexpr int PB_SEED_BINS = 11;
 
 template <int ML, int WARPS_PER_BLOCK>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__restrict__ reads,
-            const pb_pair_meta *__restrict__ meta, uint32_t *__restrict__ seeds) {
+            const pb_pair_meta *__restrict__ meta, uint32_t *__restrict__ seeds, unsigned *__restrict__ bin_count) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
+	__shared__ unsigned s_bins[PB_SEED_BINS];
 	using WS = WarpSmem<ML>;
 	static_assert(ML <= 160, "the candidate mask has 160 bits");
 	WS *wsall = reinterpret_cast<WS *>(smem_raw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid < PB_SEED_BINS)
+		s_bins[tid] = 0;
 	WS &ws = wsall[warp];
 	for (int k = lane; k < WS::NB; k += 32)
 		ws.btab[k] = ~0ull;
@@ -1273,7 +1280,7 @@ seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__re
 		mbar_wait(&ws.bar[stage], (it >> 1) & 1);
 		const pb_pair_meta m = ws.meta[stage];
 		const int F = m.flen, R = m.rlen;
-		unsigned word = 0, flags = 0;
+		unsigned word = 0, flags = 0, bin = PB_SEED_BINS - 1;
 		if (F == 0xFFFF) {
 			flags = PB_SEED_SKIP;
 		} else if (F > ML || R > ML || F < 16 || R < 16 || mo >= min(F, R)) {
@@ -1300,6 +1307,8 @@ seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__re
 					if (lane == w)
 						word = b;
 				}
+				/* the lowest candidate decides the bin */
+				bin = __reduce_min_sync(FULL, word ? (unsigned) (32 * lane + __ffs(word) - 1) : 1023u) >> 4;
 				__syncwarp();
 				if (lane < 10)
 					reinterpret_cast<uint4 *>(ws.cflag)[lane] = make_uint4(0, 0, 0, 0);
@@ -1307,12 +1316,48 @@ seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__re
 					flags = PB_SEED_GENERAL;       /* ALL_BITS_IF_NONE (assembler.c:118): every overlap is scored */
 			}
 		}
+		if (flags)
+			bin = PB_SEED_BINS - 1;
 		if (lane == 5)
 			word = flags;
+		if (lane == 6)
+			word = bin;
 		if (lane < PB_SEED_WORDS)
-			seeds[(size_t) pair * PB_SEED_WORDS + lane] = lane < 6 ? word : 0u;
+			seeds[(size_t) pair * PB_SEED_WORDS + lane] = lane < 7 ? word : 0u;
+		if (lane == 0)
+			atomicAdd(&s_bins[bin], 1u);
 		__syncwarp();      /* every lane is done with this stage before it is refilled */
 	}
+	__syncthreads();
+	if (tid < PB_SEED_BINS && s_bins[tid])
+		atomicAdd(&bin_count[tid], s_bins[tid]);
+}
+
+/* The pairs of a batch listed bin by bin (seeds[pair][6]); the order inside a bin is whatever the atomics make it, which no
+ * result depends on.  bin_state: [0 .. BINS) pairs per bin (seed_kernel), [BINS .. 2 BINS) cursors, zero at launch. */
+__global__ void __launch_bounds__(256)
+bin_order_kernel(int n, const uint32_t *__restrict__ seeds, unsigned *__restrict__ bin_state, int *__restrict__ order) {
+	__shared__ unsigned s_hist[PB_SEED_BINS], s_base[PB_SEED_BINS];
+	const int tid = threadIdx.x;
+	if (tid < PB_SEED_BINS)
+		s_hist[tid] = 0;
+	__syncthreads();
+	const int pair = blockIdx.x * blockDim.x + tid;
+	unsigned bin = 0, rank = 0;
+	if (pair < n) {
+		bin = min(seeds[(size_t) pair * PB_SEED_WORDS + 6], (unsigned) (PB_SEED_BINS - 1));
+		rank = atomicAdd(&s_hist[bin], 1u);
+	}
+	__syncthreads();
+	if (tid < PB_SEED_BINS) {
+		unsigned first = 0;                       /* pairs in the bins before this one */
+		for (int b = 0; b < tid; b++)
+			first += bin_state[b];
+		s_base[tid] = first + (s_hist[tid] ? atomicAdd(&bin_state[PB_SEED_BINS + tid], s_hist[tid]) : 0u);
+	}
+	__syncthreads();
+	if (pair < n)
+		order[s_base[bin] + rank] = pair;
 }
 
 template <int ML, bool OVER, int WARPS_PER_BLOCK> constexpr size_t assemble_smem_bytes() {

@@ -52,7 +52,7 @@ template <int ML, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
                       const uint8_t *__restrict__ reads, const pb_pair_meta *__restrict__ meta,
-                      const uint32_t *__restrict__ seeds, pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, long long seq_stride,
+                      const uint32_t *__restrict__ seeds, const int *__restrict__ order, pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, long long seq_stride,
                       unsigned long long *__restrict__ counters, int *__restrict__ defer_list, int *__restrict__ defer_count,
                       unsigned long long *__restrict__ defer_total) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -86,7 +86,8 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 	unsigned parity = 0;
 
 	for (int batch = blockIdx.x * WARPS + warp; batch < nbatch; batch += gridDim.x * WARPS) {
-		const int pair = batch * 32 + lane;
+		const int item = batch * 32 + lane;
+		const int pair = item < n ? order[item] : n;           /* pairs come bin by bin (pb::bin_order_kernel) */
 		unsigned off16 = 0;
 		int F = 0xFFFF, R = 0;
 		if (pair < n) {
@@ -104,7 +105,7 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 			sflags = s1.y;
 		}
 		const bool skip = F == 0xFFFF;              /* not a pair (FASTQ reader, fastq.c:176), or past the end of the batch */
-		bool defer = !skip && (sflags & pb::PB_SEED_GENERAL) != 0;
+		bool defer = !skip && ((sflags & pb::PB_SEED_GENERAL) != 0 || F > ML || R > ML);      /* a record must fit its slot */
 		const bool act = !skip && !defer;
 		const unsigned bytes = act ? pb::record_bytes((unsigned) F, (unsigned) R) : 0u;
 		const unsigned total = __reduce_add_sync(FULL, bytes);
@@ -114,9 +115,9 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 		if (bytes)
 			pb::bulk_g2s(wa.rec + lane * LA::REC_STRIDE, reads + (size_t) off16 * 16, bytes, &wa.bar);
 		{       /* the next batch of this warp: pull its records into L2 while this one is processed */
-			const long long np = (long long) pair + (long long) gridDim.x * WARPS * 32;
-			if (np < n) {
-				const uint2 mn = *reinterpret_cast<const uint2 *>(&meta[np]);
+			const long long ni = (long long) item + (long long) gridDim.x * WARPS * 32;
+			if (ni < n) {
+				const uint2 mn = *reinterpret_cast<const uint2 *>(&meta[order[ni]]);
 				const unsigned nF = mn.y & 0xFFFFu, nR = mn.y >> 16;
 				if (nF != 0xFFFFu && nF <= (unsigned) ML && nR <= (unsigned) ML) {
 					const unsigned nbytes = pb::record_bytes(nF, nR);
