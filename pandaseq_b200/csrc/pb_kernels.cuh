@@ -176,7 +176,7 @@ struct PairView {
 template <bool TEMPLATE_ORDER>
 __device__ int primer_offset(const uint32_t *nt32, const int8_t *q, int len,
                              const uint8_t *primer, int P, double threshold, double penalty,
-                             const double *score, const uint16_t *qoff, int lane) {
+                             const double *score, const uint16_t *qoff, double *se, int lane) {
 	if (P > len)
 		return 0;
 	/* The reference tests slot (index % P) at every index before resetting it; the value it sees at
@@ -190,58 +190,84 @@ __device__ int primer_offset(const uint32_t *nt32, const int8_t *q, int len,
 	const int nstart = len - P;                    /* starts 0 .. nstart-1 */
 	const char *tab = reinterpret_cast<const char *>(score);
 	const unsigned char *qu = reinterpret_cast<const unsigned char *>(q);
+	/* Both scores of every read position, once: se[2i] = qual_score[q_i] (the base agrees with the primer),
+	 * se[2i+1] = qual_score_err[q_i] (offset.c:93-101), i in scan order.  The scan below then costs one predicate,
+	 * one select and one 8-byte load per (start, primer base). */
+	for (int i = lane; i < len; i += 32) {
+		const unsigned off = qoff[256 + qu[TEMPLATE_ORDER ? (len - 1 - i) : i]];
+		double2 v;
+		v.x = *reinterpret_cast<const double *>(tab + off);
+		v.y = *reinterpret_cast<const double *>(tab + off + PB_NQM * 8);      /* score_err[] follows score[] */
+		reinterpret_cast<double2 *>(se)[i] = v;
+	}
+	/* The primer as masks: pm[x] = its nibble at the place base x & 7 of an 8-base window has (template order: the window
+	 * is bit-reversed below, so the nibble is too); all ones for N, which contributes nothing (offset.c:97). */
+	uint32_t *pm = reinterpret_cast<uint32_t *>(se + 2 * len);
+	bool has_n = false;
+	for (int x = lane; x - lane < P; x += 32) {
+		unsigned pn = x < P ? primer[x] : 0u;
+		const bool isn = pn == 15u;
+		has_n = has_n || isn;
+		if (TEMPLATE_ORDER)
+			pn = __brev(pn) >> 28;
+		if (x < P)
+			pm[x] = isn ? ~0u : pn << (4 * (x & 7));
+	}
+	has_n = __any_sync(FULL, has_n);
+	__syncwarp();
 	for (int base = 0; base < nstart; base += 32) {
 		const int s = min(base + lane, nstart - 1);    /* surplus lanes redo the last start; masked below */
 		double sum = 0.0;
-		int el = TEMPLATE_ORDER ? (len - 1 - s) : s;   /* element holding read position s + x */
+		const int el = TEMPLATE_ORDER ? (len - 1 - s) : s;   /* element holding read position s */
+		const char *sp = reinterpret_cast<const char *>(se + 2 * s);
 		for (int x0 = 0; x0 < P; x0 += 8) {
 			/* nibbles of the 8 read positions s+x0 .. s+x0+7 (template order: element first+7 is position s+x0) */
-			unsigned w = nibwin(nt32, TEMPLATE_ORDER ? (el - 7) : el);
-			const int xn = min(P - x0, 8);
+			unsigned w = nibwin(nt32, TEMPLATE_ORDER ? (el - x0 - 7) : (el + x0));
+			if (TEMPLATE_ORDER)
+				w = __brev(w);                         /* nibble k of the reversed word holds position s+x0+k, bits reversed inside it */
+			const uint32_t *pmb = pm + x0;
+			const char *spb = sp + 16 * x0;
+			if (P - x0 >= 8 && !has_n) {               /* warp-uniform: a full block of a primer without N */
 #pragma unroll
-			for (int t = 0; t < 8; t++) {
-				if (t >= xn)
-					break;                             /* warp-uniform */
-				const unsigned pn = primer[x0 + t];
-				unsigned b;
-				if (TEMPLATE_ORDER) {
-					b = w >> 28;
-					w <<= 4;
-				} else {
-					b = w & 15u;
-					w >>= 4;
+				for (int t = 0; t < 8; t++) {
+					const unsigned off = (w & pmb[t]) == 0u ? 8u : 0u;
+					sum += *reinterpret_cast<const double *>(spb + 16 * t + off);
 				}
-				unsigned off = qoff[256 + qu[el]];
-				el += TEMPLATE_ORDER ? -1 : 1;
-				if ((b & pn) == 0)
-					off += (unsigned) (PB_NQM * 8);    /* score_err[] follows score[] */
-				if (pn != 15u)                         /* warp-uniform: N in the primer contributes nothing */
-					sum += *reinterpret_cast<const double *>(tab + off);
+			} else {
+				const int xn = min(P - x0, 8);
+				for (int t = 0; t < xn; t++) {
+					const unsigned m = pmb[t];
+					if (m != ~0u) {                        /* warp-uniform: not an N of the primer */
+						const unsigned off = (w & m) == 0u ? 8u : 0u;
+						sum += *reinterpret_cast<const double *>(spb + 16 * t + off);
+					}
+				}
 			}
 		}
-		/* The reference scans starts in increasing order and keeps the first strictly better one:
-		 * within a batch that is the maximum value with the lowest start on ties. */
 		const int index = s + P;                   /* the index at which this slot is examined */
 		double val = sum / (double) (index + 1);
 		if (penalty != 0.0)
 			val = exp(val) - (double) index * penalty;
 		if (base + lane >= nstart)
 			val = -CUDART_INF;
-		int who = s;
+		/* The reference scans starts in increasing order and keeps the first strictly better one:
+		 * within a batch that is the maximum value with the lowest start on ties. */
+		if (__any_sync(FULL, val > best)) {
+			int who = s;
 #pragma unroll
-		for (int d = 16; d > 0; d >>= 1) {
-			const double ov = __shfl_xor_sync(FULL, val, d);
-			const int ow = __shfl_xor_sync(FULL, who, d);
-			if (ov > val || (ov == val && ow < who)) {
-				val = ov;
-				who = ow;
+			for (int d = 16; d > 0; d >>= 1) {
+				const double ov = __shfl_xor_sync(FULL, val, d);
+				const int ow = __shfl_xor_sync(FULL, who, d);
+				if (ov > val || (ov == val && ow < who)) {
+					val = ov;
+					who = ow;
+				}
 			}
-		}
-		if (val > best) {
 			best = val;
 			best_index = who + P + 1;
 		}
 	}
+	__syncwarp();      /* se[] is rewritten by the next scan */
 	return best_index;
 }
 
@@ -593,7 +619,7 @@ __device__ __forceinline__ double recon_words(const ReconArgs &ra, const double 
  * Returns false when the pair is dropped (sequence not found and hang_skip unset). */
 template <int ML>
 __device__ bool trim_overhangs(uint8_t *rec, int F0, int R0, int &F, int &R, const pb_device_params *__restrict__ prm,
-                               const double *__restrict__ s_score, const uint16_t *__restrict__ s_qoff, int lane) {
+                               const double *__restrict__ s_score, const uint16_t *__restrict__ s_qoff, double *se, int lane) {
 	const int fwb = ((F0 + 7) / 8) * 4, rwb = ((R0 + 7) / 8) * 4;
 	uint32_t *fnt32 = reinterpret_cast<uint32_t *>(rec), *rnt32 = reinterpret_cast<uint32_t *>(rec + fwb);
 	int8_t *fq = reinterpret_cast<int8_t *>(rec + fwb + rwb), *rq = fq + ((F0 + 3) / 4) * 4;
@@ -601,7 +627,7 @@ __device__ bool trim_overhangs(uint8_t *rec, int F0, int R0, int &F, int &R, con
 	R = R0;
 	if (prm->hang_forward_length > 0) {
 		/* index i of the scan is read position F-1-i: the "template order" form of primer_offset */
-		const int off = primer_offset<true>(fnt32, fq, F0, prm->hang_forward, prm->hang_forward_length, prm->hang_threshold, 0.0, s_score, s_qoff, lane);
+		const int off = primer_offset<true>(fnt32, fq, F0, prm->hang_forward, prm->hang_forward_length, prm->hang_threshold, 0.0, s_score, s_qoff, se, lane);
 		if (off == 0) {
 			if (!prm->hang_skip)
 				return false;
@@ -611,7 +637,7 @@ __device__ bool trim_overhangs(uint8_t *rec, int F0, int R0, int &F, int &R, con
 	}
 	if (prm->hang_reverse_length > 0) {
 		/* the reverse read is stored in template order: scan index i (read position R-1-i) is element i */
-		const int off = primer_offset<false>(rnt32, rq, R0, prm->hang_reverse, prm->hang_reverse_length, prm->hang_threshold, 0.0, s_score, s_qoff, lane);
+		const int off = primer_offset<false>(rnt32, rq, R0, prm->hang_reverse, prm->hang_reverse_length, prm->hang_threshold, 0.0, s_score, s_qoff, se, lane);
 		if (off == 0) {
 			if (!prm->hang_skip)
 				return false;
@@ -685,9 +711,32 @@ __device__ void process_pair(WarpSmem<ML> &ws, uint8_t *rec, int F, int R,
 	v.rnt32 = reinterpret_cast<const uint32_t *>(v.rnt);
 	v.fq = (const int8_t *) (rec + fwb + rwb);
 	v.rq = v.fq + ((F + 3) / 4) * 4;
+	/* The primer / overhang scans keep two doubles per read position in the bucket table's memory (it is idle until the
+	 * k-mer join); BucketRestore puts the table's "empty" pattern back on every way out of this function. */
+	static_assert(sizeof(ws.btab) >= (size_t) ML * 16 + (size_t) ML * 4, "the bucket table must hold two doubles per read position and the primer masks");
+	double *const se = reinterpret_cast<double *>(ws.btab);
+	struct BucketRestore {
+		WarpSmem<ML> &w;
+		bool on;
+		int lane;
+		__device__ void now() {
+			if (on) {
+				__syncwarp();
+				uint4 *t4 = reinterpret_cast<uint4 *>(w.btab);
+				const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+#pragma unroll
+				for (int k = 0; k < WarpSmem<ML>::NB * 8 / 16 / 32; k++)
+					t4[k * 32 + lane] = ones;
+				__syncwarp();
+				on = false;
+			}
+		}
+		__device__ ~BucketRestore() { now(); }      /* the early returns (NOFP, NORP, BADR, NOALGN, dropped by the trimmer) */
+	};
+	BucketRestore restore{ ws, FULLF && (prm->hang_forward_length > 0 || prm->hang_reverse_length > 0 || (prm->post_primers == 0 && (prm->forward_primer_length > 0 || prm->reverse_primer_length > 0))), lane };
 	if (FULLF && (prm->hang_forward_length > 0 || prm->hang_reverse_length > 0)) {
 		int Ft, Rt;
-		if (!trim_overhangs<ML>(rec, F, R, Ft, Rt, prm, s_score, s_qoff, lane)) {
+		if (!trim_overhangs<ML>(rec, F, R, Ft, Rt, prm, s_score, s_qoff, se, lane)) {
 			res.status = PB_PAIR_SKIP;         /* the reader drops the pair: the assembler never sees it */
 			res.slow = 0;
 			res.overlap = res.seq_len = res.mismatches = res.degenerates = res.examined = 0;
@@ -725,7 +774,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, uint8_t *rec, int F, int R,
 	} else {
 	if (FULLF && prm->forward_primer_length > 0) {
 		fo = primer_offset<false>(v.fnt32, v.fq, F, s_primer, prm->forward_primer_length,
-		                          prm->threshold, prm->primer_penalty, s_score, s_qoff, lane);
+		                          prm->threshold, prm->primer_penalty, s_score, s_qoff, se, lane);
 		if (fo == 0) {
 			res.status = PB_PAIR_NOFP;
 			return;
@@ -737,7 +786,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, uint8_t *rec, int F, int R,
 	res.fwd_offset = (uint16_t) fo;
 	if (FULLF && prm->reverse_primer_length > 0) {
 		ro = primer_offset<true>(v.rnt32, v.rq, R, s_primer + PB_MAX_LEN + 2, prm->reverse_primer_length,
-		                         prm->threshold, prm->primer_penalty, s_score, s_qoff, lane);
+		                         prm->threshold, prm->primer_penalty, s_score, s_qoff, se, lane);
 		if (ro == 0) {
 			res.status = PB_PAIR_NORP;
 			return;
@@ -766,6 +815,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, uint8_t *rec, int F, int R,
 		maxov = min(F + R - mo - fo - ro - 1, prm->maxoverlap);
 	const int nbits = (mo <= maxov) ? (maxov - mo + 1) : 1;
 
+	restore.now();       /* the scans are over: the bucket table is a bucket table again */
 	/* ---- k-mer codes of both reads ---- */
 	unsigned flg = gen_codes<WS::NTW>(v.fnt32, F, ws.code_f, lane) | gen_codes<WS::NTW>(v.rnt32, R, ws.code_r, lane);
 	flg = __reduce_or_sync(FULL, flg);
