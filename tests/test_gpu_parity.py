@@ -71,6 +71,28 @@ def test_primers_rdp_mle(ctx, penalty):
     assert rep["ok"], rep
 
 
+@pytest.mark.parametrize("plen", [1, 7, 8, 9, 15, 16, 17, 24, 31])
+def test_primers_with_n_and_iupac_codes(ctx, plen):
+    """Primer lengths either side of the 8-base blocks of the scan; N (contributes nothing, offset.c:97), IUPAC codes and the
+    invalid code 0 inside the primer; with and without a penalty; mixed read lengths (a primer longer than the read)."""
+    rng = np.random.default_rng(100 + plen)
+    fwd = 1 << rng.integers(0, 4, size=plen)
+    rev = 1 << rng.integers(0, 4, size=plen)
+    for cfg_kw in (dict(), dict(primer_penalty=0.001)):
+        for variant in range(3):
+            f, r = fwd.copy(), rev.copy()
+            if variant >= 1:
+                f[rng.integers(0, plen)] = 15
+                r[rng.integers(0, plen)] |= 1 << rng.integers(0, 4)
+            if variant == 2:
+                r[rng.integers(0, plen)] = 15
+                f[rng.integers(0, plen)] = 0
+            cfg = pb.make_config("simple_bayesian", forward_primer=f, reverse_primer=r, **cfg_kw)
+            for batch in (datasets.cfg1(600), datasets.mixed(400)):
+                got, want, rep = run_both(ctx, cfg, batch)
+                assert rep["ok"], (plen, variant, cfg_kw, rep)
+
+
 def test_primers_absent_and_partial(ctx):
     fwd, rev = datasets.primer_codes()
     cfg = pb.make_config("simple_bayesian", forward_primer=fwd, reverse_primer=rev)
