@@ -6,6 +6,9 @@
 
 struct pb_io_state;
 
+/* chunks of the host path in flight, alternating between the two streams (4 were measured: no gain, PCIe is the limit) */
+#define PB_HOST_SLOTS 2
+
 struct pb_context {
 	int device;
 	int sm_count;
@@ -48,7 +51,7 @@ struct pb_context {
 		double *d_p, *h_p;
 		size_t cap_nt, cap_p, cap_dnt, cap_dp;
 		cudaEvent_t done;
-	} slot[2];
+	} slot[PB_HOST_SLOTS];
 	pb_io_state *io;                 /* buffers of the FASTQ / text stages, allocated on first use (pb_io.cu) */
 };
 

@@ -55,7 +55,7 @@ extern "C" pb_status pb_context_create(int device, pb_context **out) {
 		CUDA_TRY(cudaEventCreate(&ctx->tev[k]));
 	CUDA_TRY(cudaMalloc(&ctx->d_defer_total, sizeof(unsigned long long)));
 	CUDA_TRY(cudaMemset(ctx->d_defer_total, 0, sizeof(unsigned long long)));
-	for (int s = 0; s < 2; s++)
+	for (int s = 0; s < PB_HOST_SLOTS; s++)
 		CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot[s].done, cudaEventDisableTiming));
 	*out = ctx;
 	return PB_OK;
@@ -77,7 +77,7 @@ extern "C" void pb_context_destroy(pb_context *ctx) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	cudaStreamSynchronize(ctx->copy_stream);
-	for (int s = 0; s < 2; s++) {
+	for (int s = 0; s < PB_HOST_SLOTS; s++) {
 		free_slot(ctx->slot[s]);
 		cudaEventDestroy(ctx->slot[s].done);
 	}
@@ -496,7 +496,7 @@ static pb_status assemble_host_locked(pb_context *ctx, const pb_config *cfg, siz
 	}
 	const size_t CHUNK = n > 2 * chunk_cfg ? chunk_cfg : (n + 1) / 2 + 1;       /* at least two chunks so the slots overlap */
 	const size_t nt_row = seq_stride / 2;
-	struct Pending { bool live; size_t begin, count; } pend[2] = { { false, 0, 0 }, { false, 0, 0 } };
+	struct Pending { bool live; size_t begin, count; } pend[PB_HOST_SLOTS] = {};
 	cudaStream_t streams[2] = { ctx->stream, ctx->copy_stream };
 	auto drain = [&](int si) -> pb_status {
 		if (!pend[si].live)
@@ -513,13 +513,13 @@ static pb_status assemble_host_locked(pb_context *ctx, const pb_config *cfg, siz
 		return PB_OK;
 	};
 	int si = 0;
-	for (size_t begin = 0; begin < n; begin += CHUNK, si ^= 1) {
+	for (size_t begin = 0; begin < n; begin += CHUNK, si = (si + 1) % PB_HOST_SLOTS) {
 		const size_t count = (n - begin < CHUNK) ? (n - begin) : CHUNK;
 		st = drain(si);
 		if (st != PB_OK)
 			return st;
 		pb_context::Slot &s = ctx->slot[si];
-		cudaStream_t stream = streams[si];
+		cudaStream_t stream = streams[si & 1];
 		const uint64_t fb = f_off[begin], rb = r_off[begin];
 		const size_t fbases = (size_t) (f_off[begin + count] - fb), rbases = (size_t) (r_off[begin + count] - rb);
 		st = ensure_slot(s, count, fbases, rbases, !pin_in, !pin_res, (seq_nt && !pin_nt) ? count * nt_row : 0, (seq_p && !pin_p) ? count * seq_stride : 0);
@@ -576,7 +576,7 @@ static pb_status assemble_host_locked(pb_context *ctx, const pb_config *cfg, siz
 		pend[si].begin = begin;
 		pend[si].count = count;
 	}
-	for (int k = 0; k < 2; k++) {
+	for (int k = 0; k < PB_HOST_SLOTS; k++) {
 		st = drain(k);
 		if (st != PB_OK)
 			return st;

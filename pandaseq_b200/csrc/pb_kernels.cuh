@@ -1131,8 +1131,11 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	using WS = WarpSmem<ML>;
 	/* list mode: assemble pairs list[0 .. *list_n) -- the ones the lane-per-pair kernel (pb_lanes.cuh) deferred */
-	if (list)
+	if (list) {
 		n = *list_n;
+		if ((long long) blockIdx.x * WARPS_PER_BLOCK >= n)      /* usually a few hundred pairs: most CTAs have nothing to do */
+			return;
+	}
 	/* block-level: LUTs + counters, then the per-warp areas */
 	constexpr int OVER_N = OVER ? 2 * PB_NQ * PB_NQ : 0;
 	double *s_recon = reinterpret_cast<double *>(smem_raw);
