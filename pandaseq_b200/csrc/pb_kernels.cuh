@@ -1271,7 +1271,7 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
  * bases of a record are staged, the candidate overlaps come out as a bit mask per pair.
  *   seeds[pair][0..4]  bit i set <=> overlap minoverlap + i shares a valid 8-mer between the reads (BIT_LIST_SET)
  *   seeds[pair][5]     PB_SEED_GENERAL: leave this pair to the general kernel (a base that is not A/C/G/T, reads
- *                      outside 16..ML, more than 160 candidate overlaps, no seed at all, k-mers crowding a bucket);
+ *                      outside 16..ML, more than 160 candidate overlaps, no seed at all);
  *                      PB_SEED_SKIP: not a pair (flen == 0xFFFF). */
 constexpr unsigned PB_SEED_GENERAL = 1u, PB_SEED_SKIP = 2u;
 constexpr int PB_SEED_WORDS = 8;
