@@ -279,6 +279,8 @@ struct pb_filter {
 	int32_t kind;         /* enum pb_filter_kind */
 	int32_t ivalue;
 	double dvalue;
+	double dvalue2;       /* pear_test only: beta */
+	double dvalue3;       /* pear_test only: cutoff */
 };
 
 /* Everything assemble_seq/align read from struct panda_assembler (assembler.h:28-79)
@@ -322,7 +324,9 @@ enum pb_filter_kind {
 	PB_FILTER_LONG = 3,            /* -L n: sequence_length <= n                    args_assembler.c:268-275 */
 	PB_FILTER_MIN_OVERLAPBITS = 4, /* min_overlapbits:bits  bits*ln2 <= estimated_overlap_probability, bits >= 0  plugin_min_overlapbits.c:17-50 */
 	PB_FILTER_MISS_THE_POINT = 5,  /* completely_miss_the_point:n  overlap_mismatches <= n   plugin_completely_miss_the_point.c:9-16 */
-	PB_FILTER_MIN_PHRED = 6        /* min_phred:v  every base's panda_result_phred >= v      plugin_min_phred.c:8-22 */
+	PB_FILTER_MIN_PHRED = 6,       /* min_phred:v  every base's panda_result_phred >= v      plugin_min_phred.c:8-22 */
+	PB_FILTER_PEAR_TEST = 7        /* pear_test:alpha=,beta=,cutoff=  the statistical test of PEAR on (overlap, overlap_mismatches, read lengths):
+	                                * dvalue = alpha, dvalue2 = beta, dvalue3 = cutoff in [0, 1]               plugin_pear_test.c:18-39 */
 };
 #define PB_PAIR_FILTERED 8
 

@@ -691,9 +691,28 @@ static int trim_overhangs(const po_config *cfg, const po_qual *F, size_t *flen, 
 	return 1;
 }
 
+/* plugin_pear_test.c:18-39.  The reference converts ceil(..) - 1 to size_t; a negative (or NaN) value makes its inner loop
+ * run for 2^64 iterations -- it never comes back -- while adding nothing once k exceeds i (lgamma of a non-positive integer
+ * is +inf, the term exp(-inf) is 0).  Defined here as what that loop has accumulated by then: all i + 1 terms. */
+static int pear_test_check(double alpha, double beta, double cutoff, size_t overlap, size_t mismatches, size_t flen, size_t rlen) {
+	double product = 1;
+	double oes = alpha * (overlap - mismatches) + beta * mismatches;
+	for (size_t i = overlap; i < flen && i < rlen; i++) {
+		double sum = 0;
+		double lraw = ceil((oes - beta * i) / (alpha - beta)) - 1;
+		size_t l_i = (lraw >= 0 && lraw < (double) (i + 1)) ? (size_t) lraw : i + 1;
+		for (size_t k = 0; k < l_i; k++) {
+			double i_choose_k = lgamma(i + 1) - lgamma(k + 1) - lgamma(i - k + 1);
+			sum += exp(i_choose_k + k * log(0.25) + (i - k) * log(0.75));
+		}
+		product *= sum;
+	}
+	return cutoff > 1 - product * product;
+}
+
 /* args_assembler.c:106-115,233-239,268-275; plugin_min_overlapbits.c:17-23; plugin_completely_miss_the_point.c:9-16;
- * plugin_min_phred.c:8-22.  Returns the index of the first check that fails, -1 if all pass. */
-static int first_failing_filter(const po_config *cfg, const po_one *one) {
+ * plugin_min_phred.c:8-22; plugin_pear_test.c.  Returns the index of the first check that fails, -1 if all pass. */
+static int first_failing_filter(const po_config *cfg, const po_one *one, size_t flen, size_t rlen) {
 	for (int k = 0; k < cfg->nfilters && k < 7; k++) {
 		const struct po_filter *f = &cfg->filters[k];
 		int pass = 1;
@@ -707,6 +726,9 @@ static int first_failing_filter(const po_config *cfg, const po_one *one) {
 			for (int it = 0; it < one->seq_len && pass; it++)
 				if (po_result_phred(one->p[it]) < f->ivalue)
 					pass = 0;
+			break;
+		case PO_FILTER_PEAR_TEST:
+			pass = pear_test_check(f->dvalue, f->dvalue2, f->dvalue3, (size_t) one->overlap, (size_t) one->mismatches, flen, rlen);
 			break;
 		}
 		if (!pass)
@@ -774,7 +796,7 @@ static void *run_job(void *arg) {
 		}
 		assemble_pair(job->cfg, table, F, flen, R, rlen, one);
 		if (one->status == PO_OK) {	/* module_checkseq, module.c:124-137: the first failing check rejects */
-			int k = first_failing_filter(job->cfg, one);
+			int k = first_failing_filter(job->cfg, one, flen, rlen);      /* the lengths the assembler saw (after the overhang trimmer) */
 			if (k >= 0) {
 				one->status = PO_FILTERED + k;
 				job->counters[PO_C_REJECTED + k]++;

@@ -37,6 +37,7 @@ bool long_check(PandaLogProxy logger, const panda_result_seq *sequence, void *us
 OPENER(min_overlapbits);
 OPENER(completely_miss_the_point);
 OPENER(min_phred);
+OPENER(pear_test);
 
 typedef struct {
 	long rejected[8];
@@ -121,12 +122,12 @@ static PandaAssembler make_assembler(const po_config *cfg) {
 	else
 		panda_assembler_set_reverse_trim(a, (size_t) cfg->reverse_trim);
 	/* module_checkseq (module.c:124-137) with the reference's own check functions: the three built into the library
-	 * (args_assembler.c) and three plugins compiled into this harness from their sources (oracle/Makefile) */
+	 * (args_assembler.c) and four plugins compiled into this harness from their sources (oracle/Makefile) */
 	PandaLogProxy quiet = panda_log_proxy_new(panda_writer_new_null());
 	for (int k = 0; k < cfg->nfilters && k < 7; k++) {
 		const struct po_filter *f = &cfg->filters[k];
 		PandaModule m = NULL;
-		char args[64];
+		char args[128];
 		PandaPreCheck precheck = NULL;
 		PandaCheck check = NULL;
 		void *user = NULL;
@@ -149,6 +150,15 @@ static PandaAssembler make_assembler(const po_config *cfg) {
 			snprintf(args, sizeof args, "%d", f->ivalue);
 			if (min_phred_LTX_opener(quiet, args, &precheck, &check, &user, &destroy))
 				m = panda_module_new("min_phred", check, precheck, user, destroy);
+			break;
+		case PO_FILTER_PEAR_TEST:
+			/* The plugin cannot be given other values than its defaults: panda_parse_key_values (args.c:613-633) rejects a
+			 * string with a second key, and the opener hands the LOGGER, not its parameter struct, to the key processor
+			 * (plugin_pear_test.c:96), so a single key overwrites the logger and leaves the parameter untouched.  The
+			 * reference therefore always tests with alpha = 1, beta = -1, cutoff = 0.01; only that is pinned here. */
+			if (f->dvalue == 1.0 && f->dvalue2 == -1.0 && f->dvalue3 == 0.01
+			    && pear_test_LTX_opener(quiet, NULL, &precheck, &check, &user, &destroy))
+				m = panda_module_new("pear_test", check, precheck, user, destroy);
 			break;
 		}
 		if (m == NULL) {

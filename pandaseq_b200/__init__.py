@@ -36,10 +36,10 @@ class PandaseqError(RuntimeError):
 
 
 class PbFilter(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("ivalue", C.c_int32), ("dvalue", C.c_double)]
+    _fields_ = [("kind", C.c_int32), ("ivalue", C.c_int32), ("dvalue", C.c_double), ("dvalue2", C.c_double), ("dvalue3", C.c_double)]
 
 
-FILTERS = {"no_n": 1, "short": 2, "long": 3, "min_overlapbits": 4, "completely_miss_the_point": 5, "min_phred": 6}
+FILTERS = {"no_n": 1, "short": 2, "long": 3, "min_overlapbits": 4, "completely_miss_the_point": 5, "min_phred": 6, "pear_test": 7}
 STATUS_FILTERED = 8
 C_REJECTED = 9
 
@@ -151,6 +151,8 @@ def make_config(algo="simple_bayesian", *, threshold=0.6, minoverlap=2, maxoverl
         cfg.filters[k].kind = FILTERS[name]
         if name == "min_overlapbits":
             cfg.filters[k].dvalue = float(value)
+        elif name == "pear_test":              # (alpha, beta, cutoff), plugin_pear_test.c
+            cfg.filters[k].dvalue, cfg.filters[k].dvalue2, cfg.filters[k].dvalue3 = (float(v) for v in value)
         else:
             cfg.filters[k].ivalue = int(value)
     return cfg

@@ -27,6 +27,7 @@ struct pb_context {
 	uint32_t *d_seeds[2];            /* candidate-overlap masks of pb::seed_kernel, 8 words per pair */
 	int *d_order[2];                 /* the pairs of a launch bin by bin (pb::bin_order_kernel) */
 	unsigned *d_bins[2];             /* 2 x PB_SEED_BINS: pairs per bin, cursors */
+	double *d_pear_cdf;              /* pear_test table (PB_PEAR_ROWS x PB_PEAR_COLS), built on first use */
 	unsigned long long *d_defer_total;   /* pairs deferred so far (device), next to lanes_pairs (host) */
 	unsigned long long lanes_pairs;
 	/* pb_set_timing / pb_last_timing: events around the kernels of the last pb_assemble_device call */

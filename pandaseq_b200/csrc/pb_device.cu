@@ -94,6 +94,7 @@ extern "C" void pb_context_destroy(pb_context *ctx) {
 	cudaFree(ctx->d_bins[0]);
 	cudaFree(ctx->d_bins[1]);
 	cudaFree(ctx->d_defer_total);
+	cudaFree(ctx->d_pear_cdf);
 	for (int k = 0; k < 4; k++)
 		cudaEventDestroy(ctx->tev[k]);
 	pb_io_release(ctx);
@@ -119,6 +120,21 @@ pb_status pb_upload_params(pb_context *ctx, const pb_config *cfg) {
 	pb_status st = pb_build_device_params(cfg, ctx->h_params);
 	if (st != PB_OK)
 		return st;
+	for (int k = 0; k < cfg->nfilters && k < PB_MAX_FILTERS; k++) {
+		if (cfg->filters[k].kind != PB_FILTER_PEAR_TEST)
+			continue;
+		if (!ctx->d_pear_cdf) {          /* 1.6 MB, once per context */
+			const size_t bytes = (size_t) PB_PEAR_ROWS * PB_PEAR_COLS * sizeof(double);
+			double *h = (double *) malloc(bytes);
+			if (!h)
+				return PB_ERR_NOMEM;
+			pb_build_pear_cdf(h);
+			CUDA_TRY(cudaMalloc(&ctx->d_pear_cdf, bytes));
+			CUDA_TRY(cudaMemcpy(ctx->d_pear_cdf, h, bytes, cudaMemcpyHostToDevice));
+			free(h);
+		}
+		ctx->h_params->pear_cdf = ctx->d_pear_cdf;
+	}
 	CUDA_TRY(cudaMemcpyAsync(ctx->d_params, ctx->h_params, sizeof(pb_device_params), cudaMemcpyHostToDevice, ctx->stream));
 	ctx->cached_cfg = *cfg;
 	ctx->cfg_valid = true;

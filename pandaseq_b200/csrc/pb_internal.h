@@ -51,7 +51,13 @@ typedef struct {
 	uint8_t hang_forward[PB_MAX_LEN + 2];
 	uint8_t hang_reverse[PB_MAX_LEN + 2];
 	struct pb_filter filters[PB_MAX_FILTERS];
+	/* pear_test: cdf[i * PB_PEAR_COLS + l] = sum over k < l of C(i,k) 0.25^k 0.75^(i-k), added in k order as
+	 * plugin_pear_test.c:31-35 adds them (device pointer, set when a pear_test filter is configured) */
+	const double *pear_cdf;
 } pb_device_params;
+#define PB_PEAR_ROWS PB_MAX_LEN
+#define PB_PEAR_COLS (PB_MAX_LEN + 2)
+void pb_build_pear_cdf(double *out);   /* PB_PEAR_ROWS x PB_PEAR_COLS doubles */
 
 /* pb_luts.c */
 pb_status pb_build_device_params(const pb_config *cfg, pb_device_params *out);

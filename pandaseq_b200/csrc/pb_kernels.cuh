@@ -157,6 +157,22 @@ __device__ __forceinline__ unsigned record_bytes(unsigned flen, unsigned rlen) {
 	return (b + 15u) & ~15u;
 }
 
+/* plugin_pear_test.c:18-39 on the result record; cdf = pb_device_params.pear_cdf (the plugin's inner sums, built on the host
+ * with its own libm calls).  A limit that is negative or not a number makes the plugin's loop run for 2^64 iterations; by
+ * then it has added all i + 1 non-zero terms, which is what cdf[i][i + 1] holds. */
+__device__ __forceinline__ bool pear_test_pass(const double *__restrict__ cdf, double alpha, double beta, double cutoff,
+                                               int overlap, int mismatches, int F, int R) {
+	double product = 1.0;
+	const double oes = alpha * (double) (unsigned long long) (overlap - mismatches) + beta * (double) (unsigned long long) mismatches;
+	const int lim = min(F, R);
+	for (int i = overlap; i < lim; i++) {
+		const double lraw = ceil((oes - beta * (double) i) / (alpha - beta)) - 1.0;
+		const int l = (lraw >= 0.0 && lraw < (double) (i + 1)) ? (int) lraw : i + 1;
+		product *= cdf[(size_t) i * PB_PEAR_COLS + l];
+	}
+	return cutoff > 1.0 - product * product;
+}
+
 struct PairView {
 	const uint8_t *fnt, *rnt;      /* packed nibbles; rnt in template order */
 	const uint32_t *fnt32, *rnt32;
@@ -1114,6 +1130,9 @@ __device__ void process_pair(WarpSmem<ML> &ws, uint8_t *rec, int F, int R,
 			pass = (int) res.mismatches <= iv;
 		else if (kind == PB_FILTER_MIN_PHRED)
 			pass = min_phred >= iv;
+		else if (kind == PB_FILTER_PEAR_TEST)
+			pass = pear_test_pass(prm->pear_cdf, prm->filters[k].dvalue, prm->filters[k].dvalue2, prm->filters[k].dvalue3,
+			                      res.overlap, res.mismatches, F, R);
 		if (!pass) {
 			res.status = (uint8_t) (PB_PAIR_FILTERED + k);
 			return;

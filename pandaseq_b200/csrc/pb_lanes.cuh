@@ -35,6 +35,7 @@ namespace pbl {
 
 using pb::FULL;
 using pb::NIB1;
+using pb::pear_test_pass;
 
 constexpr int LUT_DOUBLES = 2 * PB_NQM * PB_NQM + 256;      /* the posterior table, then qual_score[] padded to one entry per byte value */
 constexpr uint8_t ST_DEFER = 255;
@@ -378,6 +379,9 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 							pass = prm->filters[k].dvalue * 0.693147180559945309417232121458 <= best;
 						else if (kind == PB_FILTER_MISS_THE_POINT)
 							pass = mism <= iv;
+						else if (kind == PB_FILTER_PEAR_TEST)
+							pass = pear_test_pass(prm->pear_cdf, prm->filters[k].dvalue, prm->filters[k].dvalue2, prm->filters[k].dvalue3,
+							                      bestov, mism, F, R);
 						/* PB_FILTER_NO_N: reads of A/C/G/T only merge into A/C/G/T only */
 						if (!pass) {
 							status = (uint8_t) (PB_PAIR_FILTERED + k);

@@ -199,6 +199,13 @@ pb_status pb_build_device_params(const pb_config *cfg, pb_device_params *out) {
 	}
 	for (int k = 0; k < cfg->nfilters; k++) {
 		const struct pb_filter *f = &cfg->filters[k];
+		if (f->kind == PB_FILTER_PEAR_TEST) {       /* plugin_pear_test.c:97-100: the cut-off is a p-value */
+			if (!(f->dvalue3 >= 0 && f->dvalue3 <= 1)) {
+				pb_set_error("filter %d: pear_test cutoff out of range", k);
+				return PB_ERR_ARGUMENT;
+			}
+			continue;
+		}
 		if (f->kind < PB_FILTER_NO_N || f->kind > PB_FILTER_MIN_PHRED || (f->kind == PB_FILTER_MIN_OVERLAPBITS && !(f->dvalue >= 0))
 		    || (f->kind != PB_FILTER_MIN_OVERLAPBITS && f->ivalue < 0)) {
 			pb_set_error("filter %d: unknown kind or value out of range", k);
@@ -283,6 +290,23 @@ pb_status pb_build_device_params(const pb_config *cfg, pb_device_params *out) {
 	for (int i = 0; i < cfg->reverse_primer_length; i++)
 		out->reverse_primer[i] = (uint8_t) cfg->reverse_primer[i] & 0x0F;
 	return PB_OK;
+}
+
+/* plugin_pear_test.c:31-35: for every i the partial sums of its inner loop, in its order and with the same libm calls, so
+ * that the device's product over i multiplies exactly the doubles the plugin's would.  Independent of alpha / beta / cutoff. */
+void pb_build_pear_cdf(double *out) {
+	for (size_t i = 0; i < PB_PEAR_ROWS; i++) {
+		double sum = 0;
+		double *row = out + i * PB_PEAR_COLS;
+		row[0] = 0;
+		for (size_t k = 0; k <= i; k++) {
+			double i_choose_k = lgamma(i + 1) - lgamma(k + 1) - lgamma(i - k + 1);
+			sum += exp(i_choose_k + k * log(0.25) + (i - k) * log(0.75));
+			row[k + 1] = sum;
+		}
+		for (size_t l = i + 2; l < PB_PEAR_COLS; l++)
+			row[l] = sum;
+	}
 }
 
 size_t panda_max_len(void) {

@@ -123,6 +123,9 @@ def overhang_codes():
     return fwd, rev
 
 
+# pear_test with other parameters: checked against the oracle restatement only (oracle/ref_harness.c says why)
+PEAR_TEST_PARAMS = [(1.0, -1.0, 1e-9), (1.0, -1.0, 0.9), (2.0, -3.0, 0.01), (1.0, -0.5, 1e-6), (0.5, 0.5, 0.01), (1.0, 2.0, 0.3)]
+
 FILTER_SETS = [
     [("no_n", 0)],
     [("short", 200), ("long", 240)],
@@ -130,5 +133,7 @@ FILTER_SETS = [
     [("min_overlapbits", 120.0)],
     [("completely_miss_the_point", 1)],
     [("min_phred", 12)],
+    [("pear_test", (1.0, -1.0, 0.01))],                       # the plugin's defaults: the only values the reference can run it with
+    [("short", 185), ("pear_test", (1.0, -1.0, 0.01)), ("long", 270)],
     [("min_phred", 4), ("completely_miss_the_point", 3), ("min_overlapbits", 100.5), ("no_n", 0), ("short", 185), ("long", 270)],
 ]

@@ -46,6 +46,9 @@ CASES = {
     "edge_cases_rdp_maxov800": (lambda: datasets.edge_cases(), dict(algo="rdp_mle", maxoverlap=800)),
     "cfg1_filters_rdp": (lambda: datasets.cfg1(300), dict(algo="rdp_mle", filters=datasets.FILTER_SETS[-1])),
     "cfg1_filters_sb": (lambda: datasets.cfg1(300), dict(algo="simple_bayesian", filters=[("long", 230), ("no_n", 0), ("short", 190), ("min_phred", 8)])),
+    # plugin_pear_test.c at the only parameters the reference can run it with (its defaults, see oracle/ref_harness.c)
+    "stress_pear_test_sb": (lambda: datasets.stress(400), dict(algo="simple_bayesian", filters=[("pear_test", (1.0, -1.0, 0.01))])),
+    "mixed_pear_test_filters_sb": (lambda: datasets.mixed(300), dict(algo="simple_bayesian", filters=[("short", 120), ("pear_test", (1.0, -1.0, 0.01)), ("long", 500)])),
     "overhang_sb": (lambda: datasets.overhang(300), dict(algo="simple_bayesian", hang=True)),
     "overhang_strict_pear_filters": (lambda: datasets.overhang(300, seed=4), dict(algo="pear", hang=True, hang_threshold=-0.0003, filters=[("short", 80)])),
 }
@@ -66,7 +69,10 @@ def build_config(spec):
 def main():
     if not oracle_lib.have_ref():
         raise SystemExit("oracle/_ref is not built: run `make -C oracle ref` (needs /root/reference)")
+    only = set(sys.argv[1:])          # `make_golden.py name ...` regenerates just those fixtures
     for name, (mk, spec) in CASES.items():
+        if only and name not in only:
+            continue
         batch = mk()
         cfg = build_config(spec)
         out = oracle_lib.assemble("ref", cfg, batch)

@@ -205,6 +205,21 @@ def test_filters(ctx, filters, algo):
     assert (got["results"]["status"] >= 8).sum() == want["counters"][pb.C_REJECTED:pb.C_REJECTED + 7].sum()
 
 
+@pytest.mark.parametrize("params", datasets.PEAR_TEST_PARAMS)
+def test_pear_test_other_parameters(ctx, params):
+    """plugin_pear_test.c with parameters the reference's own argument parsing cannot deliver (oracle/ref_harness.c), and on
+    pairs whose limit goes negative (where the plugin's loop never ends; defined as the sum of all terms): device vs oracle,
+    general kernel (per-base p requested) and two-kernel path, read-through and mixed-length sets, three scorers."""
+    for algo, batch in (("simple_bayesian", datasets.stress(1500)), ("pear", datasets.mixed(1000)), ("flash", datasets.cfg1(800)),
+                        ("rdp_mle", datasets.overhang(800))):
+        cfg = pb.make_config(algo, filters=[("pear_test", params), ("short", 60)])
+        got, want, rep = run_both(ctx, cfg, batch)
+        assert rep["ok"], (algo, params, rep)
+        got = ctx.assemble_host(cfg, batch, want_nt=True, want_p=False)
+        rep = compare(got, want)
+        assert rep["ok"], (algo, params, "no per-base p", rep)
+
+
 def test_filters_after_primer_strip(ctx):
     fwd, rev = datasets.primer_codes()
     cfg = pb.make_config("simple_bayesian", forward_primer=fwd, reverse_primer=rev, post_primers=True,
