@@ -410,14 +410,14 @@ def main():
         # the lane kernel reads the whole record, the metadata and the mask record and writes the result + the merged read
         seed_b = ((fl0 + 1) // 2 + (rl0 + 1) // 2 + 8)
         kernels = [
-            {"name": "pb::seed_kernel (K1-K3: k-mer join, one warp per pair)", "ms": kms[0], "launches_per_step": 1,
+            {"name": "pb::seed_kernel (K1-K3: k-mer join, one warp per pair) + pb::bin_order_kernel (pairs listed by overlap bin)", "ms": kms[0], "launches_per_step": 2,
              "algorithmic_read_bytes_per_pair": seed_b, "achieved_gbs": seed_b * n / (kms[0] / 1e3) / 1e9},
             {"name": "pbl::assemble_lanes_kernel (K4-K6: score + merge, one lane per pair)", "ms": kms[1], "launches_per_step": 1,
              "algorithmic_read_bytes_per_pair": alg_bytes / n + 32, "achieved_gbs": (alg_bytes + 32 * n) / (kms[1] / 1e3) / 1e9},
             {"name": "pb::assemble_kernel, list mode (the pairs the two kernels above hand on)", "ms": kms[2], "launches_per_step": 1},
         ]
-        kernel_name = "pb::seed_kernel + pbl::assemble_lanes_kernel + pb::assemble_kernel<list> (one step; the read bytes of the path over their summed duration)"
-        launches_per_step = 3
+        kernel_name = "pb::seed_kernel + pb::bin_order_kernel + pbl::assemble_lanes_kernel + pb::assemble_kernel<list> (one step; the read bytes of the path over their summed duration)"
+        launches_per_step = 4
     else:
         kernels = [{"name": "pb::assemble_kernel", "ms": kms[2], "launches_per_step": 1}]
         kernel_name = "pb::assemble_kernel"

@@ -182,6 +182,8 @@ def lib() -> C.CDLL:
     L.pb_synchronize.restype = i32
     L.pb_lanes_stats.argtypes = [vp, vp, vp]
     L.pb_lanes_stats.restype = i32
+    L.pb_set_lanes.argtypes = [vp, i32]
+    L.pb_set_lanes.restype = i32
     L.pb_set_timing.argtypes = [vp, i32]
     L.pb_set_timing.restype = i32
     L.pb_last_timing.argtypes = [vp, vp, vp]
@@ -263,6 +265,10 @@ class Context:
         a, b = C.c_uint64(0), C.c_uint64(0)
         _check(lib().pb_lanes_stats(self._h, C.byref(a), C.byref(b)), "pb_lanes_stats")
         return int(a.value), int(b.value)
+
+    def set_lanes(self, mode: int):
+        """0 = general kernel only, 1 = two-kernel path where it applies, -1 = follow PANDASEQ_B200_LANES."""
+        _check(lib().pb_set_lanes(self._h, int(mode)), "pb_set_lanes")
 
     def set_timing(self, on: bool):
         _check(lib().pb_set_timing(self._h, 1 if on else 0), "pb_set_timing")

@@ -30,6 +30,7 @@ struct pb_context {
 	double *d_pear_cdf;              /* pear_test table (PB_PEAR_ROWS x PB_PEAR_COLS), built on first use */
 	unsigned long long *d_defer_total;   /* pairs deferred so far (device), next to lanes_pairs (host) */
 	unsigned long long lanes_pairs;
+	int lanes_mode;                  /* -1 = follow PANDASEQ_B200_LANES (default on), 0 / 1 = pb_set_lanes */
 	/* pb_set_timing / pb_last_timing: events around the kernels of the last pb_assemble_device call */
 	bool timing;
 	int timing_kind;                 /* 0 = nothing recorded, 1 = general kernel alone, 2 = seed + lanes + general(list) */

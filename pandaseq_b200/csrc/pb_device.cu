@@ -37,6 +37,7 @@ extern "C" pb_status pb_context_create(int device, pb_context **out) {
 	if (!ctx)
 		return PB_ERR_NOMEM;
 	ctx->device = device;
+	ctx->lanes_mode = -1;
 	pthread_mutex_init(&ctx->lock, NULL);
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -282,7 +283,7 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 		const char *env = getenv("PANDASEQ_B200_LANES");
 		lanes_on = (env && atoi(env) == 0) ? 0 : 1;
 	}
-	if (lanes_on && !full && !d_seq_p && max_len <= 160 && cfg->forward_trim == 0 && cfg->reverse_trim == 0
+	if ((ctx->lanes_mode < 0 ? lanes_on : ctx->lanes_mode) && !full && !d_seq_p && max_len <= 160 && cfg->forward_trim == 0 && cfg->reverse_trim == 0
 	    && (cfg->algo == PB_SIMPLE_BAYES || cfg->algo == PB_UPARSE || cfg->algo == PB_FLASH) && ((uintptr_t) d_seq_nt % 8) == 0)
 	{
 		/* reads up to 152 nt (2x150 included) leave room for a 12th warp of the lane kernel */
@@ -364,6 +365,15 @@ extern "C" pb_status pb_lanes_stats(pb_context *ctx, uint64_t *lanes_pairs, uint
 	CUDA_TRY(cudaMemcpy(&d, ctx->d_defer_total, sizeof d, cudaMemcpyDeviceToHost));
 	*lanes_pairs = ctx->lanes_pairs;
 	*deferred_pairs = d;
+	return PB_OK;
+}
+
+extern "C" pb_status pb_set_lanes(pb_context *ctx, int mode) {
+	if (!ctx || mode < -1 || mode > 1) {
+		pb_set_error("pb_set_lanes: bad argument");
+		return PB_ERR_ARGUMENT;
+	}
+	ctx->lanes_mode = mode;
 	return PB_OK;
 }
 

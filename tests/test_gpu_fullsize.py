@@ -95,3 +95,66 @@ def test_full_size_properties(full):
         got = dict(results=r[g], seq_nt=pb.unpack_nt(ntc[g]), seq_p=None, counters=None)
         rep = compare(got, want, check_counters=False)
         assert rep["ok"], rep
+
+
+def test_two_kernel_path_equals_general_kernel_at_full_size(full):
+    """All 10 M pairs through the two-kernel path and through the general kernel alone: every integer field, the overlap score
+    (bit pattern) and every byte of the merged-read rows identical; quality within 1e-12 (the two paths add the same per-base
+    terms in different orders)."""
+    import torch
+    ctx, reads, meta, max_len, flats = full
+    ctx.set_lanes(1)
+    before = ctx.lanes_stats()
+    res_a, nt_a, cnt_a = run(ctx, reads, meta, max_len, 0, N)
+    after = ctx.lanes_stats()
+    assert after[0] - before[0] == N and after[1] - before[1] < N // 1000
+    ctx.set_lanes(0)
+    res_b, nt_b, cnt_b = run(ctx, reads, meta, max_len, 0, N)
+    assert ctx.lanes_stats()[0] == after[0]
+    ctx.set_lanes(-1)
+    assert np.array_equal(cnt_a, cnt_b)
+    assert torch.equal(nt_a, nt_b)
+    a = res_a.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel()
+    b = res_b.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel()
+    for k in ("status", "slow", "overlap", "seq_len", "mismatches", "degenerates", "examined", "fwd_offset", "rev_offset"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["est_prob"].view(np.uint64), b["est_prob"].view(np.uint64))
+    assert np.abs(a["quality"] - b["quality"]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("algo,kw", [("simple_bayesian", {}), ("flash", {}), ("uparse", dict(minoverlap=12)),
+                                     ("simple_bayesian", dict(maxoverlap=140, threshold=0.8, filters=[("short", 200), ("pear_test", (1.0, -1.0, 0.01))]))])
+def test_two_paths_agree_on_decorated_reads(built, algo, kw):
+    """2 M pairs with N (0.1 % of bases), '#' tails (5 % of reads) and read-through inserts: about a third of the pairs are
+    handed from the two-kernel path to the general kernel; the outcome must not depend on who assembled a pair."""
+    import torch
+    from pandaseq_b200 import synth
+    ctx = pb.Context(0)
+    n = 2_000_000
+    rect = synth.generate(n, rl=(150, 150), tmpl=(120, 290), seed=4242, device="cuda", n_rate=0.001, btail_rate=0.05)
+    f_data, f_off, r_data, r_off = rect.to_flat_tensors()
+    reads, meta, ml, total = ctx.pack_device(f_data, f_off, r_data, r_off)
+    reads = torch.cat([reads[:total], torch.zeros(16, dtype=torch.uint8, device="cuda")])
+    cfg = pb.make_config(algo, **kw)
+    stride = (2 * ml + 15) & ~15
+    outs = []
+    for mode in (1, 0):
+        ctx.set_lanes(mode)
+        res = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+        nt = torch.zeros((n, stride // 2), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(pb.PB_NCOUNTERS, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        before = ctx.lanes_stats()
+        ctx.assemble_device(cfg, n, ml, reads, meta.contiguous(), res, nt, None, stride, cnt)
+        ctx.synchronize()
+        after = ctx.lanes_stats()
+        outs.append((res.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel(), nt, cnt.cpu().numpy(), after[0] - before[0], after[1] - before[1]))
+    ctx.close()
+    (a, nt_a, cnt_a, lanes_a, deferred_a), (b, nt_b, cnt_b, lanes_b, _) = outs
+    assert lanes_a == n and lanes_b == 0 and n // 10 < deferred_a < n
+    assert np.array_equal(cnt_a, cnt_b)
+    assert torch.equal(nt_a, nt_b)
+    for k in ("status", "slow", "overlap", "seq_len", "mismatches", "degenerates", "examined", "fwd_offset", "rev_offset"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["est_prob"].view(np.uint64), b["est_prob"].view(np.uint64))
+    assert np.abs(a["quality"] - b["quality"]).max() <= 1e-12
