@@ -178,7 +178,9 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 			CUDA_TRY(cudaMalloc(&ctx->d_scratch, need));
 			ctx->scratch_bytes = need;
 		}
-		scratch = ctx->d_scratch + (stream == ctx->copy_stream ? need / 2 : 0);
+		/* the halves are fixed by the allocation, not by this launch: the other stream may be running a kernel of another
+		 * length class (a smaller grid), and its half must not move under it */
+		scratch = ctx->d_scratch + (stream == ctx->copy_stream ? ctx->scratch_bytes / 2 : 0);
 	}
 	const bool timed = ctx->timing && stream == ctx->stream;
 	if (timed && !d_list)
