@@ -13,8 +13,11 @@ value      whole-job Mpairs/s with the packed batch already resident in HBM (CUD
            library's launch stream, max over ranks).
 e2e        the same metric through the C ABI with HOST buffers: pb_assemble_host() copies the flat
            panda_qual arrays host->device, packs, assembles, and copies results + merged reads back.
-roofline   algorithmic HBM read bytes per pair (458 B at 2x150) x pairs / kernel time vs the measured
-           copy bandwidth in MEASURED_PEAKS.json.
+roofline   algorithmic HBM read bytes per pair (458 B at 2x150) x pairs / summed duration of the step's kernels vs
+           the measured copy bandwidth in MEASURED_PEAKS.json; `kernels` lists what a step launches (the seeding
+           kernel, the bin list, the lane-per-pair kernel and the general kernel's list pass for the common
+           configurations; the general kernel alone otherwise) with each one's duration from the library's own
+           CUDA events (pb_set_timing / pb_last_timing) and its own algorithmic bytes.
 cpu_baseline / --impl reference
            the reference's own CPU implementation (oracle/_ref, compiled from the reference sources)
            or the oracle port if that is absent, all host cores, on a bounded sample of the same workload.
