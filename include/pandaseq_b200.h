@@ -112,6 +112,14 @@ typedef bool (*PandaOutputSeq) (const panda_result_seq *sequence, void *user_dat
 typedef void (*PandaFailAlign) (PandaAssembler assembler, const panda_seq_identifier *id,
                                 const panda_qual *forward, size_t forward_length,
                                 const panda_qual *reverse, size_t reverse_length, void *user_data);
+/* pandaseq-common.h:356-363, 509-522 -- the checks of a module: HOST functions.  The batch driver runs the pre-checks while it
+ * stages a pair (a rejected pair never reaches the device) and the checks while it hands the assembled pairs out. */
+typedef struct panda_module *PandaModule;
+typedef bool (*PandaCheck) (PandaLogProxy logger, const panda_result_seq *sequence, void *user_data);
+typedef bool (*PandaPreCheck) (PandaLogProxy logger, const panda_seq_identifier *id, const panda_qual *forward, size_t forward_length,
+                               const panda_qual *reverse, size_t reverse_length, void *user_data);
+/* pandaseq-common.h:474-479 */
+typedef bool (*PandaModuleCallback) (PandaAssembler assembler, PandaModule module, size_t rejected, void *data);
 /* pandaseq-common.h:342-354 -- the shape panda_diff() takes for control/experiment */
 typedef const panda_result_seq *(*PandaAssemble) (void *user_data, panda_seq_identifier *id,
                                                   const panda_qual *forward, size_t forward_length,
@@ -208,6 +216,18 @@ size_t panda_assembler_assemble_batch(PandaAssembler assembler, size_t n, const 
                                       PandaOutputSeq output, void *output_data);
 
 PandaAlgorithm panda_assembler_get_algorithm(PandaAssembler assembler);        /* assembler_support.c:177-180 */
+/* Modules with host callbacks (pandaseq-module.h:47-57, 68-79, 111-113; pandaseq-assembler.h:106-124, 152-168; module.c:124-216).
+ * Loading modules from shared objects (panda_module_load, libltdl) is out of scope; the built-in checks of the reference's
+ * command line (-N, -l, -L) and its filter plugins run on the device through pb_config.filters instead. */
+PandaModule panda_module_new(const char *name, PandaCheck check, PandaPreCheck precheck, void *user_data, PandaDestroy cleanup);
+PandaModule panda_module_ref(PandaModule module);
+void panda_module_unref(PandaModule module);
+const char *panda_module_get_name(PandaModule module);
+int panda_module_get_api(PandaModule module);                      /* PANDA_API (3) for constructed modules */
+bool panda_assembler_add_module(PandaAssembler assembler, PandaModule module);
+size_t panda_assembler_add_modules(PandaAssembler assembler, PandaModule *modules, size_t modules_length);
+bool panda_assembler_foreach_module(PandaAssembler assembler, PandaModuleCallback callback, void *data);
+void panda_assembler_module_stats(PandaAssembler assembler);       /* logging is out of scope: does nothing */
 void panda_assembler_set_algorithm(PandaAssembler assembler, PandaAlgorithm algorithm); /* assembler_support.c:182-189 */
 long panda_assembler_get_bad_read_count(PandaAssembler assembler);             /* assembler_support.c:191-194 */
 long panda_assembler_get_count(PandaAssembler assembler);                      /* assembler_support.c:196-199 */

@@ -41,6 +41,12 @@ struct panda_assembler {
 	panda_nt forward_primer[PB_MAX_LEN], reverse_primer[PB_MAX_LEN];
 	char name[PB_MAX_LEN];
 
+	/* modules with host callbacks (assembler.h:69-73, module.c:156-180) */
+	PandaModule *modules;
+	size_t *rejected;
+	size_t modules_length, modules_size;
+	bool has_check;		/* some module checks assembled pairs: OK / overlap counters are then kept on the host, after the checks */
+
 	/* counters */
 	int64_t counters[PB_NCOUNTERS];
 
@@ -117,6 +123,144 @@ PandaAssembler panda_assembler_new_kmer(PandaNextSeq next, void *next_data, Pand
 	return a;
 }
 
+/* ---- modules (module.c:31-98, 124-216; pandaseq-module.h) ------------------------------------------ */
+
+struct panda_module {
+	volatile size_t refcnt;
+	pthread_mutex_t mutex;
+	char *name;
+	PandaCheck check;
+	PandaPreCheck precheck;
+	void *user_data;
+	PandaDestroy cleanup;
+};
+
+PandaModule panda_module_new(const char *name, PandaCheck check, PandaPreCheck precheck, void *user_data, PandaDestroy cleanup) {
+	PandaModule m;
+	if (name == NULL || (check == NULL && precheck == NULL))	/* module.c:258-260 */
+		return NULL;
+	m = calloc(1, sizeof *m);
+	if (m == NULL)
+		return NULL;
+	pthread_mutex_init(&m->mutex, NULL);
+	m->refcnt = 1;
+	m->name = malloc(strlen(name) + 1);
+	if (m->name == NULL) {
+		free(m);
+		return NULL;
+	}
+	strcpy(m->name, name);
+	m->check = check;
+	m->precheck = precheck;
+	m->user_data = user_data;
+	m->cleanup = cleanup;
+	return m;
+}
+
+PandaModule panda_module_ref(PandaModule m) {
+	pthread_mutex_lock(&m->mutex);
+	m->refcnt++;
+	pthread_mutex_unlock(&m->mutex);
+	return m;
+}
+
+void panda_module_unref(PandaModule m) {
+	size_t left;
+	if (m == NULL)
+		return;
+	pthread_mutex_lock(&m->mutex);
+	left = --m->refcnt;
+	pthread_mutex_unlock(&m->mutex);
+	if (left != 0)
+		return;
+	pthread_mutex_destroy(&m->mutex);
+	if (m->cleanup != NULL)
+		m->cleanup(m->user_data);
+	free(m->name);
+	free(m);
+}
+
+const char *panda_module_get_name(PandaModule m) { return m->name; }
+int panda_module_get_api(PandaModule m) { (void) m; return 3; }	/* PANDA_API, pandaseq.h:61 */
+
+bool panda_assembler_add_module(PandaAssembler a, PandaModule m) {
+	if (m == NULL)
+		return false;
+	pthread_mutex_lock(&a->mutex);
+	if (a->modules_length == a->modules_size) {
+		size_t size = a->modules_size == 0 ? 8 : a->modules_size * 2;
+		PandaModule *mods = realloc(a->modules, size * sizeof(PandaModule));
+		size_t *rej = mods ? realloc(a->rejected, size * sizeof(size_t)) : NULL;
+		if (mods)
+			a->modules = mods;
+		if (rej)
+			a->rejected = rej;
+		if (!mods || !rej) {
+			pthread_mutex_unlock(&a->mutex);
+			return false;
+		}
+		a->modules_size = size;
+	}
+	a->rejected[a->modules_length] = 0;
+	a->modules[a->modules_length++] = panda_module_ref(m);
+	if (m->check != NULL)
+		a->has_check = true;
+	pthread_mutex_unlock(&a->mutex);
+	return true;
+}
+
+size_t panda_assembler_add_modules(PandaAssembler a, PandaModule *modules, size_t modules_length) {
+	size_t it;
+	for (it = 0; it < modules_length; it++)
+		if (!panda_assembler_add_module(a, modules[it]))
+			return it;
+	return it;
+}
+
+bool panda_assembler_foreach_module(PandaAssembler a, PandaModuleCallback callback, void *data) {
+	for (size_t it = 0; it < a->modules_length; it++)
+		if (!callback(a, a->modules[it], a->rejected[it], data))
+			return false;
+	return true;
+}
+
+void panda_assembler_module_stats(PandaAssembler a) { (void) a; }	/* module.c:208-216 only logs */
+
+/* module_precheckseq (module.c:139-154) where assemble_seq calls it (assembler.c:255-261): after the pair was counted and
+ * found to have two bases per read.  A rejected pair is counted here and never staged for the device. */
+static bool host_precheck(PandaAssembler a, const panda_seq_identifier *id, const panda_qual *f, size_t fl, const panda_qual *r, size_t rl) {
+	static const panda_seq_identifier no_id;
+	if (a->modules_length == 0 || fl < 2 || rl < 2)
+		return true;
+	for (size_t it = 0; it < a->modules_length; it++) {
+		PandaModule m = a->modules[it];
+		if (m->precheck != NULL && !m->precheck(a->logger, id ? id : &no_id, f, fl, r, rl, m->user_data)) {
+			a->rejected[it]++;
+			a->counters[PB_C_COUNT]++;
+			return false;
+		}
+	}
+	return true;
+}
+
+/* module_checkseq (module.c:124-137) and what assemble_seq does when it passes (assembler.c:339-346) */
+static bool host_check(PandaAssembler a, const panda_result_seq *res) {
+	if (!a->has_check)
+		return true;
+	for (size_t it = 0; it < a->modules_length; it++) {
+		PandaModule m = a->modules[it];
+		if (m->check != NULL && !m->check(a->logger, res, m->user_data)) {
+			a->rejected[it]++;
+			return false;
+		}
+	}
+	a->counters[PB_C_OK]++;
+	a->counters[PB_C_OVERLAPS + res->overlap]++;
+	if (a->counters[PB_C_LONGEST] < (int64_t) res->overlap)
+		a->counters[PB_C_LONGEST] = (int64_t) res->overlap;
+	return true;
+}
+
 PandaAssembler panda_assembler_ref(PandaAssembler a) {
 	pthread_mutex_lock(&a->mutex);
 	a->refcnt++;
@@ -139,6 +283,10 @@ void panda_assembler_unref(PandaAssembler a) {
 	if (a->noalgn_destroy != NULL && a->noalgn != NULL)
 		a->noalgn_destroy(a->noalgn_data);
 	panda_algorithm_unref(a->algo);
+	for (size_t it = 0; it < a->modules_length; it++)
+		panda_module_unref(a->modules[it]);
+	free(a->modules);
+	free(a->rejected);
 	free(a->ids);
 	free(a->f_data);
 	free(a->r_data);
@@ -151,6 +299,8 @@ void panda_assembler_unref(PandaAssembler a) {
 }
 
 void panda_assembler_copy_configuration(PandaAssembler dest, PandaAssembler src) {
+	for (size_t it = 0; it < src->modules_length; it++)	/* assembler_support.c:123-125 */
+		panda_assembler_add_module(dest, src->modules[it]);
 	panda_assembler_set_forward_primer(dest, src->forward_primer, src->forward_primer_length);
 	panda_assembler_set_reverse_primer(dest, src->reverse_primer, src->reverse_primer_length);
 	dest->forward_trim = src->forward_trim;
@@ -311,8 +461,21 @@ static bool run_batch(PandaAssembler a) {
 	flatten(a, &cfg, &ok);
 	if (!ok)
 		return false;
-	return pb_assemble_host(a->ctx, &cfg, a->batch_n, a->f_data, a->f_off, a->r_data, a->r_off,
-	                        a->res, a->nt, a->p, SEQ_CAP, a->counters) == PB_OK;
+	if (!a->has_check)
+		return pb_assemble_host(a->ctx, &cfg, a->batch_n, a->f_data, a->f_off, a->r_data, a->r_off,
+		                        a->res, a->nt, a->p, SEQ_CAP, a->counters) == PB_OK;
+	/* a module checks the assembled pairs on the host: the device's count of accepted pairs (and their overlap histogram) is
+	 * taken before those checks, so these counters are kept by host_check() as the pairs are handed out */
+	int64_t tmp[PB_NCOUNTERS];
+	memset(tmp, 0, sizeof tmp);
+	if (pb_assemble_host(a->ctx, &cfg, a->batch_n, a->f_data, a->f_off, a->r_data, a->r_off,
+	                     a->res, a->nt, a->p, SEQ_CAP, tmp) != PB_OK)
+		return false;
+	tmp[PB_C_OK] = 0;
+	tmp[PB_C_LONGEST] = 0;
+	memset(tmp + PB_C_OVERLAPS, 0, (PB_NCOUNTERS - PB_C_OVERLAPS) * sizeof(int64_t));
+	pb_counters_merge(a->counters, tmp);
+	return true;
 }
 
 /* Expand device record i of the staged batch into a->result (pandaseq-common.h:277-330). */
@@ -350,6 +513,8 @@ const panda_result_seq *panda_assembler_assemble(PandaAssembler a, panda_seq_ide
                                                  const panda_qual *reverse, size_t reverse_length) {
 	assert(forward_length <= PB_MAX_LEN);
 	assert(reverse_length <= PB_MAX_LEN);
+	if (!host_precheck(a, id, forward, forward_length, reverse, reverse_length))
+		return NULL;
 	if (!reserve(a, 1, forward_length, reverse_length))
 		return NULL;
 	memcpy(a->f_data, forward, forward_length * sizeof(panda_qual));
@@ -365,7 +530,8 @@ const panda_result_seq *panda_assembler_assemble(PandaAssembler a, panda_seq_ide
 		a->noalgn(a, id, forward, forward_length, reverse, reverse_length, a->noalgn_data);
 	if (a->res[0].status != PB_PAIR_OK)
 		return NULL;
-	return publish(a, 0, id, forward, forward_length, reverse, reverse_length);
+	const panda_result_seq *out = publish(a, 0, id, forward, forward_length, reverse, reverse_length);
+	return host_check(a, out) ? out : NULL;
 }
 
 size_t panda_assembler_assemble_batch(PandaAssembler a, size_t n, const panda_seq_identifier *ids,
@@ -383,31 +549,48 @@ size_t panda_assembler_assemble_batch(PandaAssembler a, size_t n, const panda_se
 	}
 	if (!reserve(a, n, fb, rb))
 		return (size_t) -1;
+	/* pairs a module's pre-check rejects are not staged; map[k] = caller's index of staged pair k */
+	size_t *map = a->modules_length ? malloc((n ? n : 1) * sizeof(size_t)) : NULL;
+	if (a->modules_length && map == NULL)
+		return (size_t) -1;
+	size_t m = 0;
 	fb = rb = 0;
 	for (size_t i = 0; i < n; i++) {
-		a->f_off[i] = fb;
-		a->r_off[i] = rb;
+		if (!host_precheck(a, ids ? &ids[i] : NULL, forward[i], forward_length[i], reverse[i], reverse_length[i]))
+			continue;
+		if (map)
+			map[m] = i;
+		a->f_off[m] = fb;
+		a->r_off[m] = rb;
 		memcpy(a->f_data + fb, forward[i], forward_length[i] * sizeof(panda_qual));
 		memcpy(a->r_data + rb, reverse[i], reverse_length[i] * sizeof(panda_qual));
 		fb += forward_length[i];
 		rb += reverse_length[i];
+		m++;
 	}
-	a->f_off[n] = fb;
-	a->r_off[n] = rb;
-	a->batch_n = n;
-	a->batch_pos = n;
-	if (!run_batch(a))
+	a->f_off[m] = fb;
+	a->r_off[m] = rb;
+	a->batch_n = m;
+	a->batch_pos = m;
+	if (m > 0 && !run_batch(a)) {
+		free(map);
 		return (size_t) -1;
-	for (size_t i = 0; i < n; i++) {
+	}
+	for (size_t k = 0; k < m; k++) {
+		const size_t i = map ? map[k] : k;
 		const panda_seq_identifier *id = ids ? &ids[i] : NULL;
-		if (a->res[i].status == PB_PAIR_NOALGN && a->noalgn != NULL)
+		if (a->res[k].status == PB_PAIR_NOALGN && a->noalgn != NULL)
 			a->noalgn(a, id, forward[i], forward_length[i], reverse[i], reverse_length[i], a->noalgn_data);
-		if (a->res[i].status != PB_PAIR_OK)
+		if (a->res[k].status != PB_PAIR_OK)
+			continue;
+		const panda_result_seq *out = publish(a, k, id, forward[i], forward_length[i], reverse[i], reverse_length[i]);
+		if (!host_check(a, out))
 			continue;
 		accepted++;
 		if (output != NULL)
-			output(publish(a, i, id, forward[i], forward_length[i], reverse[i], reverse_length[i]), output_data);
+			output(out, output_data);
 	}
+	free(map);
 	return accepted;
 }
 
@@ -422,8 +605,11 @@ const panda_result_seq *panda_assembler_next(PandaAssembler a) {
 			size_t fl = (size_t) (a->f_off[i + 1] - a->f_off[i]), rl = (size_t) (a->r_off[i + 1] - a->r_off[i]);
 			if (a->res[i].status == PB_PAIR_NOALGN && a->noalgn != NULL)
 				a->noalgn(a, &a->ids[i], f, fl, r, rl, a->noalgn_data);
-			if (a->res[i].status == PB_PAIR_OK)
-				return publish(a, i, &a->ids[i], f, fl, r, rl);
+			if (a->res[i].status == PB_PAIR_OK) {
+				const panda_result_seq *out = publish(a, i, &a->ids[i], f, fl, r, rl);
+				if (host_check(a, out))
+					return out;
+			}
 		}
 		if (a->source_dry)
 			return NULL;
@@ -441,6 +627,8 @@ const panda_result_seq *panda_assembler_next(PandaAssembler a) {
 			}
 			assert(fl <= PB_MAX_LEN);
 			assert(rl <= PB_MAX_LEN);
+			if (!host_precheck(a, &a->ids[n], f, fl, r, rl))
+				continue;	/* counted and rejected on the host: not staged */
 			if (!reserve(a, n + 1, fb + fl, rb + rl))
 				return NULL;
 			a->f_off[n] = fb;

@@ -243,3 +243,136 @@ def test_c_program_against_the_header(L, tmp_path):
         for k, i in enumerate(ok[:200]):
             assert lines[2 * k].startswith(f">pair{i};overlap={want['overlap'][i]};")
             assert lines[2 * k + 1] == letters[want["seq_nt"][i, :want["seq_len"][i]]].tobytes().decode()
+
+
+# ---- modules with host callbacks (pandaseq-module.h, module.c:124-154) -------------------------------------------------
+PRECHECK = C.CFUNCTYPE(C.c_bool, C.c_void_p, C.POINTER(SeqId), C.POINTER(Qual), C.c_size_t, C.POINTER(Qual), C.c_size_t, C.c_void_p)
+CHECK = C.CFUNCTYPE(C.c_bool, C.c_void_p, C.POINTER(ResultSeq), C.c_void_p)
+MODCB = C.CFUNCTYPE(C.c_bool, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+def _module_api(L):
+    vp = C.c_void_p
+    L.panda_module_new.restype, L.panda_module_new.argtypes = vp, [C.c_char_p, vp, vp, vp, vp]
+    L.panda_module_unref.argtypes = [vp]
+    L.panda_module_get_name.restype, L.panda_module_get_name.argtypes = C.c_char_p, [vp]
+    L.panda_assembler_add_module.restype, L.panda_assembler_add_module.argtypes = C.c_bool, [vp, vp]
+    L.panda_assembler_foreach_module.restype, L.panda_assembler_foreach_module.argtypes = C.c_bool, [vp, vp, vp]
+
+
+def _expected_with_modules(b, want, pre_reject, check_reject):
+    """What assemble_seq does with a pre-check and a check module (assembler.c:252-348): the pre-check sees every pair with two
+    bases per read, the check every pair that passed the quality threshold; only pairs passing both are counted as OK."""
+    fl, rl = b.lengths()
+    seen_pre = (fl >= 2) & (rl >= 2)
+    pre = np.array([seen_pre[i] and pre_reject(i) for i in range(b.n)])
+    okdev = (want["status"] == 0) & ~pre
+    chk = np.array([okdev[i] and check_reject(i) for i in range(b.n)])
+    return pre, chk, okdev & ~chk
+
+
+def test_modules_precheck_and_check_behind_next_batch_and_single(L, monkeypatch):
+    _module_api(L)
+    monkeypatch.setenv("PANDASEQ_B200_NEXT_BATCH", "300")
+    b = datasets.cfg1(1000)
+    want = oracle_lib.assemble("port", pb.make_config("simple_bayesian"), b)
+    pre_reject = lambda i: int(b.pair(i)[0][0, 0]) == 1                  # forward read starts with A
+    check_reject = lambda i: int(want["seq_len"][i]) % 3 == 0
+    pre, chk, ok = _expected_with_modules(b, want, pre_reject, check_reject)
+    assert pre.sum() > 50 and chk.sum() > 50 and ok.sum() > 300
+    calls = {"pre": 0, "chk": 0}
+
+    def precheck(logger, idp, f, fl, r, rl, user):
+        calls["pre"] += 1
+        return f[0].nt[0] != 1
+
+    def check(logger, res, user):
+        calls["chk"] += 1
+        return res.contents.sequence_length % 3 != 0
+
+    cb_pre, cb_chk = PRECHECK(precheck), CHECK(check)
+    m_pre = L.panda_module_new(b"starts_with_a", None, C.cast(cb_pre, C.c_void_p), None, None)
+    m_chk = L.panda_module_new(b"multiple_of_three", C.cast(cb_chk, C.c_void_p), None, None, None)
+    assert m_pre and m_chk and L.panda_module_get_name(m_chk) == b"multiple_of_three"
+    assert not L.panda_module_new(b"nothing", None, None, None, None)
+
+    def module_counts(a):
+        out = []
+        cb = MODCB(lambda asm, mod, rejected, data: out.append((L.panda_module_get_name(mod), rejected)) or True)
+        assert L.panda_assembler_foreach_module(a, C.cast(cb, C.c_void_p), None)
+        return out
+
+    def check_counters(a):
+        assert L.panda_assembler_get_count(a) == b.n
+        assert L.panda_assembler_get_ok_count(a) == int(ok.sum())
+        assert L.panda_assembler_get_low_quality_count(a) == int(((want["status"] == 5) & ~pre).sum())
+        assert L.panda_assembler_get_failed_alignment_count(a) == int(((want["status"] == 4) & ~pre).sum())
+        assert L.panda_assembler_get_longest_overlap(a) == int(want["overlap"][ok].max())
+        hist = np.bincount(want["overlap"][ok], minlength=900)
+        for ov in range(0, 900, 7):
+            assert L.panda_assembler_get_overlap_count(a, ov) == hist[ov]
+        assert module_counts(a) == [(b"starts_with_a", int(pre.sum())), (b"multiple_of_three", int(chk.sum()))]
+
+    # 1. pull source + next(), modules copied from a prototype assembler (assembler_support.c:123-125)
+    proto = L.panda_assembler_new(None, None, None, None)
+    assert L.panda_assembler_add_module(proto, m_pre) and L.panda_assembler_add_module(proto, m_chk)
+    state = {"i": 0, "keep": []}
+
+    def nxt(idp, fp, flp, rp, rlp, _):
+        i = state["i"]
+        if i >= b.n:
+            return False
+        f, r = b.pair(i)
+        f, r = np.ascontiguousarray(f), np.ascontiguousarray(r)
+        state["keep"] = [f, r]
+        idp.contents.x = i
+        fp[0], flp[0], rp[0], rlp[0] = f.ctypes.data, len(f), r.ctypes.data, len(r)
+        state["i"] = i + 1
+        return True
+
+    cb_next = NEXT(nxt)
+    a = L.panda_assembler_new(C.cast(cb_next, C.c_void_p), None, None, None)
+    L.panda_assembler_copy_configuration(a, proto)
+    got = []
+    while True:
+        res = L.panda_assembler_next(a)
+        if not res:
+            break
+        got.append(res.contents.name.x)
+        check_result(res, want, got[-1])
+    assert got == np.nonzero(ok)[0].tolist()
+    check_counters(a)
+    fl, rl = b.lengths()
+    assert calls["pre"] == int(((fl >= 2) & (rl >= 2)).sum()) and calls["chk"] == int(((want["status"] == 0) & ~pre).sum())
+    L.panda_assembler_unref(a)
+
+    # 2. the batch call
+    a = L.panda_assembler_new(None, None, None, None)
+    L.panda_assembler_copy_configuration(a, proto)
+    fs = [np.ascontiguousarray(b.pair(i)[0]) for i in range(b.n)]
+    rs = [np.ascontiguousarray(b.pair(i)[1]) for i in range(b.n)]
+    fp = (C.c_void_p * b.n)(*[x.ctypes.data for x in fs])
+    rp = (C.c_void_p * b.n)(*[x.ctypes.data for x in rs])
+    fla = (C.c_size_t * b.n)(*[len(x) for x in fs])
+    rla = (C.c_size_t * b.n)(*[len(x) for x in rs])
+    ids = (SeqId * b.n)()
+    for i in range(b.n):
+        ids[i].x = i
+    seen = []
+    cb_out = OUTPUT(lambda res, _: seen.append(res.contents.name.x) or True)
+    assert L.panda_assembler_assemble_batch(a, b.n, ids, fp, fla, rp, rla, C.cast(cb_out, C.c_void_p), None) == int(ok.sum())
+    assert seen == np.nonzero(ok)[0].tolist()
+    check_counters(a)
+    L.panda_assembler_unref(a)
+
+    # 3. one pair at a time
+    a = L.panda_assembler_new(None, None, None, None)
+    L.panda_assembler_copy_configuration(a, proto)
+    sid = SeqId()
+    for i in range(0, b.n, 5):
+        res = L.panda_assembler_assemble(a, C.byref(sid), fs[i].ctypes.data, len(fs[i]), rs[i].ctypes.data, len(rs[i]))
+        assert bool(res) == bool(ok[i])
+    L.panda_assembler_unref(a)
+    L.panda_assembler_unref(proto)
+    L.panda_module_unref(m_pre)
+    L.panda_module_unref(m_chk)
