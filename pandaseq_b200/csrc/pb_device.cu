@@ -205,6 +205,7 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 	auto seedk = pb::seed_kernel<ML, SW>;
 	auto kern = pbl::assemble_lanes_kernel<LML, LW>;      /* LML <= ML: the length class that sizes the lane kernel's record slots */
 	constexpr size_t seed_smem = sizeof(pb::WarpSmem<ML>) * SW;
+	static_assert(seed_smem <= 227 * 1024 && pbl::lanes_smem_bytes<LML, LW>() <= 227 * 1024, "per-CTA shared memory");
 	constexpr size_t smem = pbl::lanes_smem_bytes<LML, LW>();
 	static bool configured[16] = { false };
 	if (!configured[ctx->device & 15]) {
@@ -224,7 +225,7 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 		ctx->defer_cap[si] = 0;
 		const size_t cap = (size_t) n + (size_t) n / 4 + 64;
 		CUDA_TRY(cudaMalloc(&ctx->d_defer[si], cap * sizeof(int)));
-		CUDA_TRY(cudaMalloc(&ctx->d_seeds[si], cap * pb::PB_SEED_WORDS * sizeof(uint32_t)));
+		CUDA_TRY(cudaMalloc(&ctx->d_seeds[si], cap * pb::seed_words(256) * sizeof(uint32_t)));      /* sized for the widest record */
 		CUDA_TRY(cudaMalloc(&ctx->d_order[si], cap * sizeof(int)));
 		if (!ctx->d_bins[si])
 			CUDA_TRY(cudaMalloc(&ctx->d_bins[si], 2 * pb::PB_SEED_BINS * sizeof(unsigned)));
@@ -243,7 +244,7 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 			grid = ctx->sm_count;
 		seedk<<<(unsigned) (grid < 1 ? 1 : grid), SW * 32, seed_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si]);
 		CUDA_TRY(cudaGetLastError());
-		pb::bin_order_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(n, d_seeds, ctx->d_bins[si], ctx->d_order[si]);
+		pb::bin_order_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(n, d_seeds, pb::seed_words(ML), pb::seed_mask_words(ML) + 1, ctx->d_bins[si], ctx->d_order[si]);
 		CUDA_TRY(cudaGetLastError());
 	}
 	if (timed)
@@ -285,13 +286,16 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 		const char *env = getenv("PANDASEQ_B200_LANES");
 		lanes_on = (env && atoi(env) == 0) ? 0 : 1;
 	}
-	if ((ctx->lanes_mode < 0 ? lanes_on : ctx->lanes_mode) && !full && !d_seq_p && max_len <= 160 && cfg->forward_trim == 0 && cfg->reverse_trim == 0
-	    && (cfg->algo == PB_SIMPLE_BAYES || cfg->algo == PB_UPARSE || cfg->algo == PB_FLASH) && ((uintptr_t) d_seq_nt % 8) == 0)
+	if ((ctx->lanes_mode < 0 ? lanes_on : ctx->lanes_mode) && !full && !d_seq_p && max_len <= 256 && cfg->forward_trim == 0 && cfg->reverse_trim == 0
+	    && (cfg->algo == PB_SIMPLE_BAYES || cfg->algo == PB_UPARSE || cfg->algo == PB_FLASH || cfg->algo == PB_PEAR) && ((uintptr_t) d_seq_nt % 8) == 0)
 	{
-		/* reads up to 152 nt (2x150 included) leave room for a 12th warp of the lane kernel */
+		/* <seeding class, lane-kernel class, seeding warps, lane warps, general-kernel warps>: as many warps as the per-warp shared
+		 * memory allows; reads up to 152 nt (2x150 included) leave room for a 12th warp of the lane kernel */
 		if (max_len <= 152)
 			return launch_lanes<160, 152, 32, 12, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
-		return launch_lanes<160, 160, 32, 11, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
+		if (max_len <= 160)
+			return launch_lanes<160, 160, 32, 11, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
+		return launch_lanes<256, 256, 19, 7, 15>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
 	}
 #define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq); \
 	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false); } while (0)

@@ -1293,11 +1293,13 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
  *                      outside 16..ML, more than 160 candidate overlaps, no seed at all);
  *                      PB_SEED_SKIP: not a pair (flen == 0xFFFF). */
 constexpr unsigned PB_SEED_GENERAL = 1u, PB_SEED_SKIP = 2u;
-constexpr int PB_SEED_WORDS = 8;
-/*   seeds[pair][6]     bin of the pair: (lowest candidate overlap - minoverlap) / 16, or PB_SEED_BINS - 1 for the pairs that
+/* words of a seeds record for reads up to ML nt: the mask, the flag word, the bin, padded to a multiple of four */
+__host__ __device__ constexpr int seed_mask_words(int ML) { return (ML + 31) / 32; }
+__host__ __device__ constexpr int seed_words(int ML) { return (seed_mask_words(ML) + 2 + 3) & ~3; }
+/*   seeds[pair][MW+1]  (MW = mask words: flags sit at [MW]) bin of the pair: (lowest candidate overlap - minoverlap) / 16, or PB_SEED_BINS - 1 for the pairs that
  *                      carry a flag.  bin_order_kernel lists the pairs bin by bin, so that the 32 pairs a warp of the lane-per-
  *                      pair kernel takes have overlaps within 16 bases of each other and its loops end together. */
-constexpr int PB_SEED_BINS = 11;
+constexpr int PB_SEED_BINS = 17;      /* 16 x 16 overlaps (reads up to 256 nt) + the flagged pairs */
 
 template <int ML, int WARPS_PER_BLOCK>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
@@ -1306,7 +1308,8 @@ seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__re
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	__shared__ unsigned s_bins[PB_SEED_BINS];
 	using WS = WarpSmem<ML>;
-	static_assert(ML <= 160, "the candidate mask has 160 bits");
+	static_assert(ML <= 256, "bins and mask words are laid out for reads up to 256 nt");
+	constexpr int MW = seed_mask_words(ML), SWORDS = seed_words(ML);
 	WS *wsall = reinterpret_cast<WS *>(smem_raw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid < PB_SEED_BINS)
@@ -1365,7 +1368,7 @@ seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__re
 			unsigned flg = gen_codes<WS::NTW>(fnt32, F, ws.code_f, lane) | gen_codes<WS::NTW>(rnt32, R, ws.code_r, lane);
 			flg = __reduce_or_sync(FULL, flg);
 			__syncwarp();
-			if (flg != 0u || nbits > 160) {
+			if (flg != 0u || nbits > 32 * MW) {
 				flags = PB_SEED_GENERAL;
 			} else {
 				seed_candidates<ML, false>(ws, F, R, mo, nbits, lane);
@@ -1373,7 +1376,7 @@ seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__re
 				/* flag bytes -> mask words; lane w keeps word w */
 				unsigned any = 0;
 #pragma unroll
-				for (int w = 0; w < 5; w++) {
+				for (int w = 0; w < MW; w++) {
 					const unsigned b = __ballot_sync(FULL, ws.cflag[32 * w + lane] != 0);
 					any |= b;
 					if (lane == w)
@@ -1382,7 +1385,7 @@ seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__re
 				/* the lowest candidate decides the bin */
 				bin = __reduce_min_sync(FULL, word ? (unsigned) (32 * lane + __ffs(word) - 1) : 1023u) >> 4;
 				__syncwarp();
-				if (lane < 10)
+				if (lane < 2 * MW)
 					reinterpret_cast<uint4 *>(ws.cflag)[lane] = make_uint4(0, 0, 0, 0);
 				if (any == 0u)
 					flags = PB_SEED_GENERAL;       /* ALL_BITS_IF_NONE (assembler.c:118): every overlap is scored */
@@ -1390,12 +1393,12 @@ seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__re
 		}
 		if (flags)
 			bin = PB_SEED_BINS - 1;
-		if (lane == 5)
+		if (lane == MW)
 			word = flags;
-		if (lane == 6)
+		if (lane == MW + 1)
 			word = bin;
-		if (lane < PB_SEED_WORDS)
-			seeds[(size_t) pair * PB_SEED_WORDS + lane] = lane < 7 ? word : 0u;
+		if (lane < SWORDS)
+			seeds[(size_t) pair * SWORDS + lane] = lane < MW + 2 ? word : 0u;
 		if (lane == 0)
 			atomicAdd(&s_bins[bin], 1u);
 		__syncwarp();      /* every lane is done with this stage before it is refilled */
@@ -1408,7 +1411,7 @@ seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__re
 /* The pairs of a batch listed bin by bin (seeds[pair][6]); the order inside a bin is whatever the atomics make it, which no
  * result depends on.  bin_state: [0 .. BINS) pairs per bin (seed_kernel), [BINS .. 2 BINS) cursors, zero at launch. */
 __global__ void __launch_bounds__(256)
-bin_order_kernel(int n, const uint32_t *__restrict__ seeds, unsigned *__restrict__ bin_state, int *__restrict__ order) {
+bin_order_kernel(int n, const uint32_t *__restrict__ seeds, int swords, int bin_word, unsigned *__restrict__ bin_state, int *__restrict__ order) {
 	__shared__ unsigned s_hist[PB_SEED_BINS], s_base[PB_SEED_BINS];
 	const int tid = threadIdx.x;
 	if (tid < PB_SEED_BINS)
@@ -1417,7 +1420,7 @@ bin_order_kernel(int n, const uint32_t *__restrict__ seeds, unsigned *__restrict
 	const int pair = blockIdx.x * blockDim.x + tid;
 	unsigned bin = 0, rank = 0;
 	if (pair < n) {
-		bin = min(seeds[(size_t) pair * PB_SEED_WORDS + 6], (unsigned) (PB_SEED_BINS - 1));
+		bin = min(seeds[(size_t) pair * swords + bin_word], (unsigned) (PB_SEED_BINS - 1));
 		rank = atomicAdd(&s_hist[bin], 1u);
 	}
 	__syncthreads();

@@ -16,7 +16,8 @@
  *           memory at a stride of an odd number of 16-byte units; one mbarrier per warp; the warp's next batch is
  *           prefetched into L2 meanwhile.
  *   score   K4/K5 (assembler.c:120-143): candidates in increasing overlap; the count-based scorers
- *           (algo_simple_bayes.c:33-66, algo_uparse.c:33-66, algo_flash.c:30-60) need one AND + POPC per 8 bases.
+ *           (algo_simple_bayes.c:33-66, algo_uparse.c:33-66, algo_flash.c:30-60) need one AND + POPC per 8 bases, pear
+ *           (algo_pear.c:32-59) one table gather per base, added in the reference's order.
  *   merge   K6 (assembler.c:158-244): merged bases 8 per word; the per-base posterior is summed per stretch (forward-
  *           only, overlap, reverse-only) as the reference does, on two accumulators each.
  *
@@ -25,8 +26,9 @@
  * table per pair leaves 4 warps per SM, and the probe chains of 32 lanes are as long as the longest of them
  * (1,541 warp-instructions per pair at 13 active lanes, 0.17 instructions per cycle and scheduler).  DESIGN.md section 5.
  *
- * Configurations this path takes (the host decides, pb_device.cu): simple_bayesian / uparse / flash, no primers, no
- * trims, no overhang trimmer, no per-base log p requested, filters that read only the result record, reads <= 160 nt.
+ * Configurations this path takes (the host decides, pb_device.cu): simple_bayesian / uparse / flash / pear, no primers, no
+ * trims, no overhang trimmer, no per-base log p requested, filters that read only the result record, reads <= 256 nt
+ * (length classes 152, 160 and 256 nt: 12, 11 and 7 warps per SM).
  */
 #pragma once
 #include "pb_kernels.cuh"
@@ -43,8 +45,9 @@ constexpr uint8_t ST_DEFER = 255;
 template <int ML> struct LaneArea {
 	static constexpr int REC0 = (((ML + 7) / 8) * 4 * 2 + ((ML + 3) / 4) * 4 * 2 + 15) & ~15;
 	static constexpr int REC_STRIDE = ((REC0 / 16) | 1) * 16;    /* odd number of 16-byte units: a lane's 128-bit loads never collide */
-	static constexpr int CW = 5;                                 /* words of the candidate mask (pb::seed_kernel) */
-	static_assert(ML <= 160, "the candidate mask has 160 bits");
+	static constexpr int CW = pb::seed_mask_words(ML);           /* words of the candidate mask (pb::seed_kernel) */
+	static constexpr int SWORDS = pb::seed_words(ML);
+	static_assert(ML <= 256, "the seeds record is laid out for reads up to 256 nt");
 	alignas(128) uint8_t rec[32 * REC_STRIDE];
 	alignas(8) uint64_t bar;
 };
@@ -97,13 +100,22 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 			F = (int) (mraw.y & 0xFFFFu);
 			R = (int) (mraw.y >> 16);
 		}
-		unsigned cw[LA::CW] = { 0, 0, 0, 0, 0 };
+		unsigned cw[LA::CW];
 		unsigned sflags = pb::PB_SEED_SKIP;
+#pragma unroll
+		for (int w = 0; w < LA::CW; w++)
+			cw[w] = 0;
 		if (pair < n) {
-			const uint4 s0 = reinterpret_cast<const uint4 *>(seeds)[(size_t) pair * 2];
-			const uint2 s1 = reinterpret_cast<const uint2 *>(seeds)[(size_t) pair * 4 + 2];
-			cw[0] = s0.x; cw[1] = s0.y; cw[2] = s0.z; cw[3] = s0.w; cw[4] = s1.x;
-			sflags = s1.y;
+			unsigned sw[LA::SWORDS];
+#pragma unroll
+			for (int q = 0; q < LA::SWORDS / 4; q++) {
+				const uint4 v = reinterpret_cast<const uint4 *>(seeds)[(size_t) pair * (LA::SWORDS / 4) + q];
+				sw[4 * q] = v.x; sw[4 * q + 1] = v.y; sw[4 * q + 2] = v.z; sw[4 * q + 3] = v.w;
+			}
+#pragma unroll
+			for (int w = 0; w < LA::CW; w++)
+				cw[w] = sw[w];
+			sflags = sw[LA::CW];
 		}
 		const bool skip = F == 0xFFFF;              /* not a pair (FASTQ reader, fastq.c:176), or past the end of the batch */
 		bool defer = !skip && ((sflags & pb::PB_SEED_GENERAL) != 0 || F > ML || R > ML);      /* a record must fit its slot */
@@ -167,7 +179,7 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 					const uint32_t *fp = fnt + (fs >> 3);
 					unsigned lo = fp[0];
 					int matches = 0;
-					for (int k = 0; k < nw; k++) {
+					for (int k = 0; k < nw && algo != PB_PEAR; k++) {
 						const unsigned hi = fp[k + 1];
 						const unsigned f = __funnelshift_r(lo, hi, sh);
 						lo = hi;
@@ -178,7 +190,53 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 					}
 					const int mm = ov - matches;
 					double prob;
-					if (algo == PB_FLASH) {
+					if (algo == PB_PEAR) {
+						/* algo_pear.c:32-59, term by term in its order.  Both qualities come from the FORWARD read (lines 52, 54
+						 * index it with the reverse index); past its end that is the general kernel's defined case. */
+						if (R > F) {
+							defer = true;
+							continue;
+						}
+						prob = 0.0;
+						{
+							/* four bases per step: forward qualities fs+i ascending, "reverse" qualities R-1-i descending (bytes of a
+							 * window reversed), match bits from the packed bases, the match bit folded into the table row */
+							const int nfull = ov >> 2;
+							const int sha = (fs & 3) * 8, shb = ((R - 4) & 3) * 8, shn = (fs & 7) * 4;
+							const uint32_t *qap = fq32 + (fs >> 2);
+							const uint32_t *fnp = fnt + (fs >> 3);
+							int cw0 = (R - 4) >> 2;                     /* word holding byte R-4-i0 */
+							unsigned alo = qap[0], bhi = fq32[cw0 + 1], nlo = fnp[0], mw = 0;
+							for (int w = 0; w < nfull; w++) {
+								const unsigned ahi = qap[w + 1];
+								const unsigned qa4 = __funnelshift_r(alo, ahi, sha) & 0x3F3F3F3Fu;
+								alo = ahi;
+								const unsigned blo = fq32[cw0 - w];
+								const unsigned qb4 = __byte_perm(__funnelshift_r(blo, bhi, shb), 0, 0x0123) & 0x3F3F3F3Fu;
+								bhi = blo;
+								if ((w & 1) == 0) {
+									const unsigned nhi = fnp[(w >> 1) + 1];
+									mw = pb::nz_nib(__funnelshift_r(nlo, nhi, shn) & rnt[w >> 1]);
+									nlo = nhi;
+								} else {
+									mw >>= 16;
+								}
+								unsigned sp = mw & 0x1111u;
+								sp = (sp | (sp << 8)) & 0x00110011u;
+								sp = (sp | (sp << 4)) & 0x01010101u;
+								const unsigned row4 = qa4 + sp * 48u;
+#pragma unroll
+								for (int t = 0; t < 4; t++)
+									prob += s_rec[__byte_perm(row4, 0, 0x4440 + t) * PB_NQM + __byte_perm(qb4, 0, 0x4440 + t)];
+							}
+							for (int i = 4 * nfull; i < ov; i++) {
+								const int fi = fs + i;
+								const unsigned fb = (fnt[fi >> 3] >> (4 * (fi & 7))) & 15u, rbase = (rnt[i >> 3] >> (4 * (i & 7))) & 15u;
+								const unsigned qa = fq8[fi] & 0x3Fu, qb = fq8[R - 1 - i] & 0x3Fu;
+								prob += s_rec[(((fb & rbase) ? PB_NQM : 0u) + qa) * PB_NQM + qb];
+							}
+						}
+					} else if (algo == PB_FLASH) {
 						/* algo_flash.c:59: integer division inside log() */
 						prob = (mm == ov) ? 0.0 : -CUDART_INF;
 					} else {

@@ -123,7 +123,8 @@ def test_two_kernel_path_equals_general_kernel_at_full_size(full):
 
 
 @pytest.mark.parametrize("algo,kw", [("simple_bayesian", {}), ("flash", {}), ("uparse", dict(minoverlap=12)),
-                                     ("simple_bayesian", dict(maxoverlap=140, threshold=0.8, filters=[("short", 200), ("pear_test", (1.0, -1.0, 0.01))]))])
+                                     ("simple_bayesian", dict(maxoverlap=140, threshold=0.8, filters=[("short", 200), ("pear_test", (1.0, -1.0, 0.01))])),
+                                     ("pear", {})])
 def test_two_paths_agree_on_decorated_reads(built, algo, kw):
     """2 M pairs with N (0.1 % of bases), '#' tails (5 % of reads) and read-through inserts: about a third of the pairs are
     handed from the two-kernel path to the general kernel; the outcome must not depend on who assembled a pair."""
@@ -156,5 +157,8 @@ def test_two_paths_agree_on_decorated_reads(built, algo, kw):
     assert torch.equal(nt_a, nt_b)
     for k in ("status", "slow", "overlap", "seq_len", "mismatches", "degenerates", "examined", "fwd_offset", "rev_offset"):
         assert np.array_equal(a[k], b[k]), k
-    assert np.array_equal(a["est_prob"].view(np.uint64), b["est_prob"].view(np.uint64))
+    if algo == "pear":       # the lane kernel adds pear's terms in the reference's order, the general kernel with a shuffle tree
+        assert np.abs(a["est_prob"] - b["est_prob"]).max() <= 1e-9
+    else:
+        assert np.array_equal(a["est_prob"].view(np.uint64), b["est_prob"].view(np.uint64))
     assert np.abs(a["quality"] - b["quality"]).max() <= 1e-12

@@ -155,4 +155,44 @@ def test_trims_and_per_base_p_use_the_general_kernel(ctx):
     before = ctx.lanes_stats()
     ctx.assemble_host(pb.make_config("simple_bayesian"), b, want_nt=True, want_p=True)
     assert ctx.lanes_stats()[0] == before[0]
-    run_lanes(ctx, pb.make_config("pear"), b, expect_lanes=False)
+    run_lanes(ctx, pb.make_config("rdp_mle"), b, expect_lanes=False)
+
+
+@pytest.mark.parametrize("algo", ["simple_bayesian", "pear", "flash", "uparse"])
+def test_reads_up_to_256_nt(ctx, algo):
+    # the 256-nt class of the seeding kernel (8 mask words) and of the lane kernel (784-byte record slots, 7 warps)
+    got, want, rep = run_lanes(ctx, pb.make_config(algo), datasets.long250(3000))
+    assert rep["ok"], rep
+    clean250 = synth.generate(6000, rl=(250, 250), tmpl=(260, 480), seed=77).to_flat()
+    got, want, rep = run_lanes(ctx, pb.make_config(algo), clean250)
+    assert rep["ok"], rep
+    assert rep["deferred"] <= clean250.n // 100, rep
+
+
+def test_pear_on_the_lane_kernel(ctx):
+    # algo_pear.c:32-59 term by term in the lane kernel: the overlap score is the reference's sum in the reference's order
+    for batch in (clean(20_000, seed=5), datasets.cfg1(), datasets.stress(), datasets.low_complexity()):
+        got, want, rep = run_lanes(ctx, pb.make_config("pear"), batch)
+        assert rep["ok"], rep
+    got, want, rep = run_lanes(ctx, pb.make_config("pear"), clean(20_000, seed=6))
+    ok = want["status"] == 0
+    assert np.array_equal(got["results"]["est_prob"][ok].view(np.uint64), want["est_prob"][ok].view(np.uint64))
+    # reverse longer than forward: algo_pear.c:52 reads past the forward read; those pairs are handed to the general kernel
+    rng = np.random.default_rng(8)
+    pairs = []
+    for i in range(2000):
+        F, R = int(rng.integers(40, 200)), int(rng.integers(40, 200))
+        L = int(rng.integers(max(F, R), F + R - 8))
+        t = rng.integers(0, 4, size=L)
+        pairs.append((1 << t[:F], rng.integers(2, 42, size=F), 1 << t[::-1][:R], rng.integers(2, 42, size=R)))
+    b = synth.FlatBatch.from_pairs(pairs)
+    got, want, rep = run_lanes(ctx, pb.make_config("pear", minoverlap=8), b)
+    assert rep["ok"], rep
+    assert rep["deferred"] > 300, rep
+
+
+def test_mixed_lengths_up_to_256_nt(ctx):
+    b = synth.generate(5000, rl=(75, 256), tmpl=None, seed=15, mixed=True, n_rate=0.0005, btail_rate=0.05).to_flat()
+    for algo in ("simple_bayesian", "pear"):
+        got, want, rep = run_lanes(ctx, pb.make_config(algo), b)
+        assert rep["ok"], (algo, rep)
