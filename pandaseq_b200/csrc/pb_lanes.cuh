@@ -177,16 +177,18 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 					/* forward base F-ov+i against template-order reverse base i, i in [0, ov) */
 					const int fs = F - ov, nw = (ov + 7) >> 3, sh = (fs & 7) * 4;
 					const uint32_t *fp = fnt + (fs >> 3);
-					unsigned lo = fp[0];
 					int matches = 0;
-					for (int k = 0; k < nw && algo != PB_PEAR; k++) {
-						const unsigned hi = fp[k + 1];
-						const unsigned f = __funnelshift_r(lo, hi, sh);
-						lo = hi;
-						unsigned mt = f & rnt[k];
-						if (k == nw - 1)
-							mt &= pb::nibmask(ov - 8 * k);
-						matches += __popc(mt);
+					if (algo != PB_PEAR) {               /* the count-based scorers: matching bases of the overlap */
+						unsigned lo = fp[0];
+						for (int k = 0; k < nw; k++) {
+							const unsigned hi = fp[k + 1];
+							const unsigned f = __funnelshift_r(lo, hi, sh);
+							lo = hi;
+							unsigned mt = f & rnt[k];
+							if (k == nw - 1)
+								mt &= pb::nibmask(ov - 8 * k);
+							matches += __popc(mt);
+						}
 					}
 					const int mm = ov - matches;
 					double prob;
