@@ -8,7 +8,7 @@
  * bit mask, and the kernel here takes 32 consecutive pairs per warp, every lane running K4-K6 of the reference's
  * align() (assembler.c:118-250) for its own pair as straight scalar code.  What makes that affordable is that the rare
  * cases do not have to be handled here: a lane that meets one (a base that is not A/C/G/T, a quality outside 0..46, no
- * seed at all, an overlap longer than a read, a read outside 16..160 nt) appends its pair to a deferral list and the
+ * seed at all, an overlap longer than a read, a read shorter than 16 nt) appends its pair to a deferral list and the
  * exact general kernel assembles those pairs in a third launch on the same stream.  All kernels implement the same
  * function, so the split is invisible in the results.
  *

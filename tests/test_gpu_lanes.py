@@ -1,6 +1,6 @@
 """GPU parity of the lane-per-pair kernel (pb_lanes.cuh) and of its hand-over to the general kernel.
 
-Configurations without per-base log p, primers or trims and with reads <= 160 nt are dispatched to the lane-per-pair
+Configurations without per-base log p, primers or trims and with reads <= 256 nt are dispatched to the lane-per-pair
 kernel; pairs it does not cover (N or IUPAC codes, qualities outside 0..46, no seed, tiny reads) are appended to a
 deferral list and assembled by the general kernel in a second launch.  Either way the result must equal the oracle's:
 integer fields and merged bases bit-exact, quality / overlap score within 1e-6 (the lane kernel adds in the reference's
