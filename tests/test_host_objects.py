@@ -100,3 +100,29 @@ def test_layout_helper_matches_python(built):
     assert np.array_equal(rec.astype(np.int64) * 16, np.concatenate([[0], np.cumsum(sizes)[:-1]]))
     assert (sizes % 16 == 0).all() and sizes[(fl == 150) & (rl == 150)].tolist() in ([], [464] * int(((fl == 150) & (rl == 150)).sum()))
     assert pb.record_bytes(150, 150) == 464 and pb.record_bytes(0, 0) == 0
+
+
+def test_module_objects_without_a_device(built):
+    """panda_module_new / ref / unref / get_name / get_api (pandaseq-module.h:47-57, 68-79, 83-113): plain host objects; the cleanup
+    function runs exactly once, when the last reference goes."""
+    lib = pb.lib()
+    vp = C.c_void_p
+    lib.panda_module_new.restype, lib.panda_module_new.argtypes = vp, [C.c_char_p, vp, vp, vp, vp]
+    lib.panda_module_ref.restype, lib.panda_module_ref.argtypes = vp, [vp]
+    lib.panda_module_unref.argtypes = [vp]
+    lib.panda_module_get_name.restype, lib.panda_module_get_name.argtypes = C.c_char_p, [vp]
+    lib.panda_module_get_api.restype, lib.panda_module_get_api.argtypes = C.c_int, [vp]
+    CHECK = C.CFUNCTYPE(C.c_bool, vp, vp, vp)
+    DESTROY = C.CFUNCTYPE(None, vp)
+    cleaned = []
+    chk, destroy = CHECK(lambda logger, seq, user: True), DESTROY(lambda user: cleaned.append(user))
+    assert not lib.panda_module_new(b"no callbacks", None, None, None, None)          # module.c:258-260
+    assert not lib.panda_module_new(None, C.cast(chk, vp), None, None, None)
+    m = lib.panda_module_new(b"keeps everything", C.cast(chk, vp), None, 1234, C.cast(destroy, vp))
+    assert m and lib.panda_module_get_name(m) == b"keeps everything" and lib.panda_module_get_api(m) == 3
+    assert lib.panda_module_ref(m) == m
+    lib.panda_module_unref(m)
+    assert cleaned == []
+    lib.panda_module_unref(m)
+    assert cleaned == [1234]
+    lib.panda_module_unref(None)
