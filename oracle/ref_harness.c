@@ -53,8 +53,18 @@ static bool count_rejected(PandaAssembler assembler, PandaModule module, size_t 
 	return true;
 }
 
+/* A log proxy over a writer that discards everything.  panda_log_proxy_new takes its own reference on the writer
+ * (proxy.c:44), so the creator's reference is dropped right away, as the reference's own callers do (proxy.c:50-52):
+ * a leaked PandaWriter keeps a pthread_key (writer.c:93), and a process has only 1024 of them. */
+static PandaLogProxy quiet_logger(void) {
+	PandaWriter w = panda_writer_new_null();
+	PandaLogProxy logger = panda_log_proxy_new(w);
+	panda_writer_unref(w);
+	return logger;
+}
+
 static PandaAssembler make_assembler(const po_config *cfg) {
-	PandaLogProxy logger = panda_log_proxy_new(panda_writer_new_null());
+	PandaLogProxy logger = quiet_logger();
 	PandaAssembler a = panda_assembler_new_kmer(NULL, NULL, NULL, logger, (size_t) cfg->num_kmers);
 	PandaAlgorithm algo = NULL;
 	panda_log_proxy_unref(logger);
@@ -123,7 +133,7 @@ static PandaAssembler make_assembler(const po_config *cfg) {
 		panda_assembler_set_reverse_trim(a, (size_t) cfg->reverse_trim);
 	/* module_checkseq (module.c:124-137) with the reference's own check functions: the three built into the library
 	 * (args_assembler.c) and four plugins compiled into this harness from their sources (oracle/Makefile) */
-	PandaLogProxy quiet = panda_log_proxy_new(panda_writer_new_null());
+	PandaLogProxy quiet = quiet_logger();
 	for (int k = 0; k < cfg->nfilters && k < 7; k++) {
 		const struct po_filter *f = &cfg->filters[k];
 		PandaModule m = NULL;
@@ -309,7 +319,7 @@ static void *run_job(void *arg) {
 		pair_source src = { job, job->begin };
 		void *next_data = NULL;
 		PandaDestroy next_destroy = NULL;
-		PandaLogProxy logger = panda_log_proxy_new(panda_writer_new_null());
+		PandaLogProxy logger = quiet_logger();
 		PandaNextSeq next = panda_trim_overhangs(pair_source_next, &src, NULL, logger, (panda_nt *) job->cfg->hang_forward,
 		                                         (size_t) job->cfg->hang_forward_length, (panda_nt *) job->cfg->hang_reverse,
 		                                         (size_t) job->cfg->hang_reverse_length, job->cfg->hang_skip != 0, job->cfg->hang_threshold,
@@ -494,7 +504,9 @@ int ref_fastq_parse(const char *fwd, size_t fwd_len, const char *rev, size_t rev
                     size_t max_pairs, po_fastq_out *out, size_t max_read) {
 	mem_src sf = { fwd, fwd_len, 0, max_read }, sr = { rev, rev_len, 0, max_read };
 	log_sink *sink = calloc(1, sizeof(log_sink));
-	PandaLogProxy logger = panda_log_proxy_new(panda_writer_new(sink_write, sink, NULL));
+	PandaWriter sink_writer = panda_writer_new(sink_write, sink, NULL);
+	PandaLogProxy logger = panda_log_proxy_new(sink_writer);
+	panda_writer_unref(sink_writer);
 	void *next_data = NULL;
 	PandaDestroy next_destroy = NULL;
 	PandaNextSeq next;

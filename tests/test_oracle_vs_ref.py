@@ -85,3 +85,16 @@ def test_primers_after(built):
         for algo in ("simple_bayesian", "rdp_mle"):
             cfg = pb.make_config(algo, post_primers=True, **kw)
             same(oracle_lib.assemble("port", cfg, b), oracle_lib.assemble("ref", cfg, b))
+
+
+def test_many_threads_many_calls(built):
+    """The reference arm of bench.py calls the harness once per step with one assembler per host thread.  Every assembler
+    owns a PandaWriter, every PandaWriter a pthread_key (writer.c:93), and a process has 1024 keys: a harness that leaks
+    writers dies after 1024 / (2 x threads) calls (round 1: SIGSEGV on the 32-core box).  64 threads x 40 calls."""
+    b = datasets.cfg1(640)
+    cfg = pb.make_config("simple_bayesian")
+    first = oracle_lib.assemble("ref", cfg, b, threads=64)
+    for _ in range(39):
+        again = oracle_lib.assemble("ref", cfg, b, threads=64)
+    same(first, again)
+    same(oracle_lib.assemble("port", cfg, b), again)
