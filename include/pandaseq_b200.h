@@ -432,8 +432,9 @@ pb_status pb_synchronize(pb_context *ctx);
  * A/C/G/T, a quality outside 0..46, no seed, ...) to the general warp-per-pair kernel.  This reports, since the context was
  * created, how many pairs were launched that way and how many of them were handed on.  Synchronises the device. */
 pb_status pb_lanes_stats(pb_context *ctx, uint64_t *lanes_pairs, uint64_t *deferred_pairs);
-/* 0: every configuration runs the general kernel; 1: the two-kernel path where it applies; -1 (default): as the environment
- * variable PANDASEQ_B200_LANES says (unset = 1).  For A/B checks of the two paths against each other. */
+/* 0: every configuration runs the general kernel; 1: the two-kernel path where it applies, its seeding by the diagonal sweep
+ * (pb_sweep.cuh) where that applies; 2: the two-kernel path with the hash-join seeding kernel; -1 (default): as the environment
+ * variables PANDASEQ_B200_LANES / PANDASEQ_B200_SWEEP say (unset = 1).  For A/B checks of the paths against each other. */
 pb_status pb_set_lanes(pb_context *ctx, int mode);
 /* Measurement.  With timing on, pb_assemble_device records CUDA events around its kernels on the context's stream;
  * pb_last_timing waits for the last call and returns their durations in milliseconds:

@@ -395,28 +395,10 @@ static inline unsigned kcode(char nt) {
 	return nt == 8 ? 3u : nt == 4 ? 2u : nt == 2 ? 1u : 0u;
 }
 
-/* assembler.c:48-250.  `table` is the 65536 x 2 position table, all zero on entry and on exit. */
-static int align_pair(const po_config *cfg, uint16_t *table, const po_qual *F, size_t flen,
-                      const po_qual *R, size_t rlen, size_t fo, size_t ro, po_one *out) {
-	const po_tables *t = po_get_tables();
-	const double qual_nn = t->qual_nn;
-	const size_t mo = (size_t) cfg->minoverlap;
-	size_t maxov = flen + rlen - mo - fo - ro - 1;	/* assembler.c:59 */
-	double best = qual_nn * (flen + rlen);	/* assembler.c:60 */
-	ptrdiff_t bestov = -1;
-
-	if (mo + fo >= flen || mo + ro >= rlen)	/* assembler.c:73-76 */
-		return 0;
-	if (cfg->maxoverlap == 0)	/* assembler.c:78-82 */
-		maxov = flen < rlen ? flen : rlen;
-	else if (maxov > (size_t) cfg->maxoverlap)
-		maxov = (size_t) cfg->maxoverlap;
-
-	size_t nbits = mo <= maxov ? (maxov - mo + 1) : 1;	/* assembler.c:84 */
-	uint32_t bits[(2 * PO_MAX_LEN) / 32 + 2];
-	size_t nwords = nbits / 32 + 1;
-	memset(bits, 0, nwords * sizeof(uint32_t));
-
+/* K1-K3 of align() (assembler.c:92-116): the candidate-overlap bit list before ALL_BITS_IF_NONE.  `table` is the
+ * 65536 x 2 position table, all zero on entry and on exit; `bits` holds nbits / 32 + 1 zeroed words. */
+static void seed_bits(uint16_t *table, const po_qual *F, size_t flen, const po_qual *R, size_t rlen, size_t mo,
+                      size_t nbits, uint32_t *bits) {
 	/* K1: forward k-mers, assembler.c:92-101 + misc.h:41-42 */
 	{
 		unsigned code = 0;
@@ -473,6 +455,31 @@ static int align_pair(const po_config *cfg, uint16_t *table, const po_qual *F, s
 			}
 		}
 	}
+}
+
+/* assembler.c:48-250.  `table` is the 65536 x 2 position table, all zero on entry and on exit. */
+static int align_pair(const po_config *cfg, uint16_t *table, const po_qual *F, size_t flen,
+                      const po_qual *R, size_t rlen, size_t fo, size_t ro, po_one *out) {
+	const po_tables *t = po_get_tables();
+	const double qual_nn = t->qual_nn;
+	const size_t mo = (size_t) cfg->minoverlap;
+	size_t maxov = flen + rlen - mo - fo - ro - 1;	/* assembler.c:59 */
+	double best = qual_nn * (flen + rlen);	/* assembler.c:60 */
+	ptrdiff_t bestov = -1;
+
+	if (mo + fo >= flen || mo + ro >= rlen)	/* assembler.c:73-76 */
+		return 0;
+	if (cfg->maxoverlap == 0)	/* assembler.c:78-82 */
+		maxov = flen < rlen ? flen : rlen;
+	else if (maxov > (size_t) cfg->maxoverlap)
+		maxov = (size_t) cfg->maxoverlap;
+
+	size_t nbits = mo <= maxov ? (maxov - mo + 1) : 1;	/* assembler.c:84 */
+	uint32_t bits[(2 * PO_MAX_LEN) / 32 + 2];
+	size_t nwords = nbits / 32 + 1;
+	memset(bits, 0, nwords * sizeof(uint32_t));
+
+	seed_bits(table, F, flen, R, rlen, mo, nbits, bits);
 	/* assembler.c:118 */
 	{
 		uint32_t any = 0;
@@ -898,4 +905,25 @@ int po_assemble_flat(const po_config *cfg, size_t n,
 	free(jobs);
 	free(tids);
 	return failed ? -1 : 0;
+}
+
+/* Test hook: the candidate-overlap bit list of one pair exactly as K1-K3 leave it (assembler.c:84-116, before
+ * ALL_BITS_IF_NONE), with forward_offset = reverse_offset = 0.  Returns the number of bits (0: align() fails before
+ * seeding, assembler.c:73-76); `bits` must hold (2 * PO_MAX_LEN) / 32 + 2 words. */
+size_t po_seed_bits(const po_config *cfg, const po_qual *F, size_t flen, const po_qual *R, size_t rlen, uint32_t *bits) {
+	static __thread uint16_t *table;
+	const size_t mo = (size_t) cfg->minoverlap;
+	size_t maxov = flen + rlen - mo - 1;
+	if (table == NULL)
+		table = calloc(65536 * 2, sizeof(uint16_t));
+	if (mo >= flen || mo >= rlen)
+		return 0;
+	if (cfg->maxoverlap == 0)
+		maxov = flen < rlen ? flen : rlen;
+	else if (maxov > (size_t) cfg->maxoverlap)
+		maxov = (size_t) cfg->maxoverlap;
+	const size_t nbits = mo <= maxov ? (maxov - mo + 1) : 1;
+	memset(bits, 0, (nbits / 32 + 1) * sizeof(uint32_t));
+	seed_bits(table, F, flen, R, rlen, mo, nbits, bits);
+	return nbits;
 }

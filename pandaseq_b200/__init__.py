@@ -267,7 +267,8 @@ class Context:
         return int(a.value), int(b.value)
 
     def set_lanes(self, mode: int):
-        """0 = general kernel only, 1 = two-kernel path where it applies, -1 = follow PANDASEQ_B200_LANES."""
+        """0 = general kernel only, 1 = two-kernel path where it applies (seeding by the diagonal sweep), 2 = two-kernel path with
+        the hash-join seeding kernel, -1 = follow PANDASEQ_B200_LANES / PANDASEQ_B200_SWEEP."""
         _check(lib().pb_set_lanes(self._h, int(mode)), "pb_set_lanes")
 
     def set_timing(self, on: bool):

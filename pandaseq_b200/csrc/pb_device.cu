@@ -11,6 +11,7 @@
 #include <string.h>
 #include "pb_kernels.cuh"
 #include "pb_lanes.cuh"
+#include "pb_sweep.cuh"
 
 #include "pb_ctx.h"
 
@@ -198,11 +199,14 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 /* The two-kernel path for the common configurations: pb::seed_kernel (warp per pair, K1-K3) leaves the candidate
  * overlaps of every pair, pbl::assemble_lanes_kernel (lane per pair, K4-K6) scores and merges, and the general kernel
  * assembles the pairs those two handed on. */
-template <int ML, int LML, int SW, int LW, int GW>
+template <int ML, int LML, int SW, int LW, int GW, int XW>
 static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
                               pb_pair_result *d_results, uint8_t *d_seq_nt, size_t seq_stride,
-                              unsigned long long *d_counters, cudaStream_t stream) {
+                              unsigned long long *d_counters, cudaStream_t stream, bool sweep) {
 	auto seedk = pb::seed_kernel<ML, SW>;
+	auto sweepk = pbs::sweep_seed_kernel<ML / 32, XW>;      /* the same seeds by the diagonal sweep, one lane per pair (pb_sweep.cuh) */
+	constexpr size_t sweep_smem = pbs::sweep_smem_bytes<ML / 32, XW>();
+	static_assert(ML % 32 == 0 && sweep_smem <= 227 * 1024, "per-CTA shared memory");
 	auto kern = pbl::assemble_lanes_kernel<LML, LW>;      /* LML <= ML: the length class that sizes the lane kernel's record slots */
 	constexpr size_t seed_smem = sizeof(pb::WarpSmem<ML>) * SW;
 	static_assert(seed_smem <= 227 * 1024 && pbl::lanes_smem_bytes<LML, LW>() <= 227 * 1024, "per-CTA shared memory");
@@ -210,6 +214,7 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 	static bool configured[16] = { false };
 	if (!configured[ctx->device & 15]) {
 		CUDA_TRY(cudaFuncSetAttribute(seedk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) seed_smem));
+		CUDA_TRY(cudaFuncSetAttribute(sweepk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
 		CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		configured[ctx->device & 15] = true;
 	}
@@ -239,10 +244,17 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 	if (timed)
 		CUDA_TRY(cudaEventRecord(ctx->tev[0], stream));
 	{
-		long long grid = ((long long) n + SW - 1) / SW;
-		if (grid > ctx->sm_count)
-			grid = ctx->sm_count;
-		seedk<<<(unsigned) (grid < 1 ? 1 : grid), SW * 32, seed_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si]);
+		if (sweep) {
+			long long grid = (((long long) n + 31) / 32 + XW - 1) / XW;
+			if (grid > ctx->sm_count)
+				grid = ctx->sm_count;
+			sweepk<<<(unsigned) (grid < 1 ? 1 : grid), XW * 32, sweep_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si]);
+		} else {
+			long long grid = ((long long) n + SW - 1) / SW;
+			if (grid > ctx->sm_count)
+				grid = ctx->sm_count;
+			seedk<<<(unsigned) (grid < 1 ? 1 : grid), SW * 32, seed_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si]);
+		}
 		CUDA_TRY(cudaGetLastError());
 		pb::bin_order_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(n, d_seeds, pb::seed_words(ML), pb::seed_mask_words(ML) + 1, ctx->d_bins[si], ctx->d_order[si]);
 		CUDA_TRY(cudaGetLastError());
@@ -291,11 +303,19 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 	{
 		/* <seeding class, lane-kernel class, seeding warps, lane warps, general-kernel warps>: as many warps as the per-warp shared
 		 * memory allows; reads up to 152 nt (2x150 included) leave room for a 12th warp of the lane kernel */
+		/* seeding: the diagonal sweep (pb_sweep.cuh) unless an explicit maxoverlap lets overlaps run past a read's end, which
+		 * only the hash join (pb::seed_kernel) covers; PANDASEQ_B200_SWEEP=0 / pb_set_lanes(ctx, 2) keep the hash join for A/B runs */
+		static int sweep_on = -1;
+		if (sweep_on < 0) {
+			const char *env = getenv("PANDASEQ_B200_SWEEP");
+			sweep_on = (env && atoi(env) == 0) ? 0 : 1;
+		}
+		const bool sweep = sweep_on && ctx->lanes_mode != 2 && cfg->maxoverlap == 0;
 		if (max_len <= 152)
-			return launch_lanes<160, 152, 32, 12, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
+			return launch_lanes<160, 152, 32, 12, 28, 20>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 		if (max_len <= 160)
-			return launch_lanes<160, 160, 32, 11, 28>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
-		return launch_lanes<256, 256, 19, 7, 15>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream);
+			return launch_lanes<160, 160, 32, 11, 28, 20>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
+		return launch_lanes<256, 256, 19, 7, 15, 14>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 	}
 #define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq); \
 	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false); } while (0)
@@ -375,7 +395,7 @@ extern "C" pb_status pb_lanes_stats(pb_context *ctx, uint64_t *lanes_pairs, uint
 }
 
 extern "C" pb_status pb_set_lanes(pb_context *ctx, int mode) {
-	if (!ctx || mode < -1 || mode > 1) {
+	if (!ctx || mode < -1 || mode > 2) {
 		pb_set_error("pb_set_lanes: bad argument");
 		return PB_ERR_ARGUMENT;
 	}

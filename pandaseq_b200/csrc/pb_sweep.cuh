@@ -1,0 +1,400 @@
+/* pb_sweep.cuh -- K1-K3 of align() (assembler.c:84-118) as a bit-parallel sweep over diagonals, one LANE per read pair.
+ *
+ * What the reference computes with its 65536 x 2 position table is a join: overlap o is a candidate iff some valid
+ * forward 8-mer position p and some valid reverse 8-mer position share a 16-bit code and lie on diagonal o, p being
+ * one of the first two forward positions with that code ("table-free statement of seeding").
+ * pb::seed_kernel does that join with a shared-memory hash table, one warp per pair, 733 warp-instructions per pair:
+ * 284 hash operations at 32 per instruction.  Here the join is never formed.  With the reads as two bit planes of
+ * 2-bit k-mer digits (32 bases per word), the forward read shifted by s = F - o against the template-order reverse read
+ * gives, per 32-bit word, the positions where the digits differ (XOR, OR); an 8-mer match on that diagonal is a run
+ * of eight equal positions, found with three shift-OR doubling steps.  All diagonals of a pair cost
+ * (NW (NW + 1) / 2) x 32 word steps of nine instructions for reads of up to 32 NW bases, every lane busy with its own
+ * pair: 163 instructions per pair at 2x150 (NW = 5), no shared-memory traffic, no atomics.
+ *
+ * The sweep finds every diagonal with a shared 8-mer; the reference only those where the forward position was one of
+ * the first two with its code ("lost k-mers", assembler.c:95-97).  So every flagged diagonal is certified afterwards:
+ * the lowest matching forward position p on it is taken and the occurrences of its code before p are counted (the
+ * 8 digits against all forward positions, bit-parallel again).  Fewer than two: p is in the table, the diagonal is a
+ * candidate for certain.  Two or more (0.01 % of random pairs, low-complexity reads): the pair is handed to the general
+ * kernel, whose hash join is exact.  Pairs with a base that is not A/C/G/T, reads outside 16 .. 32 NW, or no candidate
+ * at all are handed on as pb::seed_kernel does.  The output is pb::seed_kernel's: the candidate mask in overlap order,
+ * a flag word and the overlap bin (pb_kernels.cuh), so the lane-per-pair kernel (pb_lanes.cuh) takes either.
+ *
+ * The functions up to sweep_resolve() are plain C++ on 32-bit words and compile for the host as well: tests/c/
+ * sweep_host.cpp runs them against the oracle's table-based seeding on the CPU (tests/test_sweep_core.py).
+ */
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PBS_HD __host__ __device__ __forceinline__
+#define PBS_HDM __host__ __device__ __forceinline__
+#else
+#define PBS_HD static inline
+#define PBS_HDM inline
+#endif
+
+namespace pbs {
+
+constexpr uint32_t NIB1 = 0x11111111u;
+constexpr unsigned SEED_GENERAL = 1u, SEED_SKIP = 2u;      /* = pb::PB_SEED_GENERAL / PB_SEED_SKIP */
+
+/* low 32 bits of (hi:lo) >> s, s in [0, 31] */
+PBS_HD uint32_t shf_r(uint32_t lo, uint32_t hi, unsigned s) {
+#if defined(__CUDA_ARCH__)
+	return __funnelshift_r(lo, hi, s);
+#else
+	return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+/* high 32 bits of (hi:lo) << s, s in [0, 31] */
+PBS_HD uint32_t shf_l(uint32_t lo, uint32_t hi, unsigned s) {
+#if defined(__CUDA_ARCH__)
+	return __funnelshift_l(lo, hi, s);
+#else
+	return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+PBS_HD int popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+	return __popc(x);
+#else
+	return __builtin_popcount(x);
+#endif
+}
+PBS_HD int ffs32(uint32_t x) {      /* 1-based, 0 for x == 0 */
+#if defined(__CUDA_ARCH__)
+	return __ffs((int) x);
+#else
+	return __builtin_ffs((int) x);
+#endif
+}
+/* the low n bits set, n in [0, 32] */
+PBS_HD uint32_t lowbits(int n) {
+	return n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+}
+/* bits 4k of d (k = 0..7) -> 8 contiguous bits: one multiply lands them at 9..12 and 25..28 without carries
+ * (the 32 partial products 4i + 3j, i < 8, j < 4, are all at different positions) */
+PBS_HD uint32_t gather8(uint32_t d) {
+	const uint32_t m = d * 0x249u;
+	return ((m >> 9) & 0xFu) | ((m >> 21) & 0xF0u);
+}
+
+/* Bit planes of one read: bit b of p0[j] / p1[j] = low / high bit of the k-mer digit (misc.h:41: T = 3, G = 2, C = 1,
+ * everything else 0) of base 32 j + b; zero past the read.  nt = the read's packed 4-bit bases, 8 per word.
+ * `bad` collects nibbles that are not exactly A, C, G or T. */
+template <int NW>
+PBS_HD void build_planes(const uint32_t *nt, int len, uint32_t (&p0)[NW], uint32_t (&p1)[NW], uint32_t &bad) {
+	const int nwords = (len + 7) >> 3;
+	int bits = 0;
+	uint32_t two = 0;
+#pragma unroll
+	for (int j = 0; j < NW; j++) {
+		uint32_t a0 = 0, a1 = 0;
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			const int k = 4 * j + t;
+			const uint32_t w = k < nwords ? nt[k] : 0u;
+			const uint32_t w1 = w >> 1, w2 = w >> 2, w3 = w >> 3;
+			a0 |= gather8((w1 | w3) & NIB1) << (8 * t);      /* C or T */
+			a1 |= gather8((w2 | w3) & NIB1) << (8 * t);      /* G or T */
+			/* exactly one bit per base: no nibble with two bits, and as many bits as bases (the padding nibbles are zero) */
+			two |= (w & w1 & 0x77777777u) | (w & w2 & 0x33333333u) | (w & w3 & NIB1);
+			bits += popc32(w);
+		}
+		p0[j] = a0;
+		p1[j] = a1;
+	}
+	bad |= two | (uint32_t) (bits ^ len);
+}
+
+/* One word step of the sweep: positions of T word k against the forward planes shifted to them.
+ * neq bit i = the digits differ, or the forward position is past the read. */
+PBS_HD uint32_t neq_word(uint32_t f0, uint32_t f1, uint32_t fv, uint32_t t0, uint32_t t1) {
+	const uint32_t a = (f0 ^ t0) | ~fv;
+	return a | (f1 ^ t1);
+}
+/* Run detection over the words of one diagonal, lowest word first: step() returns, for the word it is given, bit i set iff
+ * no position among i-7 .. i differs (three shift-OR doubling steps; the windows reach into the word below through the
+ * state). */
+struct Run8 {
+	uint32_t n = 0, y1 = 0, y2 = 0;      /* the word below: its differences and its 2- and 4-position windows */
+	PBS_HDM uint32_t step(uint32_t ne) {
+		const uint32_t a1 = ne | shf_l(n, ne, 1);
+		const uint32_t a2 = a1 | shf_l(y1, a1, 2);
+		const uint32_t a4 = a2 | shf_l(y2, a2, 4);
+		n = ne;
+		y1 = a1;
+		y2 = a2;
+		return ~a4;
+	}
+};
+
+/* All diagonals s = 32 W + b (overlap o = F - s): mask[W] bit b set iff the reads share a valid 8-mer on it, i.e.
+ * eight equal digits at template positions i-7 .. i with 8 <= i < o (the first k-mer of a read ends at position 8:
+ * misc.h:41-45 wants nine clean bases).  f0 / f1 / fv (fv = positions inside the forward read) are consumed. */
+template <int NW>
+PBS_HD void sweep(uint32_t (&f0)[NW], uint32_t (&f1)[NW], uint32_t (&fv)[NW],
+                  const uint32_t (&t0)[NW], const uint32_t (&t1)[NW], uint32_t (&mask)[NW]) {
+#pragma unroll
+	for (int W = 0; W < NW; W++)
+		mask[W] = 0;
+#pragma unroll 1
+	for (int b = 0; b < 32; b++) {
+#pragma unroll
+		for (int W = 0; W < NW; W++) {
+			uint32_t acc = 0;
+			Run8 run;
+#pragma unroll
+			for (int k = 0; k + W < NW; k++) {
+				uint32_t hit = run.step(neq_word(f0[k + W], f1[k + W], fv[k + W], t0[k], t1[k]));
+				if (k == 0)
+					hit &= ~0xFFu;     /* a k-mer that ends before position 8 does not exist (misc.h:41-45) */
+				acc |= hit;
+			}
+			if (acc)
+				mask[W] |= 1u << b;
+		}
+		/* the forward planes one position further */
+#pragma unroll
+		for (int j = 0; j < NW; j++) {
+			const bool last = j + 1 == NW;
+			f0[j] = shf_r(f0[j], last ? 0u : f0[j + 1], 1);
+			f1[j] = shf_r(f1[j], last ? 0u : f1[j + 1], 1);
+			fv[j] = shf_r(fv[j], last ? 0u : fv[j + 1], 1);
+		}
+	}
+}
+
+/* The planes of a pair where the certificate can index them with run-time positions: PL(w) = word w of this lane.
+ * Layout: F0[NW + 1], F1[NW + 1] (one zero word on top), T0[NW], T1[NW]. */
+template <int NW> struct PlaneIndex {
+	static constexpr int F0 = 0, F1 = NW + 1, T0 = 2 * (NW + 1), T1 = 2 * (NW + 1) + NW, WORDS = 2 * (NW + 1) + 2 * NW;
+};
+
+/* Lowest template position i with an 8-mer match ending there on diagonal s (o = F - s), or -1.  Same arithmetic as
+ * sweep(), with positions taken at run time. */
+template <int NW, typename PL>
+PBS_HD int first_hit(const PL &pl, int s, int o) {
+	using PI = PlaneIndex<NW>;
+	const int w0 = s >> 5, sh = s & 31;
+	Run8 run;
+	for (int k = 0; 32 * k < o && k + w0 < NW; k++) {
+		const uint32_t f0 = shf_r(pl(PI::F0 + w0 + k), pl(PI::F0 + w0 + k + 1), sh);
+		const uint32_t f1 = shf_r(pl(PI::F1 + w0 + k), pl(PI::F1 + w0 + k + 1), sh);
+		uint32_t hit = run.step(neq_word(f0, f1, lowbits(o - 32 * k), pl(PI::T0 + k), pl(PI::T1 + k)));
+		if (k == 0)
+			hit &= ~0xFFu;
+		if (hit)
+			return 32 * k + ffs32(hit) - 1;
+	}
+	return -1;
+}
+
+/* Forward positions p' in [8, p) whose 8-mer (digits at p'-7 .. p') equals the one ending at p. */
+template <int NW, typename PL>
+PBS_HD int earlier_occurrences(const PL &pl, int p) {
+	using PI = PlaneIndex<NW>;
+	const int a = p - 7;
+	const uint32_t pat0 = shf_r(pl(PI::F0 + (a >> 5)), pl(PI::F0 + (a >> 5) + 1), a & 31) & 0xFFu;
+	const uint32_t pat1 = shf_r(pl(PI::F1 + (a >> 5)), pl(PI::F1 + (a >> 5) + 1), a & 31) & 0xFFu;
+	uint32_t prev[8];
+#pragma unroll
+	for (int k = 0; k < 8; k++)
+		prev[k] = 0xFFFFFFFFu;                               /* below position 0 nothing matches */
+	int count = 0;
+#pragma unroll
+	for (int j = 0; j < NW; j++) {
+		if (32 * j >= p)
+			break;
+		const uint32_t f0 = pl(PI::F0 + j), f1 = pl(PI::F1 + j);
+		uint32_t differs = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			/* digit k of the pattern sits 7 - k positions below the position the window ends at */
+			const uint32_t m0 = 0u - ((pat0 >> k) & 1u), m1 = 0u - ((pat1 >> k) & 1u);
+			const uint32_t ne = (f0 ^ m0) | (f1 ^ m1);
+			differs |= shf_l(prev[k], ne, 7 - k);
+			prev[k] = ne;
+		}
+		uint32_t occ = ~differs & lowbits(p - 32 * j);
+		if (j == 0)
+			occ &= ~0xFFu;
+		count += popc32(occ);
+	}
+	return count;
+}
+
+/* From the sweep's diagonal mask to pb::seed_kernel's record: cw[] = candidate mask in overlap order (bit i <=> overlap
+ * mo + i, assembler.c:39), returns the flag word; *lowest = the lowest candidate bit (the lane kernel's bin).  maxov as
+ * assembler.c:78-82 with maxoverlap == 0, i.e. min(F, R); the caller guarantees mo < maxov <= 32 NW. */
+template <int NW, typename PL>
+PBS_HD unsigned sweep_resolve(const PL &pl, const uint32_t (&mask)[NW], int F, int mo, int maxov, uint32_t (&cw)[NW], int *lowest) {
+	unsigned flags = 0;
+	int low = 1 << 20;
+#pragma unroll
+	for (int w = 0; w < NW; w++)
+		cw[w] = 0;
+#pragma unroll
+	for (int W = 0; W < NW; W++) {
+		uint32_t m = mask[W];
+		while (m) {
+			const int b = ffs32(m) - 1;
+			m &= m - 1;
+			const int s = 32 * W + b, o = F - s, idx = o - mo;
+			if (idx < 0 || o > maxov)           /* BIT_LIST_SET (assembler.c:39): outside the bit list */
+				continue;
+			const int i = first_hit<NW>(pl, s, o);
+			if (i < 0)
+				continue;                       /* cannot happen: the sweep saw a match on this diagonal */
+			if (earlier_occurrences<NW>(pl, s + i) >= 2) {
+				flags |= SEED_GENERAL;          /* maybe a lost k-mer (assembler.c:95-97): the exact join decides */
+				continue;
+			}
+#pragma unroll
+			for (int w = 0; w < NW; w++)
+				if ((idx >> 5) == w)
+					cw[w] |= 1u << (idx & 31);
+			low = idx < low ? idx : low;
+		}
+	}
+	if (low == (1 << 20))
+		flags |= SEED_GENERAL;                  /* ALL_BITS_IF_NONE (assembler.c:118): every overlap is scored, the general kernel's job */
+	*lowest = low;
+	return flags;
+}
+
+}  // namespace pbs
+
+#if defined(__CUDACC__)
+#include "pb_kernels.cuh"
+
+namespace pbs {
+
+/* Per-warp shared memory: the 32 pairs' packed bases as the bulk copies land them, and the pairs' planes, word-major
+ * (word w of lane l at [w][l]) so that a warp reading one word index never collides. */
+template <int NW> struct SweepArea {
+	static constexpr int ML = 32 * NW;
+	static constexpr int NT_BYTES = ML;                                  /* 2 reads x ML / 2 bytes */
+	static constexpr int STRIDE = (((NT_BYTES + 15) / 16) | 1) * 16;     /* odd number of 16-byte units */
+	alignas(128) uint8_t nt[32 * STRIDE];
+	alignas(16) uint32_t planes[PlaneIndex<NW>::WORDS][32];
+	alignas(8) uint64_t bar;
+};
+
+struct LanePlanes {
+	const uint32_t *base;      /* &planes[0][lane] */
+	__device__ __forceinline__ uint32_t operator()(int w) const { return base[w * 32]; }
+};
+
+/* seeds / bin_count as pb::seed_kernel writes them (pb_kernels.cuh); pairs are taken 32 at a time in batch order. */
+template <int NW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__restrict__ reads,
+                  const pb_pair_meta *__restrict__ meta, uint32_t *__restrict__ seeds, unsigned *__restrict__ bin_count) {
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	__shared__ unsigned s_bins[pb::PB_SEED_BINS];
+	using SA = SweepArea<NW>;
+	using PI = PlaneIndex<NW>;
+	constexpr int ML = 32 * NW;
+	constexpr int MW = pb::seed_mask_words(ML), SWORDS = pb::seed_words(ML);
+	static_assert(MW == NW, "one mask word per plane word");
+	SA *areas = reinterpret_cast<SA *>(smem_raw);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid < pb::PB_SEED_BINS)
+		s_bins[tid] = 0;
+	SA &wa = areas[warp];
+	if (lane == 0) {
+		pb::mbar_init(&wa.bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	const int mo = prm->minoverlap;
+	const int nbatch = (n + 31) >> 5;
+	unsigned parity = 0;
+	uint32_t *const myplanes = &wa.planes[0][lane];
+	const LanePlanes pl{myplanes};
+
+	for (int batch = blockIdx.x * WARPS + warp; batch < nbatch; batch += gridDim.x * WARPS) {
+		const int pair = batch * 32 + lane;
+		unsigned off16 = 0;
+		int F = 0xFFFF, R = 0;
+		if (pair < n) {
+			const uint2 mraw = *reinterpret_cast<const uint2 *>(&meta[pair]);
+			off16 = mraw.x;
+			F = (int) (mraw.y & 0xFFFFu);
+			R = (int) (mraw.y >> 16);
+		}
+		unsigned flags = 0;
+		if (F == 0xFFFF)
+			flags = SEED_SKIP;
+		else if (F > ML || R > ML || F < 16 || R < 16 || mo >= min(F, R))
+			flags = SEED_GENERAL;
+		const int fw = (F + 7) >> 3, rw = (R + 7) >> 3;
+		const unsigned bytes = flags ? 0u : (unsigned) ((fw + rw) * 4 + 15) & ~15u;
+		const unsigned total = __reduce_add_sync(pb::FULL, bytes);
+		if (lane == 0)
+			pb::mbar_expect_tx(&wa.bar, total);
+		__syncwarp();
+		if (bytes)
+			pb::bulk_g2s(wa.nt + lane * SA::STRIDE, reads + (size_t) off16 * 16, bytes, &wa.bar);
+		pb::mbar_wait(&wa.bar, parity);
+		parity ^= 1u;
+
+		uint32_t cw[NW];
+		int lowest = 1 << 20;
+#pragma unroll
+		for (int w = 0; w < NW; w++)
+			cw[w] = 0;
+		{
+			uint32_t f0[NW], f1[NW], fv[NW], t0[NW], t1[NW], mask[NW];
+			uint32_t bad = 0;
+			const uint32_t *nt = reinterpret_cast<const uint32_t *>(wa.nt + lane * SA::STRIDE);
+			const int Fe = flags ? 0 : F, Re = flags ? 0 : R;          /* lanes without a pair sweep empty reads */
+			build_planes<NW>(nt, Fe, f0, f1, bad);
+			build_planes<NW>(nt + fw, Re, t0, t1, bad);
+			if (bad)
+				flags |= SEED_GENERAL;
+#pragma unroll
+			for (int j = 0; j < NW; j++) {
+				fv[j] = lowbits(min(max(Fe - 32 * j, 0), 32));
+				myplanes[(PI::F0 + j) * 32] = f0[j];
+				myplanes[(PI::F1 + j) * 32] = f1[j];
+				myplanes[(PI::T0 + j) * 32] = t0[j];
+				myplanes[(PI::T1 + j) * 32] = t1[j];
+			}
+			myplanes[(PI::F0 + NW) * 32] = 0;
+			myplanes[(PI::F1 + NW) * 32] = 0;
+			sweep<NW>(f0, f1, fv, t0, t1, mask);
+			if (!flags)
+				flags = sweep_resolve<NW>(pl, mask, F, mo, min(F, R), cw, &lowest);
+		}
+		unsigned bin = flags ? (unsigned) (pb::PB_SEED_BINS - 1) : (unsigned) (lowest >> 4);
+		if (bin > (unsigned) (pb::PB_SEED_BINS - 1))
+			bin = pb::PB_SEED_BINS - 1;
+		if (pair < n) {
+			uint32_t sw[SWORDS];
+#pragma unroll
+			for (int w = 0; w < SWORDS; w++)
+				sw[w] = w < MW ? cw[w] : 0u;
+			sw[MW] = flags;
+			sw[MW + 1] = bin;
+			uint4 *dst = reinterpret_cast<uint4 *>(seeds + (size_t) pair * SWORDS);
+#pragma unroll
+			for (int q = 0; q < SWORDS / 4; q++)
+				dst[q] = make_uint4(sw[4 * q], sw[4 * q + 1], sw[4 * q + 2], sw[4 * q + 3]);
+			atomicAdd(&s_bins[bin], 1u);
+		}
+		__syncwarp();      /* every lane is done with its slot before the next batch lands on it */
+	}
+	__syncthreads();
+	if (tid < pb::PB_SEED_BINS && s_bins[tid])
+		atomicAdd(&bin_count[tid], s_bins[tid]);
+}
+
+template <int NW, int WARPS> constexpr size_t sweep_smem_bytes() {
+	return sizeof(SweepArea<NW>) * WARPS;
+}
+
+}  // namespace pbs
+#endif

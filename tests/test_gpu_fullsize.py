@@ -111,7 +111,13 @@ def test_two_kernel_path_equals_general_kernel_at_full_size(full):
     ctx.set_lanes(0)
     res_b, nt_b, cnt_b = run(ctx, reads, meta, max_len, 0, N)
     assert ctx.lanes_stats()[0] == after[0]
+    # and with the candidate overlaps from the hash join (pb::seed_kernel) instead of the diagonal sweep (pb_sweep.cuh):
+    # the same records byte for byte, `examined` included
+    ctx.set_lanes(2)
+    res_c, nt_c, cnt_c = run(ctx, reads, meta, max_len, 0, N)
     ctx.set_lanes(-1)
+    assert torch.equal(res_a, res_c) and torch.equal(nt_a, nt_c) and np.array_equal(cnt_a, cnt_c)
+    del res_c, nt_c
     assert np.array_equal(cnt_a, cnt_b)
     assert torch.equal(nt_a, nt_b)
     a = res_a.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel()
@@ -139,7 +145,7 @@ def test_two_paths_agree_on_decorated_reads(built, algo, kw):
     cfg = pb.make_config(algo, **kw)
     stride = (2 * ml + 15) & ~15
     outs = []
-    for mode in (1, 0):
+    for mode in (1, 0, 2):
         ctx.set_lanes(mode)
         res = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
         nt = torch.zeros((n, stride // 2), dtype=torch.uint8, device="cuda")
@@ -151,8 +157,10 @@ def test_two_paths_agree_on_decorated_reads(built, algo, kw):
         after = ctx.lanes_stats()
         outs.append((res.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel(), nt, cnt.cpu().numpy(), after[0] - before[0], after[1] - before[1]))
     ctx.close()
-    (a, nt_a, cnt_a, lanes_a, deferred_a), (b, nt_b, cnt_b, lanes_b, _) = outs
-    assert lanes_a == n and lanes_b == 0 and n // 10 < deferred_a < n
+    (a, nt_a, cnt_a, lanes_a, deferred_a), (b, nt_b, cnt_b, lanes_b, _), (c, nt_c, cnt_c, lanes_c, _) = outs
+    assert lanes_a == n and lanes_b == 0 and n // 10 < deferred_a < n and lanes_c == n
+    # sweep seeding vs hash-join seeding: the same bytes
+    assert np.array_equal(a.view(np.uint8), c.view(np.uint8)) and torch.equal(nt_a, nt_c) and np.array_equal(cnt_a, cnt_c)
     assert np.array_equal(cnt_a, cnt_b)
     assert torch.equal(nt_a, nt_b)
     for k in ("status", "slow", "overlap", "seq_len", "mismatches", "degenerates", "examined", "fwd_offset", "rev_offset"):
