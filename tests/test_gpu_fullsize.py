@@ -112,20 +112,20 @@ def test_two_kernel_path_equals_general_kernel_at_full_size(full):
     res_b, nt_b, cnt_b = run(ctx, reads, meta, max_len, 0, N)
     assert ctx.lanes_stats()[0] == after[0]
     # and with the candidate overlaps from the hash join (pb::seed_kernel) instead of the diagonal sweep (pb_sweep.cuh):
-    # the same records byte for byte, `examined` included
+    # `examined` depends on the exact candidate set.  (The sweep hands a few more pairs to the general kernel -- the ones
+    # whose certificate fails -- so `quality` may differ in the last bits for those.)
     ctx.set_lanes(2)
     res_c, nt_c, cnt_c = run(ctx, reads, meta, max_len, 0, N)
     ctx.set_lanes(-1)
-    assert torch.equal(res_a, res_c) and torch.equal(nt_a, nt_c) and np.array_equal(cnt_a, cnt_c)
-    del res_c, nt_c
-    assert np.array_equal(cnt_a, cnt_b)
-    assert torch.equal(nt_a, nt_b)
     a = res_a.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel()
-    b = res_b.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel()
-    for k in ("status", "slow", "overlap", "seq_len", "mismatches", "degenerates", "examined", "fwd_offset", "rev_offset"):
-        assert np.array_equal(a[k], b[k]), k
-    assert np.array_equal(a["est_prob"].view(np.uint64), b["est_prob"].view(np.uint64))
-    assert np.abs(a["quality"] - b["quality"]).max() <= 1e-12
+    for res_x, nt_x, cnt_x in ((res_b, nt_b, cnt_b), (res_c, nt_c, cnt_c)):
+        assert np.array_equal(cnt_a, cnt_x)
+        assert torch.equal(nt_a, nt_x)
+        b = res_x.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel()
+        for k in ("status", "slow", "overlap", "seq_len", "mismatches", "degenerates", "examined", "fwd_offset", "rev_offset"):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a["est_prob"].view(np.uint64), b["est_prob"].view(np.uint64))
+        assert np.abs(a["quality"] - b["quality"]).max() <= 1e-12
 
 
 @pytest.mark.parametrize("algo,kw", [("simple_bayesian", {}), ("flash", {}), ("uparse", dict(minoverlap=12)),
@@ -159,8 +159,11 @@ def test_two_paths_agree_on_decorated_reads(built, algo, kw):
     ctx.close()
     (a, nt_a, cnt_a, lanes_a, deferred_a), (b, nt_b, cnt_b, lanes_b, _), (c, nt_c, cnt_c, lanes_c, _) = outs
     assert lanes_a == n and lanes_b == 0 and n // 10 < deferred_a < n and lanes_c == n
-    # sweep seeding vs hash-join seeding: the same bytes
-    assert np.array_equal(a.view(np.uint8), c.view(np.uint8)) and torch.equal(nt_a, nt_c) and np.array_equal(cnt_a, cnt_c)
+    # sweep seeding vs hash-join seeding
+    assert torch.equal(nt_a, nt_c) and np.array_equal(cnt_a, cnt_c)
+    for k in ("status", "slow", "overlap", "seq_len", "mismatches", "degenerates", "examined", "fwd_offset", "rev_offset"):
+        assert np.array_equal(a[k], c[k]), k
+    assert np.abs(a["quality"] - c["quality"]).max() <= 1e-12 and np.abs(a["est_prob"] - c["est_prob"]).max() <= 1e-9
     assert np.array_equal(cnt_a, cnt_b)
     assert torch.equal(nt_a, nt_b)
     for k in ("status", "slow", "overlap", "seq_len", "mismatches", "degenerates", "examined", "fwd_offset", "rev_offset"):
