@@ -248,7 +248,8 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 			long long grid = (((long long) n + 31) / 32 + XW - 1) / XW;
 			if (grid > ctx->sm_count)
 				grid = ctx->sm_count;
-			sweepk<<<(unsigned) (grid < 1 ? 1 : grid), XW * 32, sweep_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si]);
+			const pbs::Muls mu = { 2u, 4u, 16u };      /* run-time values on purpose: pb_sweep.cuh */
+			sweepk<<<(unsigned) (grid < 1 ? 1 : grid), XW * 32, sweep_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si], mu);
 		} else {
 			long long grid = ((long long) n + SW - 1) / SW;
 			if (grid > ctx->sm_count)
@@ -312,9 +313,9 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 		}
 		const bool sweep = sweep_on && ctx->lanes_mode != 2 && cfg->maxoverlap == 0;
 		if (max_len <= 152)
-			return launch_lanes<160, 152, 32, 12, 28, 20>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
+			return launch_lanes<160, 152, 32, 12, 28, 22>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 		if (max_len <= 160)
-			return launch_lanes<160, 160, 32, 11, 28, 20>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
+			return launch_lanes<160, 160, 32, 11, 28, 22>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 		return launch_lanes<256, 256, 19, 7, 15, 14>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 	}
 #define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq); \

@@ -111,50 +111,74 @@ PBS_HD void build_planes(const uint32_t *nt, int len, uint32_t (&p0)[NW], uint32
 /* One word step of the sweep: positions of T word k against the forward planes shifted to them.
  * neq bit i = the digits differ, or the forward position is past the read. */
 PBS_HD uint32_t neq_word(uint32_t f0, uint32_t f1, uint32_t fv, uint32_t t0, uint32_t t1) {
+#if defined(__CUDA_ARCH__)
+	/* two three-input logic operations, spelled out: left to itself the compiler forms three */
+	uint32_t a, ne;
+	asm("lop3.b32 %0, %1, %2, %3, 0x7D;" : "=r"(a) : "r"(f0), "r"(t0), "r"(fv));       /* (f0 ^ t0) | ~fv */
+	asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(ne) : "r"(a), "r"(f1), "r"(t1));        /* a | (f1 ^ t1) */
+	return ne;
+#else
 	const uint32_t a = (f0 ^ t0) | ~fv;
 	return a | (f1 ^ t1);
+#endif
 }
-/* Run detection over the words of one diagonal, lowest word first: step() returns, for the word it is given, bit i set iff
- * no position among i-7 .. i differs (three shift-OR doubling steps; the windows reach into the word below through the
- * state). */
+
+/* 2, 4 and 16 as run-time values (kernel parameters): x * m as a 32 x 32 -> 64-bit multiply gives x << s in the low word
+ * and the bits that cross into the next word in the high word, in ONE instruction of the FMA pipe (IMAD.WIDE) -- the
+ * sweep is bound by the ALU pipe (LOP3 / SHF), which a funnel shift would load further.  As compile-time constants the
+ * compiler turns them back into shifts. */
+struct Muls { uint32_t m1, m2, m4; };
+PBS_HD void shl_wide(uint32_t x, uint32_t m, uint32_t &lo, uint32_t &hi) {
+	const unsigned long long w = (unsigned long long) x * m;
+	lo = (uint32_t) w;
+	hi = (uint32_t) (w >> 32);
+}
+/* Run detection over the words of one diagonal, lowest word first: step() returns, for the word of differences it is
+ * given, bit i CLEAR iff no position among i-7 .. i differs (three shift-OR doubling steps; the windows reach into the
+ * word below through the carries).  A k-mer that ends before position 8 does not exist (misc.h:41-45: nine clean bases),
+ * so the first word's bits 0..7 are forced. */
 struct Run8 {
-	uint32_t n = 0, y1 = 0, y2 = 0;      /* the word below: its differences and its 2- and 4-position windows */
-	PBS_HDM uint32_t step(uint32_t ne) {
-		const uint32_t a1 = ne | shf_l(n, ne, 1);
-		const uint32_t a2 = a1 | shf_l(y1, a1, 2);
-		const uint32_t a4 = a2 | shf_l(y2, a2, 4);
-		n = ne;
-		y1 = a1;
-		y2 = a2;
-		return ~a4;
+	uint32_t c1 = 0, c2 = 0, c4 = 0xFFu;
+	PBS_HDM uint32_t step(uint32_t ne, const Muls &mu) {
+		uint32_t lo, hi;
+		shl_wide(ne, mu.m1, lo, hi);
+		const uint32_t y1 = ne | lo | c1;
+		c1 = hi;
+		shl_wide(y1, mu.m2, lo, hi);
+		const uint32_t y2 = y1 | lo | c2;
+		c2 = hi;
+		shl_wide(y2, mu.m4, lo, hi);
+		const uint32_t y4 = y2 | lo | c4;
+		c4 = hi;
+		return y4;
 	}
 };
 
 /* All diagonals s = 32 W + b (overlap o = F - s): mask[W] bit b set iff the reads share a valid 8-mer on it, i.e.
- * eight equal digits at template positions i-7 .. i with 8 <= i < o (the first k-mer of a read ends at position 8:
- * misc.h:41-45 wants nine clean bases).  f0 / f1 / fv (fv = positions inside the forward read) are consumed. */
+ * eight equal digits at template positions i-7 .. i with 8 <= i < o.  f0 / f1 / fv (fv = positions inside the forward
+ * read) are consumed. */
 template <int NW>
 PBS_HD void sweep(uint32_t (&f0)[NW], uint32_t (&f1)[NW], uint32_t (&fv)[NW],
-                  const uint32_t (&t0)[NW], const uint32_t (&t1)[NW], uint32_t (&mask)[NW]) {
+                  const uint32_t (&t0)[NW], const uint32_t (&t1)[NW], uint32_t (&mask)[NW], const Muls mu) {
 #pragma unroll
 	for (int W = 0; W < NW; W++)
 		mask[W] = 0;
+	uint32_t bitb = 1;
 #pragma unroll 1
 	for (int b = 0; b < 32; b++) {
 #pragma unroll
 		for (int W = 0; W < NW; W++) {
-			uint32_t acc = 0;
+			uint32_t all = 0xFFFFFFFFu;      /* AND of the words' windows: all ones <=> no match on this diagonal */
 			Run8 run;
 #pragma unroll
-			for (int k = 0; k + W < NW; k++) {
-				uint32_t hit = run.step(neq_word(f0[k + W], f1[k + W], fv[k + W], t0[k], t1[k]));
-				if (k == 0)
-					hit &= ~0xFFu;     /* a k-mer that ends before position 8 does not exist (misc.h:41-45) */
-				acc |= hit;
+			for (int k = 0; k + W < NW; k += 2) {
+				const uint32_t ya = run.step(neq_word(f0[k + W], f1[k + W], fv[k + W], t0[k], t1[k]), mu);
+				const uint32_t yb = k + 1 + W < NW ? run.step(neq_word(f0[k + 1 + W], f1[k + 1 + W], fv[k + 1 + W], t0[k + 1], t1[k + 1]), mu) : 0xFFFFFFFFu;
+				all &= ya & yb;
 			}
-			if (acc)
-				mask[W] |= 1u << b;
+			mask[W] += (all != 0xFFFFFFFFu ? 1u : 0u) * bitb;
 		}
+		bitb *= mu.m1;
 		/* the forward planes one position further */
 #pragma unroll
 		for (int j = 0; j < NW; j++) {
@@ -166,25 +190,23 @@ PBS_HD void sweep(uint32_t (&f0)[NW], uint32_t (&f1)[NW], uint32_t (&fv)[NW],
 	}
 }
 
-/* The planes of a pair where the certificate can index them with run-time positions: PL(w) = word w of this lane.
- * Layout: F0[NW + 1], F1[NW + 1] (one zero word on top), T0[NW], T1[NW]. */
+/* Where the certificate can index a pair's words with run-time positions: PL(w) = word w of this lane, PL.set(w, v).
+ * Layout: F0[NW + 1], F1[NW + 1] (one zero word on top), T0[NW], T1[NW], the sweep's mask[NW], the candidate mask CW[NW]. */
 template <int NW> struct PlaneIndex {
-	static constexpr int F0 = 0, F1 = NW + 1, T0 = 2 * (NW + 1), T1 = 2 * (NW + 1) + NW, WORDS = 2 * (NW + 1) + 2 * NW;
+	static constexpr int F0 = 0, F1 = NW + 1, T0 = 2 * (NW + 1), T1 = T0 + NW, MASK = T1 + NW, CW = MASK + NW, WORDS = CW + NW;
 };
 
 /* Lowest template position i with an 8-mer match ending there on diagonal s (o = F - s), or -1.  Same arithmetic as
  * sweep(), with positions taken at run time. */
 template <int NW, typename PL>
-PBS_HD int first_hit(const PL &pl, int s, int o) {
+PBS_HD int first_hit(const PL &pl, int s, int o, const Muls &mu) {
 	using PI = PlaneIndex<NW>;
 	const int w0 = s >> 5, sh = s & 31;
 	Run8 run;
 	for (int k = 0; 32 * k < o && k + w0 < NW; k++) {
 		const uint32_t f0 = shf_r(pl(PI::F0 + w0 + k), pl(PI::F0 + w0 + k + 1), sh);
 		const uint32_t f1 = shf_r(pl(PI::F1 + w0 + k), pl(PI::F1 + w0 + k + 1), sh);
-		uint32_t hit = run.step(neq_word(f0, f1, lowbits(o - 32 * k), pl(PI::T0 + k), pl(PI::T1 + k)));
-		if (k == 0)
-			hit &= ~0xFFu;
+		const uint32_t hit = ~run.step(neq_word(f0, f1, lowbits(o - 32 * k), pl(PI::T0 + k), pl(PI::T1 + k)), mu);
 		if (hit)
 			return 32 * k + ffs32(hit) - 1;
 	}
@@ -198,22 +220,21 @@ PBS_HD int earlier_occurrences(const PL &pl, int p) {
 	const int a = p - 7;
 	const uint32_t pat0 = shf_r(pl(PI::F0 + (a >> 5)), pl(PI::F0 + (a >> 5) + 1), a & 31) & 0xFFu;
 	const uint32_t pat1 = shf_r(pl(PI::F1 + (a >> 5)), pl(PI::F1 + (a >> 5) + 1), a & 31) & 0xFFu;
-	uint32_t prev[8];
+	uint32_t m0[8], m1[8], prev[8];
 #pragma unroll
-	for (int k = 0; k < 8; k++)
+	for (int k = 0; k < 8; k++) {
+		m0[k] = 0u - ((pat0 >> k) & 1u);
+		m1[k] = 0u - ((pat1 >> k) & 1u);
 		prev[k] = 0xFFFFFFFFu;                               /* below position 0 nothing matches */
+	}
 	int count = 0;
-#pragma unroll
-	for (int j = 0; j < NW; j++) {
-		if (32 * j >= p)
-			break;
+	for (int j = 0; 32 * j < p; j++) {
 		const uint32_t f0 = pl(PI::F0 + j), f1 = pl(PI::F1 + j);
 		uint32_t differs = 0;
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
 			/* digit k of the pattern sits 7 - k positions below the position the window ends at */
-			const uint32_t m0 = 0u - ((pat0 >> k) & 1u), m1 = 0u - ((pat1 >> k) & 1u);
-			const uint32_t ne = (f0 ^ m0) | (f1 ^ m1);
+			const uint32_t ne = (f0 ^ m0[k]) | (f1 ^ m1[k]);
 			differs |= shf_l(prev[k], ne, 7 - k);
 			prev[k] = ne;
 		}
@@ -225,36 +246,38 @@ PBS_HD int earlier_occurrences(const PL &pl, int p) {
 	return count;
 }
 
-/* From the sweep's diagonal mask to pb::seed_kernel's record: cw[] = candidate mask in overlap order (bit i <=> overlap
- * mo + i, assembler.c:39), returns the flag word; *lowest = the lowest candidate bit (the lane kernel's bin).  maxov as
- * assembler.c:78-82 with maxoverlap == 0, i.e. min(F, R); the caller guarantees mo < maxov <= 32 NW. */
+/* From the sweep's diagonal mask to pb::seed_kernel's record: PL's CW words = candidate mask in overlap order (bit i <=>
+ * overlap mo + i, assembler.c:39), returns the flag word; *lowest = the lowest candidate bit (the lane kernel's bin).
+ * maxov as assembler.c:78-82 with maxoverlap == 0, i.e. min(F, R); the caller guarantees mo < maxov <= 32 NW.
+ *
+ * The certificate.  A flagged diagonal s has a match (p, q) = (s + i, i).  The reference misses it only if p is "lost":
+ * two valid forward positions p1 < p2 < p carry p's code.  Each of them matches q as well, on diagonal p_x - q < s --
+ * flagged too, if it is not negative -- or lies in [8, q).  So with `seen` flagged diagonals below s and the lowest
+ * match of this one at i, seen + (i - 8) < 2 proves p is in the table; only otherwise are p's earlier occurrences counted. */
 template <int NW, typename PL>
-PBS_HD unsigned sweep_resolve(const PL &pl, const uint32_t (&mask)[NW], int F, int mo, int maxov, uint32_t (&cw)[NW], int *lowest) {
+PBS_HD unsigned sweep_resolve(PL &pl, int F, int mo, int maxov, int *lowest, const Muls &mu) {
+	using PI = PlaneIndex<NW>;
 	unsigned flags = 0;
-	int low = 1 << 20;
-#pragma unroll
+	int low = 1 << 20, seen = 0;
 	for (int w = 0; w < NW; w++)
-		cw[w] = 0;
-#pragma unroll
+		pl.set(PI::CW + w, 0u);
 	for (int W = 0; W < NW; W++) {
-		uint32_t m = mask[W];
+		uint32_t m = pl(PI::MASK + W);
 		while (m) {
 			const int b = ffs32(m) - 1;
 			m &= m - 1;
 			const int s = 32 * W + b, o = F - s, idx = o - mo;
+			const int below = seen++;
 			if (idx < 0 || o > maxov)           /* BIT_LIST_SET (assembler.c:39): outside the bit list */
 				continue;
-			const int i = first_hit<NW>(pl, s, o);
+			const int i = first_hit<NW>(pl, s, o, mu);
 			if (i < 0)
 				continue;                       /* cannot happen: the sweep saw a match on this diagonal */
-			if (earlier_occurrences<NW>(pl, s + i) >= 2) {
+			if (below + (i - 8) >= 2 && earlier_occurrences<NW>(pl, s + i) >= 2) {
 				flags |= SEED_GENERAL;          /* maybe a lost k-mer (assembler.c:95-97): the exact join decides */
 				continue;
 			}
-#pragma unroll
-			for (int w = 0; w < NW; w++)
-				if ((idx >> 5) == w)
-					cw[w] |= 1u << (idx & 31);
+			pl.set(PI::CW + (idx >> 5), pl(PI::CW + (idx >> 5)) | (1u << (idx & 31)));
 			low = idx < low ? idx : low;
 		}
 	}
@@ -283,15 +306,16 @@ template <int NW> struct SweepArea {
 };
 
 struct LanePlanes {
-	const uint32_t *base;      /* &planes[0][lane] */
+	uint32_t *base;      /* &planes[0][lane] */
 	__device__ __forceinline__ uint32_t operator()(int w) const { return base[w * 32]; }
+	__device__ __forceinline__ void set(int w, uint32_t v) const { base[w * 32] = v; }
 };
 
 /* seeds / bin_count as pb::seed_kernel writes them (pb_kernels.cuh); pairs are taken 32 at a time in batch order. */
 template <int NW, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__restrict__ reads,
-                  const pb_pair_meta *__restrict__ meta, uint32_t *__restrict__ seeds, unsigned *__restrict__ bin_count) {
+                  const pb_pair_meta *__restrict__ meta, uint32_t *__restrict__ seeds, unsigned *__restrict__ bin_count, const Muls mu) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	__shared__ unsigned s_bins[pb::PB_SEED_BINS];
 	using SA = SweepArea<NW>;
@@ -313,7 +337,7 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 	const int nbatch = (n + 31) >> 5;
 	unsigned parity = 0;
 	uint32_t *const myplanes = &wa.planes[0][lane];
-	const LanePlanes pl{myplanes};
+	LanePlanes pl{myplanes};
 
 	for (int batch = blockIdx.x * WARPS + warp; batch < nbatch; batch += gridDim.x * WARPS) {
 		const int pair = batch * 32 + lane;
@@ -341,11 +365,7 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 		pb::mbar_wait(&wa.bar, parity);
 		parity ^= 1u;
 
-		uint32_t cw[NW];
 		int lowest = 1 << 20;
-#pragma unroll
-		for (int w = 0; w < NW; w++)
-			cw[w] = 0;
 		{
 			uint32_t f0[NW], f1[NW], fv[NW], t0[NW], t1[NW], mask[NW];
 			uint32_t bad = 0;
@@ -365,9 +385,14 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 			}
 			myplanes[(PI::F0 + NW) * 32] = 0;
 			myplanes[(PI::F1 + NW) * 32] = 0;
-			sweep<NW>(f0, f1, fv, t0, t1, mask);
+			sweep<NW>(f0, f1, fv, t0, t1, mask, mu);
+#pragma unroll
+			for (int j = 0; j < NW; j++) {
+				myplanes[(PI::MASK + j) * 32] = mask[j];
+				myplanes[(PI::CW + j) * 32] = 0;
+			}
 			if (!flags)
-				flags = sweep_resolve<NW>(pl, mask, F, mo, min(F, R), cw, &lowest);
+				flags = sweep_resolve<NW>(pl, F, mo, min(F, R), &lowest, mu);
 		}
 		unsigned bin = flags ? (unsigned) (pb::PB_SEED_BINS - 1) : (unsigned) (lowest >> 4);
 		if (bin > (unsigned) (pb::PB_SEED_BINS - 1))
@@ -376,7 +401,7 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 			uint32_t sw[SWORDS];
 #pragma unroll
 			for (int w = 0; w < SWORDS; w++)
-				sw[w] = w < MW ? cw[w] : 0u;
+				sw[w] = w < MW ? myplanes[(PI::CW + w) * 32] : 0u;
 			sw[MW] = flags;
 			sw[MW + 1] = bin;
 			uint4 *dst = reinterpret_cast<uint4 *>(seeds + (size_t) pair * SWORDS);

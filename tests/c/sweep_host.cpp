@@ -10,6 +10,7 @@
 template <int NW> struct HostPlanes {
 	uint32_t w[pbs::PlaneIndex<NW>::WORDS];
 	uint32_t operator()(int i) const { return w[i]; }
+	void set(int i, uint32_t v) { w[i] = v; }
 };
 
 /* one pair: pack as pb::pack_kernel does (4-bit codes, reverse read in template order), then the kernel's steps */
@@ -27,7 +28,8 @@ static unsigned one_pair(const uint8_t *f, int F, const uint8_t *r, int R, int m
 		fnt[i >> 3] |= (uint32_t) (f[2 * i] & 15u) << (4 * (i & 7));
 	for (int i = 0; i < R; i++)
 		rnt[i >> 3] |= (uint32_t) (r[2 * (R - 1 - i)] & 15u) << (4 * (i & 7));
-	uint32_t f0[NW], f1[NW], fv[NW], t0[NW], t1[NW], mask[NW], cw[NW], bad = 0;
+	uint32_t f0[NW], f1[NW], fv[NW], t0[NW], t1[NW], mask[NW], bad = 0;
+	const pbs::Muls mu = { 2u, 4u, 16u };
 	pbs::build_planes<NW>(fnt, F, f0, f1, bad);
 	pbs::build_planes<NW>(rnt, R, t0, t1, bad);
 	HostPlanes<NW> pl;
@@ -42,10 +44,12 @@ static unsigned one_pair(const uint8_t *f, int F, const uint8_t *r, int R, int m
 	}
 	if (bad)
 		return pbs::SEED_GENERAL;
-	pbs::sweep<NW>(f0, f1, fv, t0, t1, mask);
-	unsigned flags = pbs::sweep_resolve<NW>(pl, mask, F, mo, F < R ? F : R, cw, lowest);
+	pbs::sweep<NW>(f0, f1, fv, t0, t1, mask, mu);
+	for (int j = 0; j < NW; j++)
+		pl.w[PI::MASK + j] = mask[j];
+	unsigned flags = pbs::sweep_resolve<NW>(pl, F, mo, F < R ? F : R, lowest, mu);
 	for (int w = 0; w < NW; w++)
-		cw_out[w] = cw[w];
+		cw_out[w] = pl.w[PI::CW + w];
 	return flags;
 }
 

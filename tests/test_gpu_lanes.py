@@ -176,7 +176,10 @@ def test_pear_on_the_lane_kernel(ctx):
         assert rep["ok"], rep
     got, want, rep = run_lanes(ctx, pb.make_config("pear"), clean(20_000, seed=6))
     ok = want["status"] == 0
-    assert np.array_equal(got["results"]["est_prob"][ok].view(np.uint64), want["est_prob"][ok].view(np.uint64))
+    # ... for the pairs the lane kernel keeps; the few it hands on get the general kernel's shuffle-tree sum (last bits)
+    differ = got["results"]["est_prob"][ok].view(np.uint64) != want["est_prob"][ok].view(np.uint64)
+    assert int(differ.sum()) <= rep["deferred"] and rep["deferred"] <= 40, rep
+    assert np.abs(got["results"]["est_prob"][ok] - want["est_prob"][ok]).max() <= 1e-9
     # reverse longer than forward: algo_pear.c:52 reads past the forward read; those pairs are handed to the general kernel
     rng = np.random.default_rng(8)
     pairs = []
