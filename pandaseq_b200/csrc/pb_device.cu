@@ -313,9 +313,9 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 		}
 		const bool sweep = sweep_on && ctx->lanes_mode != 2 && cfg->maxoverlap == 0;
 		if (max_len <= 152)
-			return launch_lanes<160, 152, 32, 12, 28, 22>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
+			return launch_lanes<160, 152, 32, 12, 28, 21>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 		if (max_len <= 160)
-			return launch_lanes<160, 160, 32, 11, 28, 22>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
+			return launch_lanes<160, 160, 32, 11, 28, 21>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 		return launch_lanes<256, 256, 19, 7, 15, 14>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 	}
 #define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq); \

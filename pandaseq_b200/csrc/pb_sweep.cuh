@@ -154,26 +154,24 @@ struct Run8 {
 	}
 };
 
-/* All diagonals s = 32 W + b (overlap o = F - s): mask[W] bit b set iff the reads share a valid 8-mer on it, i.e.
- * eight equal digits at template positions i-7 .. i with 8 <= i < o.  f0 / f1 / fv (fv = positions inside the forward
- * read) are consumed. */
-template <int NW>
-PBS_HD void sweep(uint32_t (&f0)[NW], uint32_t (&f1)[NW], uint32_t (&fv)[NW],
-                  const uint32_t (&t0)[NW], const uint32_t (&t1)[NW], uint32_t (&mask)[NW], const Muls mu) {
-#pragma unroll
-	for (int W = 0; W < NW; W++)
-		mask[W] = 0;
-	uint32_t bitb = 1;
+/* Diagonals s = 32 W + b for b in [b0, b1) (overlap o = F - s): mask[W] bit b set iff the reads share a valid 8-mer on
+ * it, i.e. eight equal digits at template positions i-7 .. i with 8 <= i < o.  TOP = false leaves out the highest word
+ * of every diagonal (and with it the diagonals of the last block, which have only that word): right when no pair of the
+ * warp has an overlap that reaches it, i.e. b >= Fmax - 32 (NW - 1). */
+template <int NW, bool TOP>
+PBS_HD void sweep_range(int b0, int b1, uint32_t (&f0)[NW], uint32_t (&f1)[NW], uint32_t (&fv)[NW],
+                        const uint32_t (&t0)[NW], const uint32_t (&t1)[NW], uint32_t (&mask)[NW], uint32_t &bitb, const Muls mu) {
+	constexpr int NK = TOP ? NW : NW - 1;      /* words of the longest diagonal */
 #pragma unroll 1
-	for (int b = 0; b < 32; b++) {
+	for (int b = b0; b < b1; b++) {
 #pragma unroll
-		for (int W = 0; W < NW; W++) {
+		for (int W = 0; W < NK; W++) {
 			uint32_t all = 0xFFFFFFFFu;      /* AND of the words' windows: all ones <=> no match on this diagonal */
 			Run8 run;
 #pragma unroll
-			for (int k = 0; k + W < NW; k += 2) {
+			for (int k = 0; k + W < NK; k += 2) {
 				const uint32_t ya = run.step(neq_word(f0[k + W], f1[k + W], fv[k + W], t0[k], t1[k]), mu);
-				const uint32_t yb = k + 1 + W < NW ? run.step(neq_word(f0[k + 1 + W], f1[k + 1 + W], fv[k + 1 + W], t0[k + 1], t1[k + 1]), mu) : 0xFFFFFFFFu;
+				const uint32_t yb = k + 1 + W < NK ? run.step(neq_word(f0[k + 1 + W], f1[k + 1 + W], fv[k + 1 + W], t0[k + 1], t1[k + 1]), mu) : 0xFFFFFFFFu;
 				all &= ya & yb;
 			}
 			mask[W] += (all != 0xFFFFFFFFu ? 1u : 0u) * bitb;
@@ -189,11 +187,28 @@ PBS_HD void sweep(uint32_t (&f0)[NW], uint32_t (&f1)[NW], uint32_t (&fv)[NW],
 		}
 	}
 }
+/* All diagonals.  fmax = the longest forward read among the pairs swept together (the warp's 32 pairs; the pair's own F
+ * on the host): a template position 32 (NW - 1) or higher lies inside an overlap only while b < fmax - 32 (NW - 1).
+ * f0 / f1 / fv (fv = positions inside the forward read) are consumed. */
+template <int NW>
+PBS_HD void sweep(uint32_t (&f0)[NW], uint32_t (&f1)[NW], uint32_t (&fv)[NW],
+                  const uint32_t (&t0)[NW], const uint32_t (&t1)[NW], uint32_t (&mask)[NW], int fmax, const Muls mu) {
+#pragma unroll
+	for (int W = 0; W < NW; W++)
+		mask[W] = 0;
+	uint32_t bitb = 1;
+	int bcut = fmax - 32 * (NW - 1);
+	bcut = bcut < 0 ? 0 : (bcut > 32 ? 32 : bcut);
+	sweep_range<NW, true>(0, bcut, f0, f1, fv, t0, t1, mask, bitb, mu);
+	sweep_range<NW, false>(bcut, 32, f0, f1, fv, t0, t1, mask, bitb, mu);
+}
 
 /* Where the certificate can index a pair's words with run-time positions: PL(w) = word w of this lane, PL.set(w, v).
- * Layout: F0[NW + 1], F1[NW + 1] (one zero word on top), T0[NW], T1[NW], the sweep's mask[NW], the candidate mask CW[NW]. */
+ * Layout: F0[NW + 1], F1[NW + 1] (one zero word on top), T0[NW], T1[NW], the sweep's mask[NW], the candidate mask CW[NW],
+ * the postponed counts PEND[NW]. */
 template <int NW> struct PlaneIndex {
-	static constexpr int F0 = 0, F1 = NW + 1, T0 = 2 * (NW + 1), T1 = T0 + NW, MASK = T1 + NW, CW = MASK + NW, WORDS = CW + NW;
+	static constexpr int F0 = 0, F1 = NW + 1, T0 = 2 * (NW + 1), T1 = T0 + NW, MASK = T1 + NW, CW = MASK + NW, PEND = CW + NW, NPEND = NW,
+	                     WORDS = PEND + NPEND;      /* PEND: the certificate's postponed counts (position p | candidate bit << 16) */
 };
 
 /* Lowest template position i with an 8-mer match ending there on diagonal s (o = F - s), or -1.  Same arithmetic as
@@ -247,45 +262,71 @@ PBS_HD int earlier_occurrences(const PL &pl, int p) {
 }
 
 /* From the sweep's diagonal mask to pb::seed_kernel's record: PL's CW words = candidate mask in overlap order (bit i <=>
- * overlap mo + i, assembler.c:39), returns the flag word; *lowest = the lowest candidate bit (the lane kernel's bin).
+ * overlap mo + i, assembler.c:39), `flags` the flag word, `low` the lowest candidate bit (the lane kernel's bin).
  * maxov as assembler.c:78-82 with maxoverlap == 0, i.e. min(F, R); the caller guarantees mo < maxov <= 32 NW.
  *
  * The certificate.  A flagged diagonal s has a match (p, q) = (s + i, i).  The reference misses it only if p is "lost":
  * two valid forward positions p1 < p2 < p carry p's code.  Each of them matches q as well, on diagonal p_x - q < s --
  * flagged too, if it is not negative -- or lies in [8, q).  So with `seen` flagged diagonals below s and the lowest
- * match of this one at i, seen + (i - 8) < 2 proves p is in the table; only otherwise are p's earlier occurrences counted. */
-template <int NW, typename PL>
-PBS_HD unsigned sweep_resolve(PL &pl, int F, int mo, int maxov, int *lowest, const Muls &mu) {
+ * match of this one at i, seen + (i - 8) < 2 proves p is in the table; only otherwise are p's earlier occurrences
+ * counted, and that is put off to a second phase so that the lanes of a warp do it together (step1 / step2 are one
+ * flagged diagonal / one postponed count per call; the kernel calls them while any lane has work). */
+template <int NW, typename PL> struct Resolver {
 	using PI = PlaneIndex<NW>;
+	PL &pl;
+	int F, mo, maxov;
+	Muls mu;
+	int W = -1, seen = 0, low = 1 << 20, npend = 0;
+	uint32_t m = 0;
 	unsigned flags = 0;
-	int low = 1 << 20, seen = 0;
-	for (int w = 0; w < NW; w++)
-		pl.set(PI::CW + w, 0u);
-	for (int W = 0; W < NW; W++) {
-		uint32_t m = pl(PI::MASK + W);
-		while (m) {
-			const int b = ffs32(m) - 1;
-			m &= m - 1;
-			const int s = 32 * W + b, o = F - s, idx = o - mo;
-			const int below = seen++;
-			if (idx < 0 || o > maxov)           /* BIT_LIST_SET (assembler.c:39): outside the bit list */
-				continue;
-			const int i = first_hit<NW>(pl, s, o, mu);
-			if (i < 0)
-				continue;                       /* cannot happen: the sweep saw a match on this diagonal */
-			if (below + (i - 8) >= 2 && earlier_occurrences<NW>(pl, s + i) >= 2) {
-				flags |= SEED_GENERAL;          /* maybe a lost k-mer (assembler.c:95-97): the exact join decides */
-				continue;
-			}
-			pl.set(PI::CW + (idx >> 5), pl(PI::CW + (idx >> 5)) | (1u << (idx & 31)));
-			low = idx < low ? idx : low;
-		}
+	PBS_HDM Resolver(PL &pl_, int F_, int mo_, int maxov_, const Muls &mu_) : pl(pl_), F(F_), mo(mo_), maxov(maxov_), mu(mu_) {}
+	PBS_HDM void accept(int idx) {
+		pl.set(PI::CW + (idx >> 5), pl(PI::CW + (idx >> 5)) | (1u << (idx & 31)));
+		low = idx < low ? idx : low;
 	}
-	if (low == (1 << 20))
-		flags |= SEED_GENERAL;                  /* ALL_BITS_IF_NONE (assembler.c:118): every overlap is scored, the general kernel's job */
-	*lowest = low;
-	return flags;
-}
+	PBS_HDM bool step1() {
+		while (m == 0) {
+			if (++W >= NW)
+				return false;
+			m = pl(PI::MASK + W);
+		}
+		const int b = ffs32(m) - 1;
+		m &= m - 1;
+		const int s = 32 * W + b, o = F - s, idx = o - mo;
+		const int below = seen++;
+		if (idx < 0 || o > maxov)           /* BIT_LIST_SET (assembler.c:39): outside the bit list */
+			return true;
+		const int i = first_hit<NW>(pl, s, o, mu);
+		if (i < 0)
+			return true;                    /* cannot happen: the sweep saw a match on this diagonal */
+		if (below + (i - 8) < 2) {
+			accept(idx);
+		} else if (npend < PI::NPEND) {
+			pl.set(PI::PEND + npend, (uint32_t) (s + i) | ((uint32_t) idx << 16));
+			npend++;
+		} else {
+			flags |= SEED_GENERAL;          /* more uncertified diagonals than this keeps: the exact join decides */
+		}
+		return true;
+	}
+	PBS_HDM bool step2() {
+		if (npend == 0)
+			return false;
+		npend--;
+		const uint32_t req = pl(PI::PEND + npend);
+		const int p = (int) (req & 0xFFFFu), idx = (int) (req >> 16);
+		if (earlier_occurrences<NW>(pl, p) >= 2)
+			flags |= SEED_GENERAL;          /* maybe a lost k-mer (assembler.c:95-97): the exact join decides */
+		else
+			accept(idx);
+		return true;
+	}
+	PBS_HDM unsigned finish() {
+		if (low == (1 << 20))
+			flags |= SEED_GENERAL;          /* ALL_BITS_IF_NONE (assembler.c:118): every overlap is scored, the general kernel's job */
+		return flags;
+	}
+};
 
 }  // namespace pbs
 
@@ -385,14 +426,31 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 			}
 			myplanes[(PI::F0 + NW) * 32] = 0;
 			myplanes[(PI::F1 + NW) * 32] = 0;
-			sweep<NW>(f0, f1, fv, t0, t1, mask, mu);
+			/* the longest forward read of the warp bounds the template positions any overlap reaches (warp-uniform) */
+			const int fmax = (int) __reduce_max_sync(pb::FULL, (unsigned) Fe);
+			sweep<NW>(f0, f1, fv, t0, t1, mask, fmax, mu);
 #pragma unroll
 			for (int j = 0; j < NW; j++) {
-				myplanes[(PI::MASK + j) * 32] = mask[j];
+				myplanes[(PI::MASK + j) * 32] = flags ? 0u : mask[j];
 				myplanes[(PI::CW + j) * 32] = 0;
 			}
-			if (!flags)
-				flags = sweep_resolve<NW>(pl, F, mo, min(F, R), &lowest, mu);
+		}
+		{
+			Resolver<NW, LanePlanes> res(pl, F, mo, min(F, R), mu);
+			bool more = flags == 0;
+			while (__any_sync(pb::FULL, more)) {
+				if (more)
+					more = res.step1();
+			}
+			more = flags == 0;
+			while (__any_sync(pb::FULL, more)) {
+				if (more)
+					more = res.step2();
+			}
+			if (!flags) {
+				flags = res.finish();
+				lowest = res.low;
+			}
 		}
 		unsigned bin = flags ? (unsigned) (pb::PB_SEED_BINS - 1) : (unsigned) (lowest >> 4);
 		if (bin > (unsigned) (pb::PB_SEED_BINS - 1))

@@ -15,7 +15,7 @@ template <int NW> struct HostPlanes {
 
 /* one pair: pack as pb::pack_kernel does (4-bit codes, reverse read in template order), then the kernel's steps */
 template <int NW>
-static unsigned one_pair(const uint8_t *f, int F, const uint8_t *r, int R, int mo, uint32_t *cw_out, int *lowest) {
+static unsigned one_pair(const uint8_t *f, int F, const uint8_t *r, int R, int mo, int fmax, uint32_t *cw_out, int *lowest) {
 	using PI = pbs::PlaneIndex<NW>;
 	constexpr int ML = 32 * NW;
 	for (int w = 0; w < NW; w++)
@@ -44,10 +44,14 @@ static unsigned one_pair(const uint8_t *f, int F, const uint8_t *r, int R, int m
 	}
 	if (bad)
 		return pbs::SEED_GENERAL;
-	pbs::sweep<NW>(f0, f1, fv, t0, t1, mask, mu);
+	pbs::sweep<NW>(f0, f1, fv, t0, t1, mask, fmax > F ? fmax : F, mu);
 	for (int j = 0; j < NW; j++)
 		pl.w[PI::MASK + j] = mask[j];
-	unsigned flags = pbs::sweep_resolve<NW>(pl, F, mo, F < R ? F : R, lowest, mu);
+	pbs::Resolver<NW, HostPlanes<NW>> res(pl, F, mo, F < R ? F : R, mu);
+	while (res.step1()) {}
+	while (res.step2()) {}
+	unsigned flags = res.finish();
+	*lowest = res.low;
 	for (int w = 0; w < NW; w++)
 		cw_out[w] = pl.w[PI::CW + w];
 	return flags;
@@ -57,16 +61,23 @@ static unsigned one_pair(const uint8_t *f, int F, const uint8_t *r, int R, int m
 extern "C" int sweep_host_run(int nw, size_t n, const uint8_t *f_data, const uint64_t *f_off, const uint8_t *r_data, const uint64_t *r_off,
                               int minoverlap, uint32_t *cw, uint32_t *flags, int32_t *lowest) {
 	for (size_t i = 0; i < n; i++) {
+		/* the kernel sweeps 32 pairs together and leaves out the top word where the longest forward read of the 32 allows */
+		int fmax = 0;
+		for (size_t j = i & ~(size_t) 31; j < n && j < (i | 31) + 1; j++) {
+			const int Fj = (int) (f_off[j + 1] - f_off[j]);
+			if (Fj <= 32 * nw && Fj > fmax)
+				fmax = Fj;
+		}
 		const uint8_t *f = f_data + 2 * f_off[i], *r = r_data + 2 * r_off[i];
 		const int F = (int) (f_off[i + 1] - f_off[i]), R = (int) (r_off[i + 1] - r_off[i]);
 		uint32_t *c = cw + 16 * i;
 		memset(c, 0, 16 * sizeof(uint32_t));
 		int low = 0;
 		switch (nw) {
-		case 3: flags[i] = one_pair<3>(f, F, r, R, minoverlap, c, &low); break;
-		case 5: flags[i] = one_pair<5>(f, F, r, R, minoverlap, c, &low); break;
-		case 8: flags[i] = one_pair<8>(f, F, r, R, minoverlap, c, &low); break;
-		case 10: flags[i] = one_pair<10>(f, F, r, R, minoverlap, c, &low); break;
+		case 3: flags[i] = one_pair<3>(f, F, r, R, minoverlap, fmax, c, &low); break;
+		case 5: flags[i] = one_pair<5>(f, F, r, R, minoverlap, fmax, c, &low); break;
+		case 8: flags[i] = one_pair<8>(f, F, r, R, minoverlap, fmax, c, &low); break;
+		case 10: flags[i] = one_pair<10>(f, F, r, R, minoverlap, fmax, c, &low); break;
 		default: return -1;
 		}
 		lowest[i] = low;
