@@ -233,13 +233,13 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 		CUDA_TRY(cudaMalloc(&ctx->d_seeds[si], cap * pb::seed_words(256) * sizeof(uint32_t)));      /* sized for the widest record */
 		CUDA_TRY(cudaMalloc(&ctx->d_order[si], cap * sizeof(int)));
 		if (!ctx->d_bins[si])
-			CUDA_TRY(cudaMalloc(&ctx->d_bins[si], 2 * pb::PB_SEED_BINS * sizeof(unsigned)));
+			CUDA_TRY(cudaMalloc(&ctx->d_bins[si], (2 * pb::PB_SEED_BINS + 4) * sizeof(unsigned)));      /* + the kernels' batch counters */
 		ctx->defer_cap[si] = cap;
 	}
 	int *d_count = ctx->d_defer[si], *d_list = ctx->d_defer[si] + 4;
 	uint32_t *d_seeds = ctx->d_seeds[si];
 	CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
-	CUDA_TRY(cudaMemsetAsync(ctx->d_bins[si], 0, 2 * pb::PB_SEED_BINS * sizeof(unsigned), stream));
+	CUDA_TRY(cudaMemsetAsync(ctx->d_bins[si], 0, (2 * pb::PB_SEED_BINS + 4) * sizeof(unsigned), stream));
 	const bool timed = ctx->timing && stream == ctx->stream;
 	if (timed)
 		CUDA_TRY(cudaEventRecord(ctx->tev[0], stream));
@@ -249,7 +249,7 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 			if (grid > ctx->sm_count)
 				grid = ctx->sm_count;
 			const pbs::Muls mu = { 2u, 4u, 16u };      /* run-time values on purpose: pb_sweep.cuh */
-			sweepk<<<(unsigned) (grid < 1 ? 1 : grid), XW * 32, sweep_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si], mu);
+			sweepk<<<(unsigned) (grid < 1 ? 1 : grid), XW * 32, sweep_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si], ctx->d_bins[si] + 2 * pb::PB_SEED_BINS, mu);
 		} else {
 			long long grid = ((long long) n + SW - 1) / SW;
 			if (grid > ctx->sm_count)
@@ -269,7 +269,7 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 	if (grid < 1)
 		grid = 1;
 	kern<<<(unsigned) grid, LW * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_order[si], d_results, d_seq_nt, (long long) seq_stride,
-	                                                   d_counters, d_list, d_count, ctx->d_defer_total);
+	                                                   d_counters, d_list, d_count, ctx->d_defer_total, ctx->d_bins[si] + 2 * pb::PB_SEED_BINS + 1);
 	CUDA_TRY(cudaGetLastError());
 	if (timed)
 		CUDA_TRY(cudaEventRecord(ctx->tev[2], stream));

@@ -58,7 +58,7 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
                       const uint8_t *__restrict__ reads, const pb_pair_meta *__restrict__ meta,
                       const uint32_t *__restrict__ seeds, const int *__restrict__ order, pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, long long seq_stride,
                       unsigned long long *__restrict__ counters, int *__restrict__ defer_list, int *__restrict__ defer_count,
-                      unsigned long long *__restrict__ defer_total) {
+                      unsigned long long *__restrict__ defer_total, unsigned *__restrict__ next_batch) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	using LA = LaneArea<ML>;
 	double *s_rec = reinterpret_cast<double *>(smem_raw);                 /* recon[2][48][48], row = quality a + 48 * match */
@@ -89,7 +89,17 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 	const uint8_t *const rb = wa.rec + lane * LA::REC_STRIDE;
 	unsigned parity = 0;
 
-	for (int batch = blockIdx.x * WARPS + warp; batch < nbatch; batch += gridDim.x * WARPS) {
+	/* which 32 entries of the bin list a warp takes next comes from a counter in global memory (*next_batch, zero at launch): with a
+	 * fixed share per warp the warps the scheduler favours finish early and leave the SM half empty at the end */
+	auto grab = [&]() {
+		int b = 0;
+		if (lane == 0)
+			b = (int) atomicAdd(next_batch, 1u);
+		return __shfl_sync(FULL, b, 0);
+	};
+	int batch = grab();
+	while (batch < nbatch) {
+		const int batch_after = grab();
 		const int item = batch * 32 + lane;
 		const int pair = item < n ? order[item] : n;           /* pairs come bin by bin (pb::bin_order_kernel) */
 		unsigned off16 = 0;
@@ -128,7 +138,7 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 		if (bytes)
 			pb::bulk_g2s(wa.rec + lane * LA::REC_STRIDE, reads + (size_t) off16 * 16, bytes, &wa.bar);
 		{       /* the next batch of this warp: pull its records into L2 while this one is processed */
-			const long long ni = (long long) item + (long long) gridDim.x * WARPS * 32;
+			const long long ni = (long long) batch_after * 32 + lane;
 			if (ni < n) {
 				const uint2 mn = *reinterpret_cast<const uint2 *>(&meta[order[ni]]);
 				const unsigned nF = mn.y & 0xFFFFu, nR = mn.y >> 16;
@@ -508,6 +518,7 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 				defer_list[dbase + __popc(m_defer & pb::lanemask_lt())] = pair;
 		}
 		__syncwarp();      /* every lane is done with its record before the next batch lands on it */
+		batch = batch_after;
 	}
 	__syncthreads();
 	for (int i = tid; i < PB_NCOUNTERS; i += blockDim.x) {

@@ -352,11 +352,14 @@ struct LanePlanes {
 	__device__ __forceinline__ void set(int w, uint32_t v) const { base[w * 32] = v; }
 };
 
-/* seeds / bin_count as pb::seed_kernel writes them (pb_kernels.cuh); pairs are taken 32 at a time in batch order. */
+/* seeds / bin_count as pb::seed_kernel writes them (pb_kernels.cuh).  A warp takes 32 consecutive pairs at a time; which 32
+ * comes from a counter in global memory (*next_batch, zero at launch): the scheduler favours some warps of an SM over others,
+ * and with a fixed share per warp the favoured ones would sit at the final barrier while the rest finish alone. */
 template <int NW, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__restrict__ reads,
-                  const pb_pair_meta *__restrict__ meta, uint32_t *__restrict__ seeds, unsigned *__restrict__ bin_count, const Muls mu) {
+                  const pb_pair_meta *__restrict__ meta, uint32_t *__restrict__ seeds, unsigned *__restrict__ bin_count,
+                  unsigned *__restrict__ next_batch, const Muls mu) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	__shared__ unsigned s_bins[pb::PB_SEED_BINS];
 	using SA = SweepArea<NW>;
@@ -380,7 +383,13 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 	uint32_t *const myplanes = &wa.planes[0][lane];
 	LanePlanes pl{myplanes};
 
-	for (int batch = blockIdx.x * WARPS + warp; batch < nbatch; batch += gridDim.x * WARPS) {
+	for (;;) {
+		int batch = 0;
+		if (lane == 0)
+			batch = (int) atomicAdd(next_batch, 1u);
+		batch = __shfl_sync(pb::FULL, batch, 0);
+		if (batch >= nbatch)
+			break;
 		const int pair = batch * 32 + lane;
 		unsigned off16 = 0;
 		int F = 0xFFFF, R = 0;
