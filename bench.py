@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- read-pairs/s of the paired-end assembly hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2] [--pairs P]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2] [--pairs P] [--path pairs|text|api|copy]
 
 A "step" is one pass of the hot path (primer scan when configured, k-mer seeded overlap selection,
 reconstruction with posterior qualities) over one batch of synthetic read pairs.  At N = 1 the batch is
@@ -21,6 +21,12 @@ roofline   algorithmic HBM read bytes per pair (458 B at 2x150) x pairs / summed
 cpu_baseline / --impl reference
            the reference's own CPU implementation (oracle/_ref, compiled from the reference sources)
            or the oracle port if that is absent, all host cores, on a bounded sample of the same workload.
+--path api the same metric through the reference's OWN entry points -- a PandaNextSeq source, panda_run_pool(), a
+           PandaOutputSeq callback that reads every base of every result (tools/api_bench.c, one source file built against
+           this library and against the compiled reference) -- for 1 .. all host threads on both sides.
+--path copy
+           what the platform gives the host path: pinned host <-> device copies of the e2e leg's sizes, both directions at
+           once, no kernels, on every rank at the same time (the ceiling e2e is measured against).
 """
 from __future__ import annotations
 
@@ -100,6 +106,19 @@ def workload(cfg_id):
     return c, kw
 
 
+def shape_label(c):
+    """read lengths of a BASELINE config as the config states them (not as pair 0 happens to have them)"""
+    lo, hi = c["rl"]
+    return f"2x({lo}-{hi}) bp mixed lengths" if c.get("mixed") else f"2x{lo} bp"
+
+
+def pairs_per_gpu(c, args):
+    """BASELINE sizes: 10 M pairs per GPU; config 5 is 100 M pairs over 8 GPUs, i.e. 12.5 M per GPU (weak scaling: the same at every N)"""
+    if args.pairs is not None:
+        return args.pairs
+    return 12_500_000 if c.get("mixed") else min(c["n"], 10_000_000)
+
+
 def cpu_rate(cfg, flat, threads):
     """Mpairs/s of the CPU reference on `flat`, and which implementation ran."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -123,7 +142,7 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     probe = synth.generate_config(args.config, n=20_000, device="cpu").to_flat()
     rate, kind = cpu_rate(cfg, probe, cores)
-    sample = int(min(max(rate * 1e6 * 6.0, 20_000), 4_000_000))        # ~6 s per step
+    sample = int(min(max(rate * 1e6 * 6.0, 20_000), 10_000_000))        # ~6 s per step, at most the config's 10 M
     flat = synth.generate_config(args.config, n=sample, device="cpu", chunk_index=1).to_flat()
     for _ in range(args.warmup):
         cpu_rate(cfg, flat.slice(0, min(sample, 50_000)), cores)
@@ -137,8 +156,8 @@ def reference_arm(args):
         "impl": "reference", "metric": "read-pairs/s (Mpairs/s), pair assembly hot path", "value": value, "unit": "Mpairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
-        "config": {"workload": f"BASELINE config {args.config}: synthetic 2x{int(fl[0])} bp pairs, {c['algo']}, "
-                               f"bounded sample of {sample} pairs per step on the host CPU"},
+        "config": {"workload": f"BASELINE config {args.config}: synthetic {shape_label(c)} pairs, {c['algo']}"
+                               + (", primer strip" if kw else "") + f", bounded sample of {sample} pairs per step on the host CPU"},
         "cpu_baseline": {"value": value, "unit": "Mpairs/s", "cores": cores, "kind": kind,
                          "sample": f"{sample} pairs x {args.steps} steps, panda_assembler_assemble loop, one assembler per thread, logging off"},
         "e2e": {"value": value, "unit": "Mpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -280,6 +299,105 @@ def text_path(args):
     ctx.close()
 
 
+def api_path(args):
+    """--path api: pairs per second through panda_run_pool() with a PandaNextSeq source and a PandaOutputSeq callback that reads
+    every base of every result -- tools/api_bench.c, the same source built against this library (pandaseq_b200/api_bench) and
+    against the compiled reference (oracle/_ref/api_bench_ref), for 1 .. all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ours, ref = os.path.join(ROOT, "pandaseq_b200", "api_bench"), os.path.join(ROOT, "oracle", "_ref", "api_bench_ref")
+    cores = os.cpu_count() or 1
+    n = args.pairs if args.pairs is not None else 4_000_000
+    rl = 150
+    rows = {"ours": [], "reference": []}
+    tlist = sorted({1, 2, 4, 8, min(16, cores), cores})
+    for t in tlist:
+        out = subprocess.run([ours, str(n), str(rl), str(t)], check=True, capture_output=True, text=True).stdout
+        rows["ours"].append(json.loads(out.strip().split("\n")[-1]))
+    if os.path.exists(ref) and not args.no_cpu:
+        for t in tlist:
+            nr = min(n, max(200_000, 150_000 * t))          # ~ 2-6 s of CPU work per run
+            out = subprocess.run([ref, str(nr), str(rl), str(t)], check=True, capture_output=True, text=True).stdout
+            rows["reference"].append(json.loads(out.strip().split("\n")[-1]))
+    best = max(rows["ours"], key=lambda r: r["mpairs_per_s"])
+    best_ref = max(rows["reference"], key=lambda r: r["mpairs_per_s"]) if rows["reference"] else None
+    # the two libraries were given the same generator: the number of accepted pairs per input pair must agree
+    same = None
+    if best_ref:
+        a, b = rows["ours"][0], rows["reference"][0]
+        same = abs(a["ok"] / a["pairs"] - b["ok"] / b["pairs"]) < 1e-3
+    line = {
+        "metric": "read-pairs/s (Mpairs/s) through panda_run_pool / panda_assembler_next with host callbacks", "value": best["mpairs_per_s"],
+        "unit": "Mpairs/s", "n_gpus": args.gpus, "steps": 1, "warmup": 1, "ms_per_step": best["seconds"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8 + f64", "data": "synthetic",
+        "config": {"workload": f"{n} synthetic 2x{rl} bp pairs, simple_bayesian, pulled one pair at a time from a PandaNextSeq source; every base "
+                               "and log p of every result read by the PandaOutputSeq callback (tools/api_bench.c)", "threads": best["threads"]},
+        "e2e": {"value": best["mpairs_per_s"], "unit": "Mpairs/s", "h2d_bytes_per_step": int(n * (4 * rl + 16 + 4)),
+                "d2h_bytes_per_step": int(n * (32 + (2 * rl + 15) // 16 * 16 // 2 + (2 * rl + 15) // 16 * 16 * 2))},
+        "by_threads": rows, "same_outcome_as_reference": same,
+        "cpu_baseline": None if not best_ref else {"value": best_ref["mpairs_per_s"], "unit": "Mpairs/s", "cores": best_ref["threads"], "kind": "reference",
+                                                   "sample": "the reference's own panda_run_pool + PandaMux over the same source and callback "
+                                                             f"(oracle/_ref/api_bench_ref), best of {tlist} threads"},
+        "gpu_launches": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def copy_path(args):
+    """--path copy: pinned host -> device and device -> host copies of the sizes the e2e leg moves per chunk, both directions at
+    once on two streams, no kernels; every rank at the same time (max over ranks).  The platform's ceiling for the host path."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    pairs = 1 << 18                                   # one chunk of the host path
+    h2d_b, d2h_b = pairs * 620, pairs * 184           # AoS in, result record + merged read out (2x150)
+    hin = torch.empty(h2d_b, dtype=torch.uint8).pin_memory()
+    hout = torch.empty(d2h_b, dtype=torch.uint8).pin_memory()
+    din = torch.empty(h2d_b, dtype=torch.uint8, device=dev)
+    dout = torch.empty(d2h_b, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    res = {}
+    for mode in ("h2d", "d2h", "both"):
+        chunks = 16 * max(1, args.steps)
+        for it in range(2):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(chunks):
+                if mode in ("h2d", "both"):
+                    with torch.cuda.stream(s1):
+                        din.copy_(hin, non_blocking=True)
+                if mode in ("d2h", "both"):
+                    with torch.cuda.stream(s2):
+                        hout.copy_(dout, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        res[mode] = {"seconds": dt, "h2d_gbs_per_gpu": (h2d_b * chunks / dt / 1e9) if mode != "d2h" else 0.0,
+                     "d2h_gbs_per_gpu": (d2h_b * chunks / dt / 1e9) if mode != "h2d" else 0.0,
+                     "mpairs_per_s_all_gpus": pairs * chunks * world / dt / 1e6}
+    if rank == 0:
+        line = {"metric": "pinned host <-> device copies of the host path's chunk sizes (no kernels)", "value": res["both"]["mpairs_per_s_all_gpus"],
+                "unit": "Mpairs/s equivalent", "n_gpus": world, "steps": args.steps, "warmup": 1, "higher_is_better": True, "scaling": "weak",
+                "config": {"workload": f"{pairs} pairs per chunk: {h2d_b} B in (620 B per pair), {d2h_b} B out (184 B per pair), 2 streams per GPU"},
+                "modes": res}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -288,8 +406,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU (default: the config's, capped at 10 M per GPU)")
-    ap.add_argument("--path", default="pairs", choices=["pairs", "text"],
-                    help="pairs: the BASELINE metric on panda_qual pairs (default); text: FASTQ text in -> FASTA text out (SURVEY.md 8f rank 1+2)")
+    ap.add_argument("--path", default="pairs", choices=["pairs", "text", "api", "copy"],
+                    help="pairs: the BASELINE metric on panda_qual pairs (default); text: FASTQ text in -> FASTA text out (SURVEY.md 8f rank 1+2); "
+                         "api: through panda_run_pool and the reference's callbacks; copy: host <-> device copies alone")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -298,6 +417,12 @@ def main():
         return
     if args.path == "text":
         text_path(args)
+        return
+    if args.path == "api":
+        api_path(args)
+        return
+    if args.path == "copy":
+        copy_path(args)
         return
 
     import torch
@@ -318,7 +443,7 @@ def main():
 
     c, kw = workload(args.config)
     cfg = pb.make_config(c["algo"], **kw)
-    n = args.pairs if args.pairs is not None else min(c["n"], 10_000_000)
+    n = pairs_per_gpu(c, args)
     ctx = pb.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream_handle, device=dev)
 
@@ -413,13 +538,16 @@ def main():
         # the lane kernel reads the whole record, the metadata and the mask record and writes the result + the merged read
         seed_b = ((fl0 + 1) // 2 + (rl0 + 1) // 2 + 8)
         kernels = [
-            {"name": "pb::seed_kernel (K1-K3: k-mer join, one warp per pair) + pb::bin_order_kernel (pairs listed by overlap bin)", "ms": kms[0], "launches_per_step": 2,
+            {"name": ("pbs::sweep_seed_kernel (K1-K3 as a bit-parallel sweep over diagonals, one lane per pair)" if cfg.maxoverlap == 0
+                      else "pb::seed_kernel (K1-K3: k-mer join, one warp per pair)") + " + pb::bin_order_kernel (pairs listed by overlap bin)",
+             "ms": kms[0], "launches_per_step": 2,
              "algorithmic_read_bytes_per_pair": seed_b, "achieved_gbs": seed_b * n / (kms[0] / 1e3) / 1e9},
             {"name": "pbl::assemble_lanes_kernel (K4-K6: score + merge, one lane per pair)", "ms": kms[1], "launches_per_step": 1,
              "algorithmic_read_bytes_per_pair": alg_bytes / n + 32, "achieved_gbs": (alg_bytes + 32 * n) / (kms[1] / 1e3) / 1e9},
             {"name": "pb::assemble_kernel, list mode (the pairs the two kernels above hand on)", "ms": kms[2], "launches_per_step": 1},
         ]
-        kernel_name = "pb::seed_kernel + pb::bin_order_kernel + pbl::assemble_lanes_kernel + pb::assemble_kernel<list> (one step; the read bytes of the path over their summed duration)"
+        kernel_name = ("pbs::sweep_seed_kernel" if cfg.maxoverlap == 0 else "pb::seed_kernel") + \
+            " + pb::bin_order_kernel + pbl::assemble_lanes_kernel + pb::assemble_kernel<list> (one step; the read bytes of the path over their summed duration)"
         launches_per_step = 4
     else:
         kernels = [{"name": "pb::assemble_kernel", "ms": kms[2], "launches_per_step": 1}]
@@ -498,10 +626,35 @@ def main():
         e2e = {"value": ne * world * ksteps / dt / 1e6, "unit": "Mpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "pairs_per_step_per_gpu": ne, "steps": ksteps,
                "note": "pb_assemble_host(): pinned host panda_qual arrays -> H2D -> pack -> assemble -> D2H (results + merged reads) into pinned host arrays, 2 streams"}
+        # the same with records the caller keeps in the packed layout (pb_assemble_host_packed): 26 % fewer bytes in, no pack kernel.
+        # The packing itself (pb_pack_host, once, outside the timing) is what a parser writing this layout would do instead of AoS.
+        reads_h, meta_h, ml_h = pb.pack_host(flat)
+        reads_p, meta_p = pinned(reads_h), pinned(meta_h.view(np.int64))
+        del reads_h, meta_h
+
+        def e2e_packed_step():
+            rc = L.pb_assemble_host_packed(ctx._h, C.byref(cfg), ne, ml_h, reads_p.data_ptr(), meta_p.data_ptr(), res_h.ctypes.data,
+                                           nt_h.ctypes.data, seq_stride, cnt_h.ctypes.data)
+            if rc != 0:
+                raise RuntimeError(L.pb_last_error().decode())
+
+        e2e_packed_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_packed_step()
+        dtp = time.perf_counter() - t0
+        tt = torch.tensor([dtp], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dtp = float(tt.item())
+        e2e["packed_input"] = {"value": ne * world * ksteps / dtp / 1e6, "unit": "Mpairs/s",
+                               "h2d_bytes_per_step": int(reads_p.numel() + meta_p.numel() * 8), "d2h_bytes_per_step": int(d2h),
+                               "note": "pb_assemble_host_packed(): pinned host records in the packed layout (4-bit nt + 8-bit PHRED) -> H2D -> assemble -> D2H"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         probe = synth.generate_config(args.config, n=20_000, device="cpu").to_flat()
         r0, kind = cpu_rate(cfg, probe, cores)
@@ -510,14 +663,15 @@ def main():
         r1, kind = cpu_rate(cfg, flat_c, cores)
         cpu = {"value": r1, "unit": "Mpairs/s", "cores": cores, "kind": kind,
                "sample": f"{sample} synthetic pairs of the same config, panda_assembler_assemble loop, one assembler per thread, logging off"}
+    if dist is not None:
+        dist.barrier()          # the other ranks wait for rank 0's CPU leg, so that all leave together
 
     if rank == 0:
-        fl = int(meta[0, 1].item()) & 0xFFFF
         line = {
             "metric": "read-pairs/s (Mpairs/s), pair assembly hot path", "value": value, "unit": "Mpairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 (4-bit nt, 8-bit PHRED) + f64 log-probabilities", "data": "synthetic",
-            "config": {"workload": f"BASELINE config {args.config}: {n} synthetic 2x{fl} bp pairs per GPU, {c['algo']}"
+            "config": {"workload": f"BASELINE config {args.config}: {n} synthetic {shape_label(c)} pairs per GPU, {c['algo']}"
                                    + (", primer strip" if kw else ""),
                        "pairs_per_gpu": n, "l2_policy": f"inputs larger than L2 ({reads.numel() / 1e6:.0f} MB packed per GPU), no flush",
                        "outputs": "32 B result record + merged read (4 bit/base) per pair; per-base log p not requested",

@@ -458,6 +458,33 @@ pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, size_t n,
                            pb_pair_result *results, uint8_t *seq_nt, double *seq_p,
                            size_t seq_stride, int64_t *counters);
 
+/* pb_assemble_host with the per-base log p as 16-bit codes: seq_code[i][k] (row capacity seq_stride) is the index of base
+ * k's log p in the table pb_posterior_table() fills -- every per-base log p the reference computes is an entry of one
+ * 2 x 48 x 48 table (match_probability of the algorithm, qual_score[], qual_nn; assembler.c:162-243), so 2 bytes per base
+ * cross the link instead of 8 and the caller expands them with the same doubles the device would have written.  Not
+ * available together with primers-after or the min_phred filter (PB_ERR_ARGUMENT). */
+#define PB_POSTERIOR_CODES (2 * 48 * 48)
+pb_status pb_assemble_host_codes(pb_context *ctx, const pb_config *cfg, size_t n,
+                                 const panda_qual *f_data, const uint64_t *f_off,
+                                 const panda_qual *r_data, const uint64_t *r_off,
+                                 pb_pair_result *results, uint8_t *seq_nt, uint16_t *seq_code,
+                                 size_t seq_stride, int64_t *counters);
+pb_status pb_posterior_table(const pb_config *cfg, double *table /* PB_POSTERIOR_CODES */);
+
+/* The host path for callers that keep their reads in the packed layout above (a FASTQ parser can write it directly):
+ * 458 instead of 620 bytes per 2x150 pair cross the link, and no pack kernel runs.  reads / meta as described under
+ * "packed device layout", records in pair order and contiguous; max_read_len = longest read (0 = PB_MAX_LEN).
+ * pb_pack_host is the layout done on the host (no arithmetic on the reads' content beyond `nt & 15`): reads must hold
+ * pb_layout_host()'s total, meta n entries. */
+pb_status pb_assemble_host_packed(pb_context *ctx, const pb_config *cfg, size_t n, int max_read_len,
+                                  const uint8_t *reads, const pb_pair_meta *meta,
+                                  pb_pair_result *results, uint8_t *seq_nt, size_t seq_stride, int64_t *counters);
+void pb_pack_host(size_t n, const panda_qual *f_data, const uint64_t *f_off, const panda_qual *r_data, const uint64_t *r_off,
+                  uint8_t *reads, pb_pair_meta *meta);
+/* page-locked host memory (what the host path copies from / into without a staging copy) */
+void *pb_host_alloc(size_t bytes);
+void pb_host_free(void *p);
+
 /* ======================================================================
  * Layer 2b: the stages either side of the hot path, on the device
  *   FASTQ text -> packed records   (fastq.c:44-193, linebuf.c:57-89, seqid.c:136-285, nt.c:48-124)

@@ -198,6 +198,17 @@ def lib() -> C.CDLL:
     L.pb_assemble_device.restype = i32
     L.pb_assemble_host.argtypes = [vp, C.POINTER(PbConfig), sz, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.pb_assemble_host.restype = i32
+    L.pb_assemble_host_codes.argtypes = [vp, C.POINTER(PbConfig), sz, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.pb_assemble_host_codes.restype = i32
+    L.pb_assemble_host_packed.argtypes = [vp, C.POINTER(PbConfig), sz, i32, vp, vp, vp, vp, sz, vp]
+    L.pb_assemble_host_packed.restype = i32
+    L.pb_pack_host.argtypes = [sz, vp, vp, vp, vp, vp, vp]
+    L.pb_pack_host.restype = None
+    L.pb_posterior_table.argtypes = [C.POINTER(PbConfig), vp]
+    L.pb_posterior_table.restype = i32
+    L.pb_host_alloc.argtypes = [sz]
+    L.pb_host_alloc.restype = vp
+    L.pb_host_free.argtypes = [vp]
     L.pb_counters_merge.argtypes = [vp, vp]
     L.pb_fastq_parse_device.argtypes = [vp, vp, sz, vp, sz, i32, i32, sz, vp, sz, vp, vp, C.POINTER(PbFastqInfo)]
     L.pb_fastq_parse_device.restype = i32
@@ -300,6 +311,36 @@ class Context:
         return dict(results=res, seq_nt=unpack_nt(nt) if nt is not None else None, seq_nt_packed=nt, seq_p=p, counters=counters,
                     seq_stride=seq_stride)
 
+    def assemble_host_codes(self, cfg: PbConfig, batch, *, seq_stride=None):
+        """As assemble_host(want_p=True), the per-base log p shipped as 16-bit codes (pb_assemble_host_codes) and expanded here
+        with pb_posterior_table(): dict(results, seq_nt, seq_p, seq_code, counters)."""
+        n = batch.n
+        if seq_stride is None:
+            fl, rl = batch.lengths()
+            seq_stride = ((int((fl + rl).max()) if n else 0) + 15) & ~15
+        res = np.zeros(n, dtype=PAIR_RESULT_DTYPE)
+        nt = np.zeros((n, seq_stride // 2), dtype=np.uint8)
+        code = np.zeros((n, seq_stride), dtype=np.uint16)
+        counters = np.zeros(PB_NCOUNTERS, dtype=np.int64)
+        f_data, r_data = np.ascontiguousarray(batch.f_data), np.ascontiguousarray(batch.r_data)
+        f_off, r_off = np.ascontiguousarray(batch.f_off, dtype=np.uint64), np.ascontiguousarray(batch.r_off, dtype=np.uint64)
+        _check(lib().pb_assemble_host_codes(self._h, C.byref(cfg), n, _np_ptr(f_data), _np_ptr(f_off), _np_ptr(r_data), _np_ptr(r_off),
+                                            _np_ptr(res), _np_ptr(nt), _np_ptr(code), seq_stride, _np_ptr(counters)), "pb_assemble_host_codes")
+        table = posterior_table(cfg)
+        p = table[np.minimum(code, len(table) - 1)]
+        p[np.arange(seq_stride)[None, :] >= res["seq_len"][:, None]] = 0.0
+        return dict(results=res, seq_nt=unpack_nt(nt), seq_nt_packed=nt, seq_p=p, seq_code=code, counters=counters, seq_stride=seq_stride)
+
+    def assemble_host_packed(self, cfg: PbConfig, reads, meta, max_len, *, seq_stride):
+        """reads / meta: numpy arrays in the packed layout (pack_host); -> dict(results, seq_nt, counters)."""
+        n = len(meta)
+        res = np.zeros(n, dtype=PAIR_RESULT_DTYPE)
+        nt = np.zeros((n, seq_stride // 2), dtype=np.uint8)
+        counters = np.zeros(PB_NCOUNTERS, dtype=np.int64)
+        _check(lib().pb_assemble_host_packed(self._h, C.byref(cfg), n, int(max_len), _np_ptr(reads), _np_ptr(meta), _np_ptr(res), _np_ptr(nt),
+                                             seq_stride, _np_ptr(counters)), "pb_assemble_host_packed")
+        return dict(results=res, seq_nt=unpack_nt(nt), seq_nt_packed=nt, seq_p=None, counters=counters, seq_stride=seq_stride)
+
     # ---- device-resident path (torch tensors own the HBM) ---------------------------
     def pack_device(self, f_data, f_off, r_data, r_off):
         """flat AoS torch CUDA tensors -> (reads u8, meta (n,2) i32 view, max_len, record bytes).
@@ -391,6 +432,30 @@ class Context:
         d = {k: getattr(info, k) for k, _ in PbStreamInfo._fields_}
         text = bytes(out[:d["out_bytes"]]) if own else None
         return text, d, counters
+
+
+PAIR_META_DTYPE = np.dtype([("off16", "<u4"), ("flen", "<u2"), ("rlen", "<u2")])
+
+
+def pack_host(batch):
+    """FlatBatch -> (reads uint8, meta PAIR_META_DTYPE, longest read): the packed layout written on the host (pb_pack_host)."""
+    n = batch.n
+    f_data, r_data = np.ascontiguousarray(batch.f_data), np.ascontiguousarray(batch.r_data)
+    f_off, r_off = np.ascontiguousarray(batch.f_off, dtype=np.uint64), np.ascontiguousarray(batch.r_off, dtype=np.uint64)
+    rec = np.zeros(max(n, 1), dtype=np.uint32)
+    total = int(lib().pb_layout_host(n, _np_ptr(f_off), _np_ptr(r_off), _np_ptr(rec)))
+    reads = np.zeros(total + 16, dtype=np.uint8)
+    meta = np.zeros(n, dtype=PAIR_META_DTYPE)
+    lib().pb_pack_host(n, _np_ptr(f_data), _np_ptr(f_off), _np_ptr(r_data), _np_ptr(r_off), _np_ptr(reads), _np_ptr(meta))
+    fl, rl = batch.lengths()
+    return reads, meta, int(max(fl.max(), rl.max())) if n else 0
+
+
+def posterior_table(cfg: PbConfig) -> np.ndarray:
+    """the 2 x 48 x 48 table the per-base codes of pb_assemble_host_codes index (pb_posterior_table)"""
+    t = np.zeros(2 * 48 * 48, dtype=np.float64)
+    _check(lib().pb_posterior_table(C.byref(cfg), _np_ptr(t)), "pb_posterior_table")
+    return t
 
 
 def expand_ids(ids: np.ndarray, fwd_text: bytes) -> np.ndarray:

@@ -18,6 +18,22 @@
 #define NEXT_BATCH_DEFAULT 65536	/* pairs pulled from a PandaNextSeq source per launch (env PANDASEQ_B200_NEXT_BATCH overrides) */
 #define SEQ_CAP (2 * PB_MAX_LEN + 12)	/* 912: multiple of 16 */
 
+/* One batch on its way through the device.  The arrays the device path copies from / into are page-locked (pb_host_alloc),
+ * so pb_assemble_host moves them without a staging copy; the per-base log p comes back as 16-bit codes into the posterior
+ * table (pb_assemble_host_codes) and rows are as long as the batch's longest F + R, not 912 doubles. */
+struct pb_stage {
+	size_t cap_pairs, cap_f, cap_r, cap_res, cap_nt, cap_code, cap_p;
+	panda_seq_identifier *ids;
+	panda_qual *f_data, *r_data;
+	uint64_t *f_off, *r_off;
+	pb_pair_result *res;
+	uint8_t *nt;
+	uint16_t *code;
+	double *p;		/* instead of code when the configuration has no codes (primers-after) */
+	bool has_codes;
+	size_t n, pos, stride, max_seq;
+};
+
 struct panda_assembler {
 	volatile size_t refcnt;
 	pthread_mutex_t mutex;
@@ -54,16 +70,17 @@ struct panda_assembler {
 	panda_result_seq result;
 	panda_result result_seq[SEQ_CAP];
 
-	/* batch state for panda_assembler_next / assemble_batch */
-	size_t cap_pairs, cap_f, cap_r;
-	panda_seq_identifier *ids;
-	panda_qual *f_data, *r_data;
-	uint64_t *f_off, *r_off;
-	pb_pair_result *res;
-	uint8_t *nt;
-	double *p;
-	size_t batch_n, batch_pos, next_batch;
+	/* batch state: the stream of panda_assembler_next() and the calls (panda_assembler_assemble / _assemble_batch) have a
+	 * stage each, so that a call between two next()s does not disturb the batch next() is handing out (assembler.c:350-383:
+	 * the two are independent in the reference) */
+	struct pb_stage stream, call;
+	size_t next_batch;
 	bool source_dry;
+	bool failed;		/* a device call failed: next() stays at the end of its stream, pb_last_error() has the reason */
+	/* the posterior table the codes index (pb_posterior_table), rebuilt when the configuration changes */
+	double *ptable;
+	pb_config ptable_cfg;
+	bool ptable_valid;
 };
 
 static void flatten(PandaAssembler a, pb_config *cfg, bool *ok) {
@@ -261,6 +278,19 @@ static bool host_check(PandaAssembler a, const panda_result_seq *res) {
 	return true;
 }
 
+static void stage_free(struct pb_stage *st) {
+	free(st->ids);
+	pb_host_free(st->f_data);
+	pb_host_free(st->r_data);
+	pb_host_free(st->f_off);
+	pb_host_free(st->r_off);
+	pb_host_free(st->res);
+	pb_host_free(st->nt);
+	pb_host_free(st->code);
+	pb_host_free(st->p);
+	memset(st, 0, sizeof *st);
+}
+
 PandaAssembler panda_assembler_ref(PandaAssembler a) {
 	pthread_mutex_lock(&a->mutex);
 	a->refcnt++;
@@ -287,14 +317,9 @@ void panda_assembler_unref(PandaAssembler a) {
 		panda_module_unref(a->modules[it]);
 	free(a->modules);
 	free(a->rejected);
-	free(a->ids);
-	free(a->f_data);
-	free(a->r_data);
-	free(a->f_off);
-	free(a->r_off);
-	free(a->res);
-	free(a->nt);
-	free(a->p);
+	stage_free(&a->stream);
+	stage_free(&a->call);
+	free(a->ptable);
 	free(a);
 }
 
@@ -416,72 +441,124 @@ void panda_assembler_set_primer_penalty(PandaAssembler a, double penalty) {
 
 /* ---- batches ------------------------------------------------------------------------ */
 
-static bool reserve(PandaAssembler a, size_t pairs, size_t fbases, size_t rbases) {
-	if (pairs > a->cap_pairs) {
-		size_t cap = pairs < 64 ? 64 : pairs;
-		void *ids = realloc(a->ids, cap * sizeof(panda_seq_identifier));
-		if (ids) a->ids = ids;
-		void *fo = realloc(a->f_off, (cap + 1) * sizeof(uint64_t));
-		if (fo) a->f_off = fo;
-		void *ro = realloc(a->r_off, (cap + 1) * sizeof(uint64_t));
-		if (ro) a->r_off = ro;
-		void *res = realloc(a->res, cap * sizeof(pb_pair_result));
-		if (res) a->res = res;
-		void *nt = realloc(a->nt, cap * (SEQ_CAP / 2));
-		if (nt) a->nt = nt;
-		void *p = realloc(a->p, cap * SEQ_CAP * sizeof(double));
-		if (p) a->p = p;
-		if (!ids || !fo || !ro || !res || !nt || !p)
-			return false;
-		a->cap_pairs = cap;
-	}
-	if (fbases > a->cap_f) {
-		size_t cap = fbases + fbases / 2 + 1024;
-		void *f = realloc(a->f_data, cap * sizeof(panda_qual));
-		if (!f)
-			return false;
-		a->f_data = f;
-		a->cap_f = cap;
-	}
-	if (rbases > a->cap_r) {
-		size_t cap = rbases + rbases / 2 + 1024;
-		void *r = realloc(a->r_data, cap * sizeof(panda_qual));
-		if (!r)
-			return false;
-		a->r_data = r;
-		a->cap_r = cap;
-	}
+/* grow a page-locked array, keeping `keep` bytes of its content; false (array untouched) when out of memory */
+static bool grow_pinned(void **p, size_t *cap, size_t need, size_t elem, size_t keep) {
+	if (need <= *cap)
+		return true;
+	void *q = pb_host_alloc(need * elem);
+	if (q == NULL)
+		return false;
+	if (*p != NULL && keep > 0)
+		memcpy(q, *p, keep);
+	pb_host_free(*p);
+	*p = q;
+	*cap = need;
 	return true;
 }
 
-/* Run the staged batch [0, a->batch_n) on the device and fold its counters in. */
-static bool run_batch(PandaAssembler a) {
+/* room for `pairs` pairs with `fbases` / `rbases` bases in a stage's input arrays; `used_*` = what is already staged */
+static bool reserve(struct pb_stage *st, size_t pairs, size_t fbases, size_t rbases, size_t used_pairs, size_t used_f, size_t used_r) {
+	if (pairs > st->cap_pairs) {
+		size_t cap = pairs < 64 ? 64 : pairs + pairs / 2, c1 = st->cap_pairs ? st->cap_pairs + 1 : 0, c2 = c1;
+		void *ids = realloc(st->ids, cap * sizeof(panda_seq_identifier));
+		if (ids == NULL)
+			return false;
+		st->ids = ids;
+		if (!grow_pinned((void **) &st->f_off, &c1, cap + 1, sizeof(uint64_t), (used_pairs + 1) * sizeof(uint64_t))
+		    || !grow_pinned((void **) &st->r_off, &c2, cap + 1, sizeof(uint64_t), (used_pairs + 1) * sizeof(uint64_t)))
+			return false;		/* cap_pairs unchanged: the arrays that did grow are simply larger than recorded */
+		st->cap_pairs = cap;
+	}
+	if (fbases > st->cap_f && !grow_pinned((void **) &st->f_data, &st->cap_f, fbases + fbases / 2 + 1024, sizeof(panda_qual), used_f * sizeof(panda_qual)))
+		return false;
+	if (rbases > st->cap_r && !grow_pinned((void **) &st->r_data, &st->cap_r, rbases + rbases / 2 + 1024, sizeof(panda_qual), used_r * sizeof(panda_qual)))
+		return false;
+	return true;
+}
+
+static void stage_begin(struct pb_stage *st) {
+	st->n = st->pos = 0;
+	st->max_seq = 0;
+}
+
+/* copy one pair behind the staged ones (the source's arrays are only valid until its next call: mux.c:150-157 copies too) */
+static bool stage_push(struct pb_stage *st, const panda_seq_identifier *id, const panda_qual *f, size_t fl, const panda_qual *r, size_t rl) {
+	const size_t n = st->n, fb = n ? (size_t) st->f_off[n] : 0, rb = n ? (size_t) st->r_off[n] : 0;
+	if (!reserve(st, n + 1, fb + fl, rb + rl, n, fb, rb))
+		return false;
+	if (id != NULL)
+		st->ids[n] = *id;
+	else
+		memset(&st->ids[n], 0, sizeof st->ids[n]);
+	st->f_off[n] = fb;
+	st->r_off[n] = rb;
+	memcpy(st->f_data + fb, f, fl * sizeof(panda_qual));
+	memcpy(st->r_data + rb, r, rl * sizeof(panda_qual));
+	st->f_off[n + 1] = fb + fl;
+	st->r_off[n + 1] = rb + rl;
+	if (fl + rl > st->max_seq)
+		st->max_seq = fl + rl;
+	st->n = n + 1;
+	return true;
+}
+
+/* Run the staged batch [0, st->n) on the device and fold its counters in. */
+static bool run_batch(PandaAssembler a, struct pb_stage *st) {
 	pb_config cfg;
 	bool ok;
+	int64_t tmp[PB_NCOUNTERS];
+	int64_t *cnt = a->has_check ? tmp : a->counters;
+	pb_status rc;
+	st->pos = 0;
+	if (st->n == 0)
+		return true;
 	flatten(a, &cfg, &ok);
 	if (!ok)
 		return false;
-	if (!a->has_check)
-		return pb_assemble_host(a->ctx, &cfg, a->batch_n, a->f_data, a->f_off, a->r_data, a->r_off,
-		                        a->res, a->nt, a->p, SEQ_CAP, a->counters) == PB_OK;
-	/* a module checks the assembled pairs on the host: the device's count of accepted pairs (and their overlap histogram) is
-	 * taken before those checks, so these counters are kept by host_check() as the pairs are handed out */
-	int64_t tmp[PB_NCOUNTERS];
-	memset(tmp, 0, sizeof tmp);
-	if (pb_assemble_host(a->ctx, &cfg, a->batch_n, a->f_data, a->f_off, a->r_data, a->r_off,
-	                     a->res, a->nt, a->p, SEQ_CAP, tmp) != PB_OK)
+	st->stride = (st->max_seq + 15) & ~(size_t) 15;
+	if (st->stride < 16)
+		st->stride = 16;
+	st->has_codes = !cfg.post_primers;	/* the staged sequence of primers-after exists as doubles only (pb_assemble_host_codes) */
+	if (!grow_pinned((void **) &st->res, &st->cap_res, st->n, sizeof(pb_pair_result), 0)
+	    || !grow_pinned((void **) &st->nt, &st->cap_nt, st->n * (st->stride / 2), 1, 0))
 		return false;
-	tmp[PB_C_OK] = 0;
-	tmp[PB_C_LONGEST] = 0;
-	memset(tmp + PB_C_OVERLAPS, 0, (PB_NCOUNTERS - PB_C_OVERLAPS) * sizeof(int64_t));
-	pb_counters_merge(a->counters, tmp);
+	if (st->has_codes) {
+		if (!a->ptable_valid || memcmp(&a->ptable_cfg, &cfg, sizeof cfg) != 0) {
+			if (a->ptable == NULL)
+				a->ptable = malloc(PB_POSTERIOR_CODES * sizeof(double));
+			if (a->ptable == NULL || pb_posterior_table(&cfg, a->ptable) != PB_OK)
+				return false;
+			a->ptable_cfg = cfg;
+			a->ptable_valid = true;
+		}
+		if (!grow_pinned((void **) &st->code, &st->cap_code, st->n * st->stride, sizeof(uint16_t), 0))
+			return false;
+	} else if (!grow_pinned((void **) &st->p, &st->cap_p, st->n * st->stride, sizeof(double), 0)) {
+		return false;
+	}
+	/* when a module checks the assembled pairs on the host, the device's count of accepted pairs (and their overlap
+	 * histogram) is taken before those checks: these counters are then kept by host_check() as the pairs are handed out */
+	if (a->has_check)
+		memset(tmp, 0, sizeof tmp);
+	if (st->has_codes)
+		rc = pb_assemble_host_codes(a->ctx, &cfg, st->n, st->f_data, st->f_off, st->r_data, st->r_off, st->res, st->nt, st->code, st->stride, cnt);
+	else
+		rc = pb_assemble_host(a->ctx, &cfg, st->n, st->f_data, st->f_off, st->r_data, st->r_off, st->res, st->nt, st->p, st->stride, cnt);
+	if (rc != PB_OK)
+		return false;
+	if (a->has_check) {
+		tmp[PB_C_OK] = 0;
+		tmp[PB_C_LONGEST] = 0;
+		memset(tmp + PB_C_OVERLAPS, 0, (PB_NCOUNTERS - PB_C_OVERLAPS) * sizeof(int64_t));
+		pb_counters_merge(a->counters, tmp);
+	}
 	return true;
 }
 
-/* Expand device record i of the staged batch into a->result (pandaseq-common.h:277-330). */
-static const panda_result_seq *publish(PandaAssembler a, size_t i, const panda_seq_identifier *id,
+/* Expand device record i of a stage into a->result (pandaseq-common.h:277-330). */
+static const panda_result_seq *publish(PandaAssembler a, const struct pb_stage *st, size_t i, const panda_seq_identifier *id,
                                        const panda_qual *fwd, size_t flen, const panda_qual *rev, size_t rlen) {
-	const pb_pair_result *r = &a->res[i];
+	const pb_pair_result *r = &st->res[i];
 	panda_result_seq *out = &a->result;
 	if (id != NULL)
 		out->name = *id;
@@ -499,11 +576,21 @@ static const panda_result_seq *publish(PandaAssembler a, size_t i, const panda_s
 	out->overlaps_examined = r->examined;
 	out->overlap = r->overlap;
 	out->estimated_overlap_probability = r->est_prob;
-	const uint8_t *nt = a->nt + i * (SEQ_CAP / 2);	/* 4 bit per base, base 2k in the low nibble */
-	const double *p = a->p + i * SEQ_CAP;
-	for (size_t k = 0; k < r->seq_len; k++) {
-		a->result_seq[k].nt = (panda_nt) ((nt[k >> 1] >> ((k & 1) * 4)) & 0x0F);
-		a->result_seq[k].p = p[k];
+	const uint8_t *nt = st->nt + i * (st->stride / 2);	/* 4 bit per base, base 2k in the low nibble */
+	const size_t len = r->seq_len < st->stride ? r->seq_len : st->stride;
+	if (st->has_codes) {
+		const uint16_t *code = st->code + i * st->stride;
+		const double *table = a->ptable;
+		for (size_t k = 0; k < len; k++) {
+			a->result_seq[k].nt = (panda_nt) ((nt[k >> 1] >> ((k & 1) * 4)) & 0x0F);
+			a->result_seq[k].p = table[code[k] < PB_POSTERIOR_CODES ? code[k] : 0];
+		}
+	} else {
+		const double *p = st->p + i * st->stride;
+		for (size_t k = 0; k < len; k++) {
+			a->result_seq[k].nt = (panda_nt) ((nt[k >> 1] >> ((k & 1) * 4)) & 0x0F);
+			a->result_seq[k].p = p[k];
+		}
 	}
 	return out;
 }
@@ -511,26 +598,19 @@ static const panda_result_seq *publish(PandaAssembler a, size_t i, const panda_s
 const panda_result_seq *panda_assembler_assemble(PandaAssembler a, panda_seq_identifier *id,
                                                  const panda_qual *forward, size_t forward_length,
                                                  const panda_qual *reverse, size_t reverse_length) {
+	struct pb_stage *st = &a->call;
 	assert(forward_length <= PB_MAX_LEN);
 	assert(reverse_length <= PB_MAX_LEN);
 	if (!host_precheck(a, id, forward, forward_length, reverse, reverse_length))
 		return NULL;
-	if (!reserve(a, 1, forward_length, reverse_length))
+	stage_begin(st);
+	if (!stage_push(st, id, forward, forward_length, reverse, reverse_length) || !run_batch(a, st))
 		return NULL;
-	memcpy(a->f_data, forward, forward_length * sizeof(panda_qual));
-	memcpy(a->r_data, reverse, reverse_length * sizeof(panda_qual));
-	a->f_off[0] = a->r_off[0] = 0;
-	a->f_off[1] = forward_length;
-	a->r_off[1] = reverse_length;
-	a->batch_n = 1;
-	a->batch_pos = 1;	/* not part of a next() stream */
-	if (!run_batch(a))
-		return NULL;
-	if (a->res[0].status == PB_PAIR_NOALGN && a->noalgn != NULL)
+	if (st->res[0].status == PB_PAIR_NOALGN && a->noalgn != NULL)
 		a->noalgn(a, id, forward, forward_length, reverse, reverse_length, a->noalgn_data);
-	if (a->res[0].status != PB_PAIR_OK)
+	if (st->res[0].status != PB_PAIR_OK)
 		return NULL;
-	const panda_result_seq *out = publish(a, 0, id, forward, forward_length, reverse, reverse_length);
+	const panda_result_seq *out = publish(a, st, 0, id, forward, forward_length, reverse, reverse_length);
 	return host_check(a, out) ? out : NULL;
 }
 
@@ -538,6 +618,7 @@ size_t panda_assembler_assemble_batch(PandaAssembler a, size_t n, const panda_se
                                       const panda_qual *const *forward, const size_t *forward_length,
                                       const panda_qual *const *reverse, const size_t *reverse_length,
                                       PandaOutputSeq output, void *output_data) {
+	struct pb_stage *st = &a->call;
 	size_t fb = 0, rb = 0, accepted = 0;
 	for (size_t i = 0; i < n; i++) {
 		if (forward_length[i] > PB_MAX_LEN || reverse_length[i] > PB_MAX_LEN) {
@@ -547,43 +628,35 @@ size_t panda_assembler_assemble_batch(PandaAssembler a, size_t n, const panda_se
 		fb += forward_length[i];
 		rb += reverse_length[i];
 	}
-	if (!reserve(a, n, fb, rb))
+	stage_begin(st);
+	if (!reserve(st, n, fb, rb, 0, 0, 0))
 		return (size_t) -1;
 	/* pairs a module's pre-check rejects are not staged; map[k] = caller's index of staged pair k */
 	size_t *map = a->modules_length ? malloc((n ? n : 1) * sizeof(size_t)) : NULL;
 	if (a->modules_length && map == NULL)
 		return (size_t) -1;
-	size_t m = 0;
-	fb = rb = 0;
 	for (size_t i = 0; i < n; i++) {
 		if (!host_precheck(a, ids ? &ids[i] : NULL, forward[i], forward_length[i], reverse[i], reverse_length[i]))
 			continue;
 		if (map)
-			map[m] = i;
-		a->f_off[m] = fb;
-		a->r_off[m] = rb;
-		memcpy(a->f_data + fb, forward[i], forward_length[i] * sizeof(panda_qual));
-		memcpy(a->r_data + rb, reverse[i], reverse_length[i] * sizeof(panda_qual));
-		fb += forward_length[i];
-		rb += reverse_length[i];
-		m++;
+			map[st->n] = i;
+		if (!stage_push(st, ids ? &ids[i] : NULL, forward[i], forward_length[i], reverse[i], reverse_length[i])) {
+			free(map);
+			return (size_t) -1;
+		}
 	}
-	a->f_off[m] = fb;
-	a->r_off[m] = rb;
-	a->batch_n = m;
-	a->batch_pos = m;
-	if (m > 0 && !run_batch(a)) {
+	if (!run_batch(a, st)) {
 		free(map);
 		return (size_t) -1;
 	}
-	for (size_t k = 0; k < m; k++) {
+	for (size_t k = 0; k < st->n; k++) {
 		const size_t i = map ? map[k] : k;
 		const panda_seq_identifier *id = ids ? &ids[i] : NULL;
-		if (a->res[k].status == PB_PAIR_NOALGN && a->noalgn != NULL)
+		if (st->res[k].status == PB_PAIR_NOALGN && a->noalgn != NULL)
 			a->noalgn(a, id, forward[i], forward_length[i], reverse[i], reverse_length[i], a->noalgn_data);
-		if (a->res[k].status != PB_PAIR_OK)
+		if (st->res[k].status != PB_PAIR_OK)
 			continue;
-		const panda_result_seq *out = publish(a, k, id, forward[i], forward_length[i], reverse[i], reverse_length[i]);
+		const panda_result_seq *out = publish(a, st, k, id, forward[i], forward_length[i], reverse[i], reverse_length[i]);
 		if (!host_check(a, out))
 			continue;
 		accepted++;
@@ -594,82 +667,202 @@ size_t panda_assembler_assemble_batch(PandaAssembler a, size_t n, const panda_se
 	return accepted;
 }
 
+/* the next accepted pair of a stage that has been through the device, or NULL when it is used up */
+static const panda_result_seq *stage_next_result(PandaAssembler a, struct pb_stage *st) {
+	while (st->pos < st->n) {
+		const size_t i = st->pos++;
+		const panda_qual *f = st->f_data + st->f_off[i], *r = st->r_data + st->r_off[i];
+		const size_t fl = (size_t) (st->f_off[i + 1] - st->f_off[i]), rl = (size_t) (st->r_off[i + 1] - st->r_off[i]);
+		if (st->res[i].status == PB_PAIR_NOALGN && a->noalgn != NULL)
+			a->noalgn(a, &st->ids[i], f, fl, r, rl, a->noalgn_data);
+		if (st->res[i].status == PB_PAIR_OK) {
+			const panda_result_seq *out = publish(a, st, i, &st->ids[i], f, fl, r, rl);
+			if (host_check(a, out))
+				return out;
+		}
+	}
+	return NULL;
+}
+
+/* Pull up to `limit` pairs from `src`'s source into `st` (pre-checks run here, against `a`'s modules and counters).
+ * Returns false when staging failed; *dry is set when the source ended. */
+static bool stage_fill(PandaAssembler a, PandaAssembler src, struct pb_stage *st, size_t limit, bool *dry) {
+	stage_begin(st);
+	if (!reserve(st, limit, limit * 160, limit * 160, 0, 0, 0))
+		return false;
+	while (st->n < limit) {
+		panda_seq_identifier id;
+		const panda_qual *f, *r;
+		size_t fl, rl;
+		if (!src->next(&id, &f, &fl, &r, &rl, src->next_data)) {
+			*dry = true;
+			break;
+		}
+		assert(fl <= PB_MAX_LEN);
+		assert(rl <= PB_MAX_LEN);
+		if (!host_precheck(a, &id, f, fl, r, rl))
+			continue;	/* counted and rejected on the host: not staged */
+		if (!stage_push(st, &id, f, fl, r, rl))
+			return false;
+	}
+	return true;
+}
+
 const panda_result_seq *panda_assembler_next(PandaAssembler a) {
+	struct pb_stage *st = &a->stream;
 	if (a->next == NULL)
 		return NULL;
 	for (;;) {
 		/* hand out what the last launch produced, in input order */
-		while (a->batch_pos < a->batch_n) {
-			size_t i = a->batch_pos++;
-			const panda_qual *f = a->f_data + a->f_off[i], *r = a->r_data + a->r_off[i];
-			size_t fl = (size_t) (a->f_off[i + 1] - a->f_off[i]), rl = (size_t) (a->r_off[i + 1] - a->r_off[i]);
-			if (a->res[i].status == PB_PAIR_NOALGN && a->noalgn != NULL)
-				a->noalgn(a, &a->ids[i], f, fl, r, rl, a->noalgn_data);
-			if (a->res[i].status == PB_PAIR_OK) {
-				const panda_result_seq *out = publish(a, i, &a->ids[i], f, fl, r, rl);
-				if (host_check(a, out))
-					return out;
-			}
-		}
-		if (a->source_dry)
+		const panda_result_seq *out = stage_next_result(a, st);
+		if (out != NULL)
+			return out;
+		if (a->source_dry || a->failed)
 			return NULL;
-		/* refill: the source's arrays are only valid until its next call, so copy as we pull
-		 * (the reference's mux does the same, mux.c:150-157) */
-		size_t n = 0, fb = 0, rb = 0;
-		if (!reserve(a, a->next_batch, a->next_batch * 160, a->next_batch * 160))
-			return NULL;
-		while (n < a->next_batch) {
-			const panda_qual *f, *r;
-			size_t fl, rl;
-			if (!a->next(&a->ids[n], &f, &fl, &r, &rl, a->next_data)) {
-				a->source_dry = true;
-				break;
-			}
-			assert(fl <= PB_MAX_LEN);
-			assert(rl <= PB_MAX_LEN);
-			if (!host_precheck(a, &a->ids[n], f, fl, r, rl))
-				continue;	/* counted and rejected on the host: not staged */
-			if (!reserve(a, n + 1, fb + fl, rb + rl))
-				return NULL;
-			a->f_off[n] = fb;
-			a->r_off[n] = rb;
-			memcpy(a->f_data + fb, f, fl * sizeof(panda_qual));
-			memcpy(a->r_data + rb, r, rl * sizeof(panda_qual));
-			fb += fl;
-			rb += rl;
-			n++;
-		}
-		a->f_off[n] = fb;
-		a->r_off[n] = rb;
-		a->batch_n = n;
-		a->batch_pos = 0;
-		if (n == 0)
-			return NULL;
-		if (!run_batch(a)) {
-			a->batch_n = a->batch_pos = 0;
+		/* refill */
+		if (!stage_fill(a, a, st, a->next_batch, &a->source_dry) || !run_batch(a, st)) {
+			/* NULL is also the end of the stream, so the failure is made to stick: no later call pulls further pairs and
+			 * leaves a hole; pb_last_error() has the reason */
+			a->failed = true;
+			st->n = st->pos = 0;
 			return NULL;
 		}
+		if (st->n == 0 && a->source_dry)
+			return NULL;
 	}
 }
 
-/* pool.c:110-181.  The reference fans one assembler out over `threads` workers that pull from a shared PandaMux; here
- * the one assembler already drains its source in device-sized batches (panda_assembler_next), so `threads` and `mux` only
- * keep the signature: the mux is an opaque handle this library never creates, and is ignored.  Ownership follows the
- * reference: the assembler is consumed (unref), output_destroy(output_data) is called at the end.  Returns whether any
- * pair was read. */
+/* ---- panda_run_pool (pool.c:110-181) ------------------------------------------------------------------------------------
+ * The reference fans one assembler out over `threads` workers, each with a clone made by panda_assembler_copy_configuration,
+ * all pulling pairs from one mutex-protected source, each handing its results to `output` from its own thread, in no
+ * particular order (pandaseq.1:208).  The same here, with a GPU behind every worker: worker w gets device w mod D, D = the
+ * visible GPUs (PANDASEQ_B200_DEVICES caps it), pulls a batch while it holds the source, runs it on its device and hands the
+ * results out while the other workers pull and compute.  The workers' counters are merged into `assembler` at the end (the STAT
+ * merge), so the caller's getters see the whole run.  The mux is an opaque handle this library
+ * never creates, and is ignored.  Ownership follows the reference: the assembler is consumed (unref),
+ * output_destroy(output_data) is called at the end.  Returns whether any pair was read. */
+struct pool_shared {
+	PandaAssembler source;
+	pthread_mutex_t source_mutex;
+	bool dry, stop, failed;
+	PandaOutputSeq output;
+	void *output_data;
+};
+struct pool_worker {
+	struct pool_shared *shared;
+	PandaAssembler self;
+	pthread_t tid;
+};
+
+static void *pool_work(void *arg) {
+	struct pool_worker *w = arg;
+	struct pool_shared *sh = w->shared;
+	PandaAssembler a = w->self;
+	struct pb_stage *st = &a->stream;
+	for (;;) {
+		bool ok, dry = false;
+		pthread_mutex_lock(&sh->source_mutex);
+		if (sh->dry || sh->stop || sh->failed) {
+			pthread_mutex_unlock(&sh->source_mutex);
+			break;
+		}
+		ok = stage_fill(a, sh->source, st, a->next_batch, &dry);
+		if (dry)
+			sh->dry = true;
+		if (!ok)
+			sh->failed = true;
+		pthread_mutex_unlock(&sh->source_mutex);
+		if (!ok || !run_batch(a, st)) {
+			pthread_mutex_lock(&sh->source_mutex);
+			sh->failed = true;
+			pthread_mutex_unlock(&sh->source_mutex);
+			break;
+		}
+		const panda_result_seq *result;
+		while ((result = stage_next_result(a, st)) != NULL) {
+			if (sh->output != NULL && !sh->output(result, sh->output_data)) {
+				pthread_mutex_lock(&sh->source_mutex);
+				sh->stop = true;
+				pthread_mutex_unlock(&sh->source_mutex);
+				break;
+			}
+		}
+	}
+	return NULL;
+}
+
 bool panda_run_pool(int threads, PandaAssembler assembler, PandaMux mux, PandaOutputSeq output, void *output_data, PandaDestroy output_destroy) {
-	const panda_result_seq *result;
 	bool some_seqs;
-	(void) threads;
 	(void) mux;
 	if (assembler == NULL) {
 		if (output_destroy != NULL)
 			output_destroy(output_data);
 		return false;
 	}
-	while ((result = panda_assembler_next(assembler)) != NULL) {
-		if (output != NULL && !output(result, output_data))
-			break;
+	if (threads > 64)
+		threads = 64;
+	if (threads <= 1 || assembler->next == NULL) {
+		const panda_result_seq *result;
+		while ((result = panda_assembler_next(assembler)) != NULL) {
+			if (output != NULL && !output(result, output_data))
+				break;
+		}
+	} else {
+		struct pool_shared sh;
+		struct pool_worker *workers = calloc((size_t) threads, sizeof *workers);
+		int devices = pb_device_count(), started = 0;
+		const char *env = getenv("PANDASEQ_B200_DEVICES");
+		if (env != NULL && atoi(env) > 0 && atoi(env) < devices)
+			devices = atoi(env);
+		if (devices < 1)
+			devices = 1;
+		memset(&sh, 0, sizeof sh);
+		sh.source = assembler;
+		sh.output = output;
+		sh.output_data = output_data;
+		pthread_mutex_init(&sh.source_mutex, NULL);
+		for (int k = 0; workers != NULL && k < threads; k++) {
+			pb_context *ctx = NULL;
+			PandaAssembler c;
+			if (pb_device_context(k % devices, &ctx) != PB_OK)
+				break;
+			c = panda_assembler_new_kmer(NULL, NULL, NULL, assembler->logger, assembler->num_kmers);
+			if (c == NULL)
+				break;
+			panda_assembler_copy_configuration(c, assembler);
+			c->ctx = ctx;
+			c->next_batch = assembler->next_batch;
+			c->noalgn = assembler->noalgn;		/* called from the worker's thread, as the reference's clones do; not owned */
+			c->noalgn_data = assembler->noalgn_data;
+			c->noalgn_destroy = NULL;
+			workers[k].shared = &sh;
+			workers[k].self = c;
+			if (pthread_create(&workers[k].tid, NULL, pool_work, &workers[k]) != 0) {
+				panda_assembler_unref(c);
+				break;
+			}
+			started++;
+		}
+		if (started == 0) {		/* no worker could be set up: the plain loop still works */
+			const panda_result_seq *result;
+			while ((result = panda_assembler_next(assembler)) != NULL) {
+				if (output != NULL && !output(result, output_data))
+					break;
+			}
+		}
+		for (int k = 0; k < started; k++) {
+			PandaAssembler c = workers[k].self;
+			pthread_join(workers[k].tid, NULL);
+			pb_counters_merge(assembler->counters, c->counters);
+			for (size_t it = 0; it < c->modules_length && it < assembler->modules_length; it++)
+				assembler->rejected[it] += c->rejected[it];
+			c->noalgn = NULL;
+			panda_assembler_unref(c);
+		}
+		if (sh.failed)
+			assembler->failed = true;
+		pthread_mutex_destroy(&sh.source_mutex);
+		free(workers);
 	}
 	some_seqs = panda_assembler_get_count(assembler) > 0;
 	panda_assembler_unref(assembler);

@@ -38,20 +38,31 @@ struct pb_context {
 	pthread_mutex_t lock;            /* one host-path call at a time per context (assemblers share the process-wide one) */
 	/* host-path staging (grown on demand) */
 	struct Slot {
-		size_t cap_pairs, cap_bases, cap_hpairs, cap_hbases, cap_hres;
-		uint8_t *h_f, *h_r;              /* pinned AoS */
+		/* every buffer with its own capacity (elements) */
+		uint8_t *h_f, *h_r;              /* pinned AoS staging */
+		size_t cap_hf, cap_hr;
 		unsigned long long *h_foff, *h_roff;
+		size_t cap_hfoff, cap_hroff;
 		uint32_t *h_recoff;
+		size_t cap_hrecoff;
 		uint8_t *d_f, *d_r;
+		size_t cap_f, cap_r;
 		unsigned long long *d_foff, *d_roff;
+		size_t cap_foff, cap_roff;
 		uint32_t *d_recoff;
+		size_t cap_recoff;
 		uint8_t *d_reads;
 		size_t cap_reads;
 		pb_pair_meta *d_meta;
+		size_t cap_meta;
 		pb_pair_result *d_res, *h_res;
+		size_t cap_res, cap_hres;
 		uint8_t *d_nt, *h_nt;
 		double *d_p, *h_p;
-		size_t cap_nt, cap_p, cap_dnt, cap_dp;
+		uint16_t *d_code, *h_code;       /* per-base posterior codes (pb_assemble_host_codes) */
+		pb_pair_meta *h_meta;            /* pinned staging of caller-packed input (pb_assemble_host_packed) */
+		uint8_t *h_reads;
+		size_t cap_nt, cap_p, cap_dnt, cap_dp, cap_code, cap_dcode, cap_hmeta, cap_hreads;
 		cudaEvent_t done;
 	} slot[PB_HOST_SLOTS];
 	pb_io_state *io;                 /* buffers of the FASTQ / text stages, allocated on first use (pb_io.cu) */
@@ -70,7 +81,7 @@ struct pb_context {
 pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int max_len,
                                const uint8_t *d_reads, const pb_pair_meta *d_meta, pb_pair_result *d_results,
                                uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride, unsigned long long *d_counters,
-                               cudaStream_t stream);
+                               cudaStream_t stream, uint16_t *d_seq_code = nullptr);
 pb_status pb_upload_params(pb_context *ctx, const pb_config *cfg);
 bool pb_is_pinned(const void *p);
 void pb_io_release(pb_context *ctx);

@@ -68,6 +68,7 @@ static void free_slot(pb_context::Slot &s) {
 	cudaFree(s.d_f); cudaFree(s.d_r); cudaFree(s.d_foff); cudaFree(s.d_roff); cudaFree(s.d_recoff);
 	cudaFree(s.d_reads); cudaFree(s.d_meta); cudaFree(s.d_res); cudaFreeHost(s.h_res);
 	cudaFree(s.d_nt); cudaFreeHost(s.h_nt); cudaFree(s.d_p); cudaFreeHost(s.h_p);
+	cudaFree(s.d_code); cudaFreeHost(s.h_code); cudaFreeHost(s.h_meta); cudaFreeHost(s.h_reads);
 	cudaEvent_t ev = s.done;
 	memset(&s, 0, sizeof s);
 	s.done = ev;
@@ -147,7 +148,7 @@ template <int ML, bool OVER, int WARPS, bool FULLF>
 static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
                                  pb_pair_result *d_results, uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride,
                                  unsigned long long *d_counters, cudaStream_t stream, bool post,
-                                 const int *d_list = nullptr, const int *d_list_n = nullptr) {
+                                 const int *d_list = nullptr, const int *d_list_n = nullptr, uint16_t *d_seq_code = nullptr) {
 	auto kern = pb::assemble_kernel<ML, OVER, WARPS, FULLF>;
 	constexpr size_t smem = pb::assemble_smem_bytes<ML, OVER, WARPS>();
 	static bool configured[16] = { false };
@@ -187,7 +188,7 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 	if (timed && !d_list)
 		CUDA_TRY(cudaEventRecord(ctx->tev[0], stream));
 	kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p,
-	                                                           (long long) seq_stride, d_counters, scratch, d_list, d_list_n);
+	                                                           (long long) seq_stride, d_counters, scratch, d_list, d_list_n, d_seq_code);
 	CUDA_TRY(cudaGetLastError());
 	if (timed) {
 		CUDA_TRY(cudaEventRecord(ctx->tev[3], stream));
@@ -281,7 +282,7 @@ static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, co
 pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int max_len,
                                    const uint8_t *d_reads, const pb_pair_meta *d_meta, pb_pair_result *d_results,
                                    uint8_t *d_seq_nt, double *d_seq_p, size_t seq_stride, unsigned long long *d_counters,
-                                   cudaStream_t stream) {
+                                   cudaStream_t stream, uint16_t *d_seq_code) {
 	const bool over = cfg->algo == PB_RDP_MLE;      /* pear scores from the reconstruction table, only rdp_mle needs its own */
 	if (max_len <= 0 || max_len > PB_MAX_LEN)
 		max_len = PB_MAX_LEN;
@@ -299,7 +300,11 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 		const char *env = getenv("PANDASEQ_B200_LANES");
 		lanes_on = (env && atoi(env) == 0) ? 0 : 1;
 	}
-	if ((ctx->lanes_mode < 0 ? lanes_on : ctx->lanes_mode) && !full && !d_seq_p && max_len <= 256 && cfg->forward_trim == 0 && cfg->reverse_trim == 0
+	if (d_seq_code && stage_seq) {
+		pb_set_error("per-base codes are not available together with primers-after or min_phred (the sequence is staged as doubles)");
+		return PB_ERR_ARGUMENT;
+	}
+	if ((ctx->lanes_mode < 0 ? lanes_on : ctx->lanes_mode) && !full && !d_seq_p && !d_seq_code && max_len <= 256 && cfg->forward_trim == 0 && cfg->reverse_trim == 0
 	    && (cfg->algo == PB_SIMPLE_BAYES || cfg->algo == PB_UPARSE || cfg->algo == PB_FLASH || cfg->algo == PB_PEAR) && ((uintptr_t) d_seq_nt % 8) == 0)
 	{
 		/* <seeding class, lane-kernel class, seeding warps, lane warps, general-kernel warps>: as many warps as the per-warp shared
@@ -318,8 +323,8 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 			return launch_lanes<160, 160, 32, 11, 28, 21>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 		return launch_lanes<256, 256, 19, 7, 15, 14>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 	}
-#define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq); \
-	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false); } while (0)
+#define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq, nullptr, nullptr, d_seq_code); \
+	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false, nullptr, nullptr, d_seq_code); } while (0)
 	/* warps per CTA: as many as the per-warp shared memory of the class allows next to the LUTs (227 KB per SM) */
 	if (max_len <= 160) {
 		if (over) PB_GO(160, true, 23);
@@ -358,7 +363,7 @@ extern "C" pb_status pb_assemble_device(pb_context *ctx, const pb_config *cfg, s
 	if (n == 0)
 		return PB_OK;
 	return pb_assemble_dispatch(ctx, cfg, (int) n, max_read_len, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride,
-	                         (unsigned long long *) d_counters, ctx->stream);
+	                         (unsigned long long *) d_counters, ctx->stream, nullptr);
 }
 
 extern "C" pb_status pb_pack_device(pb_context *ctx, size_t n,
@@ -448,61 +453,45 @@ template <typename T> static cudaError_t regrow_dev(T **p, size_t *cap, size_t n
 		*cap = need;
 	return e;
 }
+template <typename T> static cudaError_t regrow_host(T **p, size_t *cap, size_t need) {
+	if (need <= *cap)
+		return cudaSuccess;
+	cudaFreeHost(*p);
+	*p = nullptr;
+	*cap = 0;
+	cudaError_t e = cudaMallocHost((void **) p, need * sizeof(T));
+	if (e == cudaSuccess)
+		*cap = need;
+	return e;
+}
 
-static pb_status ensure_slot(pb_context::Slot &s, size_t pairs, size_t fbases, size_t rbases, bool stage_in,
-                             bool stage_res, size_t nt_bytes, size_t p_elems) {
-	size_t bases = fbases > rbases ? fbases : rbases;
-	if (pairs > s.cap_pairs) {
-		size_t cap = pairs + pairs / 4 + 16;
-		cudaFreeHost(s.h_recoff);
-		cudaFree(s.d_foff); cudaFree(s.d_roff); cudaFree(s.d_recoff); cudaFree(s.d_meta); cudaFree(s.d_res);
-		CUDA_TRY(cudaMallocHost(&s.h_recoff, cap * 4));
-		CUDA_TRY(cudaMalloc(&s.d_foff, (cap + 1) * 8));
-		CUDA_TRY(cudaMalloc(&s.d_roff, (cap + 1) * 8));
-		CUDA_TRY(cudaMalloc(&s.d_recoff, cap * 4));
-		CUDA_TRY(cudaMalloc(&s.d_meta, cap * sizeof(pb_pair_meta)));
-		CUDA_TRY(cudaMalloc(&s.d_res, cap * sizeof(pb_pair_result)));
-		s.cap_pairs = cap;
+/* Every buffer of a slot has its own capacity and is grown on its own (freed pointer nulled, capacity zeroed first), so a
+ * failed allocation leaves the slot consistent. */
+static pb_status ensure_slot(pb_context::Slot &s, size_t pairs, size_t fbases, size_t rbases, bool aos_in, bool stage_in,
+                             bool stage_res, size_t nt_bytes, size_t p_elems, size_t code_elems) {
+	const size_t bases = fbases > rbases ? fbases : rbases;
+	const size_t pcap = pairs + pairs / 4 + 16, bcap = bases + bases / 4 + 64;
+	CUDA_TRY(regrow_dev(&s.d_meta, &s.cap_meta, pcap));
+	CUDA_TRY(regrow_dev(&s.d_res, &s.cap_res, pcap));
+	if (aos_in) {
+		CUDA_TRY(regrow_host(&s.h_recoff, &s.cap_hrecoff, pcap));
+		CUDA_TRY(regrow_dev(&s.d_foff, &s.cap_foff, pcap + 1));
+		CUDA_TRY(regrow_dev(&s.d_roff, &s.cap_roff, pcap + 1));
+		CUDA_TRY(regrow_dev(&s.d_recoff, &s.cap_recoff, pcap));
+		CUDA_TRY(regrow_dev(&s.d_f, &s.cap_f, bcap * 2));
+		CUDA_TRY(regrow_dev(&s.d_r, &s.cap_r, bcap * 2));
+		if (stage_in) {          /* pinned staging for pageable caller arrays */
+			CUDA_TRY(regrow_host(&s.h_foff, &s.cap_hfoff, pcap + 1));
+			CUDA_TRY(regrow_host(&s.h_roff, &s.cap_hroff, pcap + 1));
+			CUDA_TRY(regrow_host(&s.h_f, &s.cap_hf, bcap * 2));
+			CUDA_TRY(regrow_host(&s.h_r, &s.cap_hr, bcap * 2));
+		}
 	}
-	if (stage_in && pairs > s.cap_hpairs) {          /* pinned staging for pageable caller offsets */
-		size_t cap = pairs + pairs / 4 + 16;
-		cudaFreeHost(s.h_foff); cudaFreeHost(s.h_roff);
-		CUDA_TRY(cudaMallocHost(&s.h_foff, (cap + 1) * 8));
-		CUDA_TRY(cudaMallocHost(&s.h_roff, (cap + 1) * 8));
-		s.cap_hpairs = cap;
-	}
-	if (stage_res && pairs > s.cap_hres) {
-		size_t cap = pairs + pairs / 4 + 16;
-		cudaFreeHost(s.h_res);
-		CUDA_TRY(cudaMallocHost(&s.h_res, cap * sizeof(pb_pair_result)));
-		s.cap_hres = cap;
-	}
-	if (bases > s.cap_bases) {
-		size_t cap = bases + bases / 4 + 64;
-		cudaFree(s.d_f); cudaFree(s.d_r);
-		CUDA_TRY(cudaMalloc(&s.d_f, cap * 2));
-		CUDA_TRY(cudaMalloc(&s.d_r, cap * 2));
-		s.cap_bases = cap;
-	}
-	if (stage_in && bases > s.cap_hbases) {
-		size_t cap = bases + bases / 4 + 64;
-		cudaFreeHost(s.h_f); cudaFreeHost(s.h_r);
-		CUDA_TRY(cudaMallocHost(&s.h_f, cap * 2));
-		CUDA_TRY(cudaMallocHost(&s.h_r, cap * 2));
-		s.cap_hbases = cap;
-	}
-	if (nt_bytes > s.cap_nt) {          /* pinned staging, only for pageable caller buffers */
-		cudaFreeHost(s.h_nt);
-		s.h_nt = nullptr;
-		CUDA_TRY(cudaMallocHost(&s.h_nt, nt_bytes));
-		s.cap_nt = nt_bytes;
-	}
-	if (p_elems > s.cap_p) {
-		cudaFreeHost(s.h_p);
-		s.h_p = nullptr;
-		CUDA_TRY(cudaMallocHost(&s.h_p, p_elems * sizeof(double)));
-		s.cap_p = p_elems;
-	}
+	if (stage_res)
+		CUDA_TRY(regrow_host(&s.h_res, &s.cap_hres, pcap));
+	CUDA_TRY(regrow_host(&s.h_nt, &s.cap_nt, nt_bytes));
+	CUDA_TRY(regrow_host(&s.h_p, &s.cap_p, p_elems));
+	CUDA_TRY(regrow_host(&s.h_code, &s.cap_code, code_elems));
 	return PB_OK;
 }
 
@@ -517,132 +506,227 @@ bool pb_is_pinned(const void *p) {
 	return attr.type == cudaMemoryTypeHost;
 }
 
-/* Chunked over two slots, each with its own stream: while chunk k is packed/assembled on the GPU, chunk k+1's
- * host->device copies and chunk k-1's device->host copies run on the other stream.  Caller buffers that are
- * pinned (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are copied from/to directly; pageable
- * buffers go through the slot's pinned staging area first. */
-static pb_status assemble_host_locked(pb_context *ctx, const pb_config *cfg, size_t n,
-                                      const panda_qual *f_data, const uint64_t *f_off,
-                                      const panda_qual *r_data, const uint64_t *r_off,
-                                      pb_pair_result *results, uint8_t *seq_nt, double *seq_p,
-                                      size_t seq_stride, int64_t *counters) {
-	if (!cfg || (!results && n) || (n && (!f_data || !f_off || !r_data || !r_off)) || ((seq_nt || seq_p) && (seq_stride % 16) != 0)) {
-		pb_set_error("pb_assemble_host: bad argument (seq_stride must be a multiple of 16)");
-		return PB_ERR_ARGUMENT;
-	}
-	CUDA_TRY(cudaSetDevice(ctx->device));
-	pb_status st = pb_upload_params(ctx, cfg);
-	if (st != PB_OK)
-		return st;
-	if (n == 0)
-		return PB_OK;
-	CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, PB_NCOUNTERS * sizeof(unsigned long long), ctx->stream));
-	CUDA_TRY(cudaStreamSynchronize(ctx->stream));      /* parameters + zeroed counters visible to both streams */
-	const bool pin_in = pb_is_pinned(f_data) && pb_is_pinned(r_data) && pb_is_pinned(f_off) && pb_is_pinned(r_off);
-	const bool pin_res = pb_is_pinned(results), pin_nt = pb_is_pinned(seq_nt), pin_p = pb_is_pinned(seq_p);
-	static size_t chunk_cfg = 0;
-	if (chunk_cfg == 0) {
+static size_t host_chunk_pairs() {
+	static pthread_once_t once = PTHREAD_ONCE_INIT;
+	static size_t chunk_cfg;
+	pthread_once(&once, [] {
 		const char *env = getenv("PANDASEQ_B200_CHUNK");      /* pairs per chunk of the host path (experiments) */
 		chunk_cfg = env ? (size_t) atol(env) : (size_t) (1u << 18);      /* 256 K pairs: measured best on B200 (82 vs 76 Mpairs/s at 1 M) */
 		if (chunk_cfg < 1024)
 			chunk_cfg = 1024;
-	}
+	});
+	return chunk_cfg;
+}
+
+/* What a host-path call works on.  Input is either the flat AoS arrays of the reference's API (f_data .. r_off; packed on the
+ * device) or records the caller packed itself (reads / meta in the layout of include/pandaseq_b200.h: 26 % fewer bytes on
+ * the link).  Per-base log p leaves either as doubles (seq_p) or as 16-bit codes into the posterior table (seq_code). */
+struct HostJob {
+	size_t n;
+	const panda_qual *f_data, *r_data;
+	const uint64_t *f_off, *r_off;
+	const uint8_t *reads;
+	const pb_pair_meta *meta;
+	int packed_max_len;
+	pb_pair_result *results;
+	uint8_t *seq_nt;
+	double *seq_p;
+	uint16_t *seq_code;
+	size_t seq_stride;
+	int64_t *counters;
+};
+
+/* Chunked over two slots, each with its own stream: while chunk k is packed/assembled on the GPU, chunk k+1's
+ * host->device copies and chunk k-1's device->host copies run on the other stream.  Caller buffers that are
+ * pinned (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are copied from/to directly; pageable
+ * buffers go through the slot's pinned staging area first. */
+static pb_status assemble_host_chunks(pb_context *ctx, const pb_config *cfg, const HostJob &j) {
+	const size_t n = j.n;
+	const bool aos = j.reads == nullptr;
+	const bool pin_in = aos ? (pb_is_pinned(j.f_data) && pb_is_pinned(j.r_data) && pb_is_pinned(j.f_off) && pb_is_pinned(j.r_off))
+	                        : (pb_is_pinned(j.reads) && pb_is_pinned(j.meta));
+	const bool pin_res = pb_is_pinned(j.results), pin_nt = pb_is_pinned(j.seq_nt), pin_p = pb_is_pinned(j.seq_p), pin_code = pb_is_pinned(j.seq_code);
+	const size_t chunk_cfg = host_chunk_pairs();
 	const size_t CHUNK = n > 2 * chunk_cfg ? chunk_cfg : (n + 1) / 2 + 1;       /* at least two chunks so the slots overlap */
-	const size_t nt_row = seq_stride / 2;
+	const size_t nt_row = j.seq_stride / 2, stride = j.seq_stride;
 	struct Pending { bool live; size_t begin, count; } pend[PB_HOST_SLOTS] = {};
 	cudaStream_t streams[2] = { ctx->stream, ctx->copy_stream };
 	auto drain = [&](int si) -> pb_status {
 		if (!pend[si].live)
 			return PB_OK;
 		pb_context::Slot &s = ctx->slot[si];
+		pend[si].live = false;
 		CUDA_TRY(cudaEventSynchronize(s.done));
 		if (!pin_res)
-			memcpy(results + pend[si].begin, s.h_res, pend[si].count * sizeof(pb_pair_result));
-		if (seq_nt && !pin_nt)
-			memcpy(seq_nt + pend[si].begin * nt_row, s.h_nt, pend[si].count * nt_row);
-		if (seq_p && !pin_p)
-			memcpy(seq_p + pend[si].begin * seq_stride, s.h_p, pend[si].count * seq_stride * sizeof(double));
-		pend[si].live = false;
+			memcpy(j.results + pend[si].begin, s.h_res, pend[si].count * sizeof(pb_pair_result));
+		if (j.seq_nt && !pin_nt)
+			memcpy(j.seq_nt + pend[si].begin * nt_row, s.h_nt, pend[si].count * nt_row);
+		if (j.seq_p && !pin_p)
+			memcpy(j.seq_p + pend[si].begin * stride, s.h_p, pend[si].count * stride * sizeof(double));
+		if (j.seq_code && !pin_code)
+			memcpy(j.seq_code + pend[si].begin * stride, s.h_code, pend[si].count * stride * sizeof(uint16_t));
 		return PB_OK;
 	};
+	/* packed input: every read length is checked before anything is queued */
+	if (!aos) {
+		for (size_t i = 0; i < n; i++)
+			if (j.meta[i].flen != 0xFFFFu && (j.meta[i].flen > PB_MAX_LEN || j.meta[i].rlen > PB_MAX_LEN)) {
+				pb_set_error("read longer than PANDA_MAX_LEN (pair %zu)", i);
+				return PB_ERR_ARGUMENT;
+			}
+	}
 	int si = 0;
 	for (size_t begin = 0; begin < n; begin += CHUNK, si = (si + 1) % PB_HOST_SLOTS) {
 		const size_t count = (n - begin < CHUNK) ? (n - begin) : CHUNK;
-		st = drain(si);
+		pb_status st = drain(si);
 		if (st != PB_OK)
 			return st;
 		pb_context::Slot &s = ctx->slot[si];
 		cudaStream_t stream = streams[si & 1];
-		const uint64_t fb = f_off[begin], rb = r_off[begin];
-		const size_t fbases = (size_t) (f_off[begin + count] - fb), rbases = (size_t) (r_off[begin + count] - rb);
-		st = ensure_slot(s, count, fbases, rbases, !pin_in, !pin_res, (seq_nt && !pin_nt) ? count * nt_row : 0, (seq_p && !pin_p) ? count * seq_stride : 0);
+		size_t max_len = 0, total16 = 0, fbases = 0, rbases = 0;
+		uint64_t fb = 0, rb = 0;
+		if (aos) {
+			fb = j.f_off[begin];
+			rb = j.r_off[begin];
+			fbases = (size_t) (j.f_off[begin + count] - fb);
+			rbases = (size_t) (j.r_off[begin + count] - rb);
+		}
+		st = ensure_slot(s, count, fbases, rbases, aos, !pin_in, !pin_res, (j.seq_nt && !pin_nt) ? count * nt_row : 0,
+		                 (j.seq_p && !pin_p) ? count * stride : 0, (j.seq_code && !pin_code) ? count * stride : 0);
 		if (st != PB_OK)
 			return st;
-		/* layout: record offsets (integer bookkeeping only) and the longest read of the chunk */
-		size_t max_len = 0, total16 = 0;
-		for (size_t i = 0; i < count; i++) {
-			const size_t fl = (size_t) (f_off[begin + i + 1] - f_off[begin + i]), rl = (size_t) (r_off[begin + i + 1] - r_off[begin + i]);
-			if (fl > max_len) max_len = fl;
-			if (rl > max_len) max_len = rl;
-			s.h_recoff[i] = (uint32_t) total16;
-			total16 += pb_record_bytes(fl, rl) / 16;
-		}
-		if (max_len > PB_MAX_LEN) {
-			pb_set_error("read longer than PANDA_MAX_LEN (%zu > %d)", max_len, PB_MAX_LEN);
-			return PB_ERR_ARGUMENT;
+		if (aos) {
+			/* layout: record offsets (integer bookkeeping only) and the longest read of the chunk */
+			for (size_t i = 0; i < count; i++) {
+				const size_t fl = (size_t) (j.f_off[begin + i + 1] - j.f_off[begin + i]), rl = (size_t) (j.r_off[begin + i + 1] - j.r_off[begin + i]);
+				if (fl > max_len) max_len = fl;
+				if (rl > max_len) max_len = rl;
+				s.h_recoff[i] = (uint32_t) total16;
+				total16 += pb_record_bytes(fl, rl) / 16;
+			}
+			if (max_len > PB_MAX_LEN) {
+				pb_set_error("read longer than PANDA_MAX_LEN (%zu > %d)", max_len, PB_MAX_LEN);
+				return PB_ERR_ARGUMENT;
+			}
+		} else {
+			/* the chunk's records are contiguous in the caller's buffer: [off16 of its first pair, end of its last pair) */
+			const pb_pair_meta &first = j.meta[begin], &last = j.meta[begin + count - 1];
+			const size_t last_bytes = last.flen == 0xFFFFu ? 0 : pb_record_bytes(last.flen, last.rlen);
+			total16 = (size_t) last.off16 + last_bytes / 16 - first.off16;
+			max_len = (size_t) j.packed_max_len;
 		}
 		CUDA_TRY(regrow_dev(&s.d_reads, &s.cap_reads, total16 * 16 + 16));
-		if (seq_nt)
+		if (j.seq_nt)
 			CUDA_TRY(regrow_dev(&s.d_nt, &s.cap_dnt, count * nt_row));
-		if (seq_p)
-			CUDA_TRY(regrow_dev(&s.d_p, &s.cap_dp, count * seq_stride));
-		const void *src_f = f_data + fb, *src_r = r_data + rb, *src_fo = f_off + begin, *src_ro = r_off + begin;
-		if (!pin_in) {
-			memcpy(s.h_f, src_f, fbases * 2);
-			memcpy(s.h_r, src_r, rbases * 2);
-			memcpy(s.h_foff, src_fo, (count + 1) * 8);
-			memcpy(s.h_roff, src_ro, (count + 1) * 8);
-			src_f = s.h_f; src_r = s.h_r; src_fo = s.h_foff; src_ro = s.h_roff;
-		}
-		CUDA_TRY(cudaMemcpyAsync(s.d_f, src_f, fbases * 2, cudaMemcpyHostToDevice, stream));
-		CUDA_TRY(cudaMemcpyAsync(s.d_r, src_r, rbases * 2, cudaMemcpyHostToDevice, stream));
-		CUDA_TRY(cudaMemcpyAsync(s.d_foff, src_fo, (count + 1) * 8, cudaMemcpyHostToDevice, stream));
-		CUDA_TRY(cudaMemcpyAsync(s.d_roff, src_ro, (count + 1) * 8, cudaMemcpyHostToDevice, stream));
-		CUDA_TRY(cudaMemcpyAsync(s.d_recoff, s.h_recoff, count * 4, cudaMemcpyHostToDevice, stream));
-		{
+		if (j.seq_p)
+			CUDA_TRY(regrow_dev(&s.d_p, &s.cap_dp, count * stride));
+		if (j.seq_code)
+			CUDA_TRY(regrow_dev(&s.d_code, &s.cap_dcode, count * stride));
+		if (aos) {
+			const void *src_f = j.f_data + fb, *src_r = j.r_data + rb, *src_fo = j.f_off + begin, *src_ro = j.r_off + begin;
+			if (!pin_in) {
+				memcpy(s.h_f, src_f, fbases * 2);
+				memcpy(s.h_r, src_r, rbases * 2);
+				memcpy(s.h_foff, src_fo, (count + 1) * 8);
+				memcpy(s.h_roff, src_ro, (count + 1) * 8);
+				src_f = s.h_f; src_r = s.h_r; src_fo = s.h_foff; src_ro = s.h_roff;
+			}
+			CUDA_TRY(cudaMemcpyAsync(s.d_f, src_f, fbases * 2, cudaMemcpyHostToDevice, stream));
+			CUDA_TRY(cudaMemcpyAsync(s.d_r, src_r, rbases * 2, cudaMemcpyHostToDevice, stream));
+			CUDA_TRY(cudaMemcpyAsync(s.d_foff, src_fo, (count + 1) * 8, cudaMemcpyHostToDevice, stream));
+			CUDA_TRY(cudaMemcpyAsync(s.d_roff, src_ro, (count + 1) * 8, cudaMemcpyHostToDevice, stream));
+			CUDA_TRY(cudaMemcpyAsync(s.d_recoff, s.h_recoff, count * 4, cudaMemcpyHostToDevice, stream));
 			const int threads = 256;
 			const unsigned blocks = (unsigned) (((long long) count * 32 + threads - 1) / threads);
 			pb::pack_kernel<<<blocks, threads, 0, stream>>>((int) count, s.d_f, s.d_foff, fb, s.d_r, s.d_roff, rb, s.d_recoff, s.d_reads, s.d_meta);
 			CUDA_TRY(cudaGetLastError());
+		} else {
+			const uint8_t *src_reads = j.reads + (size_t) j.meta[begin].off16 * 16;
+			const pb_pair_meta *src_meta = j.meta + begin;
+			if (!pin_in) {
+				CUDA_TRY(regrow_host(&s.h_reads, &s.cap_hreads, total16 * 16));
+				CUDA_TRY(regrow_host(&s.h_meta, &s.cap_hmeta, count));
+				memcpy(s.h_reads, src_reads, total16 * 16);
+				memcpy(s.h_meta, src_meta, count * sizeof(pb_pair_meta));
+				src_reads = s.h_reads;
+				src_meta = s.h_meta;
+			}
+			CUDA_TRY(cudaMemcpyAsync(s.d_reads, src_reads, total16 * 16, cudaMemcpyHostToDevice, stream));
+			CUDA_TRY(cudaMemcpyAsync(s.d_meta, src_meta, count * sizeof(pb_pair_meta), cudaMemcpyHostToDevice, stream));
+			if (j.meta[begin].off16 != 0) {      /* offsets are relative to the caller's buffer: rebase them on the chunk */
+				const unsigned blocks = (unsigned) ((count + 255) / 256);
+				pb::rebase_meta_kernel<<<blocks, 256, 0, stream>>>((int) count, s.d_meta, j.meta[begin].off16);
+				CUDA_TRY(cudaGetLastError());
+			}
 		}
 		st = pb_assemble_dispatch(ctx, cfg, (int) count, (int) max_len, s.d_reads, s.d_meta, s.d_res,
-		                       seq_nt ? s.d_nt : nullptr, seq_p ? s.d_p : nullptr, seq_stride, ctx->d_counters, stream);
+		                       j.seq_nt ? s.d_nt : nullptr, j.seq_p ? s.d_p : nullptr, stride, ctx->d_counters, stream,
+		                       j.seq_code ? s.d_code : nullptr);
 		if (st != PB_OK)
 			return st;
-		CUDA_TRY(cudaMemcpyAsync(pin_res ? (void *) (results + begin) : (void *) s.h_res, s.d_res, count * sizeof(pb_pair_result), cudaMemcpyDeviceToHost, stream));
-		if (seq_nt)
-			CUDA_TRY(cudaMemcpyAsync(pin_nt ? (void *) (seq_nt + begin * nt_row) : (void *) s.h_nt, s.d_nt, count * nt_row, cudaMemcpyDeviceToHost, stream));
-		if (seq_p)
-			CUDA_TRY(cudaMemcpyAsync(pin_p ? (void *) (seq_p + begin * seq_stride) : (void *) s.h_p, s.d_p, count * seq_stride * sizeof(double), cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaMemcpyAsync(pin_res ? (void *) (j.results + begin) : (void *) s.h_res, s.d_res, count * sizeof(pb_pair_result), cudaMemcpyDeviceToHost, stream));
+		if (j.seq_nt)
+			CUDA_TRY(cudaMemcpyAsync(pin_nt ? (void *) (j.seq_nt + begin * nt_row) : (void *) s.h_nt, s.d_nt, count * nt_row, cudaMemcpyDeviceToHost, stream));
+		if (j.seq_p)
+			CUDA_TRY(cudaMemcpyAsync(pin_p ? (void *) (j.seq_p + begin * stride) : (void *) s.h_p, s.d_p, count * stride * sizeof(double), cudaMemcpyDeviceToHost, stream));
+		if (j.seq_code)
+			CUDA_TRY(cudaMemcpyAsync(pin_code ? (void *) (j.seq_code + begin * stride) : (void *) s.h_code, s.d_code, count * stride * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream));
 		CUDA_TRY(cudaEventRecord(s.done, stream));
 		pend[si].live = true;
 		pend[si].begin = begin;
 		pend[si].count = count;
 	}
 	for (int k = 0; k < PB_HOST_SLOTS; k++) {
-		st = drain(k);
+		pb_status st = drain(k);
 		if (st != PB_OK)
 			return st;
 	}
-	if (counters) {
+	return PB_OK;
+}
+
+static pb_status assemble_host_locked(pb_context *ctx, const pb_config *cfg, const HostJob &j) {
+	const bool aos = j.reads == nullptr;
+	if (!cfg || (!j.results && j.n) || (j.n && aos && (!j.f_data || !j.f_off || !j.r_data || !j.r_off)) || (j.n && !aos && !j.meta)
+	    || ((j.seq_nt || j.seq_p || j.seq_code) && (j.seq_stride % 16) != 0) || (j.seq_p && j.seq_code)) {
+		pb_set_error("pb_assemble_host: bad argument (seq_stride must be a multiple of 16; per-base log p as doubles or as codes, not both)");
+		return PB_ERR_ARGUMENT;
+	}
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	pb_status st = pb_upload_params(ctx, cfg);
+	if (st != PB_OK)
+		return st;
+	if (j.n == 0)
+		return PB_OK;
+	CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, PB_NCOUNTERS * sizeof(unsigned long long), ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));      /* parameters + zeroed counters visible to both streams */
+	st = assemble_host_chunks(ctx, cfg, j);
+	if (st != PB_OK) {
+		/* chunks queued before the failure may still be copying from / into the caller's buffers and the slots' staging:
+		 * nothing is left in flight when the call returns */
+		cudaStreamSynchronize(ctx->stream);
+		cudaStreamSynchronize(ctx->copy_stream);
+		return st;
+	}
+	if (j.counters) {
 		unsigned long long hc[PB_NCOUNTERS];
 		CUDA_TRY(cudaMemcpy(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost));
 		int64_t tmp[PB_NCOUNTERS];
 		for (int i = 0; i < PB_NCOUNTERS; i++)
 			tmp[i] = (int64_t) hc[i];
-		pb_counters_merge(counters, tmp);
+		pb_counters_merge(j.counters, tmp);
 	}
 	return PB_OK;
+}
+
+static pb_status assemble_host_entry(pb_context *ctx, const pb_config *cfg, const HostJob &j, const char *who) {
+	if (!ctx) {
+		pb_set_error("%s: no context", who);
+		return PB_ERR_ARGUMENT;
+	}
+	pthread_mutex_lock(&ctx->lock);
+	pb_status st = assemble_host_locked(ctx, cfg, j);
+	pthread_mutex_unlock(&ctx->lock);
+	return st;
 }
 
 extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, size_t n,
@@ -650,31 +734,68 @@ extern "C" pb_status pb_assemble_host(pb_context *ctx, const pb_config *cfg, siz
                                       const panda_qual *r_data, const uint64_t *r_off,
                                       pb_pair_result *results, uint8_t *seq_nt, double *seq_p,
                                       size_t seq_stride, int64_t *counters) {
-	if (!ctx) {
-		pb_set_error("pb_assemble_host: no context");
+	const HostJob j = { n, f_data, r_data, f_off, r_off, nullptr, nullptr, 0, results, seq_nt, seq_p, nullptr, seq_stride, counters };
+	return assemble_host_entry(ctx, cfg, j, "pb_assemble_host");
+}
+
+extern "C" pb_status pb_assemble_host_codes(pb_context *ctx, const pb_config *cfg, size_t n,
+                                            const panda_qual *f_data, const uint64_t *f_off,
+                                            const panda_qual *r_data, const uint64_t *r_off,
+                                            pb_pair_result *results, uint8_t *seq_nt, uint16_t *seq_code,
+                                            size_t seq_stride, int64_t *counters) {
+	const HostJob j = { n, f_data, r_data, f_off, r_off, nullptr, nullptr, 0, results, seq_nt, nullptr, seq_code, seq_stride, counters };
+	return assemble_host_entry(ctx, cfg, j, "pb_assemble_host_codes");
+}
+
+extern "C" pb_status pb_assemble_host_packed(pb_context *ctx, const pb_config *cfg, size_t n, int max_read_len,
+                                             const uint8_t *reads, const pb_pair_meta *meta,
+                                             pb_pair_result *results, uint8_t *seq_nt, size_t seq_stride, int64_t *counters) {
+	if (n && !reads) {
+		pb_set_error("pb_assemble_host_packed: no records");
 		return PB_ERR_ARGUMENT;
 	}
-	pthread_mutex_lock(&ctx->lock);
-	pb_status st = assemble_host_locked(ctx, cfg, n, f_data, f_off, r_data, r_off, results, seq_nt, seq_p, seq_stride, counters);
-	pthread_mutex_unlock(&ctx->lock);
+	const HostJob j = { n, nullptr, nullptr, nullptr, nullptr, reads, meta, max_read_len <= 0 ? PB_MAX_LEN : max_read_len,
+	                    results, seq_nt, nullptr, nullptr, seq_stride, counters };
+	return assemble_host_entry(ctx, cfg, j, "pb_assemble_host_packed");
+}
+
+/* Page-locked host memory for callers that have no CUDA runtime of their own (the panda_* object layer is plain C). */
+extern "C" void *pb_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void pb_host_free(void *p) {
+	if (p)
+		cudaFreeHost(p);
+}
+
+/* process-wide contexts for the panda_* object layer: one per GPU, made on first use.  The default one is the device
+ * PANDASEQ_B200_DEVICE names (0 if unset). */
+static pb_context *g_device_ctx[64];
+static pthread_mutex_t g_shared_lock = PTHREAD_MUTEX_INITIALIZER;
+
+extern "C" pb_status pb_device_context(int device, pb_context **out) {
+	pb_status st = PB_OK;
+	if (device < 0 || device >= 64) {
+		pb_set_error("device %d out of range", device);
+		return PB_ERR_ARGUMENT;
+	}
+	pthread_mutex_lock(&g_shared_lock);
+	if (!g_device_ctx[device])
+		st = pb_context_create(device, &g_device_ctx[device]);
+	*out = g_device_ctx[device];
+	pthread_mutex_unlock(&g_shared_lock);
 	return st;
 }
 
-/* process-wide default context for the panda_* object layer */
-static pb_context *g_shared = nullptr;
-static pthread_mutex_t g_shared_lock = PTHREAD_MUTEX_INITIALIZER;
-
 extern "C" pb_status pb_shared_context(pb_context **out) {
-	pb_status st = PB_OK;
-	pthread_mutex_lock(&g_shared_lock);
-	if (!g_shared) {
-		int dev = 0;
-		const char *env = getenv("PANDASEQ_B200_DEVICE");
-		if (env)
-			dev = atoi(env);
-		st = pb_context_create(dev, &g_shared);
-	}
-	*out = g_shared;
-	pthread_mutex_unlock(&g_shared_lock);
-	return st;
+	int dev = 0;
+	const char *env = getenv("PANDASEQ_B200_DEVICE");
+	if (env)
+		dev = atoi(env);
+	return pb_device_context(dev, out);
 }

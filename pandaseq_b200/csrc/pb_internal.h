@@ -79,6 +79,7 @@ int pb_algorithm_fill_config(PandaAlgorithm algo, pb_config *cfg);
 
 /* pb_device.cu */
 pb_status pb_shared_context(pb_context **out);
+pb_status pb_device_context(int device, pb_context **out);   /* the process-wide context of one GPU (panda_run_pool's workers) */
 
 #ifdef __cplusplus
 }

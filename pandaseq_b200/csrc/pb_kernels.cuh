@@ -560,6 +560,7 @@ struct ReconArgs {
 	int fo, df, dfp, fend, seq_len, unmasked_f, lead_r, out_cap;
 	uint8_t *out_nt;
 	double *out_p;
+	uint16_t *out_code;            /* instead of out_p: the per-base log p as its index into recon[2][48][48] (what the object layer ships to the host) */
 	const uint16_t *qoff;          /* [0..255]: clamp(q)*48*8, [256..511]: clamp(q)*8, indexed by the raw quality byte */
 };
 
@@ -622,6 +623,8 @@ __device__ __forceinline__ double recon_words(const ReconArgs &ra, const double 
 				qsum += p;
 				if (GENERAL && ra.out_p && t < nV && idx0 + t < ra.out_cap)
 					ra.out_p[idx0 + t] = p;
+				if (GENERAL && ra.out_code && t < nV && idx0 + t < ra.out_cap)
+					ra.out_code[idx0 + t] = (uint16_t) (off >> 3);
 			}
 		}
 	}
@@ -717,7 +720,7 @@ __device__ void process_pair(WarpSmem<ML> &ws, uint8_t *rec, int F, int R,
                              const double *__restrict__ s_recon, const double *__restrict__ s_over,
                              const double *__restrict__ s_score, const double *__restrict__ s_score_err,
                              const uint16_t *__restrict__ s_qoff, const uint8_t *__restrict__ s_primer, uint8_t *scratch,
-                             pb_pair_result &res, uint8_t *out_nt, double *out_p, int out_cap, int lane) {
+                             pb_pair_result &res, uint8_t *out_nt, double *out_p, uint16_t *out_code, int out_cap, int lane) {
 	using WS = WarpSmem<ML>;
 	PairView v;
 	const int fwb = ((F + 7) / 8) * 4, rwb = ((R + 7) / 8) * 4;
@@ -1011,13 +1014,14 @@ __device__ void process_pair(WarpSmem<ML> &ws, uint8_t *rec, int F, int R,
 		ReconArgs ra;
 		ra.fnt32 = v.fnt32; ra.rnt32 = v.rnt32; ra.fq = v.fq; ra.rq = v.rq;
 		ra.fo = fo; ra.df = df; ra.dfp = dfp; ra.fend = dfp + nover; ra.seq_len = seq_len;
-		ra.unmasked_f = unmasked_f; ra.lead_r = lead_r; ra.out_nt = out_nt; ra.out_p = out_p; ra.out_cap = out_cap; ra.qoff = s_qoff;
+		ra.unmasked_f = unmasked_f; ra.lead_r = lead_r; ra.out_nt = out_nt; ra.out_p = out_p; ra.out_code = out_code; ra.out_cap = out_cap; ra.qoff = s_qoff;
 		if (staged) {      /* the whole assembled sequence goes to this warp's scratch first */
 			ra.out_p = reinterpret_cast<double *>(scratch);
+			ra.out_code = nullptr;         /* the host asks for codes only when nothing is staged (pb_device.cu) */
 			ra.out_nt = scratch + 912 * 8;
 			ra.out_cap = 912;
 		}
-		if (cliff || anyDeg || ra.out_p != nullptr)
+		if (cliff || anyDeg || ra.out_p != nullptr || ra.out_code != nullptr)
 			qsum = recon_words<true>(ra, s_recon, mism, degen, lane);
 		else
 			qsum = recon_words<false>(ra, s_recon, mism, degen, lane);
@@ -1146,7 +1150,7 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
                 const uint8_t *__restrict__ reads, const pb_pair_meta *__restrict__ meta,
                 pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, double *__restrict__ seq_p,
                 long long seq_stride, unsigned long long *__restrict__ counters, uint8_t *__restrict__ scratch_all,
-                const int *__restrict__ list, const int *__restrict__ list_n) {
+                const int *__restrict__ list, const int *__restrict__ list_n, uint16_t *__restrict__ seq_code) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	using WS = WarpSmem<ML>;
 	/* list mode: assemble pairs list[0 .. *list_n) -- the ones the lane-per-pair kernel (pb_lanes.cuh) deferred */
@@ -1247,7 +1251,8 @@ assemble_kernel(const pb_device_params *__restrict__ prm, int n,
 		}
 		uint8_t *o_nt = seq_nt ? seq_nt + (size_t) pair * nt_row : nullptr;
 		double *o_p = seq_p ? seq_p + (size_t) pair * seq_stride : nullptr;
-		process_pair<ML, FULLF>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, s_qoff, s_primer, scratch, res, o_nt, o_p, (int) seq_stride, lane);
+		uint16_t *o_c = seq_code ? seq_code + (size_t) pair * seq_stride : nullptr;
+		process_pair<ML, FULLF>(ws, ws.stage[stage], m.flen, m.rlen, prm, s_recon, s_over, s_score, s_score_err, s_qoff, s_primer, scratch, res, o_nt, o_p, o_c, (int) seq_stride, lane);
 		if (lane == 0) {
 			uint4 *dst = reinterpret_cast<uint4 *>(&results[pair]);
 			dst[0] = ru.v[0];
@@ -1479,6 +1484,13 @@ __global__ void pack_kernel(int n, const uint8_t *__restrict__ f_data, const uns
 	const int used = fw + rw + fqb + rqb, total = (used + 15) & ~15;
 	for (int k = used + lane; k < total; k += 32)
 		rec[k] = 0;
+}
+
+/* records the caller packed into one buffer, shipped chunk by chunk: the chunk's offsets start at its first record */
+__global__ void rebase_meta_kernel(int n, pb_pair_meta *__restrict__ meta, unsigned base16) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+		meta[i].off16 -= base16;
 }
 
 }  // namespace pb

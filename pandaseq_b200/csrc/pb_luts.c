@@ -321,3 +321,46 @@ size_t pb_layout_host(size_t n, const uint64_t *f_off, const uint64_t *r_off, ui
 	}
 	return total16 * 16;
 }
+
+pb_status pb_posterior_table(const pb_config *cfg, double *table) {
+	pb_device_params *prm;
+	pb_status st;
+	if (cfg == NULL || table == NULL) {
+		pb_set_error("pb_posterior_table: bad argument");
+		return PB_ERR_ARGUMENT;
+	}
+	prm = malloc(sizeof *prm);
+	if (prm == NULL)
+		return PB_ERR_NOMEM;
+	st = pb_build_device_params(cfg, prm);
+	if (st == PB_OK)
+		memcpy(table, prm->recon, sizeof prm->recon);
+	free(prm);
+	return st;
+}
+
+/* The packed layout of include/pandaseq_b200.h written on the host: what pb::pack_kernel does on the device. */
+void pb_pack_host(size_t n, const panda_qual *f_data, const uint64_t *f_off, const panda_qual *r_data, const uint64_t *r_off,
+                  uint8_t *reads, pb_pair_meta *meta) {
+	size_t total16 = 0;
+	for (size_t i = 0; i < n; i++) {
+		const size_t F = (size_t) (f_off[i + 1] - f_off[i]), R = (size_t) (r_off[i + 1] - r_off[i]);
+		const panda_qual *f = f_data + f_off[i], *r = r_data + r_off[i];
+		const size_t fw = ((F + 7) / 8) * 4, rw = ((R + 7) / 8) * 4, fq = ((F + 3) / 4) * 4, bytes = pb_record_bytes(F, R);
+		uint8_t *rec = reads + total16 * 16;
+		memset(rec, 0, bytes);
+		for (size_t k = 0; k < F; k++) {
+			rec[k >> 1] |= (uint8_t) ((f[k].nt & 15) << ((k & 1) * 4));
+			rec[fw + rw + k] = (uint8_t) f[k].qual;
+		}
+		for (size_t k = 0; k < R; k++) {      /* template order */
+			const panda_qual *e = &r[R - 1 - k];
+			rec[fw + (k >> 1)] |= (uint8_t) ((e->nt & 15) << ((k & 1) * 4));
+			rec[fw + rw + fq + k] = (uint8_t) e->qual;
+		}
+		meta[i].off16 = (uint32_t) total16;
+		meta[i].flen = (uint16_t) F;
+		meta[i].rlen = (uint16_t) R;
+		total16 += bytes / 16;
+	}
+}

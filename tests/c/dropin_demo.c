@@ -1,8 +1,11 @@
 /* dropin_demo.c -- a plain C program written against the reference's API shape, compiled against
  * include/pandaseq_b200.h and linked with -lpandaseq_b200.  It is the loop of pool.c:71-108 (pull pairs from a
  * PandaNextSeq source, assemble, hand each result to an output callback, print the STAT block) with the GPU behind
- * panda_assembler_next().  Usage: dropin_demo <pairs.bin> <algo>; pairs.bin is the flat dump written by the test. */
+ * panda_assembler_next().  Usage: dropin_demo <pairs.bin> <algo> [threads]; pairs.bin is the flat dump written by the test.
+ * With threads > 1 panda_run_pool fans the work out over that many workers (one GPU each while there are GPUs), which call
+ * the output function concurrently, as the reference's pool does: the callback below takes a lock. */
 #include <pandaseq_b200.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -27,13 +30,17 @@ static bool next_pair(panda_seq_identifier *id, const panda_qual **f, size_t *fl
 	return true;
 }
 
+static pthread_mutex_t out_lock = PTHREAD_MUTEX_INITIALIZER;
+
 static bool print_fasta(const panda_result_seq *seq, void *user) {
 	static const char letters[] = "NACMGRSVTWYHKDBN";
 	FILE *out = user;
+	pthread_mutex_lock(&out_lock);
 	fprintf(out, ">pair%d;overlap=%zu;mismatches=%zu;q=%.6f\n", seq->name.x, seq->overlap, seq->overlap_mismatches, seq->quality);
 	for (size_t k = 0; k < seq->sequence_length; k++)
 		fputc(letters[seq->sequence[k].nt & 15], out);
 	fputc('\n', out);
+	pthread_mutex_unlock(&out_lock);
 	return true;
 }
 
@@ -82,7 +89,7 @@ int main(int argc, char **argv) {
 	panda_assembler_set_threshold(a, 0.6);
 	panda_assembler_set_minimum_overlap(a, 2);
 	b = panda_assembler_ref(a);     /* keep the counters readable after run_pool consumed its reference */
-	bool any = panda_run_pool(1, a, NULL, print_fasta, stdout, NULL);
+	bool any = panda_run_pool(argc > 3 ? atoi(argv[3]) : 1, a, NULL, print_fasta, stdout, NULL);
 	fprintf(stderr, "STAT\tREADS\t%ld\nSTAT\tNOALGN\t%ld\nSTAT\tLOWQ\t%ld\nSTAT\tBADR\t%ld\nSTAT\tSLOW\t%ld\nSTAT\tOK\t%ld\nSTAT\tLONGEST\t%zu\n",
 	        panda_assembler_get_count(b), panda_assembler_get_failed_alignment_count(b), panda_assembler_get_low_quality_count(b),
 	        panda_assembler_get_bad_read_count(b), panda_assembler_get_slow_count(b), panda_assembler_get_ok_count(b),

@@ -223,7 +223,7 @@ def test_c_program_against_the_header(L, tmp_path):
     exe = str(tmp_path / "dropin_demo")
     subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "dropin_demo.c"),
                     "-L", os.path.join(ROOT, "pandaseq_b200"), "-lpandaseq_b200", "-Wl,-rpath," + os.path.join(ROOT, "pandaseq_b200"),
-                    "-o", exe], check=True)
+                    "-lpthread", "-o", exe], check=True)
     b = datasets.cfg1(2500)
     path = str(tmp_path / "pairs.bin")
     with open(path, "wb") as f:
@@ -243,6 +243,73 @@ def test_c_program_against_the_header(L, tmp_path):
         for k, i in enumerate(ok[:200]):
             assert lines[2 * k].startswith(f">pair{i};overlap={want['overlap'][i]};")
             assert lines[2 * k + 1] == letters[want["seq_nt"][i, :want["seq_len"][i]]].tobytes().decode()
+
+
+def test_c_program_with_a_pool_of_workers(L, tmp_path):
+    """panda_run_pool(threads = 5): five workers, each on GPU (worker mod visible GPUs), pull batches of 300 pairs from the one
+    source and hand their results out concurrently.  The output order is unspecified (pandaseq.1:208); the set of records and
+    the merged STAT counters are the single-threaded run's."""
+    exe = str(tmp_path / "dropin_demo")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "dropin_demo.c"),
+                    "-L", os.path.join(ROOT, "pandaseq_b200"), "-lpandaseq_b200", "-Wl,-rpath," + os.path.join(ROOT, "pandaseq_b200"),
+                    "-lpthread", "-o", exe], check=True)
+    b = datasets.cfg1(4000)
+    path = str(tmp_path / "pairs.bin")
+    with open(path, "wb") as f:
+        f.write(np.array([b.n, len(b.f_data), len(b.r_data)], dtype=np.uint64).tobytes())
+        f.write(b.f_off.tobytes()); f.write(b.r_off.tobytes()); f.write(b.f_data.tobytes()); f.write(b.r_data.tobytes())
+    env = dict(os.environ, PANDASEQ_B200_NEXT_BATCH="300")
+    runs = {}
+    for threads in (1, 5):
+        run = subprocess.run([exe, path, "simple_bayesian", str(threads)], capture_output=True, text=True, env=env)
+        assert run.returncode == 0, run.stderr
+        lines = run.stdout.strip().split("\n")
+        recs = sorted(zip(lines[0::2], lines[1::2]), key=lambda t: int(t[0][5:t[0].index(";")]))
+        runs[threads] = (recs, [ln for ln in run.stderr.strip().split("\n") if ln.startswith("STAT")])
+    assert runs[1][0] == runs[5][0] and len(runs[1][0]) > 3900
+    assert runs[1][1] == runs[5][1]
+
+
+def test_a_call_between_two_next_calls_leaves_the_stream_alone(L, monkeypatch):
+    """assembler.c:350-383: panda_assembler_assemble() and panda_assembler_next() are independent.  next() works through a
+    prefetched batch here; a single-pair call in between uses its own staging and must not drop what is left of that batch."""
+    monkeypatch.setenv("PANDASEQ_B200_NEXT_BATCH", "128")
+    b = datasets.cfg1(300)
+    want = oracle_lib.assemble("port", pb.make_config("simple_bayesian"), b)
+    state = {"i": 0, "keep": []}
+
+    def nxt(idp, fp, flp, rp, rlp, _):
+        i = state["i"]
+        if i >= b.n:
+            return False
+        f, r = b.pair(i)
+        f, r = np.ascontiguousarray(f), np.ascontiguousarray(r)
+        state["keep"] = [f, r]
+        idp.contents.x = i
+        fp[0], flp[0], rp[0], rlp[0] = f.ctypes.data, len(f), r.ctypes.data, len(r)
+        state["i"] = i + 1
+        return True
+
+    cb = NEXT(nxt)
+    a = L.panda_assembler_new(C.cast(cb, C.c_void_p), None, None, None)
+    got, sid, extra = [], SeqId(), 0
+    ef, er = (np.ascontiguousarray(x) for x in b.pair(7))
+    while True:
+        res = L.panda_assembler_next(a)
+        if not res:
+            break
+        i = res.contents.name.x
+        got.append(i)
+        check_result(res, want, i)
+        if len(got) % 10 == 3:          # in the middle of a batch
+            one = L.panda_assembler_assemble(a, C.byref(sid), ef.ctypes.data, len(ef), er.ctypes.data, len(er))
+            assert bool(one) == (want["status"][7] == 0)
+            if one:
+                check_result(one, want, 7)
+            extra += 1
+    assert got == np.nonzero(want["status"] == 0)[0].tolist()
+    assert L.panda_assembler_get_count(a) == b.n + extra
+    L.panda_assembler_unref(a)
 
 
 # ---- modules with host callbacks (pandaseq-module.h, module.c:124-154) -------------------------------------------------

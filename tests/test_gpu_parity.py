@@ -254,3 +254,45 @@ def test_overhang_mixed_lengths_and_long_reads(ctx):
     for b in (datasets.mixed(1500), datasets.long250(600), datasets.primers300(400)):
         got, want, rep = run_both(ctx, pb.make_config("simple_bayesian", hang_forward=hf[:9], hang_reverse=hr[:9]), b)
         assert rep["ok"], rep
+
+
+# ---- the other host entry points: per-base log p as codes, caller-packed records -------------------------------------------
+@pytest.mark.parametrize("algo,kw", [("simple_bayesian", {}), ("pear", {}), ("rdp_mle", dict(forward_trim=7, reverse_trim=3)),
+                                     ("uparse", dict(minoverlap=10)), ("flash", {}), ("stitch", {})])
+def test_codes_expand_to_the_same_doubles(ctx, algo, kw):
+    """pb_assemble_host_codes + pb_posterior_table give bit for bit the per-base log p pb_assemble_host writes as doubles."""
+    for b in (datasets.cfg1(3000), datasets.stress(1500), datasets.edge_cases(), datasets.mixed(1500)):
+        cfg = pb.make_config(algo, **kw)
+        a = ctx.assemble_host(cfg, b, want_nt=True, want_p=True)
+        c = ctx.assemble_host_codes(cfg, b)
+        assert np.array_equal(a["results"].view(np.uint8), c["results"].view(np.uint8))
+        assert np.array_equal(a["seq_nt_packed"], c["seq_nt_packed"]) and np.array_equal(a["counters"], c["counters"])
+        ok = a["results"]["status"] == 0
+        mask = ok[:, None] & (np.arange(a["seq_stride"])[None, :] < a["results"]["seq_len"][:, None])
+        assert np.array_equal(a["seq_p"][mask].view(np.uint64), c["seq_p"][mask].view(np.uint64))
+        rep = compare(c, oracle_lib.assemble("port", cfg, b, seq_stride=c["seq_stride"]))
+        assert rep["ok"], rep
+
+
+def test_codes_refused_with_primers_after(ctx):
+    fwd, rev = datasets.primer_codes()
+    cfg = pb.make_config("simple_bayesian", forward_primer=fwd, reverse_primer=rev, post_primers=True)
+    with pytest.raises(pb.PandaseqError):
+        ctx.assemble_host_codes(cfg, datasets.primers300(50))
+
+
+@pytest.mark.parametrize("algo", ["simple_bayesian", "pear", "rdp_mle"])
+def test_packed_host_entry_point(ctx, algo):
+    """Records packed on the host (pb_pack_host) through pb_assemble_host_packed: the same bytes as the AoS entry point, over
+    several chunks of the host path (the chunk's offsets are rebased on the device)."""
+    for b in (datasets.cfg1(5000), datasets.mixed(3000), datasets.edge_cases()):
+        cfg = pb.make_config(algo)
+        a = ctx.assemble_host(cfg, b, want_nt=True, want_p=False)
+        reads, meta, max_len = pb.pack_host(b)
+        c = ctx.assemble_host_packed(cfg, reads, meta, max_len, seq_stride=a["seq_stride"])
+        assert np.array_equal(a["seq_nt_packed"], c["seq_nt_packed"]) and np.array_equal(a["counters"], c["counters"])
+        for k in a["results"].dtype.names:
+            if k in ("quality", "est_prob"):
+                assert np.array_equal(a["results"][k].view(np.uint64), c["results"][k].view(np.uint64)), k
+            else:
+                assert np.array_equal(a["results"][k], c["results"][k]), k
