@@ -311,7 +311,7 @@ def api_path(args):
     n = args.pairs if args.pairs is not None else 4_000_000
     rl = 150
     rows = {"ours": [], "reference": []}
-    tlist = sorted({1, 2, 4, 8, min(16, cores), cores})
+    tlist = sorted({1, 2, 4, 8, min(16, cores), min(32, cores)})
     for t in tlist:
         out = subprocess.run([ours, str(n), str(rl), str(t)], check=True, capture_output=True, text=True).stdout
         rows["ours"].append(json.loads(out.strip().split("\n")[-1]))

@@ -278,17 +278,52 @@ static bool host_check(PandaAssembler a, const panda_result_seq *res) {
 	return true;
 }
 
+/* Page-locked memory is expensive to get (tens of milliseconds for a stage of 64 K pairs), and panda_run_pool makes a clone
+ * with its own stage per worker and per call: stages that are given up go to a small process-wide free list and are handed
+ * to the next assembler that needs one. */
+#define STAGE_POOL 64
+static struct pb_stage stage_pool[STAGE_POOL];
+static int stage_pool_n;
+static pthread_mutex_t stage_pool_lock = PTHREAD_MUTEX_INITIALIZER;
+
 static void stage_free(struct pb_stage *st) {
-	free(st->ids);
-	pb_host_free(st->f_data);
-	pb_host_free(st->r_data);
-	pb_host_free(st->f_off);
-	pb_host_free(st->r_off);
-	pb_host_free(st->res);
-	pb_host_free(st->nt);
-	pb_host_free(st->code);
-	pb_host_free(st->p);
+	bool kept = false;
+	if (st->cap_pairs == 0 && st->ids == NULL)
+		return;
+	pthread_mutex_lock(&stage_pool_lock);
+	if (stage_pool_n < STAGE_POOL) {
+		stage_pool[stage_pool_n++] = *st;
+		kept = true;
+	}
+	pthread_mutex_unlock(&stage_pool_lock);
+	if (!kept) {
+		free(st->ids);
+		pb_host_free(st->f_data);
+		pb_host_free(st->r_data);
+		pb_host_free(st->f_off);
+		pb_host_free(st->r_off);
+		pb_host_free(st->res);
+		pb_host_free(st->nt);
+		pb_host_free(st->code);
+		pb_host_free(st->p);
+	}
 	memset(st, 0, sizeof *st);
+}
+
+/* an empty stage takes over the largest pooled one, if there is any */
+static void stage_adopt(struct pb_stage *st) {
+	if (st->cap_pairs != 0 || st->ids != NULL)
+		return;
+	pthread_mutex_lock(&stage_pool_lock);
+	int best = -1;
+	for (int k = 0; k < stage_pool_n; k++)
+		if (best < 0 || stage_pool[k].cap_pairs > stage_pool[best].cap_pairs)
+			best = k;
+	if (best >= 0) {
+		*st = stage_pool[best];
+		stage_pool[best] = stage_pool[--stage_pool_n];
+	}
+	pthread_mutex_unlock(&stage_pool_lock);
 }
 
 PandaAssembler panda_assembler_ref(PandaAssembler a) {
@@ -687,6 +722,7 @@ static const panda_result_seq *stage_next_result(PandaAssembler a, struct pb_sta
 /* Pull up to `limit` pairs from `src`'s source into `st` (pre-checks run here, against `a`'s modules and counters).
  * Returns false when staging failed; *dry is set when the source ended. */
 static bool stage_fill(PandaAssembler a, PandaAssembler src, struct pb_stage *st, size_t limit, bool *dry) {
+	stage_adopt(st);
 	stage_begin(st);
 	if (!reserve(st, limit, limit * 160, limit * 160, 0, 0, 0))
 		return false;

@@ -291,8 +291,10 @@ def test_packed_host_entry_point(ctx, algo):
         reads, meta, max_len = pb.pack_host(b)
         c = ctx.assemble_host_packed(cfg, reads, meta, max_len, seq_stride=a["seq_stride"])
         assert np.array_equal(a["seq_nt_packed"], c["seq_nt_packed"]) and np.array_equal(a["counters"], c["counters"])
+        # (the AoS entry point picks the kernel class by the longest read of each chunk, the packed one by the caller's
+        # max_read_len: a chunk may run on another kernel, whose sums add the same terms in another order)
         for k in a["results"].dtype.names:
             if k in ("quality", "est_prob"):
-                assert np.array_equal(a["results"][k].view(np.uint64), c["results"][k].view(np.uint64)), k
+                assert np.abs(a["results"][k] - c["results"][k]).max() <= 1e-9, k
             else:
                 assert np.array_equal(a["results"][k], c["results"][k]), k
