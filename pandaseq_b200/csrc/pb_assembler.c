@@ -867,7 +867,15 @@ bool panda_run_pool(int threads, PandaAssembler assembler, PandaMux mux, PandaOu
 				break;
 			panda_assembler_copy_configuration(c, assembler);
 			c->ctx = ctx;
-			c->next_batch = assembler->next_batch;
+			c->next_batch = assembler->next_batch > 32768 ? 32768 : assembler->next_batch;
+			/* the worker's stage is set up here, before any worker runs: page-locked allocations made while other threads
+			 * copy and launch stall them all (and a stage a previous run_pool gave up is simply taken over) */
+			stage_adopt(&c->stream);
+			if (reserve(&c->stream, c->next_batch, c->next_batch * 160, c->next_batch * 160, 0, 0, 0)) {
+				grow_pinned((void **) &c->stream.res, &c->stream.cap_res, c->next_batch, sizeof(pb_pair_result), 0);
+				grow_pinned((void **) &c->stream.nt, &c->stream.cap_nt, c->next_batch * 160, 1, 0);
+				grow_pinned((void **) &c->stream.code, &c->stream.cap_code, c->next_batch * 320, sizeof(uint16_t), 0);
+			}
 			c->noalgn = assembler->noalgn;		/* called from the worker's thread, as the reference's clones do; not owned */
 			c->noalgn_data = assembler->noalgn_data;
 			c->noalgn_destroy = NULL;

@@ -173,7 +173,7 @@ int main(int argc, char **argv) {
 		struct sink ws;
 		memset(&ws, 0, sizeof ws);
 		pthread_mutex_init(&ws.lock, NULL);
-		warm.n = src.n < 200000 ? src.n : 200000;
+		warm.n = src.n < 400000 ? src.n : 400000;
 		panda_run_pool(threads, w, NULL, count_output, &ws, NULL);
 	}
 	t0 = now();
