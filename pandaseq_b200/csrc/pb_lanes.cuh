@@ -265,8 +265,22 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 			}
 			if ((long long) examined == (long long) maxov - mo + 1)    /* assembler.c:135-137 */
 				slow = 1;
-			if (!defer && bestov < 0)
+			if (!defer && bestov < 0) {
 				status = PB_PAIR_NOALGN;
+				if (algo == PB_PEAR) {
+					/* pear's scores above came from the low six bits of the raw qualities; a read with a quality outside 0..46
+					 * (PHREDCLAMP, prob.h:23) may have lost its overlap to that, and only the merge below checks the range.
+					 * Rare (no alignment): look at every quality of the pair before the verdict stands. */
+					unsigned qb = 0;
+					const int nq = ((F + 3) >> 2) + ((R + 3) >> 2);
+					for (int w = 0; w < nq; w++) {
+						const unsigned q4 = fq32[w];
+						qb |= ((q4 & 0x7F7F7F7Fu) + 0x51515151u) | q4;
+					}
+					if (qb & 0x80808080u)
+						defer = true;
+				}
+			}
 		}
 		if (act && !defer && status == PB_PAIR_OK) {
 			/* ---- K6: reconstruction (assembler.c:145-250) with forward_offset = reverse_offset = 0 ---- */

@@ -173,3 +173,94 @@ def test_two_paths_agree_on_decorated_reads(built, algo, kw):
     else:
         assert np.array_equal(a["est_prob"].view(np.uint64), b["est_prob"].view(np.uint64))
     assert np.abs(a["quality"] - b["quality"]).max() <= 1e-12
+
+
+# ---- BASELINE configs 3, 4 and 5 at 4 M pairs ---------------------------------------------------------------------------------------
+N345 = 4_000_000
+
+
+def _config_batch(ctx, cfg_id, n):
+    """n pairs of a BASELINE config packed on the device, two of the 1 M-pair chunks kept on the host for the oracle sample"""
+    import torch
+    from pandaseq_b200 import synth
+    parts_r, parts_m, flats, base16, max_len = [], [], [], 0, 0
+    for ci in range(n // CHUNK):
+        rect = synth.generate_config(cfg_id, n=CHUNK, device="cuda", chunk_index=ci)
+        f_data, f_off, r_data, r_off = rect.to_flat_tensors()
+        reads, meta, ml, total = ctx.pack_device(f_data, f_off, r_data, r_off)
+        meta[:, 0] += base16
+        base16 += total // 16
+        max_len = max(max_len, ml)
+        parts_r.append(reads[:total])
+        parts_m.append(meta)
+        if ci in (0, n // CHUNK - 1):
+            flats.append((ci, synth.FlatBatch(f_data.cpu().numpy(), f_off.cpu().numpy().astype(np.uint64),
+                                              r_data.cpu().numpy(), r_off.cpu().numpy().astype(np.uint64))))
+    reads = torch.cat(parts_r + [torch.zeros(16, dtype=torch.uint8, device="cuda")])
+    return reads, torch.cat(parts_m), max_len, flats
+
+
+def _config_of(cfg_id):
+    from pandaseq_b200 import synth
+    c = synth.CONFIGS[cfg_id]
+    kw = {}
+    if c.get("primers"):
+        kw = dict(forward_primer=synth.encode(synth.FWD_PRIMER),
+                  reverse_primer=synth.encode("".join(synth._COMP[ch] for ch in synth.REV_PRIMER)))
+    return pb.make_config(c["algo"], **kw)
+
+
+@pytest.mark.parametrize("cfg_id", [3, 4, 5])
+def test_configs_3_4_5_at_4m_pairs(built, cfg_id):
+    """4 M pairs of BASELINE config 3 (2x250, pear), 4 (2x300, rdp_mle, both primers stripped) and 5 (2x(75-300) mixed lengths):
+    counter identities, determinism, every available kernel path giving the same records (no status / overlap / base differs,
+    i.e. no near-tie flips an arg-max or the threshold test between paths), and exact parity with the oracle on 10 k sampled pairs
+    (status, overlap, offsets, mismatches, every merged base; quality and overlap score within 1e-6)."""
+    import torch
+    ctx = pb.Context(0)
+    cfg = _config_of(cfg_id)
+    reads, meta, max_len, flats = _config_batch(ctx, cfg_id, N345)
+    stride = (2 * max_len + 15) & ~15
+
+    def go():
+        res = torch.zeros((N345, 32), dtype=torch.uint8, device="cuda")
+        nt = torch.zeros((N345, stride // 2), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(pb.PB_NCOUNTERS, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        before = ctx.lanes_stats()
+        ctx.assemble_device(cfg, N345, max_len, reads, meta, res, nt, None, stride, cnt)
+        ctx.synchronize()
+        return res, nt, cnt.cpu().numpy(), ctx.lanes_stats()[0] - before[0]
+
+    res, nt, cnt, on_lanes = go()
+    assert cnt[pb.C_COUNT] == N345
+    assert cnt[pb.C_OK] + cnt[pb.C_LOWQ] + cnt[pb.C_NOALGN] + cnt[pb.C_BADR] + cnt[pb.C_NOFP] + cnt[pb.C_NORP] == N345
+    assert cnt[pb.C_OVERLAPS:].sum() == cnt[pb.C_OK] and cnt[pb.C_OK] > 0.9 * N345
+    r = res.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel()
+    ok = r["status"] == 0
+    assert int(ok.sum()) == cnt[pb.C_OK] and int(r["slow"].sum()) == cnt[pb.C_SLOW]
+    assert np.array_equal(np.bincount(r["overlap"][ok], minlength=900)[:900], cnt[pb.C_OVERLAPS:pb.C_OVERLAPS + 900])
+    res2, nt2, cnt2, _ = go()
+    assert digest(res, nt) == digest(res2, nt2) and np.array_equal(cnt, cnt2)
+    # the other kernel paths on the same pairs: the general kernel alone, and (where the two-kernel path ran) the hash-join seeding
+    for mode in ((0, 2) if on_lanes else ()):
+        ctx.set_lanes(mode)
+        res_x, nt_x, cnt_x, _ = go()
+        ctx.set_lanes(-1)
+        assert np.array_equal(cnt, cnt_x), mode
+        assert torch.equal(nt, nt_x), mode
+        x = res_x.cpu().numpy().view(pb.PAIR_RESULT_DTYPE).ravel()
+        for k in ("status", "slow", "overlap", "seq_len", "mismatches", "degenerates", "examined", "fwd_offset", "rev_offset"):
+            assert np.array_equal(r[k], x[k]), (mode, k)
+        assert np.abs(r["quality"] - x["quality"]).max() <= 1e-9 and np.abs(r["est_prob"][ok] - x["est_prob"][ok]).max() <= 1e-9, mode
+    rng = np.random.default_rng(cfg_id)
+    ntc = nt.cpu().numpy()
+    for ci, flat in flats:
+        idx = np.sort(rng.choice(CHUNK, 5_000, replace=False))
+        sub = pb.synth.FlatBatch.from_pairs([(flat.pair(i)[0][:, 0], flat.pair(i)[0][:, 1], flat.pair(i)[1][:, 0], flat.pair(i)[1][:, 1]) for i in idx])
+        want = oracle_lib.assemble("port", cfg, sub)
+        g = ci * CHUNK + idx
+        got = dict(results=r[g], seq_nt=pb.unpack_nt(ntc[g]), seq_p=None, counters=None)
+        rep = compare(got, want, check_counters=False)
+        assert rep["ok"], (cfg_id, rep)
+    ctx.close()

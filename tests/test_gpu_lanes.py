@@ -194,6 +194,27 @@ def test_pear_on_the_lane_kernel(ctx):
     assert rep["deferred"] > 300, rep
 
 
+def test_pear_with_qualities_above_the_clamp(ctx):
+    # qualities above 46 (PHREDCLAMP, prob.h:23): the lane kernel scores pear's candidates from the low six bits of the raw byte, so
+    # a verdict reached that way (NOALGN included) must not stand -- the pair has to reach the general kernel, which clamps
+    rng = np.random.default_rng(19)
+    pairs = []
+    for i in range(6000):
+        F, R = int(rng.integers(90, 151)), int(rng.integers(60, 91))
+        L = int(rng.integers(F, F + R - 20))
+        t = rng.integers(0, 4, size=L)
+        f, r = t[:F].copy(), t[::-1][:R].copy()
+        # heavy damage in the overlap so that many pairs sit near the no-alignment verdict
+        hit = rng.random(R) < rng.choice([0.0, 0.3, 0.5, 0.7])
+        r[hit] = (r[hit] + rng.integers(1, 4, size=int(hit.sum()))) % 4
+        hi = 94 if i % 3 else 64
+        pairs.append((1 << f, rng.integers(30, hi, size=F), 1 << r, rng.integers(30, hi, size=R)))
+    b = synth.FlatBatch.from_pairs(pairs)
+    got, want, rep = run_lanes(ctx, pb.make_config("pear", minoverlap=8), b)
+    assert rep["ok"], rep
+    assert int((want["status"] == 4).sum()) > 50 and int((want["status"] == 0).sum()) > 500, np.bincount(want["status"])
+
+
 def test_mixed_lengths_up_to_256_nt(ctx):
     b = synth.generate(5000, rl=(75, 256), tmpl=None, seed=15, mixed=True, n_rate=0.0005, btail_rate=0.05).to_flat()
     for algo in ("simple_bayesian", "pear"):
