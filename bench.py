@@ -95,6 +95,36 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_near_gpu(local):
+    """Run this rank on the host cores next to its GPU (sysfs: the PCI device's local_cpulist / numa_node), so that the page-locked
+    buffers it allocates afterwards land in that socket's memory and the copies do not cross the socket link.  Done before the
+    CUDA context and every pinned allocation; silently a no-op where the container's cpuset leaves no choice."""
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        dev = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{dev}"
+        info["numa_node"] = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        near = cpus & allowed
+        info["cpus"] = len(near)
+        info["allowed_cpus"] = len(allowed)
+        if near and near != allowed:
+            os.sched_setaffinity(0, near)
+            info["bound"] = True
+    except Exception as e:          # no sysfs entry, no permission: run unbound
+        info["error"] = str(e)[:80]
+    return info
+
+
 def workload(cfg_id):
     from pandaseq_b200 import synth
     c = synth.CONFIGS[cfg_id]
@@ -351,6 +381,7 @@ def copy_path(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    affinity = bind_near_gpu(local) if os.environ.get("PANDASEQ_B200_NOBIND") is None else {"bound": False}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -392,7 +423,7 @@ def copy_path(args):
         line = {"metric": "pinned host <-> device copies of the host path's chunk sizes (no kernels)", "value": res["both"]["mpairs_per_s_all_gpus"],
                 "unit": "Mpairs/s equivalent", "n_gpus": world, "steps": args.steps, "warmup": 1, "higher_is_better": True, "scaling": "weak",
                 "config": {"workload": f"{pairs} pairs per chunk: {h2d_b} B in (620 B per pair), {d2h_b} B out (184 B per pair), 2 streams per GPU"},
-                "modes": res}
+                "modes": res, "host_affinity_rank0": affinity}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -434,6 +465,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    affinity = bind_near_gpu(local) if os.environ.get("PANDASEQ_B200_NOBIND") is None else {"bound": False}
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -680,6 +712,7 @@ def main():
                          "peak_source": peak_src, "algorithmic_bytes_per_pair": alg_bytes / n,
                          "kernel": kernel_name, "kernel_ms": kern_ms, "kernels": kernels},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks, "stat": stat,
+            "host_affinity": affinity,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -616,9 +616,18 @@ static const panda_result_seq *publish(PandaAssembler a, const struct pb_stage *
 	if (st->has_codes) {
 		const uint16_t *code = st->code + i * st->stride;
 		const double *table = a->ptable;
-		for (size_t k = 0; k < len; k++) {
-			a->result_seq[k].nt = (panda_nt) ((nt[k >> 1] >> ((k & 1) * 4)) & 0x0F);
-			a->result_seq[k].p = table[code[k] < PB_POSTERIOR_CODES ? code[k] : 0];
+		panda_result *seq = a->result_seq;
+		size_t k = 0;
+		for (; k + 2 <= len; k += 2) {		/* two bases per packed byte */
+			const unsigned b = nt[k >> 1], c0 = code[k], c1 = code[k + 1];
+			seq[k].nt = (panda_nt) (b & 0x0F);
+			seq[k].p = table[c0 < PB_POSTERIOR_CODES ? c0 : 0];
+			seq[k + 1].nt = (panda_nt) (b >> 4);
+			seq[k + 1].p = table[c1 < PB_POSTERIOR_CODES ? c1 : 0];
+		}
+		if (k < len) {
+			seq[k].nt = (panda_nt) (nt[k >> 1] & 0x0F);
+			seq[k].p = table[code[k] < PB_POSTERIOR_CODES ? code[k] : 0];
 		}
 	} else {
 		const double *p = st->p + i * st->stride;
@@ -788,6 +797,7 @@ struct pool_worker {
 	struct pool_shared *shared;
 	PandaAssembler self;
 	pthread_t tid;
+	int device;	/* -1: one GPU, the workers run wherever the scheduler puts them */
 };
 
 static void *pool_work(void *arg) {
@@ -795,6 +805,8 @@ static void *pool_work(void *arg) {
 	struct pool_shared *sh = w->shared;
 	PandaAssembler a = w->self;
 	struct pb_stage *st = &a->stream;
+	if (w->device >= 0)
+		pb_bind_thread_near_device(w->device);	/* only with several GPUs: a worker stays on the socket of its own */
 	for (;;) {
 		bool ok, dry = false;
 		pthread_mutex_lock(&sh->source_mutex);
@@ -881,6 +893,7 @@ bool panda_run_pool(int threads, PandaAssembler assembler, PandaMux mux, PandaOu
 			c->noalgn_destroy = NULL;
 			workers[k].shared = &sh;
 			workers[k].self = c;
+			workers[k].device = devices > 1 ? k % devices : -1;
 			if (pthread_create(&workers[k].tid, NULL, pool_work, &workers[k]) != 0) {
 				panda_assembler_unref(c);
 				break;

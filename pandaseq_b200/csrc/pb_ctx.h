@@ -21,12 +21,14 @@ struct pb_context {
 	unsigned long long *d_counters;  /* scratch counters for the host path */
 	uint8_t *d_scratch;              /* per-warp scratch of the primers-after path, allocated on first use */
 	size_t scratch_bytes;
-	/* deferral lists of the lane-per-pair kernel, one per stream of the host path: [0] = count, [4 ..] = pair indices */
+	/* deferral lists of the lane-per-pair kernel, one per stream of the host path: [0] = count, [1 .. 3] = pairs per length class, [8 ..] = pair indices */
 	int *d_defer[2];
 	size_t defer_cap[2];
 	uint32_t *d_seeds[2];            /* candidate-overlap masks of pb::seed_kernel, 8 words per pair */
 	int *d_order[2];                 /* the pairs of a launch bin by bin (pb::bin_order_kernel) */
-	unsigned *d_bins[2];             /* 2 x PB_SEED_BINS: pairs per bin, cursors */
+	unsigned *d_bins[2];             /* per length class: 2 x PB_SEED_BINS (pairs per bin, cursors) + the kernels' batch counters */
+	int *d_classes[2];               /* the pairs of a batch listed by length class (pb::class_list_kernel); allocated on first use */
+	bool classes_on[2];
 	double *d_pear_cdf;              /* pear_test table (PB_PEAR_ROWS x PB_PEAR_COLS), built on first use */
 	unsigned long long *d_defer_total;   /* pairs deferred so far (device), next to lanes_pairs (host) */
 	unsigned long long lanes_pairs;

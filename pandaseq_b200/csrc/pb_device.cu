@@ -6,6 +6,8 @@
  * the host only lays out offsets and moves bytes.
  */
 #include <cuda_runtime.h>
+#include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -94,6 +96,8 @@ extern "C" void pb_context_destroy(pb_context *ctx) {
 	cudaFree(ctx->d_seeds[1]);
 	cudaFree(ctx->d_order[0]);
 	cudaFree(ctx->d_order[1]);
+	cudaFree(ctx->d_classes[0]);
+	cudaFree(ctx->d_classes[1]);
 	cudaFree(ctx->d_bins[0]);
 	cudaFree(ctx->d_bins[1]);
 	cudaFree(ctx->d_defer_total);
@@ -197,86 +201,197 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 	return PB_OK;
 }
 
-/* The two-kernel path for the common configurations: pb::seed_kernel (warp per pair, K1-K3) leaves the candidate
- * overlaps of every pair, pbl::assemble_lanes_kernel (lane per pair, K4-K6) scores and merges, and the general kernel
- * assembles the pairs those two handed on. */
-template <int ML, int LML, int SW, int LW, int GW, int XW>
-static pb_status launch_lanes(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta,
-                              pb_pair_result *d_results, uint8_t *d_seq_nt, size_t seq_stride,
-                              unsigned long long *d_counters, cudaStream_t stream, bool sweep) {
-	auto seedk = pb::seed_kernel<ML, SW>;
-	auto sweepk = pbs::sweep_seed_kernel<ML / 32, XW>;      /* the same seeds by the diagonal sweep, one lane per pair (pb_sweep.cuh) */
-	constexpr size_t sweep_smem = pbs::sweep_smem_bytes<ML / 32, XW>();
-	static_assert(ML % 32 == 0 && sweep_smem <= 227 * 1024, "per-CTA shared memory");
-	auto kern = pbl::assemble_lanes_kernel<LML, LW>;      /* LML <= ML: the length class that sizes the lane kernel's record slots */
-	constexpr size_t seed_smem = sizeof(pb::WarpSmem<ML>) * SW;
-	static_assert(seed_smem <= 227 * 1024 && pbl::lanes_smem_bytes<LML, LW>() <= 227 * 1024, "per-CTA shared memory");
-	constexpr size_t smem = pbl::lanes_smem_bytes<LML, LW>();
-	static bool configured[16] = { false };
-	if (!configured[ctx->device & 15]) {
-		CUDA_TRY(cudaFuncSetAttribute(seedk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) seed_smem));
-		CUDA_TRY(cudaFuncSetAttribute(sweepk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
-		CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		configured[ctx->device & 15] = true;
-	}
-	const int si = stream == ctx->copy_stream ? 1 : 0;
-	if ((size_t) n + 4 > ctx->defer_cap[si]) {
+/* The two-kernel path for the common configurations: the seeding kernel (pbs::sweep_seed_kernel, one lane per pair; or
+ * pb::seed_kernel, the hash join, one warp per pair) leaves the candidate overlaps of every pair, pbl::assemble_lanes_kernel
+ * (lane per pair, K4-K6) scores and merges, and the general kernel assembles the pairs those two handed on.  A batch whose
+ * reads are all <= 160 nt runs as one class in batch order; longer or mixed batches are first listed by length class
+ * (pb::class_list_kernel) and every class runs the kernels sized for it. */
+constexpr int PB_BINS_STRIDE = 2 * pb::PB_SEED_BINS + 4;      /* pairs per bin, cursors, the two kernels' batch counters */
+struct LanesState {
+	pb_context *ctx;
+	int n, si;
+	const uint8_t *d_reads;
+	const pb_pair_meta *d_meta;
+	pb_pair_result *d_results;
+	uint8_t *d_seq_nt;
+	size_t seq_stride;
+	unsigned long long *d_counters;
+	cudaStream_t stream;
+	int *d_count, *d_list;          /* the general kernel's list: count, entries */
+	uint32_t *d_seeds;
+	size_t cap;
+	uint32_t *seeds(int c) const { return c == 0 && ctx->classes_on[si] ? d_seeds + cap * pb::seed_words(320) : d_seeds; }
+	int *class_list(int c) const { return ctx->d_classes[si] + (size_t) c * cap; }
+	int *class_count(int c) const { return ctx->d_defer[si] + 1 + c; }
+	int *order(int c) const { return ctx->d_order[si] + (size_t) c * cap; }
+	unsigned *bins(int c) const { return ctx->d_bins[si] + (size_t) c * PB_BINS_STRIDE; }
+};
+
+static pb_status lanes_prepare(LanesState &L, bool classes) {
+	pb_context *ctx = L.ctx;
+	const int si = L.si;
+	const size_t n = (size_t) L.n;
+	const bool grow = n + 4 > ctx->defer_cap[si], need_lists = classes && !ctx->classes_on[si];
+	if (grow || need_lists) {
+		const size_t cap = grow ? n + n / 4 + 64 : ctx->defer_cap[si];
+		const bool lists = classes || ctx->classes_on[si];
 		CUDA_TRY(cudaDeviceSynchronize());
 		cudaFree(ctx->d_defer[si]);
 		cudaFree(ctx->d_seeds[si]);
 		cudaFree(ctx->d_order[si]);
+		cudaFree(ctx->d_classes[si]);
 		ctx->d_defer[si] = nullptr;
 		ctx->d_seeds[si] = nullptr;
 		ctx->d_order[si] = nullptr;
+		ctx->d_classes[si] = nullptr;
 		ctx->defer_cap[si] = 0;
-		const size_t cap = (size_t) n + (size_t) n / 4 + 64;
-		CUDA_TRY(cudaMalloc(&ctx->d_defer[si], cap * sizeof(int)));
-		CUDA_TRY(cudaMalloc(&ctx->d_seeds[si], cap * pb::seed_words(256) * sizeof(uint32_t)));      /* sized for the widest record */
-		CUDA_TRY(cudaMalloc(&ctx->d_order[si], cap * sizeof(int)));
+		ctx->classes_on[si] = false;
+		CUDA_TRY(cudaMalloc(&ctx->d_defer[si], (cap + 8) * sizeof(int)));
+		/* sized for the widest record; by length class, the 160-nt class (8-word records) has its own region behind the one the two
+		 * longer classes (12-word records) share: every class indexes by pair, and all classes are seeded before any is assembled */
+		CUDA_TRY(cudaMalloc(&ctx->d_seeds[si], cap * (pb::seed_words(320) + (lists ? pb::seed_words(160) : 0)) * sizeof(uint32_t)));
+		CUDA_TRY(cudaMalloc(&ctx->d_order[si], (lists ? pb::PB_LEN_CLASSES : 1) * cap * sizeof(int)));
+		if (lists)
+			CUDA_TRY(cudaMalloc(&ctx->d_classes[si], pb::PB_LEN_CLASSES * cap * sizeof(int)));
 		if (!ctx->d_bins[si])
-			CUDA_TRY(cudaMalloc(&ctx->d_bins[si], (2 * pb::PB_SEED_BINS + 4) * sizeof(unsigned)));      /* + the kernels' batch counters */
+			CUDA_TRY(cudaMalloc(&ctx->d_bins[si], pb::PB_LEN_CLASSES * PB_BINS_STRIDE * sizeof(unsigned)));      /* bins + the kernels' batch counters, per class */
+		ctx->classes_on[si] = lists;
 		ctx->defer_cap[si] = cap;
 	}
-	int *d_count = ctx->d_defer[si], *d_list = ctx->d_defer[si] + 4;
-	uint32_t *d_seeds = ctx->d_seeds[si];
-	CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
-	CUDA_TRY(cudaMemsetAsync(ctx->d_bins[si], 0, (2 * pb::PB_SEED_BINS + 4) * sizeof(unsigned), stream));
-	const bool timed = ctx->timing && stream == ctx->stream;
-	if (timed)
-		CUDA_TRY(cudaEventRecord(ctx->tev[0], stream));
-	{
-		if (sweep) {
-			long long grid = (((long long) n + 31) / 32 + XW - 1) / XW;
-			if (grid > ctx->sm_count)
-				grid = ctx->sm_count;
-			const pbs::Muls mu = { 2u, 4u, 16u };      /* run-time values on purpose: pb_sweep.cuh */
-			sweepk<<<(unsigned) (grid < 1 ? 1 : grid), XW * 32, sweep_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si], ctx->d_bins[si] + 2 * pb::PB_SEED_BINS, mu);
-		} else {
+	L.cap = ctx->defer_cap[si];
+	L.d_count = ctx->d_defer[si];          /* [0] the general kernel's list length, [1 ..] the class lists' lengths, [8 ..] the general kernel's list */
+	L.d_list = ctx->d_defer[si] + 8;
+	L.d_seeds = ctx->d_seeds[si];
+	CUDA_TRY(cudaMemsetAsync(L.d_count, 0, 8 * sizeof(int), L.stream));
+	CUDA_TRY(cudaMemsetAsync(ctx->d_bins[si], 0, pb::PB_LEN_CLASSES * PB_BINS_STRIDE * sizeof(unsigned), L.stream));
+	return PB_OK;
+}
+
+/* seeding + bin list of one class (c < 0: the whole batch in batch order) */
+template <int ML, int SW, int XW>
+static pb_status lanes_seed(const LanesState &L, int c, bool sweep) {
+	pb_context *ctx = L.ctx;
+	const int cc = c < 0 ? 0 : c;
+	const int *list = c < 0 ? nullptr : L.class_list(c), *list_n = c < 0 ? nullptr : L.class_count(c);
+	const int n = L.n;
+	static bool configured[16] = { false }, configured_join[16] = { false };
+	if (sweep) {
+		auto sweepk = pbs::sweep_seed_kernel<ML / 32, XW>;      /* the diagonal sweep, one lane per pair (pb_sweep.cuh) */
+		constexpr size_t sweep_smem = pbs::sweep_smem_bytes<ML / 32, XW>();
+		static_assert(ML % 32 == 0 && sweep_smem <= 227 * 1024, "per-CTA shared memory");
+		if (!configured[ctx->device & 15]) {
+			CUDA_TRY(cudaFuncSetAttribute(sweepk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
+			configured[ctx->device & 15] = true;
+		}
+		long long grid = (((long long) n + 31) / 32 + XW - 1) / XW;
+		if (grid > ctx->sm_count)
+			grid = ctx->sm_count;
+		const pbs::Muls mu = { 2u, 4u, 16u };      /* run-time values on purpose: pb_sweep.cuh */
+		sweepk<<<(unsigned) (grid < 1 ? 1 : grid), XW * 32, sweep_smem, L.stream>>>(ctx->d_params, n, L.d_reads, L.d_meta, L.seeds(c), L.bins(cc),
+		                                                                          L.bins(cc) + 2 * pb::PB_SEED_BINS, mu, list, list_n);
+	} else {
+		if constexpr (SW > 0) {
+			auto seedk = pb::seed_kernel<ML, SW>;               /* the hash join, one warp per pair: whole batches only */
+			constexpr size_t seed_smem = sizeof(pb::WarpSmem<ML>) * SW;
+			static_assert(seed_smem <= 227 * 1024, "per-CTA shared memory");
+			if (!configured_join[ctx->device & 15]) {
+				CUDA_TRY(cudaFuncSetAttribute(seedk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) seed_smem));
+				configured_join[ctx->device & 15] = true;
+			}
 			long long grid = ((long long) n + SW - 1) / SW;
 			if (grid > ctx->sm_count)
 				grid = ctx->sm_count;
-			seedk<<<(unsigned) (grid < 1 ? 1 : grid), SW * 32, seed_smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_bins[si]);
+			seedk<<<(unsigned) (grid < 1 ? 1 : grid), SW * 32, seed_smem, L.stream>>>(ctx->d_params, n, L.d_reads, L.d_meta, L.seeds(c), L.bins(cc));
+		} else {
+			pb_set_error("internal: no hash-join seeding for this length class");
+			return PB_ERR_ARGUMENT;
 		}
-		CUDA_TRY(cudaGetLastError());
-		pb::bin_order_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(n, d_seeds, pb::seed_words(ML), pb::seed_mask_words(ML) + 1, ctx->d_bins[si], ctx->d_order[si]);
-		CUDA_TRY(cudaGetLastError());
 	}
-	if (timed)
-		CUDA_TRY(cudaEventRecord(ctx->tev[1], stream));
-	const long long nbatch = ((long long) n + 31) / 32;
+	CUDA_TRY(cudaGetLastError());
+	pb::bin_order_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, L.stream>>>(n, L.seeds(c), pb::seed_words(ML), pb::seed_mask_words(ML) + 1, L.bins(cc), L.order(cc),
+	                                                                         list, list_n);
+	CUDA_TRY(cudaGetLastError());
+	return PB_OK;
+}
+
+/* the lane-per-pair kernel over one class's bin list */
+template <int LML, int LW>
+static pb_status lanes_assemble(const LanesState &L, int c) {
+	pb_context *ctx = L.ctx;
+	const int cc = c < 0 ? 0 : c;
+	auto kern = pbl::assemble_lanes_kernel<LML, LW>;
+	constexpr size_t smem = pbl::lanes_smem_bytes<LML, LW>();
+	static_assert(smem <= 227 * 1024, "per-CTA shared memory");
+	static bool configured[16] = { false };
+	if (!configured[ctx->device & 15]) {
+		CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		configured[ctx->device & 15] = true;
+	}
+	const long long nbatch = ((long long) L.n + 31) / 32;
 	long long grid = ((long long) nbatch + LW - 1) / LW;
 	if (grid > ctx->sm_count)
 		grid = ctx->sm_count;
 	if (grid < 1)
 		grid = 1;
-	kern<<<(unsigned) grid, LW * 32, smem, stream>>>(ctx->d_params, n, d_reads, d_meta, d_seeds, ctx->d_order[si], d_results, d_seq_nt, (long long) seq_stride,
-	                                                   d_counters, d_list, d_count, ctx->d_defer_total, ctx->d_bins[si] + 2 * pb::PB_SEED_BINS + 1);
+	kern<<<(unsigned) grid, LW * 32, smem, L.stream>>>(ctx->d_params, L.n, L.d_reads, L.d_meta, L.seeds(c), L.order(cc), L.d_results, L.d_seq_nt, (long long) L.seq_stride,
+	                                                     L.d_counters, L.d_list, L.d_count, ctx->d_defer_total, L.bins(cc) + 2 * pb::PB_SEED_BINS + 1,
+	                                                     c < 0 ? nullptr : L.class_count(c));
 	CUDA_TRY(cudaGetLastError());
+	return PB_OK;
+}
+
+#define PB_TRY(x) do { pb_status st__ = (x); if (st__ != PB_OK) return st__; } while (0)
+
+static pb_status launch_lanes(pb_context *ctx, int n, int max_len, const uint8_t *d_reads, const pb_pair_meta *d_meta,
+                              pb_pair_result *d_results, uint8_t *d_seq_nt, size_t seq_stride,
+                              unsigned long long *d_counters, cudaStream_t stream, bool sweep) {
+	LanesState L = { ctx, n, stream == ctx->copy_stream ? 1 : 0, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, nullptr, nullptr, nullptr, 0 };
+	/* one class in batch order while every read fits the 160-nt kernels (or the hash join is asked for, which takes whole
+	 * batches of reads up to 256 nt); by length class otherwise */
+	const bool classes = sweep && max_len > 160;
+	PB_TRY(lanes_prepare(L, classes));
+	const bool timed = ctx->timing && stream == ctx->stream;
+	if (timed)
+		CUDA_TRY(cudaEventRecord(ctx->tev[0], stream));
+	/* <seeding class, hash-join warps, sweep warps> / <lane-kernel class, lane warps>: as many warps as the per-warp shared memory
+	 * allows; reads up to 152 nt (2x150 included) leave room for a 12th warp of the lane kernel */
+	const int top = max_len <= 256 ? 1 : 2;      /* the highest class that can hold a pair of this batch */
+	if (classes) {
+		pb::class_list_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(n, d_meta, ctx->d_classes[L.si], L.cap, L.class_count(0), L.d_list, L.d_count, ctx->d_defer_total);
+		CUDA_TRY(cudaGetLastError());
+		PB_TRY((lanes_seed<160, 0, 21>(L, 0, true)));
+		PB_TRY((lanes_seed<256, 0, 14>(L, 1, true)));
+		if (top >= 2)
+			PB_TRY((lanes_seed<320, 0, 10>(L, 2, true)));
+	} else if (max_len <= 160) {
+		PB_TRY((lanes_seed<160, 32, 21>(L, -1, sweep)));
+	} else {
+		PB_TRY((lanes_seed<256, 19, 14>(L, -1, sweep)));
+	}
+	if (timed)
+		CUDA_TRY(cudaEventRecord(ctx->tev[1], stream));
+	if (classes) {
+		PB_TRY((lanes_assemble<160, 11>(L, 0)));
+		PB_TRY((lanes_assemble<256, 7>(L, 1)));
+		if (top >= 2)
+			PB_TRY((lanes_assemble<320, 6>(L, 2)));
+	} else if (max_len <= 152) {
+		PB_TRY((lanes_assemble<152, 12>(L, -1)));
+	} else if (max_len <= 160) {
+		PB_TRY((lanes_assemble<160, 11>(L, -1)));
+	} else {
+		PB_TRY((lanes_assemble<256, 7>(L, -1)));
+	}
 	if (timed)
 		CUDA_TRY(cudaEventRecord(ctx->tev[2], stream));
 	ctx->lanes_pairs += (unsigned long long) n;
-	return launch_assemble<ML, false, GW, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, nullptr, seq_stride, d_counters, stream, false,
-	                                             d_list, d_count);
+	/* the pairs handed on, by the general kernel of the batch's length class */
+#define PB_LIST(ML, W) return launch_assemble<ML, false, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, nullptr, seq_stride, d_counters, stream, false, L.d_list, L.d_count)
+	if (max_len <= 160) PB_LIST(160, 28);
+	if (max_len <= 256) PB_LIST(256, 15);
+	if (max_len <= 320) PB_LIST(320, 14);
+	PB_LIST(456, 8);
+#undef PB_LIST
 }
 
 pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int max_len,
@@ -304,11 +419,9 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 		pb_set_error("per-base codes are not available together with primers-after or min_phred (the sequence is staged as doubles)");
 		return PB_ERR_ARGUMENT;
 	}
-	if ((ctx->lanes_mode < 0 ? lanes_on : ctx->lanes_mode) && !full && !d_seq_p && !d_seq_code && max_len <= 256 && cfg->forward_trim == 0 && cfg->reverse_trim == 0
+	if ((ctx->lanes_mode < 0 ? lanes_on : ctx->lanes_mode) && !full && !d_seq_p && !d_seq_code && cfg->forward_trim == 0 && cfg->reverse_trim == 0
 	    && (cfg->algo == PB_SIMPLE_BAYES || cfg->algo == PB_UPARSE || cfg->algo == PB_FLASH || cfg->algo == PB_PEAR) && ((uintptr_t) d_seq_nt % 8) == 0)
 	{
-		/* <seeding class, lane-kernel class, seeding warps, lane warps, general-kernel warps>: as many warps as the per-warp shared
-		 * memory allows; reads up to 152 nt (2x150 included) leave room for a 12th warp of the lane kernel */
 		/* seeding: the diagonal sweep (pb_sweep.cuh) unless an explicit maxoverlap lets overlaps run past a read's end, which
 		 * only the hash join (pb::seed_kernel) covers; PANDASEQ_B200_SWEEP=0 / pb_set_lanes(ctx, 2) keep the hash join for A/B runs */
 		static int sweep_on = -1;
@@ -317,11 +430,8 @@ pb_status pb_assemble_dispatch(pb_context *ctx, const pb_config *cfg, int n, int
 			sweep_on = (env && atoi(env) == 0) ? 0 : 1;
 		}
 		const bool sweep = sweep_on && ctx->lanes_mode != 2 && cfg->maxoverlap == 0;
-		if (max_len <= 152)
-			return launch_lanes<160, 152, 32, 12, 28, 21>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
-		if (max_len <= 160)
-			return launch_lanes<160, 160, 32, 11, 28, 21>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
-		return launch_lanes<256, 256, 19, 7, 15, 14>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
+		if (sweep || max_len <= 256)
+			return launch_lanes(ctx, n, max_len, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, sweep);
 	}
 #define PB_GO(ML, OVER, W) do { if (full) return launch_assemble<ML, OVER, W, true>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, stage_seq, nullptr, nullptr, d_seq_code); \
 	return launch_assemble<ML, OVER, W, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, d_seq_p, seq_stride, d_counters, stream, false, nullptr, nullptr, d_seq_code); } while (0)
@@ -790,6 +900,49 @@ extern "C" pb_status pb_device_context(int device, pb_context **out) {
 	*out = g_device_ctx[device];
 	pthread_mutex_unlock(&g_shared_lock);
 	return st;
+}
+
+/* The calling thread onto the host cores of the socket a GPU hangs off (sysfs: local_cpulist of its PCI device), so that the
+ * page-locked staging it allocates and fills afterwards lies in that socket's memory and the copies do not cross the socket link.
+ * Best effort: without the sysfs entry, or where the process's cpuset leaves no such core, nothing changes. */
+extern "C" void pb_bind_thread_near_device(int device) {
+	char bus[32], path[128], list[4096];
+	if (cudaDeviceGetPCIBusId(bus, (int) sizeof bus, device) != cudaSuccess) {
+		cudaGetLastError();
+		return;
+	}
+	for (char *c = bus; *c; c++)
+		if (*c >= 'A' && *c <= 'F')
+			*c = (char) (*c - 'A' + 'a');
+	snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+	FILE *f = fopen(path, "r");
+	if (!f)
+		return;
+	const bool got = fgets(list, (int) sizeof list, f) != nullptr;
+	fclose(f);
+	if (!got)
+		return;
+	cpu_set_t allowed, want;
+	if (sched_getaffinity(0, sizeof allowed, &allowed) != 0)
+		return;
+	CPU_ZERO(&want);
+	int picked = 0;
+	for (char *p = list; *p && *p != '\n';) {
+		char *end;
+		long a = strtol(p, &end, 10), b = a;
+		if (end == p)
+			break;
+		if (*end == '-')
+			b = strtol(end + 1, &end, 10);
+		for (long c = a; c <= b && c < CPU_SETSIZE; c++)
+			if (CPU_ISSET((int) c, &allowed)) {
+				CPU_SET((int) c, &want);
+				picked++;
+			}
+		p = *end == ',' ? end + 1 : end;
+	}
+	if (picked > 0)
+		pthread_setaffinity_np(pthread_self(), sizeof want, &want);
 }
 
 extern "C" pb_status pb_shared_context(pb_context **out) {

@@ -79,7 +79,9 @@ int pb_algorithm_fill_config(PandaAlgorithm algo, pb_config *cfg);
 
 /* pb_device.cu */
 pb_status pb_shared_context(pb_context **out);
-pb_status pb_device_context(int device, pb_context **out);   /* the process-wide context of one GPU (panda_run_pool's workers) */
+pb_status pb_device_context(int device, pb_context **out);
+void pb_bind_thread_near_device(int device);   /* the calling thread onto the host cores next to a GPU (sysfs local_cpulist); best effort */
+   /* the process-wide context of one GPU (panda_run_pool's workers) */
 
 #ifdef __cplusplus
 }

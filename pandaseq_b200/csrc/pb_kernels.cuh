@@ -1304,7 +1304,7 @@ __host__ __device__ constexpr int seed_words(int ML) { return (seed_mask_words(M
 /*   seeds[pair][MW+1]  (MW = mask words: flags sit at [MW]) bin of the pair: (lowest candidate overlap - minoverlap) / 16, or PB_SEED_BINS - 1 for the pairs that
  *                      carry a flag.  bin_order_kernel lists the pairs bin by bin, so that the 32 pairs a warp of the lane-per-
  *                      pair kernel takes have overlaps within 16 bases of each other and its loops end together. */
-constexpr int PB_SEED_BINS = 17;      /* 16 x 16 overlaps (reads up to 256 nt) + the flagged pairs */
+constexpr int PB_SEED_BINS = 21;      /* 20 x 16 overlaps (reads up to 320 nt) + the flagged pairs */
 
 template <int ML, int WARPS_PER_BLOCK>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
@@ -1416,15 +1416,21 @@ seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__re
 /* The pairs of a batch listed bin by bin (seeds[pair][6]); the order inside a bin is whatever the atomics make it, which no
  * result depends on.  bin_state: [0 .. BINS) pairs per bin (seed_kernel), [BINS .. 2 BINS) cursors, zero at launch. */
 __global__ void __launch_bounds__(256)
-bin_order_kernel(int n, const uint32_t *__restrict__ seeds, int swords, int bin_word, unsigned *__restrict__ bin_state, int *__restrict__ order) {
+bin_order_kernel(int n, const uint32_t *__restrict__ seeds, int swords, int bin_word, unsigned *__restrict__ bin_state, int *__restrict__ order,
+                 const int *__restrict__ list, const int *__restrict__ list_n) {
 	__shared__ unsigned s_hist[PB_SEED_BINS], s_base[PB_SEED_BINS];
 	const int tid = threadIdx.x;
+	if (list_n)
+		n = *list_n;          /* the pairs of one length class, listed by index (class_list_kernel) */
+	if ((int) (blockIdx.x * blockDim.x) >= n)
+		return;
 	if (tid < PB_SEED_BINS)
 		s_hist[tid] = 0;
 	__syncthreads();
-	const int pair = blockIdx.x * blockDim.x + tid;
+	const int item = blockIdx.x * blockDim.x + tid;
+	const int pair = item < n ? (list ? list[item] : item) : -1;
 	unsigned bin = 0, rank = 0;
-	if (pair < n) {
+	if (pair >= 0) {
 		bin = min(seeds[(size_t) pair * swords + bin_word], (unsigned) (PB_SEED_BINS - 1));
 		rank = atomicAdd(&s_hist[bin], 1u);
 	}
@@ -1436,8 +1442,46 @@ bin_order_kernel(int n, const uint32_t *__restrict__ seeds, int swords, int bin_
 		s_base[tid] = first + (s_hist[tid] ? atomicAdd(&bin_state[PB_SEED_BINS + tid], s_hist[tid]) : 0u);
 	}
 	__syncthreads();
-	if (pair < n)
+	if (pair >= 0)
 		order[s_base[bin] + rank] = pair;
+}
+
+/* Batches of mixed read lengths: the pairs listed by length class -- longest read of the pair <= 160, <= 256, <= 320 nt -- so that
+ * every class runs the seeding sweep and the lane-per-pair kernel sized for it (the sweep's work grows with the square of the
+ * length class, the lane kernel's shared memory per pair with the class).  lists[c * cap ..] = indices of class c, counts[c] their
+ * number (zero at launch); pairs with a longer read go straight to the general kernel's list.  Order inside a list: whatever the
+ * atomics make it; no result depends on it. */
+constexpr int PB_LEN_CLASSES = 3;
+__host__ __device__ constexpr int len_class_max(int c) { return c == 0 ? 160 : (c == 1 ? 256 : 320); }
+__global__ void __launch_bounds__(256)
+class_list_kernel(int n, const pb_pair_meta *__restrict__ meta, int *__restrict__ lists, size_t cap, int *__restrict__ counts,
+                  int *__restrict__ general_list, int *__restrict__ general_count, unsigned long long *__restrict__ general_total) {
+	const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	int cls = -1;
+	if (pair < n) {
+		const uint2 m = *reinterpret_cast<const uint2 *>(&meta[pair]);
+		const int F = (int) (m.y & 0xFFFFu), R = (int) (m.y >> 16);
+		const int longest = F == 0xFFFF ? 0 : max(F, R);        /* not a pair: any class reports it as such */
+		cls = longest <= len_class_max(0) ? 0 : (longest <= len_class_max(1) ? 1 : (longest <= len_class_max(2) ? 2 : 3));
+	}
+#pragma unroll
+	for (int c = 0; c <= PB_LEN_CLASSES; c++) {
+		const unsigned m = __ballot_sync(FULL, cls == c);
+		if (m == 0)
+			continue;
+		int base = 0;
+		if (lane == __ffs(m) - 1) {
+			base = atomicAdd(c < PB_LEN_CLASSES ? &counts[c] : general_count, __popc(m));
+			if (c == PB_LEN_CLASSES)
+				atomicAdd(general_total, (unsigned long long) __popc(m));
+		}
+		base = __shfl_sync(FULL, base, __ffs(m) - 1);
+		if (cls == c) {
+			int *dst = c < PB_LEN_CLASSES ? lists + (size_t) c * cap : general_list;
+			dst[base + __popc(m & lanemask_lt())] = pair;
+		}
+	}
 }
 
 template <int ML, bool OVER, int WARPS_PER_BLOCK> constexpr size_t assemble_smem_bytes() {

@@ -47,7 +47,7 @@ template <int ML> struct LaneArea {
 	static constexpr int REC_STRIDE = ((REC0 / 16) | 1) * 16;    /* odd number of 16-byte units: a lane's 128-bit loads never collide */
 	static constexpr int CW = pb::seed_mask_words(ML);           /* words of the candidate mask (pb::seed_kernel) */
 	static constexpr int SWORDS = pb::seed_words(ML);
-	static_assert(ML <= 256, "the seeds record is laid out for reads up to 256 nt");
+	static_assert(ML <= 320, "the bins of the seeds record reach up to 320 nt");
 	alignas(128) uint8_t rec[32 * REC_STRIDE];
 	alignas(8) uint64_t bar;
 };
@@ -58,7 +58,7 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
                       const uint8_t *__restrict__ reads, const pb_pair_meta *__restrict__ meta,
                       const uint32_t *__restrict__ seeds, const int *__restrict__ order, pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, long long seq_stride,
                       unsigned long long *__restrict__ counters, int *__restrict__ defer_list, int *__restrict__ defer_count,
-                      unsigned long long *__restrict__ defer_total, unsigned *__restrict__ next_batch) {
+                      unsigned long long *__restrict__ defer_total, unsigned *__restrict__ next_batch, const int *__restrict__ order_n) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	using LA = LaneArea<ML>;
 	double *s_rec = reinterpret_cast<double *>(smem_raw);                 /* recon[2][48][48], row = quality a + 48 * match */
@@ -85,49 +85,76 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 	const int mo = prm->minoverlap, cfg_maxov = prm->maxoverlap, algo = prm->algo, nf = prm->nfilters;
 	const long long nt_row = seq_stride / 2;
 	const int out_cap = (int) seq_stride;
+	if (order_n)
+		n = *order_n;         /* `order` holds the pairs of one length class (pb::class_list_kernel) */
 	const int nbatch = (n + 31) >> 5;
 	const uint8_t *const rb = wa.rec + lane * LA::REC_STRIDE;
 	unsigned parity = 0;
 
-	/* which 32 entries of the bin list a warp takes next comes from a counter in global memory (*next_batch, zero at launch): with a
-	 * fixed share per warp the warps the scheduler favours finish early and leave the SM half empty at the end */
-	auto grab = [&]() {
+	/* Which 32 entries of the bin list a warp takes next comes from a counter in global memory (*next_batch, zero at launch): with a
+	 * fixed share per warp the warps the scheduler favours finish early and leave the SM half empty at the end.  Everything a batch
+	 * needs before its records can be fetched -- its number (an atomic), its pairs (the bin list), their metadata and seeds records --
+	 * is a chain of dependent global loads; it is run one batch ahead, each link issued where the previous one has long arrived, so
+	 * that no iteration waits for it: the counter is bumped for the batch after next at the top of an iteration and read at its bottom,
+	 * the next batch's pair index is loaded at the bottom of the iteration before, its metadata and seeds record after this batch's
+	 * records have landed, and its records are pulled into L2 after the scoring. */
+	struct Head {
+		int pair;
+		unsigned off16;
+		int F, R;
+		unsigned cw[LA::CW], sflags;
+	};
+	auto take = [&]() {
 		int b = 0;
 		if (lane == 0)
 			b = (int) atomicAdd(next_batch, 1u);
-		return __shfl_sync(FULL, b, 0);
+		return b;                                              /* lane 0's value counts: __shfl_sync(FULL, b, 0) where it is needed */
 	};
-	int batch = grab();
-	while (batch < nbatch) {
-		const int batch_after = grab();
-		const int item = batch * 32 + lane;
-		const int pair = item < n ? order[item] : n;           /* pairs come bin by bin (pb::bin_order_kernel) */
-		unsigned off16 = 0;
-		int F = 0xFFFF, R = 0;
-		if (pair < n) {
-			const uint2 mraw = *reinterpret_cast<const uint2 *>(&meta[pair]);
-			off16 = mraw.x;
-			F = (int) (mraw.y & 0xFFFFu);
-			R = (int) (mraw.y >> 16);
-		}
-		unsigned cw[LA::CW];
-		unsigned sflags = pb::PB_SEED_SKIP;
+	auto pair_of = [&](int b) {
+		const long long item = (long long) b * 32 + lane;
+		return (b < nbatch && item < n) ? order[item] : -1;    /* pairs come bin by bin (pb::bin_order_kernel) */
+	};
+	auto load_head = [&](int pair, Head &h) {
+		h.pair = pair;
+		h.off16 = 0;
+		h.F = 0xFFFF;                                          /* not a pair (FASTQ reader, fastq.c:176), or past the end of the list */
+		h.R = 0;
+		h.sflags = pb::PB_SEED_SKIP;
 #pragma unroll
 		for (int w = 0; w < LA::CW; w++)
-			cw[w] = 0;
-		if (pair < n) {
+			h.cw[w] = 0;
+		if (pair >= 0) {
+			const uint2 mraw = *reinterpret_cast<const uint2 *>(&meta[pair]);
 			unsigned sw[LA::SWORDS];
 #pragma unroll
 			for (int q = 0; q < LA::SWORDS / 4; q++) {
 				const uint4 v = reinterpret_cast<const uint4 *>(seeds)[(size_t) pair * (LA::SWORDS / 4) + q];
 				sw[4 * q] = v.x; sw[4 * q + 1] = v.y; sw[4 * q + 2] = v.z; sw[4 * q + 3] = v.w;
 			}
+			h.off16 = mraw.x;
+			h.F = (int) (mraw.y & 0xFFFFu);
+			h.R = (int) (mraw.y >> 16);
 #pragma unroll
 			for (int w = 0; w < LA::CW; w++)
-				cw[w] = sw[w];
-			sflags = sw[LA::CW];
+				h.cw[w] = sw[w];
+			h.sflags = sw[LA::CW];
 		}
-		const bool skip = F == 0xFFFF;              /* not a pair (FASTQ reader, fastq.c:176), or past the end of the batch */
+	};
+	int batch = __shfl_sync(FULL, take(), 0);
+	int batch1 = __shfl_sync(FULL, take(), 0);
+	Head cur, nxt;
+	load_head(pair_of(batch), cur);
+	int pair1 = pair_of(batch1);
+	while (batch < nbatch) {
+		const int taken = take();                              /* the batch after next; read at the bottom */
+		const int pair = cur.pair;
+		const int F = cur.F, R = cur.R;
+		unsigned cw[LA::CW];
+#pragma unroll
+		for (int w = 0; w < LA::CW; w++)
+			cw[w] = cur.cw[w];
+		const unsigned sflags = cur.sflags;
+		const bool skip = F == 0xFFFF;
 		bool defer = !skip && ((sflags & pb::PB_SEED_GENERAL) != 0 || F > ML || R > ML);      /* a record must fit its slot */
 		const bool act = !skip && !defer;
 		const unsigned bytes = act ? pb::record_bytes((unsigned) F, (unsigned) R) : 0u;
@@ -136,20 +163,10 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 			pb::mbar_expect_tx(&wa.bar, total);
 		__syncwarp();
 		if (bytes)
-			pb::bulk_g2s(wa.rec + lane * LA::REC_STRIDE, reads + (size_t) off16 * 16, bytes, &wa.bar);
-		{       /* the next batch of this warp: pull its records into L2 while this one is processed */
-			const long long ni = (long long) batch_after * 32 + lane;
-			if (ni < n) {
-				const uint2 mn = *reinterpret_cast<const uint2 *>(&meta[order[ni]]);
-				const unsigned nF = mn.y & 0xFFFFu, nR = mn.y >> 16;
-				if (nF != 0xFFFFu && nF <= (unsigned) ML && nR <= (unsigned) ML) {
-					const unsigned nbytes = pb::record_bytes(nF, nR);
-					asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(reads + (size_t) mn.x * 16), "r"(nbytes) : "memory");
-				}
-			}
-		}
+			pb::bulk_g2s(wa.rec + lane * LA::REC_STRIDE, reads + (size_t) cur.off16 * 16, bytes, &wa.bar);
 		pb::mbar_wait(&wa.bar, parity);
 		parity ^= 1u;
+		load_head(pair1, nxt);                                 /* consumed by the next iteration */
 
 		uint8_t status = PB_PAIR_OK;
 		int slow = 0, bestov = -1, examined = 0, seq_len = 0, mism = 0;
@@ -281,6 +298,10 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 						defer = true;
 				}
 			}
+		}
+		if (nxt.F != 0xFFFF && nxt.F <= ML && nxt.R <= ML) {      /* the next batch of this warp: pull its records into L2 meanwhile */
+			const unsigned nbytes = pb::record_bytes((unsigned) nxt.F, (unsigned) nxt.R);
+			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(reads + (size_t) nxt.off16 * 16), "r"(nbytes) : "memory");
 		}
 		if (act && !defer && status == PB_PAIR_OK) {
 			/* ---- K6: reconstruction (assembler.c:145-250) with forward_offset = reverse_offset = 0 ---- */
@@ -414,17 +435,31 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 				defer = true;                           /* a quality outside 0..46: PHREDCLAMP (prob.h:23) is the general kernel's job */
 			quality = (fquality + rquality + oquality) / (double) len;      /* assembler.c:244: divides by len, not seq_len */
 
-			/* merged bases, eight per word */
+			/* merged bases, eight per word: the words that lie in the forward-only stretch are copies of the forward read's, the
+			 * words past the forward read's end are a shifted window of the (template-order) reverse read; only the words in
+			 * between see both reads */
 			uint8_t *const orow = seq_nt ? seq_nt + (size_t) pair * nt_row : nullptr;
 			const int nwords = (seq_len + 7) >> 3;
 			unsigned prev = 0;
-			for (int k = 0; k < nwords; k++) {
+			auto emit = [&](int k, unsigned nt) {
+				if (k & 1) {
+					if (orow && 8 * (k - 1) < out_cap)
+						*reinterpret_cast<uint2 *>(orow + (size_t) (k - 1) * 4) = make_uint2(prev, nt);
+				} else {
+					prev = nt;
+				}
+			};
+			const int k1 = df >> 3, k2 = min((F + 7) >> 3, nwords);
+			int k = 0;
+			for (; k < k1; k++)
+				emit(k, fnt[k]);
+			for (; k < k2; k++) {
 				const int idx0 = 8 * k;
 				const int nV = min(seq_len - idx0, 8);
-				const int nF = min(max(F - idx0, 0), 8);
+				const int nF = min(F - idx0, 8);
 				const int r0 = min(max(df - idx0, 0), 8);
 				const unsigned maskV = pb::nibmask(nV), maskF = pb::nibmask(nF) & maskV, maskR = maskV & ~pb::nibmask(r0);
-				const unsigned fw = (idx0 < F ? fnt[k] : 0u) & maskF;
+				const unsigned fw = fnt[k] & maskF;
 				const unsigned rw = pb::nibwin(rnt, idx0 - df) & maskR;
 				const unsigned both = maskF & maskR;
 				const unsigned andw = fw & rw;
@@ -437,11 +472,20 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 					if (fq8[idx0 + t] < rq8[idx0 - df + t])
 						nt = (nt & ~(15u << (4 * t))) | (rw & (15u << (4 * t)));
 				}
-				if (k & 1) {
-					if (orow && idx0 - 8 < out_cap)
-						*reinterpret_cast<uint2 *>(orow + (size_t) (k - 1) * 4) = make_uint2(prev, nt);
-				} else {
-					prev = nt;
+				emit(k, nt);
+			}
+			if (k < nwords) {
+				const int pos = 8 * k - df;              /* >= overlap: these words lie past the forward read */
+				const uint32_t *rp = rnt + (pos >> 3);
+				const int sh = (pos & 7) * 4;
+				unsigned lo = rp[0];
+				for (; k < nwords; k++) {
+					const unsigned hi = *++rp;
+					unsigned nt = __funnelshift_r(lo, hi, sh);
+					lo = hi;
+					if (k == nwords - 1)
+						nt &= pb::nibmask(seq_len - 8 * k);
+					emit(k, nt);
 				}
 			}
 			if ((nwords & 1) && orow && 8 * (nwords - 1) < out_cap)
@@ -480,7 +524,7 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 			status = ST_DEFER;
 		else if (skip)
 			status = PB_PAIR_SKIP;
-		if (pair < n && status != ST_DEFER) {
+		if (pair >= 0 && status != ST_DEFER) {
 			union { pb_pair_result r; uint4 v[2]; } ru;
 			ru.v[0] = make_uint4(0, 0, 0, 0);
 			ru.v[1] = make_uint4(0, 0, 0, 0);
@@ -532,7 +576,10 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 				defer_list[dbase + __popc(m_defer & pb::lanemask_lt())] = pair;
 		}
 		__syncwarp();      /* every lane is done with its record before the next batch lands on it */
-		batch = batch_after;
+		batch = batch1;
+		batch1 = __shfl_sync(FULL, taken, 0);
+		cur = nxt;
+		pair1 = pair_of(batch1);
 	}
 	__syncthreads();
 	for (int i = tid; i < PB_NCOUNTERS; i += blockDim.x) {

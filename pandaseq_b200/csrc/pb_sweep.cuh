@@ -359,7 +359,7 @@ template <int NW, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t *__restrict__ reads,
                   const pb_pair_meta *__restrict__ meta, uint32_t *__restrict__ seeds, unsigned *__restrict__ bin_count,
-                  unsigned *__restrict__ next_batch, const Muls mu) {
+                  unsigned *__restrict__ next_batch, const Muls mu, const int *__restrict__ list, const int *__restrict__ list_n) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	__shared__ unsigned s_bins[pb::PB_SEED_BINS];
 	using SA = SweepArea<NW>;
@@ -378,6 +378,8 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 	}
 	__syncthreads();
 	const int mo = prm->minoverlap;
+	if (list_n)
+		n = *list_n;          /* the pairs of one length class (pb::class_list_kernel), listed by index */
 	const int nbatch = (n + 31) >> 5;
 	unsigned parity = 0;
 	uint32_t *const myplanes = &wa.planes[0][lane];
@@ -390,10 +392,11 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 		batch = __shfl_sync(pb::FULL, batch, 0);
 		if (batch >= nbatch)
 			break;
-		const int pair = batch * 32 + lane;
+		const int item = batch * 32 + lane;
+		const int pair = item < n ? (list ? list[item] : item) : -1;
 		unsigned off16 = 0;
 		int F = 0xFFFF, R = 0;
-		if (pair < n) {
+		if (pair >= 0) {
 			const uint2 mraw = *reinterpret_cast<const uint2 *>(&meta[pair]);
 			off16 = mraw.x;
 			F = (int) (mraw.y & 0xFFFFu);
@@ -464,7 +467,7 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 		unsigned bin = flags ? (unsigned) (pb::PB_SEED_BINS - 1) : (unsigned) (lowest >> 4);
 		if (bin > (unsigned) (pb::PB_SEED_BINS - 1))
 			bin = pb::PB_SEED_BINS - 1;
-		if (pair < n) {
+		if (pair >= 0) {
 			uint32_t sw[SWORDS];
 #pragma unroll
 			for (int w = 0; w < SWORDS; w++)

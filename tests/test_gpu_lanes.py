@@ -220,3 +220,41 @@ def test_mixed_lengths_up_to_256_nt(ctx):
     for algo in ("simple_bayesian", "pear"):
         got, want, rep = run_lanes(ctx, pb.make_config(algo), b)
         assert rep["ok"], (algo, rep)
+
+
+@pytest.mark.parametrize("algo", ["simple_bayesian", "pear", "flash", "uparse"])
+def test_length_classes_up_to_320_nt(ctx, algo):
+    # mixed batches are listed by length class (<= 160, <= 256, <= 320 nt: pb::class_list_kernel) and every class runs the sweep and
+    # the lane kernel sized for it; BASELINE config 5's shape (2x(75-300)), with N and '#' tails so that pairs are handed on as well
+    b = synth.generate(6000, rl=(75, 300), tmpl=None, seed=25, mixed=True, n_rate=0.0005, btail_rate=0.05).to_flat()
+    got, want, rep = run_lanes(ctx, pb.make_config(algo), b)
+    assert rep["ok"], (algo, rep)
+    clean = synth.generate(6000, rl=(75, 300), tmpl=None, seed=26, mixed=True).to_flat()
+    got, want, rep = run_lanes(ctx, pb.make_config(algo), clean)
+    assert rep["ok"], (algo, rep)
+    if algo != "pear":          # pear hands on every pair whose reverse read is the longer one (algo_pear.c:52 reads past the forward read)
+        assert rep["deferred"] <= clean.n // 50, rep
+    # 2x300 exactly: everything in the 320-nt class
+    b300 = synth.generate(3000, rl=(300, 300), tmpl=(320, 580), seed=27, n_rate=0.0002).to_flat()
+    got, want, rep = run_lanes(ctx, pb.make_config(algo), b300)
+    assert rep["ok"], (algo, rep)
+
+
+def test_length_classes_with_reads_up_to_450_nt(ctx):
+    # pairs with a read above 320 nt go straight to the general kernel's list; the rest of the batch stays on the two-kernel path
+    rng = np.random.default_rng(31)
+    pairs = []
+    for i in range(3000):
+        F, R = int(rng.integers(20, 451)), int(rng.integers(20, 451))
+        L = int(rng.integers(max(F, R), F + R - 12))
+        t = rng.integers(0, 4, size=L)
+        f, r = t[:F].copy(), t[::-1][:R].copy()
+        for arr in (f, r):
+            m = rng.random(len(arr)) < 0.01
+            arr[m] = (arr[m] + rng.integers(1, 4, size=int(m.sum()))) & 3
+        pairs.append((1 << f, rng.integers(2, 42, size=F), 1 << r, rng.integers(2, 42, size=R)))
+    b = synth.FlatBatch.from_pairs(pairs)
+    for algo in ("simple_bayesian", "pear"):
+        got, want, rep = run_lanes(ctx, pb.make_config(algo, minoverlap=10), b)
+        assert rep["ok"], (algo, rep)
+        assert 500 < rep["deferred"] < b.n, rep
