@@ -318,34 +318,78 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 				while (lead_r < R && rq8[lead_r] == 2)
 					lead_r++;
 			}
-			unsigned qbad = 0;
+			/* Range check of every quality that is added up (PHREDCLAMP, prob.h:23, is the general kernel's job): bit 7 of a byte of
+			 * q + 0x51.. is set iff that quality is 47 or more, as long as no byte has its own bit 7 set (no carries between the
+			 * bytes then) -- which the OR of the words themselves tells at the end. */
+			unsigned qsum = 0, qor = 0;
+			auto qcheck2 = [&](unsigned x, unsigned y) {
+				qsum |= (x + 0x51515151u) | (y + 0x51515151u);
+				qor |= x | y;
+			};
 			/* The sums below run on two accumulators each (even / odd bases): the additions are the reference's, their
 			 * order is not, which moves `quality` by an ulp or two (tolerance 1e-6, BASELINE.json north_star).
-			 * forward-only stretch: positions [0, df) (assembler.c:162-173) */
-			double fquality = 0.0, fquality1 = 0.0;
+			 * forward-only stretch: positions [0, df) (assembler.c:162-173); reverse-only stretch: template-order reverse bases
+			 * [bestov, R) (assembler.c:231-243).  Two independent streams of qual_score[] gathers: they share one loop as far as both
+			 * reach, which halves the loop overhead and lets the two chains of additions overlap. */
+			double fquality = 0.0, fquality1 = 0.0, rquality = 0.0, rquality1 = 0.0;
 			{
-				const int nfull = df >> 2;
-#pragma unroll 2
-				for (int w = 0; w < nfull; w++) {
-					const unsigned q4 = fq32[w];
-					qbad |= ((q4 & 0x7F7F7F7Fu) + 0x51515151u) | q4;
-					fquality += s_score[__byte_perm(q4, 0, 0x4440)];
-					fquality1 += s_score[__byte_perm(q4, 0, 0x4441)];
-					fquality += s_score[__byte_perm(q4, 0, 0x4442)];
-					fquality1 += s_score[__byte_perm(q4, 0, 0x4443)];
+				const int shr = (bestov & 3) * 8;
+				const uint32_t *rqp = rq32 + (bestov >> 2);
+				const int nff = df >> 2, nfr = dr >> 2, nfc = min(nff, nfr);
+				unsigned rlo = rqp[0];
+				int w = 0;
+				for (; w < nfc; w++) {
+					const unsigned qf = fq32[w];
+					const unsigned rhi = rqp[w + 1];
+					const unsigned qr = __funnelshift_r(rlo, rhi, shr);
+					rlo = rhi;
+					qcheck2(qf, qr);
+					fquality += s_score[__byte_perm(qf, 0, 0x4440)];
+					rquality += s_score[__byte_perm(qr, 0, 0x4440)];
+					fquality1 += s_score[__byte_perm(qf, 0, 0x4441)];
+					rquality1 += s_score[__byte_perm(qr, 0, 0x4441)];
+					fquality += s_score[__byte_perm(qf, 0, 0x4442)];
+					rquality += s_score[__byte_perm(qr, 0, 0x4442)];
+					fquality1 += s_score[__byte_perm(qf, 0, 0x4443)];
+					rquality1 += s_score[__byte_perm(qr, 0, 0x4443)];
 				}
-				const int nb = df & 3;
-				if (nb) {
-					const unsigned q4 = fq32[nfull] & ((1u << (8 * nb)) - 1u);      /* the rest of this word belongs to the overlap and is checked there */
-					qbad |= ((q4 & 0x7F7F7F7Fu) + 0x51515151u) | q4;
-					for (int t = 0; t < nb; t++)
-						fquality += s_score[(q4 >> (8 * t)) & 0xFFu];
+				for (int v = w; v < nff; v++) {
+					const unsigned qf = fq32[v];
+					qcheck2(qf, 0u);
+					fquality += s_score[__byte_perm(qf, 0, 0x4440)];
+					fquality1 += s_score[__byte_perm(qf, 0, 0x4441)];
+					fquality += s_score[__byte_perm(qf, 0, 0x4442)];
+					fquality1 += s_score[__byte_perm(qf, 0, 0x4443)];
 				}
+				for (; w < nfr; w++) {
+					const unsigned rhi = rqp[w + 1];
+					const unsigned qr = __funnelshift_r(rlo, rhi, shr);
+					rlo = rhi;
+					qcheck2(qr, 0u);
+					rquality += s_score[__byte_perm(qr, 0, 0x4440)];
+					rquality1 += s_score[__byte_perm(qr, 0, 0x4441)];
+					rquality += s_score[__byte_perm(qr, 0, 0x4442)];
+					rquality1 += s_score[__byte_perm(qr, 0, 0x4443)];
+				}
+				/* the last one to three bases of each stretch; what lies beyond them in the word is checked where it belongs
+				 * (the overlap) or is not a quality at all (what follows the read in shared memory) */
+				const int nbf = df & 3, nbr = dr & 3;
+				const unsigned qf = nbf ? fq32[nff] & ((1u << (8 * nbf)) - 1u) : 0u;
+				const unsigned qr = nbr ? __funnelshift_r(rlo, rqp[nfr + 1], shr) & ((1u << (8 * nbr)) - 1u) : 0u;
+				qcheck2(qf, qr);
+				if (nbf > 0) fquality += s_score[__byte_perm(qf, 0, 0x4440)];
+				if (nbr > 0) rquality += s_score[__byte_perm(qr, 0, 0x4440)];
+				if (nbf > 1) fquality1 += s_score[__byte_perm(qf, 0, 0x4441)];
+				if (nbr > 1) rquality1 += s_score[__byte_perm(qr, 0, 0x4441)];
+				if (nbf > 2) fquality += s_score[__byte_perm(qf, 0, 0x4442)];
+				if (nbr > 2) rquality += s_score[__byte_perm(qr, 0, 0x4442)];
 				fquality += fquality1;
+				rquality += rquality1;
 			}
-			/* overlap: position df+i pairs forward base df+i with template-order reverse base i (assembler.c:181-228).
-			 * The posterior is recon[match][a][b]; the match bit is folded into the row index (row = a + 48 * match),
-			 * B-cliff masked bases get index 47 (assembler.c:194-210). */
+			/* overlap: position df+i pairs forward base df+i with template-order reverse base i (assembler.c:181-228), eight bases
+			 * per step.  The posterior is recon[match][a][b]; the match bit is folded into the row index (row = a + 48 * match),
+			 * B-cliff masked bases get index 47 (assembler.c:194-210).  The last step of a pair is the same code with the bases past
+			 * the overlap zeroed and their additions predicated off, so that the lanes of a warp stay together. */
 			double oquality = 0.0, oquality1 = 0.0;
 			{
 				const bool cliff = unmasked_f < F || lead_r > 0;
@@ -354,84 +398,57 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 				const uint32_t *fqp = fq32 + (df >> 2);
 				const uint32_t *fnp = fnt + (df >> 3);
 				unsigned qlo = fqp[0], nlo = fnp[0];
-				unsigned mw = 0;
-				const int nwq = (bestov + 3) >> 2;
-				for (int w = 0; w < nwq; w++) {
-					const unsigned qhi = fqp[w + 1];
-					unsigned qa4 = __funnelshift_r(qlo, qhi, shq);
-					qlo = qhi;
-					unsigned qb4 = rq32[w];
-					const int nb = min(bestov - 4 * w, 4);
-					if (nb < 4) {                        /* the last word: what lies past the overlap must not reach the range check */
-						const unsigned keep = (1u << (8 * nb)) - 1u;
-						qa4 &= keep;
-						qb4 &= keep;
+				const int nw8 = (bestov + 7) >> 3;
+				for (int k = 0; k < nw8; k++) {
+					const unsigned q1 = fqp[2 * k + 1], q2 = fqp[2 * k + 2];
+					unsigned qa0 = __funnelshift_r(qlo, q1, shq), qa1 = __funnelshift_r(q1, q2, shq);
+					qlo = q2;
+					unsigned qb0 = rq32[2 * k], qb1 = rq32[2 * k + 1];
+					const unsigned nhi = fnp[k + 1];
+					const unsigned mw = pb::nz_nib(__funnelshift_r(nlo, nhi, shn) & rnt[k]);      /* bit 4t: bases t of this word match */
+					nlo = nhi;
+					const int nb = bestov - 8 * k;       /* bases of this step: 8, fewer in the last one */
+					if (nb < 8) {                        /* what lies past the overlap must not reach the range check */
+						const unsigned k0 = nb >= 4 ? 0xFFFFFFFFu : (1u << (8 * nb)) - 1u;
+						const unsigned k1 = nb > 4 ? (1u << (8 * (nb - 4))) - 1u : 0u;
+						qa0 &= k0; qb0 &= k0;
+						qa1 &= k1; qb1 &= k1;
 					}
-					qbad |= ((qa4 & 0x7F7F7F7Fu) + 0x51515151u) | qa4;
-					qbad |= ((qb4 & 0x7F7F7F7Fu) + 0x51515151u) | qb4;
-					qa4 &= 0x3F3F3F3Fu;                  /* keeps the table index inside shared memory for pairs that are handed on */
-					qb4 &= 0x3F3F3F3Fu;
-					if ((w & 1) == 0) {
-						const int k = w >> 1;
-						const unsigned nhi = fnp[k + 1];
-						const unsigned f = __funnelshift_r(nlo, nhi, shn);
-						nlo = nhi;
-						mw = pb::nz_nib(f & rnt[k]);      /* bit 4t: bases t of this word match */
-					} else {
-						mw >>= 16;
-					}
+					qcheck2(qa0, qb0);
+					qcheck2(qa1, qb1);
+					qa0 &= 0x3F3F3F3Fu;                  /* keeps the table index inside shared memory for pairs that are handed on */
+					qb0 &= 0x3F3F3F3Fu;
+					qa1 &= 0x3F3F3F3Fu;
+					qb1 &= 0x3F3F3F3Fu;
 					if (cliff) {
-						const unsigned ma = __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 8 * min(max(ia - 4 * w, 0), 4));
-						const unsigned mb = __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 8 * min(max(lead_r - 4 * w, 0), 4));
-						qa4 = (qa4 & ma) | (0x2F2F2F2Fu & ~ma);
-						qb4 = (qb4 & ~mb) | (0x2F2F2F2Fu & mb);
+						const unsigned ma0 = __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 8 * min(max(ia - 8 * k, 0), 4));
+						const unsigned ma1 = __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 8 * min(max(ia - 8 * k - 4, 0), 4));
+						const unsigned mb0 = __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 8 * min(max(lead_r - 8 * k, 0), 4));
+						const unsigned mb1 = __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 8 * min(max(lead_r - 8 * k - 4, 0), 4));
+						qa0 = (qa0 & ma0) | (0x2F2F2F2Fu & ~ma0);
+						qa1 = (qa1 & ma1) | (0x2F2F2F2Fu & ~ma1);
+						qb0 = (qb0 & ~mb0) | (0x2F2F2F2Fu & mb0);
+						qb1 = (qb1 & ~mb1) | (0x2F2F2F2Fu & mb1);
 					}
-					/* match bits 0,4,8,12 -> bits 0,8,16,24, times 48, added to the forward qualities */
-					unsigned sp = mw & 0x1111u;
-					sp = (sp | (sp << 8)) & 0x00110011u;
-					sp = (sp | (sp << 4)) & 0x01010101u;
-					const unsigned row4 = qa4 + sp * 48u;
-					if (nb == 4) {
-						oquality += s_rec[__byte_perm(row4, 0, 0x4440) * PB_NQM + __byte_perm(qb4, 0, 0x4440)];
-						oquality1 += s_rec[__byte_perm(row4, 0, 0x4441) * PB_NQM + __byte_perm(qb4, 0, 0x4441)];
-						oquality += s_rec[__byte_perm(row4, 0, 0x4442) * PB_NQM + __byte_perm(qb4, 0, 0x4442)];
-						oquality1 += s_rec[__byte_perm(row4, 0, 0x4443) * PB_NQM + __byte_perm(qb4, 0, 0x4443)];
-					} else {
-						for (int t = 0; t < nb; t++)
-							oquality += s_rec[((row4 >> (8 * t)) & 0xFFu) * PB_NQM + ((qb4 >> (8 * t)) & 0xFFu)];
-					}
+					/* match bits 0,4,8,12 (16,20,24,28) -> bits 0,8,16,24, times 48, added to the forward qualities */
+					unsigned s0 = mw & 0x1111u, s1 = (mw >> 16) & 0x1111u;
+					s0 = (s0 | (s0 << 8)) & 0x00110011u;
+					s1 = (s1 | (s1 << 8)) & 0x00110011u;
+					s0 = (s0 | (s0 << 4)) & 0x01010101u;
+					s1 = (s1 | (s1 << 4)) & 0x01010101u;
+					const unsigned r0 = qa0 + s0 * 48u, r1 = qa1 + s1 * 48u;
+					oquality += s_rec[__byte_perm(r0, 0, 0x4440) * PB_NQM + __byte_perm(qb0, 0, 0x4440)];
+					if (nb > 1) oquality1 += s_rec[__byte_perm(r0, 0, 0x4441) * PB_NQM + __byte_perm(qb0, 0, 0x4441)];
+					if (nb > 2) oquality += s_rec[__byte_perm(r0, 0, 0x4442) * PB_NQM + __byte_perm(qb0, 0, 0x4442)];
+					if (nb > 3) oquality1 += s_rec[__byte_perm(r0, 0, 0x4443) * PB_NQM + __byte_perm(qb0, 0, 0x4443)];
+					if (nb > 4) oquality += s_rec[__byte_perm(r1, 0, 0x4440) * PB_NQM + __byte_perm(qb1, 0, 0x4440)];
+					if (nb > 5) oquality1 += s_rec[__byte_perm(r1, 0, 0x4441) * PB_NQM + __byte_perm(qb1, 0, 0x4441)];
+					if (nb > 6) oquality += s_rec[__byte_perm(r1, 0, 0x4442) * PB_NQM + __byte_perm(qb1, 0, 0x4442)];
+					if (nb > 7) oquality1 += s_rec[__byte_perm(r1, 0, 0x4443) * PB_NQM + __byte_perm(qb1, 0, 0x4443)];
 				}
 			}
 			oquality += oquality1;
-			/* reverse-only stretch: template-order reverse bases [bestov, R) (assembler.c:231-243) */
-			double rquality = 0.0, rquality1 = 0.0;
-			{
-				const int shq = (bestov & 3) * 8;
-				const uint32_t *rqp = rq32 + (bestov >> 2);
-				const int nfull = dr >> 2;
-				unsigned qlo = rqp[0];
-#pragma unroll 2
-				for (int w = 0; w < nfull; w++) {
-					const unsigned qhi = rqp[w + 1];
-					const unsigned q4 = __funnelshift_r(qlo, qhi, shq);
-					qlo = qhi;
-					qbad |= ((q4 & 0x7F7F7F7Fu) + 0x51515151u) | q4;
-					rquality += s_score[__byte_perm(q4, 0, 0x4440)];
-					rquality1 += s_score[__byte_perm(q4, 0, 0x4441)];
-					rquality += s_score[__byte_perm(q4, 0, 0x4442)];
-					rquality1 += s_score[__byte_perm(q4, 0, 0x4443)];
-				}
-				const int nb = dr & 3;
-				if (nb) {
-					unsigned q4 = __funnelshift_r(qlo, rqp[nfull + 1], shq);
-					q4 &= (1u << (8 * nb)) - 1u;          /* what follows the read in shared memory is not a quality */
-					qbad |= ((q4 & 0x7F7F7F7Fu) + 0x51515151u) | q4;
-					for (int t = 0; t < nb; t++)
-						rquality += s_score[(q4 >> (8 * t)) & 0xFFu];
-				}
-				rquality += rquality1;
-			}
-			if (qbad & 0x80808080u)
+			if ((qsum | qor) & 0x80808080u)
 				defer = true;                           /* a quality outside 0..46: PHREDCLAMP (prob.h:23) is the general kernel's job */
 			quality = (fquality + rquality + oquality) / (double) len;      /* assembler.c:244: divides by len, not seq_len */
 

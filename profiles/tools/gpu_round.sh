@@ -8,7 +8,7 @@ timeout 900 python -m pytest tests -m gpu -x -q "$@" > gpurun_out/${TAG}_pytest.
 tail -4 gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 cat gpurun_out/${TAG}_bench.json | cut -c1-1500
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^pb|pb[a-z]*::' -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'seed_kernel|lanes_kernel|assemble_kernel|bin_order|pack_kernel|class_list' -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --pairs 2000000 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'sweep_seed_kernel|assemble_lanes_kernel' -s 2 -c 2 -f -o gpurun_out/${TAG}_prof \
     python bench.py --steps 2 --warmup 1 --pairs 2000000 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
