@@ -172,7 +172,7 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     probe = synth.generate_config(args.config, n=20_000, device="cpu").to_flat()
     rate, kind = cpu_rate(cfg, probe, cores)
-    sample = int(min(max(rate * 1e6 * 6.0, 20_000), 10_000_000))        # ~6 s per step, at most the config's 10 M
+    sample = int(min(max(rate * 1e6 * 6.0, 20_000), 10_000_000 * 300 // (2 * c["rl"][1])))        # ~6 s per step, at most the config's 10 M (fewer of longer reads: host memory)
     flat = synth.generate_config(args.config, n=sample, device="cpu", chunk_index=1).to_flat()
     for _ in range(args.warmup):
         cpu_rate(cfg, flat.slice(0, min(sample, 50_000)), cores)
@@ -482,7 +482,9 @@ def main():
     # ---- build the resident batch: generate on the device, pack with the library's pack kernel ------
     reads_parts, meta_parts, alg_bytes, max_len, base16 = [], [], 0, 0, 0
     keep_flat = []          # AoS chunks kept (on the host) for the e2e leg
-    e2e_pairs = 0 if args.no_e2e else min(n, 4_000_000)
+    # host memory of the e2e and CPU legs is budgeted in bases, not pairs: 4 M pairs of 2x150, fewer of longer reads
+    per_pair = 2 * c["rl"][1]
+    e2e_pairs = 0 if args.no_e2e else min(n, max(1_000_000, (4_000_000 * 300 // per_pair) // GEN_CHUNK * GEN_CHUNK))
     for ci, start in enumerate(range(0, n, GEN_CHUNK)):
         cnt = min(GEN_CHUNK, n - start)
         rect = synth.generate_config(args.config, n=cnt, device=dev, chunk_index=rank * 100_000 + ci)
@@ -685,12 +687,16 @@ def main():
                                "note": "pb_assemble_host_packed(): pinned host records in the packed layout (4-bit nt + 8-bit PHRED) -> H2D -> assemble -> D2H"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
+    if e2e is not None:          # the e2e leg's host buffers are done with
+        del flat, keep, res_t, nt_t, res_h, nt_h, reads_p, meta_p
+        import gc
+        gc.collect()
     cpu = None
     if rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         probe = synth.generate_config(args.config, n=20_000, device="cpu").to_flat()
         r0, kind = cpu_rate(cfg, probe, cores)
-        sample = int(min(max(r0 * 1e6 * 12.0, 20_000), 8_000_000))
+        sample = int(min(max(r0 * 1e6 * 12.0, 20_000), 8_000_000 * 300 // per_pair))
         flat_c = synth.generate_config(args.config, n=sample, device="cpu", chunk_index=1).to_flat()
         r1, kind = cpu_rate(cfg, flat_c, cores)
         cpu = {"value": r1, "unit": "Mpairs/s", "cores": cores, "kind": kind,

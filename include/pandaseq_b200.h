@@ -427,7 +427,7 @@ pb_status pb_assemble_device(pb_context *ctx, const pb_config *cfg, size_t n, in
                              pb_pair_result *d_results, uint8_t *d_seq_nt, double *d_seq_p,
                              size_t seq_stride, int64_t *d_counters);
 pb_status pb_synchronize(pb_context *ctx);
-/* Diagnostics.  Configurations of the common kind (simple_bayesian / uparse / flash / pear, no primers/trims/trimmer, reads <= 256 nt, no
+/* Diagnostics.  Configurations of the common kind (simple_bayesian / uparse / flash / pear, no primers/trims/trimmer, no
  * per-base log p) are assembled by a lane-per-pair kernel that hands the pairs it does not cover (a base that is not
  * A/C/G/T, a quality outside 0..46, no seed, ...) to the general warp-per-pair kernel.  This reports, since the context was
  * created, how many pairs were launched that way and how many of them were handed on.  Synchronises the device. */

@@ -209,13 +209,16 @@ __device__ int primer_offset(const uint32_t *nt32, const int8_t *q, int len,
 	/* Both scores of every read position, once: se[2i] = qual_score[q_i] (the base agrees with the primer),
 	 * se[2i+1] = qual_score_err[q_i] (offset.c:93-101), i in scan order.  The scan below then costs one predicate,
 	 * one select and one 8-byte load per (start, primer base). */
-	for (int i = lane; i < len; i += 32) {
-		const unsigned off = qoff[256 + qu[TEMPLATE_ORDER ? (len - 1 - i) : i]];
-		double2 v;
-		v.x = *reinterpret_cast<const double *>(tab + off);
-		v.y = *reinterpret_cast<const double *>(tab + off + PB_NQM * 8);      /* score_err[] follows score[] */
-		reinterpret_cast<double2 *>(se)[i] = v;
-	}
+	auto stage_scores = [&]() {
+		for (int i = lane; i < len; i += 32) {
+			const unsigned off = qoff[256 + qu[TEMPLATE_ORDER ? (len - 1 - i) : i]];
+			double2 v;
+			v.x = *reinterpret_cast<const double *>(tab + off);
+			v.y = *reinterpret_cast<const double *>(tab + off + PB_NQM * 8);      /* score_err[] follows score[] */
+			reinterpret_cast<double2 *>(se)[i] = v;
+		}
+		__syncwarp();
+	};
 	/* The primer as masks: pm[x] = its nibble at the place base x & 7 of an 8-base window has (template order: the window
 	 * is bit-reversed below, so the nibble is too); all ones for N, which contributes nothing (offset.c:97). */
 	uint32_t *pm = reinterpret_cast<uint32_t *>(se + 2 * len);
@@ -231,8 +234,8 @@ __device__ int primer_offset(const uint32_t *nt32, const int8_t *q, int len,
 	}
 	has_n = __any_sync(FULL, has_n);
 	__syncwarp();
-	for (int base = 0; base < nstart; base += 32) {
-		const int s = min(base + lane, nstart - 1);    /* surplus lanes redo the last start; masked below */
+	/* the sum of start s, every term in primer order */
+	auto exact_sum = [&](int s) -> double {
 		double sum = 0.0;
 		const int el = TEMPLATE_ORDER ? (len - 1 - s) : s;   /* element holding read position s */
 		const char *sp = reinterpret_cast<const char *>(se + 2 * s);
@@ -260,6 +263,117 @@ __device__ int primer_offset(const uint32_t *nt32, const int8_t *q, int len,
 				}
 			}
 		}
+		return sum;
+	};
+	if (penalty == 0.0 && nstart > 0) {
+		/* Without a penalty the winner is the start with the largest sum / (index + 1), the lowest one among equals, if that beats
+		 * P * threshold.  Every term is a log-probability, i.e. <= 0, and a base that disagrees with the primer adds
+		 * qual_score_err[q] <= emax, the largest such value over this read's qualities.  So a start with m disagreeing bases among
+		 * the primer's first eight cannot reach more than m * emax / (index + 1): a first pass counts those m for every start (one
+		 * AND + POPC on the window instead of P loads and additions), the start with the fewest is summed exactly, and after that
+		 * only starts whose bound still reaches the best value are.  On a read that carries the primer the bound removes every other
+		 * start; the sums that are formed are formed exactly as before, so the result is the full scan's, bit for bit. */
+		/* qual_score_err[] falls with the quality (mktable.c:75-82: log of the error probability), so emax belongs to the lowest
+		 * quality of the read (as a signed char: PHREDCLAMP takes anything below zero to zero) */
+		int qmin = 127;
+		for (int i = lane; i < len; i += 32)
+			qmin = min(qmin, (int) q[i]);
+		qmin = __reduce_min_sync(FULL, qmin);
+		const double emax = *reinterpret_cast<const double *>(tab + qoff[256 + (unsigned) (unsigned char) qmin] + PB_NQM * 8);
+		unsigned pw0 = 0, np0 = 0;                     /* the primer's first eight bases as one word of nibbles, and how many of them count: an N adds nothing (offset.c:97) */
+		for (int t = 0; t < 8 && t < P; t++)
+			if (pm[t] != ~0u) {
+				pw0 |= pm[t];
+				np0++;
+			}
+		unsigned mlo = 0, mhi = 0, keymin = 0x7FFFFFFFu;      /* m of this lane's starts, four bits per round */
+		unsigned clean = 0;                            /* starts of this lane that agree with all of the primer's first eight bases */
+		int round = 0;
+		for (int base = 0; base < nstart; base += 32, round++) {
+			const int s = min(base + lane, nstart - 1);
+			const int el = TEMPLATE_ORDER ? (len - 1 - s) : s;
+			unsigned w = nibwin(nt32, TEMPLATE_ORDER ? (el - 7) : el);
+			if (TEMPLATE_ORDER)
+				w = __brev(w);
+			const unsigned m = np0 - (unsigned) __popc(nz_nib(w & pw0));      /* the window's nibbles outside the primer meet zeros */
+			if (round < 8)
+				mlo |= m << (4 * round);
+			else
+				mhi |= m << (4 * (round - 8));
+			if (base + lane < nstart) {
+				keymin = min(keymin, (m << 16) | (unsigned) s);
+				clean += m == 0u;
+			}
+		}
+		keymin = __reduce_min_sync(FULL, keymin);
+		clean = __reduce_add_sync(FULL, clean);
+		const int s0 = (int) (keymin & 0xFFFFu);
+		int best_s = -1;                               /* -1: `best` is still the threshold, which an equal value does not beat */
+		{
+			/* the sum of start s0 straight from the tables (the same addends in the same order as exact_sum(), which needs
+			 * both scores of every read position staged first: not worth it for one start) */
+			double sum = 0.0;
+			const int el = TEMPLATE_ORDER ? (len - 1 - s0) : s0;
+			for (int x0 = 0; x0 < P; x0 += 8) {
+				unsigned w = nibwin(nt32, TEMPLATE_ORDER ? (el - x0 - 7) : (el + x0));
+				if (TEMPLATE_ORDER)
+					w = __brev(w);
+				const int xn = min(P - x0, 8);
+				for (int t = 0; t < xn; t++) {
+					const unsigned m = pm[x0 + t];
+					if (m != ~0u) {
+						const int pos = s0 + x0 + t;
+						const unsigned off = qoff[256 + qu[TEMPLATE_ORDER ? (len - 1 - pos) : pos]] + ((w & m) == 0u ? PB_NQM * 8u : 0u);
+						sum += *reinterpret_cast<const double *>(tab + off);
+					}
+				}
+			}
+			const double v0 = sum / (double) (s0 + P + 1);
+			if (v0 > best) {
+				best = v0;
+				best_s = s0;
+			}
+		}
+		/* One disagreeing base already rules a start out if it does so at the largest index, len; then only the other clean starts
+		 * are left to look at -- on a read that carries the primer once, none. */
+		if (emax * 0.999999999 < best * (double) len && clean == ((keymin >> 16) == 0u ? 1u : 0u)) {
+			__syncwarp();
+			return best_s < 0 ? 0 : best_s + P + 1;
+		}
+		stage_scores();
+		round = 0;
+		for (int base = 0; base < nstart; base += 32, round++) {
+			const int s = base + lane;
+			const unsigned m = ((round < 8 ? mlo >> (4 * round) : mhi >> (4 * (round - 8))) & 15u);
+			/* skipped only if the bound, loosened by 1e-9 of itself against the rounding of either side, stays below the best */
+			const bool cand = s < nstart && s != s0 && !((double) m * emax * 0.999999999 < best * (double) (s + P + 1));
+			if (!__any_sync(FULL, cand))
+				continue;
+			double val = -CUDART_INF;
+			if (cand)
+				val = exact_sum(s) / (double) (s + P + 1);
+			int who = s;
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) {
+				const double ov = __shfl_xor_sync(FULL, val, d);
+				const int ow = __shfl_xor_sync(FULL, who, d);
+				if (ov > val || (ov == val && ow < who)) {
+					val = ov;
+					who = ow;
+				}
+			}
+			if (val > best || (val == best && best_s >= 0 && who < best_s)) {
+				best = val;
+				best_s = who;
+			}
+		}
+		__syncwarp();      /* se[] is rewritten by the next scan */
+		return best_s < 0 ? 0 : best_s + P + 1;
+	}
+	stage_scores();
+	for (int base = 0; base < nstart; base += 32) {
+		const int s = min(base + lane, nstart - 1);    /* surplus lanes redo the last start; masked below */
+		const double sum = exact_sum(s);
 		const int index = s + P;                   /* the index at which this slot is examined */
 		double val = sum / (double) (index + 1);
 		if (penalty != 0.0)
@@ -1450,37 +1564,37 @@ bin_order_kernel(int n, const uint32_t *__restrict__ seeds, int swords, int bin_
  * every class runs the seeding sweep and the lane-per-pair kernel sized for it (the sweep's work grows with the square of the
  * length class, the lane kernel's shared memory per pair with the class).  lists[c * cap ..] = indices of class c, counts[c] their
  * number (zero at launch); pairs with a longer read go straight to the general kernel's list.  Order inside a list: whatever the
- * atomics make it; no result depends on it. */
+ * atomics make it; no result depends on it.  (Shared-memory ranks, one global atomic per class and block: with one per warp the
+ * three hot counters cost 64 ns per thousand pairs.) */
 constexpr int PB_LEN_CLASSES = 3;
 __host__ __device__ constexpr int len_class_max(int c) { return c == 0 ? 160 : (c == 1 ? 256 : 320); }
 __global__ void __launch_bounds__(256)
 class_list_kernel(int n, const pb_pair_meta *__restrict__ meta, int *__restrict__ lists, size_t cap, int *__restrict__ counts,
                   int *__restrict__ general_list, int *__restrict__ general_count, unsigned long long *__restrict__ general_total) {
-	const int pair = blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31;
-	int cls = -1;
+	__shared__ int s_n[PB_LEN_CLASSES + 1], s_base[PB_LEN_CLASSES + 1];
+	const int tid = threadIdx.x;
+	if (tid <= PB_LEN_CLASSES)
+		s_n[tid] = 0;
+	__syncthreads();
+	const int pair = blockIdx.x * blockDim.x + tid;
+	int cls = -1, rank = 0;
 	if (pair < n) {
 		const uint2 m = *reinterpret_cast<const uint2 *>(&meta[pair]);
 		const int F = (int) (m.y & 0xFFFFu), R = (int) (m.y >> 16);
 		const int longest = F == 0xFFFF ? 0 : max(F, R);        /* not a pair: any class reports it as such */
 		cls = longest <= len_class_max(0) ? 0 : (longest <= len_class_max(1) ? 1 : (longest <= len_class_max(2) ? 2 : 3));
+		rank = atomicAdd(&s_n[cls], 1);                         /* place inside the block's share of the class */
 	}
-#pragma unroll
-	for (int c = 0; c <= PB_LEN_CLASSES; c++) {
-		const unsigned m = __ballot_sync(FULL, cls == c);
-		if (m == 0)
-			continue;
-		int base = 0;
-		if (lane == __ffs(m) - 1) {
-			base = atomicAdd(c < PB_LEN_CLASSES ? &counts[c] : general_count, __popc(m));
-			if (c == PB_LEN_CLASSES)
-				atomicAdd(general_total, (unsigned long long) __popc(m));
-		}
-		base = __shfl_sync(FULL, base, __ffs(m) - 1);
-		if (cls == c) {
-			int *dst = c < PB_LEN_CLASSES ? lists + (size_t) c * cap : general_list;
-			dst[base + __popc(m & lanemask_lt())] = pair;
-		}
+	__syncthreads();
+	if (tid <= PB_LEN_CLASSES && s_n[tid] > 0) {                /* one global atomic per class and block */
+		s_base[tid] = atomicAdd(tid < PB_LEN_CLASSES ? &counts[tid] : general_count, s_n[tid]);
+		if (tid == PB_LEN_CLASSES)
+			atomicAdd(general_total, (unsigned long long) s_n[tid]);
+	}
+	__syncthreads();
+	if (cls >= 0) {
+		int *dst = cls < PB_LEN_CLASSES ? lists + (size_t) cls * cap : general_list;
+		dst[s_base[cls] + rank] = pair;
 	}
 }
 
