@@ -218,7 +218,7 @@ struct LanesState {
 	unsigned long long *d_counters;
 	cudaStream_t stream;
 	int *d_count, *d_list;          /* the general kernel's list: count, entries */
-	uint32_t *d_seeds;
+	uint32_t *d_seeds;              /* seeds records (see seeds()) */
 	size_t cap;
 	uint32_t *seeds(int c) const { return c == 0 && ctx->classes_on[si] ? d_seeds + cap * pb::seed_words(320) : d_seeds; }
 	int *class_list(int c) const { return ctx->d_classes[si] + (size_t) c * cap; }

@@ -280,51 +280,67 @@ __device__ int primer_offset(const uint32_t *nt32, const int8_t *q, int len,
 			qmin = min(qmin, (int) q[i]);
 		qmin = __reduce_min_sync(FULL, qmin);
 		const double emax = *reinterpret_cast<const double *>(tab + qoff[256 + (unsigned) (unsigned char) qmin] + PB_NQM * 8);
-		unsigned pw0 = 0, np0 = 0;                     /* the primer's first eight bases as one word of nibbles, and how many of them count: an N adds nothing (offset.c:97) */
-		for (int t = 0; t < 8 && t < P; t++)
-			if (pm[t] != ~0u) {
-				pw0 |= pm[t];
-				np0++;
-			}
-		unsigned mlo = 0, mhi = 0, keymin = 0x7FFFFFFFu;      /* m of this lane's starts, four bits per round */
-		unsigned clean = 0;                            /* starts of this lane that agree with all of the primer's first eight bases */
-		int round = 0;
-		for (int base = 0; base < nstart; base += 32, round++) {
+		/* the primer's first eight bases as one word of nibbles, and how many of them count: an N adds nothing (offset.c:97) */
+		const unsigned pmine = (lane < 8 && lane < P) ? pm[lane] : ~0u;
+		const unsigned pw0 = __reduce_or_sync(FULL, pmine == ~0u ? 0u : pmine);
+		const unsigned np0 = (unsigned) __popc(__ballot_sync(FULL, pmine != ~0u));
+		/* m of this lane's starts, four bits per round (15 where the lane has no start), rounds 0..7 in mlo, 8..15 in mhi */
+		unsigned mlo = 0xFFFFFFFFu, mhi = 0xFFFFFFFFu, keymin = 0x7FFFFFFFu;
+		auto count_round = [&](int base) -> unsigned {
 			const int s = min(base + lane, nstart - 1);
 			const int el = TEMPLATE_ORDER ? (len - 1 - s) : s;
 			unsigned w = nibwin(nt32, TEMPLATE_ORDER ? (el - 7) : el);
 			if (TEMPLATE_ORDER)
 				w = __brev(w);
-			const unsigned m = np0 - (unsigned) __popc(nz_nib(w & pw0));      /* the window's nibbles outside the primer meet zeros */
-			if (round < 8)
-				mlo |= m << (4 * round);
-			else
-				mhi |= m << (4 * (round - 8));
-			if (base + lane < nstart) {
-				keymin = min(keymin, (m << 16) | (unsigned) s);
-				clean += m == 0u;
-			}
+			unsigned m = np0 - (unsigned) __popc(nz_nib(w & pw0));      /* the window's nibbles outside the primer meet zeros */
+			m = base + lane < nstart ? m : 15u;
+			keymin = min(keymin, (m << 16) | (unsigned) s);
+			return m;
+		};
+		{
+			unsigned acc = 0;
+			int sh = 0;
+			for (int base = 0; base < nstart && sh < 32; base += 32, sh += 4)
+				acc |= count_round(base) << sh;
+			mlo = acc | (sh < 32 ? 0xFFFFFFFFu << sh : 0u);
+			acc = 0;
+			sh = 0;
+			for (int base = 256; base < nstart; base += 32, sh += 4)
+				acc |= count_round(base) << sh;
+			mhi = acc | (sh < 32 ? 0xFFFFFFFFu << sh : 0u);
 		}
 		keymin = __reduce_min_sync(FULL, keymin);
-		clean = __reduce_add_sync(FULL, clean);
+		/* starts that agree with all of the primer's first eight bases: the zero nibbles */
+		auto zero_nibbles = [](unsigned x) { x |= x >> 1; x |= x >> 2; return (unsigned) __popc(~x & NIB1); };
+		const unsigned clean = __reduce_add_sync(FULL, zero_nibbles(mlo) + zero_nibbles(mhi));
 		const int s0 = (int) (keymin & 0xFFFFu);
 		int best_s = -1;                               /* -1: `best` is still the threshold, which an equal value does not beat */
 		{
-			/* the sum of start s0 straight from the tables (the same addends in the same order as exact_sum(), which needs
-			 * both scores of every read position staged first: not worth it for one start) */
+			/* The sum of start s0 straight from the tables: the same addends in the same order as exact_sum(), which needs both
+			 * scores of every read position staged first -- not worth it for one start.  Lane x fetches the term of primer base x,
+			 * the terms are then added in primer order. */
+			const uint8_t *ntb = reinterpret_cast<const uint8_t *>(nt32);
 			double sum = 0.0;
-			const int el = TEMPLATE_ORDER ? (len - 1 - s0) : s0;
-			for (int x0 = 0; x0 < P; x0 += 8) {
-				unsigned w = nibwin(nt32, TEMPLATE_ORDER ? (el - x0 - 7) : (el + x0));
-				if (TEMPLATE_ORDER)
-					w = __brev(w);
-				const int xn = min(P - x0, 8);
-				for (int t = 0; t < xn; t++) {
-					const unsigned m = pm[x0 + t];
-					if (m != ~0u) {
-						const int pos = s0 + x0 + t;
-						const unsigned off = qoff[256 + qu[TEMPLATE_ORDER ? (len - 1 - pos) : pos]] + ((w & m) == 0u ? PB_NQM * 8u : 0u);
-						sum += *reinterpret_cast<const double *>(tab + off);
+			for (int xb = 0; xb < P; xb += 32) {
+				const int x = xb + lane;
+				double term = 0.0;
+				bool use = false;
+				if (x < P && primer[x] != 15u) {
+					const int pos = s0 + x, el = TEMPLATE_ORDER ? (len - 1 - pos) : pos;
+					const bool hit = (nib(ntb, el) & primer[x]) != 0u;
+					term = *reinterpret_cast<const double *>(tab + qoff[256 + qu[el]] + (hit ? 0u : PB_NQM * 8u));
+					use = true;
+				}
+				const unsigned um = __ballot_sync(FULL, use);
+				const int xn = min(P - xb, 32);
+				if (um == (xn == 32 ? 0xFFFFFFFFu : (1u << xn) - 1u)) {      /* no N among these primer bases */
+					for (int t = 0; t < xn; t++)
+						sum += __shfl_sync(FULL, term, t);
+				} else {
+					for (int t = 0; t < xn; t++) {
+						const double v = __shfl_sync(FULL, term, t);
+						if ((um >> t) & 1u)
+							sum += v;
 					}
 				}
 			}
@@ -341,10 +357,10 @@ __device__ int primer_offset(const uint32_t *nt32, const int8_t *q, int len,
 			return best_s < 0 ? 0 : best_s + P + 1;
 		}
 		stage_scores();
-		round = 0;
-		for (int base = 0; base < nstart; base += 32, round++) {
+		int rnd = 0;
+		for (int base = 0; base < nstart; base += 32, rnd++) {
 			const int s = base + lane;
-			const unsigned m = ((round < 8 ? mlo >> (4 * round) : mhi >> (4 * (round - 8))) & 15u);
+			const unsigned m = ((rnd < 8 ? mlo >> (4 * rnd) : mhi >> (4 * (rnd - 8))) & 15u);
 			/* skipped only if the bound, loosened by 1e-9 of itself against the rounding of either side, stays below the best */
 			const bool cand = s < nstart && s != s0 && !((double) m * emax * 0.999999999 < best * (double) (s + P + 1));
 			if (!__any_sync(FULL, cand))

@@ -4,8 +4,8 @@
  * (K1-K3, which does want 32 lanes on one pair) everything that is left -- scoring a handful of candidate overlaps,
  * merging the reads, summing the per-base posterior -- is a stream of 32-bit words of packed bases, and a warp-wide
  * formulation pays for partly filled lane rounds, shuffles, ballots and per-pair bookkeeping.  So the common
- * configurations run as two kernels: pb::seed_kernel (warp per pair) leaves the candidate overlaps of every pair as a
- * bit mask, and the kernel here takes 32 consecutive pairs per warp, every lane running K4-K6 of the reference's
+ * configurations run as two kernels: the seeding kernel (pbs::sweep_seed_kernel, lane per pair, or pb::seed_kernel, warp per
+ * pair) leaves the candidate overlaps of every pair as a bit mask, and the kernel here takes 32 pairs of one overlap bin per warp, every lane running K4-K6 of the reference's
  * align() (assembler.c:118-250) for its own pair as straight scalar code.  What makes that affordable is that the rare
  * cases do not have to be handled here: a lane that meets one (a base that is not A/C/G/T, a quality outside 0..46, no
  * seed at all, an overlap longer than a read, a read shorter than 16 nt) appends its pair to a deferral list and the
@@ -13,13 +13,15 @@
  * function, so the split is invisible in the results.
  *
  *   stage   32 bulk async copies (one per lane, cp.async.bulk / UBLKCP) land the 32 records in this warp's shared
- *           memory at a stride of an odd number of 16-byte units; one mbarrier per warp; the warp's next batch is
- *           prefetched into L2 meanwhile.
+ *           memory at a stride of an odd number of 16-byte units; one mbarrier per warp; the warp's next batch (its
+ *           number, pairs, metadata and seeds records) is fetched one batch ahead and its records are prefetched into L2
+ *           (cp.async.bulk.prefetch / UBLKPF) meanwhile.
  *   score   K4/K5 (assembler.c:120-143): candidates in increasing overlap; the count-based scorers
  *           (algo_simple_bayes.c:33-66, algo_uparse.c:33-66, algo_flash.c:30-60) need one AND + POPC per 8 bases, pear
  *           (algo_pear.c:32-59) one table gather per base, added in the reference's order.
- *   merge   K6 (assembler.c:158-244): merged bases 8 per word; the per-base posterior is summed per stretch (forward-
- *           only, overlap, reverse-only) as the reference does, on two accumulators each.
+ *   merge   K6 (assembler.c:158-244): merged bases 8 per word (copy of the forward words / both reads / shifted copy of the
+ *           reverse words); the per-base posterior is summed per stretch (forward-only, overlap, reverse-only) as the
+ *           reference does, on two accumulators each, the two outer stretches in one loop, the overlap eight bases per step.
  *
  * A first version of this file also did the k-mer join per lane (a 256-slot open-addressing table per lane, lane-
  * interleaved in shared memory).  Measured on B200: 124 Mpairs/s against 650 for the warp-per-pair kernel -- 1 KB of
@@ -27,8 +29,9 @@
  * (1,541 warp-instructions per pair at 13 active lanes, 0.17 instructions per cycle and scheduler).  DESIGN.md section 5.
  *
  * Configurations this path takes (the host decides, pb_device.cu): simple_bayesian / uparse / flash / pear, no primers, no
- * trims, no overhang trimmer, no per-base log p requested, filters that read only the result record, reads <= 256 nt
- * (length classes 152, 160 and 256 nt: 12, 11 and 7 warps per SM).
+ * trims, no overhang trimmer, no per-base log p requested, filters that read only the result record; length classes 152, 160,
+ * 256 and 320 nt (12, 11, 7 and 6 warps per SM); a batch of mixed lengths is listed by class first (pb::class_list_kernel) and
+ * every class runs the kernel sized for it, pairs with a read above 320 nt go to the general kernel.
  */
 #pragma once
 #include "pb_kernels.cuh"

@@ -9,7 +9,8 @@
  * gives, per 32-bit word, the positions where the digits differ (XOR, OR); an 8-mer match on that diagonal is a run
  * of eight equal positions, found with three shift-OR doubling steps.  All diagonals of a pair cost
  * (NW (NW + 1) / 2) x 32 word steps of nine instructions for reads of up to 32 NW bases, every lane busy with its own
- * pair: 163 instructions per pair at 2x150 (NW = 5), no shared-memory traffic, no atomics.
+ * pair (NW = 5, 8 or 10: the length classes of pb_device.cu): measured 230 warp-instructions per pair at 2x150 with the planes and
+ * the certificate (profiles/r2/), no shared-memory traffic and no atomics in the sweep itself.
  *
  * The sweep finds every diagonal with a shared 8-mer; the reference only those where the forward position was one of
  * the first two with its code ("lost k-mers", assembler.c:95-97).  So every flagged diagonal is certified afterwards:

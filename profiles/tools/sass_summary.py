@@ -23,7 +23,7 @@ for l in res.splitlines():
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 names = subprocess.run(["cu++filt"], input="\n".join(usage), capture_output=True, text=True).stdout.splitlines()
 demangled = dict(zip(usage, names))
-WATCH = ["UBLKCP", "UTMALDG", "SYNCS", "ATOMS", "ATOMG", "RED", "VIMNMX", "VIMNMX3", "LOP3", "SHF", "IMAD", "IMAD.WIDE", "POPC", "PRMT",
+WATCH = ["UBLKCP", "UBLKPF", "UTMALDG", "SYNCS", "ATOMS", "ATOMG", "RED", "VIMNMX", "VIMNMX3", "LOP3", "SHF", "IMAD", "IMAD.WIDE", "POPC", "PRMT",
          "LDS", "STS", "LDG", "STG", "DADD", "DMUL", "DFMA", "SHFL", "VOTE", "REDUX", "MATCH", "BAR", "CCTL", "UTCMMA", "HMMA"]
 print(f"# {lib}: cuobjdump -sass -res-usage, sm_100a")
 arch = re.search(r"arch = (sm_\w+)", txt)
