@@ -570,19 +570,23 @@ def main():
     if kind == 2:
         # algorithmic bytes per pair of each kernel: seeding reads the packed bases + metadata and writes a 32-byte mask record;
         # the lane kernel reads the whole record, the metadata and the mask record and writes the result + the merged read
-        seed_b = ((fl0 + 1) // 2 + (rl0 + 1) // 2 + 8)
+        seed_b = ((fl0 + 1) // 2 + (rl0 + 1) // 2 + 8) if max_len <= 160 else (alg_bytes / n - (alg_bytes / n - 8) * 2 / 3)
+        # batches with reads above 160 nt are listed by length class first (pb::class_list_kernel) and every class that can hold
+        # a pair of the batch (<= 160, <= 256, <= 320 nt) runs its own seeding, bin list and lane kernel
+        ncls = 1 if (max_len <= 160 or cfg.maxoverlap != 0) else (2 if max_len <= 256 else 3)
+        by_class = "" if ncls == 1 else f", once per length class ({ncls} classes; pb::class_list_kernel first)"
         kernels = [
             {"name": ("pbs::sweep_seed_kernel (K1-K3 as a bit-parallel sweep over diagonals, one lane per pair)" if cfg.maxoverlap == 0
-                      else "pb::seed_kernel (K1-K3: k-mer join, one warp per pair)") + " + pb::bin_order_kernel (pairs listed by overlap bin)",
-             "ms": kms[0], "launches_per_step": 2,
+                      else "pb::seed_kernel (K1-K3: k-mer join, one warp per pair)") + " + pb::bin_order_kernel (pairs listed by overlap bin)" + by_class,
+             "ms": kms[0], "launches_per_step": 2 * ncls + (1 if ncls > 1 else 0),
              "algorithmic_read_bytes_per_pair": seed_b, "achieved_gbs": seed_b * n / (kms[0] / 1e3) / 1e9},
-            {"name": "pbl::assemble_lanes_kernel (K4-K6: score + merge, one lane per pair)", "ms": kms[1], "launches_per_step": 1,
+            {"name": "pbl::assemble_lanes_kernel (K4-K6: score + merge, one lane per pair)" + by_class, "ms": kms[1], "launches_per_step": ncls,
              "algorithmic_read_bytes_per_pair": alg_bytes / n + 32, "achieved_gbs": (alg_bytes + 32 * n) / (kms[1] / 1e3) / 1e9},
             {"name": "pb::assemble_kernel, list mode (the pairs the two kernels above hand on)", "ms": kms[2], "launches_per_step": 1},
         ]
         kernel_name = ("pbs::sweep_seed_kernel" if cfg.maxoverlap == 0 else "pb::seed_kernel") + \
             " + pb::bin_order_kernel + pbl::assemble_lanes_kernel + pb::assemble_kernel<list> (one step; the read bytes of the path over their summed duration)"
-        launches_per_step = 4
+        launches_per_step = 3 * ncls + 1 + (1 if ncls > 1 else 0)
     else:
         kernels = [{"name": "pb::assemble_kernel", "ms": kms[2], "launches_per_step": 1}]
         kernel_name = "pb::assemble_kernel"

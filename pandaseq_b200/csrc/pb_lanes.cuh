@@ -97,10 +97,10 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 	/* Which 32 entries of the bin list a warp takes next comes from a counter in global memory (*next_batch, zero at launch): with a
 	 * fixed share per warp the warps the scheduler favours finish early and leave the SM half empty at the end.  Everything a batch
 	 * needs before its records can be fetched -- its number (an atomic), its pairs (the bin list), their metadata and seeds records --
-	 * is a chain of dependent global loads; it is run one batch ahead, each link issued where the previous one has long arrived, so
-	 * that no iteration waits for it: the counter is bumped for the batch after next at the top of an iteration and read at its bottom,
-	 * the next batch's pair index is loaded at the bottom of the iteration before, its metadata and seeds record after this batch's
-	 * records have landed, and its records are pulled into L2 after the scoring. */
+	 * is a chain of dependent global loads; it runs ahead of the batch in flight, every link one whole iteration after the one it
+	 * depends on, so that no iteration waits for any of it: at the top of an iteration the counter is bumped (read at the top of the
+	 * next one: three batches ahead), the pairs of the batch three ahead are looked up in the bin list, the metadata and seeds records
+	 * of the batch two ahead are loaded, and the records of the next batch are pulled into L2. */
 	struct Head {
 		int pair;
 		unsigned off16;
@@ -145,11 +145,16 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 	};
 	int batch = __shfl_sync(FULL, take(), 0);
 	int batch1 = __shfl_sync(FULL, take(), 0);
-	Head cur, nxt;
+	int batch2 = __shfl_sync(FULL, take(), 0);
+	int taken = take();                                        /* the third batch from here; read one iteration later */
+	Head cur, nxt, far;
 	load_head(pair_of(batch), cur);
-	int pair1 = pair_of(batch1);
+	load_head(pair_of(batch1), nxt);
+	int pair2 = pair_of(batch2);
 	while (batch < nbatch) {
-		const int taken = take();                              /* the batch after next; read at the bottom */
+		const int batch3 = __shfl_sync(FULL, taken, 0);        /* asked for one iteration ago */
+		taken = take();
+		const int pair3 = pair_of(batch3);                     /* used one iteration from here */
 		const int pair = cur.pair;
 		const int F = cur.F, R = cur.R;
 		unsigned cw[LA::CW];
@@ -167,9 +172,13 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 		__syncwarp();
 		if (bytes)
 			pb::bulk_g2s(wa.rec + lane * LA::REC_STRIDE, reads + (size_t) cur.off16 * 16, bytes, &wa.bar);
+		load_head(pair2, far);                                 /* the batch after next: its pairs were looked up one iteration ago */
+		if (nxt.F != 0xFFFF && nxt.F <= ML && nxt.R <= ML) {      /* the next batch, known for an iteration: pull its records into L2 now */
+			const unsigned nbytes = pb::record_bytes((unsigned) nxt.F, (unsigned) nxt.R);
+			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(reads + (size_t) nxt.off16 * 16), "r"(nbytes) : "memory");
+		}
 		pb::mbar_wait(&wa.bar, parity);
 		parity ^= 1u;
-		load_head(pair1, nxt);                                 /* consumed by the next iteration */
 
 		uint8_t status = PB_PAIR_OK;
 		int slow = 0, bestov = -1, examined = 0, seq_len = 0, mism = 0;
@@ -301,10 +310,6 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 						defer = true;
 				}
 			}
-		}
-		if (nxt.F != 0xFFFF && nxt.F <= ML && nxt.R <= ML) {      /* the next batch of this warp: pull its records into L2 meanwhile */
-			const unsigned nbytes = pb::record_bytes((unsigned) nxt.F, (unsigned) nxt.R);
-			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(reads + (size_t) nxt.off16 * 16), "r"(nbytes) : "memory");
 		}
 		if (act && !defer && status == PB_PAIR_OK) {
 			/* ---- K6: reconstruction (assembler.c:145-250) with forward_offset = reverse_offset = 0 ---- */
@@ -597,9 +602,11 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 		}
 		__syncwarp();      /* every lane is done with its record before the next batch lands on it */
 		batch = batch1;
-		batch1 = __shfl_sync(FULL, taken, 0);
+		batch1 = batch2;
+		batch2 = batch3;
 		cur = nxt;
-		pair1 = pair_of(batch1);
+		nxt = far;
+		pair2 = pair3;
 	}
 	__syncthreads();
 	for (int i = tid; i < PB_NCOUNTERS; i += blockDim.x) {
