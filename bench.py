@@ -440,6 +440,9 @@ def main():
     ap.add_argument("--path", default="pairs", choices=["pairs", "text", "api", "copy"],
                     help="pairs: the BASELINE metric on panda_qual pairs (default); text: FASTQ text in -> FASTA text out (SURVEY.md 8f rank 1+2); "
                          "api: through panda_run_pool and the reference's callbacks; copy: host <-> device copies alone")
+    ap.add_argument("--per-base-p", action="store_true",
+                    help="also produce the per-base log p of every merged base (what FASTQ output and the quality plugins need): doubles on the "
+                         "device-resident leg, 16-bit codes into the posterior table on the e2e leg (pb_assemble_host_codes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -507,10 +510,11 @@ def main():
     results = torch.empty((n, 32), dtype=torch.uint8, device=dev)
     seq_nt = torch.empty((n, seq_stride // 2), dtype=torch.uint8, device=dev)
     counters = torch.zeros(pb.PB_NCOUNTERS, dtype=torch.int64, device=dev)
+    seq_p = torch.empty((n, seq_stride), dtype=torch.float64, device=dev) if args.per_base_p else None
     torch.cuda.synchronize(dev)
 
     def step():
-        ctx.assemble_device(cfg, n, max_len, reads, meta, results, seq_nt, None, seq_stride, counters)
+        ctx.assemble_device(cfg, n, max_len, reads, meta, results, seq_nt, seq_p, seq_stride, counters)
 
     def barrier():
         if dist is not None:
@@ -608,7 +612,7 @@ def main():
     traffic, traffic_src = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(str(args.config))
-        if tr:
+        if tr and not args.per_base_p:
             traffic, traffic_src = tr["dram_bytes_per_pair"] * n, tr["source"]
     except Exception:
         pass
@@ -639,12 +643,17 @@ def main():
         nt_t = torch.zeros((ne, seq_stride // 2), dtype=torch.uint8, pin_memory=True)
         res_h, nt_h = res_t.numpy(), nt_t.numpy()
         cnt_h = np.zeros(pb.PB_NCOUNTERS, dtype=np.int64)
+        code_t = torch.zeros((ne, seq_stride), dtype=torch.int16, pin_memory=True) if args.per_base_p else None
         import ctypes as C
         L = pb.lib()
 
         def e2e_step():
-            rc = L.pb_assemble_host(ctx._h, C.byref(cfg), ne, flat.f_data.ctypes.data, flat.f_off.ctypes.data, flat.r_data.ctypes.data,
-                                    flat.r_off.ctypes.data, res_h.ctypes.data, nt_h.ctypes.data, None, seq_stride, cnt_h.ctypes.data)
+            if code_t is not None:
+                rc = L.pb_assemble_host_codes(ctx._h, C.byref(cfg), ne, flat.f_data.ctypes.data, flat.f_off.ctypes.data, flat.r_data.ctypes.data,
+                                              flat.r_off.ctypes.data, res_h.ctypes.data, nt_h.ctypes.data, code_t.data_ptr(), seq_stride, cnt_h.ctypes.data)
+            else:
+                rc = L.pb_assemble_host(ctx._h, C.byref(cfg), ne, flat.f_data.ctypes.data, flat.f_off.ctypes.data, flat.r_data.ctypes.data,
+                                        flat.r_off.ctypes.data, res_h.ctypes.data, nt_h.ctypes.data, None, seq_stride, cnt_h.ctypes.data)
             if rc != 0:
                 raise RuntimeError(L.pb_last_error().decode())
 
@@ -660,39 +669,43 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         h2d = flat.f_data.nbytes + flat.r_data.nbytes + flat.f_off.nbytes + flat.r_off.nbytes + 4 * ne
-        d2h = res_h.nbytes + nt_h.nbytes
+        d2h = res_h.nbytes + nt_h.nbytes + (code_t.numel() * 2 if code_t is not None else 0)
         e2e = {"value": ne * world * ksteps / dt / 1e6, "unit": "Mpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "pairs_per_step_per_gpu": ne, "steps": ksteps,
-               "note": "pb_assemble_host(): pinned host panda_qual arrays -> H2D -> pack -> assemble -> D2H (results + merged reads) into pinned host arrays, 2 streams"}
+               "note": ("pb_assemble_host_codes(): as pb_assemble_host(), plus the per-base log p of every merged base as 16-bit codes into the posterior table (D2H-bound: 792 B per pair out)"
+                        if code_t is not None else
+                        "pb_assemble_host(): pinned host panda_qual arrays -> H2D -> pack -> assemble -> D2H (results + merged reads) into pinned host arrays, 2 streams")}
         # the same with records the caller keeps in the packed layout (pb_assemble_host_packed): 26 % fewer bytes in, no pack kernel.
         # The packing itself (pb_pack_host, once, outside the timing) is what a parser writing this layout would do instead of AoS.
-        reads_h, meta_h, ml_h = pb.pack_host(flat)
-        reads_p, meta_p = pinned(reads_h), pinned(meta_h.view(np.int64))
-        del reads_h, meta_h
+        reads_p = meta_p = None
+        if code_t is None:          # (the packed entry point has no per-base variant)
+            reads_h, meta_h, ml_h = pb.pack_host(flat)
+            reads_p, meta_p = pinned(reads_h), pinned(meta_h.view(np.int64))
+            del reads_h, meta_h
 
-        def e2e_packed_step():
-            rc = L.pb_assemble_host_packed(ctx._h, C.byref(cfg), ne, ml_h, reads_p.data_ptr(), meta_p.data_ptr(), res_h.ctypes.data,
-                                           nt_h.ctypes.data, seq_stride, cnt_h.ctypes.data)
-            if rc != 0:
-                raise RuntimeError(L.pb_last_error().decode())
+            def e2e_packed_step():
+                rc = L.pb_assemble_host_packed(ctx._h, C.byref(cfg), ne, ml_h, reads_p.data_ptr(), meta_p.data_ptr(), res_h.ctypes.data,
+                                               nt_h.ctypes.data, seq_stride, cnt_h.ctypes.data)
+                if rc != 0:
+                    raise RuntimeError(L.pb_last_error().decode())
 
-        e2e_packed_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
             e2e_packed_step()
-        dtp = time.perf_counter() - t0
-        tt = torch.tensor([dtp], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dtp = float(tt.item())
-        e2e["packed_input"] = {"value": ne * world * ksteps / dtp / 1e6, "unit": "Mpairs/s",
-                               "h2d_bytes_per_step": int(reads_p.numel() + meta_p.numel() * 8), "d2h_bytes_per_step": int(d2h),
-                               "note": "pb_assemble_host_packed(): pinned host records in the packed layout (4-bit nt + 8-bit PHRED) -> H2D -> assemble -> D2H"}
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                e2e_packed_step()
+            dtp = time.perf_counter() - t0
+            tt = torch.tensor([dtp], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dtp = float(tt.item())
+            e2e["packed_input"] = {"value": ne * world * ksteps / dtp / 1e6, "unit": "Mpairs/s",
+                                   "h2d_bytes_per_step": int(reads_p.numel() + meta_p.numel() * 8), "d2h_bytes_per_step": int(d2h),
+                                   "note": "pb_assemble_host_packed(): pinned host records in the packed layout (4-bit nt + 8-bit PHRED) -> H2D -> assemble -> D2H"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
     if e2e is not None:          # the e2e leg's host buffers are done with
-        del flat, keep, res_t, nt_t, res_h, nt_h, reads_p, meta_p
+        del flat, keep, res_t, nt_t, res_h, nt_h, reads_p, meta_p, code_t
         import gc
         gc.collect()
     cpu = None
@@ -716,7 +729,9 @@ def main():
             "config": {"workload": f"BASELINE config {args.config}: {n} synthetic {shape_label(c)} pairs per GPU, {c['algo']}"
                                    + (", primer strip" if kw else ""),
                        "pairs_per_gpu": n, "l2_policy": f"inputs larger than L2 ({reads.numel() / 1e6:.0f} MB packed per GPU), no flush",
-                       "outputs": "32 B result record + merged read (4 bit/base) per pair; per-base log p not requested",
+                       "outputs": "32 B result record + merged read (4 bit/base) per pair; "
+                                  + ("per-base log p of every merged base as well (f64 on the device-resident leg, 16-bit codes into the posterior table on the e2e leg)"
+                                     if args.per_base_p else "per-base log p not requested"),
                        "parallelism": f"{world} x independent shards, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_pair": alg_bytes / n,
