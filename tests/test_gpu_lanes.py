@@ -258,3 +258,28 @@ def test_length_classes_with_reads_up_to_450_nt(ctx):
         got, want, rep = run_lanes(ctx, pb.make_config(algo, minoverlap=10), b)
         assert rep["ok"], (algo, rep)
         assert 500 < rep["deferred"] < b.n, rep
+
+
+def test_length_classes_small_batches_filters_and_no_rows(ctx):
+    # the length-class path at its edges: one pair, one more than a warp-batch, classes that stay empty, checks on the result record,
+    # a caller that does not want the merged reads, an explicit maxoverlap (hash-join seeding: whole batches, reads up to 256 nt only)
+    big = synth.generate(2000, rl=(75, 300), tmpl=None, seed=41, mixed=True, n_rate=0.0003).to_flat()
+    for n in (1, 2, 33, 65):
+        b = big.slice(0, n)
+        got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian"), b)
+        assert rep["ok"], (n, rep)
+    only300 = synth.generate(40, rl=(300, 300), tmpl=(330, 560), seed=42).to_flat()          # classes 0 and 1 stay empty
+    got, want, rep = run_lanes(ctx, pb.make_config("flash"), only300)
+    assert rep["ok"], rep
+    for filters in ([("short", 250), ("long", 420)], [("pear_test", (1.0, -1.0, 0.01))], [("min_overlapbits", 80.0), ("completely_miss_the_point", 2)]):
+        got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian", filters=filters), big)
+        assert rep["ok"], (filters, rep)
+    before = ctx.lanes_stats()
+    got = ctx.assemble_host(pb.make_config("simple_bayesian"), big, want_nt=False)
+    assert ctx.lanes_stats()[0] - before[0] == big.n
+    want = oracle_lib.assemble("port", pb.make_config("simple_bayesian"), big)
+    rep = compare(got, want)
+    assert rep["ok"], rep
+    # reads above 256 nt with an explicit maxoverlap: no sweep, no hash-join class for them -> the general kernel takes the batch
+    got, want, rep = run_lanes(ctx, pb.make_config("simple_bayesian", maxoverlap=200), big, expect_lanes=False)
+    assert rep["ok"], rep
