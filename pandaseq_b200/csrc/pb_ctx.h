@@ -27,6 +27,11 @@ struct pb_context {
 	uint32_t *d_seeds[2];            /* candidate-overlap masks of pb::seed_kernel, 8 words per pair */
 	int *d_order[2];                 /* the pairs of a launch bin by bin (pb::bin_order_kernel) */
 	unsigned *d_bins[2];             /* per length class: 2 x PB_SEED_BINS (pairs per bin, cursors) + the kernels' batch counters */
+	/* the two kernels side by side on slices of a large batch (pb_device.cu, launch_lanes_overlap): second stream, events, per-slice bin state */
+	cudaStream_t ovl_stream;
+	cudaEvent_t ovl_ev[20];
+	unsigned *d_ovl;
+	bool ovl_ready, timing_overlap;
 	int *d_classes[2];               /* the pairs of a batch listed by length class (pb::class_list_kernel); allocated on first use */
 	bool classes_on[2];
 	double *d_pear_cdf;              /* pear_test table (PB_PEAR_ROWS x PB_PEAR_COLS), built on first use */

@@ -96,6 +96,13 @@ extern "C" void pb_context_destroy(pb_context *ctx) {
 	cudaFree(ctx->d_seeds[1]);
 	cudaFree(ctx->d_order[0]);
 	cudaFree(ctx->d_order[1]);
+	if (ctx->ovl_ready) {
+		cudaStreamSynchronize(ctx->ovl_stream);
+		for (int k = 0; k < 18; k++)
+			cudaEventDestroy(ctx->ovl_ev[k]);
+		cudaStreamDestroy(ctx->ovl_stream);
+		cudaFree(ctx->d_ovl);
+	}
 	cudaFree(ctx->d_classes[0]);
 	cudaFree(ctx->d_classes[1]);
 	cudaFree(ctx->d_bins[0]);
@@ -196,7 +203,7 @@ static pb_status launch_assemble(pb_context *ctx, int n, const uint8_t *d_reads,
 	CUDA_TRY(cudaGetLastError());
 	if (timed) {
 		CUDA_TRY(cudaEventRecord(ctx->tev[3], stream));
-		ctx->timing_kind = d_list ? 2 : 1;
+		ctx->timing_kind = d_list ? (ctx->timing_overlap ? 3 : 2) : 1;
 	}
 	return PB_OK;
 }
@@ -335,16 +342,132 @@ static pb_status lanes_assemble(const LanesState &L, int c) {
 		grid = 1;
 	kern<<<(unsigned) grid, LW * 32, smem, L.stream>>>(ctx->d_params, L.n, L.d_reads, L.d_meta, L.seeds(c), L.order(cc), L.d_results, L.d_seq_nt, (long long) L.seq_stride,
 	                                                     L.d_counters, L.d_list, L.d_count, ctx->d_defer_total, L.bins(cc) + 2 * pb::PB_SEED_BINS + 1,
-	                                                     c < 0 ? nullptr : L.class_count(c));
+	                                                     c < 0 ? nullptr : L.class_count(c), 0);
 	CUDA_TRY(cudaGetLastError());
 	return PB_OK;
 }
 
 #define PB_TRY(x) do { pb_status st__ = (x); if (st__ != PB_OK) return st__; } while (0)
 
+/* Large batches of the 152-nt class: the two kernels side by side.  The sweep keeps the ALU pipe busy and little else; the lane kernel
+ * waits on dependent scalar code at the few warps its shared memory allows.  Cut into slices, the sweep of slice i + 1 (on the caller's
+ * stream) runs next to the lane kernel of slice i (on a second stream), each with fewer warps than alone -- XWO + LWO warps and their
+ * shared memory fit one SM together (the sweep's bases and planes share their memory for that) -- and each slice is a batch of its own:
+ * pointers offset, pair indices counted from the slice, only the general kernel's list is the whole batch's.  The first sweep and the
+ * last lane kernel have the SMs to themselves and run at full width. */
+constexpr int PB_OVL_SLICES = 16;
+static pb_status ensure_overlap(pb_context *ctx) {
+	if (ctx->ovl_ready)
+		return PB_OK;
+	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->ovl_stream, cudaStreamNonBlocking));
+	for (int k = 0; k < PB_OVL_SLICES + 2; k++)
+		CUDA_TRY(cudaEventCreateWithFlags(&ctx->ovl_ev[k], cudaEventDisableTiming));
+	CUDA_TRY(cudaMalloc(&ctx->d_ovl, PB_OVL_SLICES * PB_BINS_STRIDE * sizeof(unsigned)));
+	ctx->ovl_ready = true;
+	return PB_OK;
+}
+
+template <int NW, int XW>
+static pb_status overlap_sweep(pb_context *ctx, int cnt, const uint8_t *d_reads, const pb_pair_meta *meta, uint32_t *seeds, unsigned *bins, cudaStream_t stream) {
+	auto k = pbs::sweep_seed_kernel<NW, XW>;
+	constexpr size_t smem = pbs::sweep_smem_bytes<NW, XW>();
+	static bool configured[16] = { false };
+	if (!configured[ctx->device & 15]) {
+		CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		configured[ctx->device & 15] = true;
+	}
+	long long grid = (((long long) cnt + 31) / 32 + XW - 1) / XW;
+	if (grid > ctx->sm_count)
+		grid = ctx->sm_count;
+	const pbs::Muls mu = { 2u, 4u, 16u };
+	k<<<(unsigned) (grid < 1 ? 1 : grid), XW * 32, smem, stream>>>(ctx->d_params, cnt, d_reads, meta, seeds, bins, bins + 2 * pb::PB_SEED_BINS, mu, nullptr, nullptr);
+	CUDA_TRY(cudaGetLastError());
+	return PB_OK;
+}
+
+template <int LML, int LW>
+static pb_status overlap_lanes(pb_context *ctx, const LanesState &L, int cnt, int base, const uint32_t *seeds, const int *order, unsigned *bins, cudaStream_t stream) {
+	auto k = pbl::assemble_lanes_kernel<LML, LW>;
+	constexpr size_t smem = pbl::lanes_smem_bytes<LML, LW>();
+	static bool configured[16] = { false };
+	if (!configured[ctx->device & 15]) {
+		CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		configured[ctx->device & 15] = true;
+	}
+	long long grid = (((long long) cnt + 31) / 32 + LW - 1) / LW;
+	if (grid > ctx->sm_count)
+		grid = ctx->sm_count;
+	const size_t nt_row = L.seq_stride / 2;
+	k<<<(unsigned) (grid < 1 ? 1 : grid), LW * 32, smem, stream>>>(ctx->d_params, cnt, L.d_reads, L.d_meta + base, seeds, order, L.d_results + base,
+	                                                                L.d_seq_nt ? L.d_seq_nt + (size_t) base * nt_row : nullptr, (long long) L.seq_stride, L.d_counters,
+	                                                                L.d_list, L.d_count, ctx->d_defer_total, bins + 2 * pb::PB_SEED_BINS + 1, nullptr, base);
+	CUDA_TRY(cudaGetLastError());
+	return PB_OK;
+}
+
+template <int XWO, int LWO>
+static pb_status launch_lanes_overlap(pb_context *ctx, int n, const uint8_t *d_reads, const pb_pair_meta *d_meta, pb_pair_result *d_results,
+                                      uint8_t *d_seq_nt, size_t seq_stride, unsigned long long *d_counters, cudaStream_t stream, int slices) {
+	LanesState L = { ctx, n, 0, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, nullptr, nullptr, nullptr, 0 };
+	PB_TRY(lanes_prepare(L, false));
+	PB_TRY(ensure_overlap(ctx));
+	cudaStream_t aux = ctx->ovl_stream;
+	CUDA_TRY(cudaMemsetAsync(ctx->d_ovl, 0, PB_OVL_SLICES * PB_BINS_STRIDE * sizeof(unsigned), stream));
+	const bool timed = ctx->timing && stream == ctx->stream;
+	if (timed)
+		CUDA_TRY(cudaEventRecord(ctx->tev[0], stream));
+	CUDA_TRY(cudaEventRecord(ctx->ovl_ev[PB_OVL_SLICES], stream));
+	CUDA_TRY(cudaStreamWaitEvent(aux, ctx->ovl_ev[PB_OVL_SLICES], 0));
+	const int per = (((n + slices - 1) / slices) + 31) & ~31;
+	constexpr int SW = pb::seed_words(160);
+	int i = 0;
+	for (int base = 0; base < n; base += per, i++) {
+		const int cnt = n - base < per ? n - base : per;
+		unsigned *bins = ctx->d_ovl + (size_t) i * PB_BINS_STRIDE;
+		uint32_t *seeds = L.d_seeds + (size_t) base * SW;
+		int *order = ctx->d_order[0] + base;
+		if (i == 0)
+			PB_TRY((overlap_sweep<5, 21>(ctx, cnt, d_reads, d_meta + base, seeds, bins, stream)));
+		else
+			PB_TRY((overlap_sweep<5, XWO>(ctx, cnt, d_reads, d_meta + base, seeds, bins, stream)));
+		pb::bin_order_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, stream>>>(cnt, seeds, SW, pb::seed_mask_words(160) + 1, bins, order, nullptr, nullptr);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventRecord(ctx->ovl_ev[i], stream));
+		CUDA_TRY(cudaStreamWaitEvent(aux, ctx->ovl_ev[i], 0));
+		if (base + per >= n)
+			PB_TRY((overlap_lanes<152, 12>(ctx, L, cnt, base, seeds, order, bins, aux)));
+		else
+			PB_TRY((overlap_lanes<152, LWO>(ctx, L, cnt, base, seeds, order, bins, aux)));
+	}
+	CUDA_TRY(cudaEventRecord(ctx->ovl_ev[PB_OVL_SLICES + 1], aux));
+	CUDA_TRY(cudaStreamWaitEvent(stream, ctx->ovl_ev[PB_OVL_SLICES + 1], 0));
+	if (timed) {
+		CUDA_TRY(cudaEventRecord(ctx->tev[1], stream));
+		CUDA_TRY(cudaEventRecord(ctx->tev[2], stream));
+	}
+	ctx->lanes_pairs += (unsigned long long) n;
+	ctx->timing_overlap = true;
+	pb_status st = launch_assemble<160, false, 28, false>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, nullptr, seq_stride, d_counters, stream, false, L.d_list, L.d_count);
+	ctx->timing_overlap = false;
+	return st;
+}
+
 static pb_status launch_lanes(pb_context *ctx, int n, int max_len, const uint8_t *d_reads, const pb_pair_meta *d_meta,
                               pb_pair_result *d_results, uint8_t *d_seq_nt, size_t seq_stride,
                               unsigned long long *d_counters, cudaStream_t stream, bool sweep) {
+	/* experiment, off unless PANDASEQ_B200_OVERLAP=N (N slices) asks for it: large batches of the 152-nt class on the context's own
+	 * stream with the two kernels side by side, slice by slice.  Measured slower than back to back. */
+	static int overlap_cfg = -1;
+	if (overlap_cfg < 0) {
+		const char *env = getenv("PANDASEQ_B200_OVERLAP");
+		overlap_cfg = env ? atoi(env) : 0;
+		if (overlap_cfg > PB_OVL_SLICES)
+			overlap_cfg = PB_OVL_SLICES;
+	}
+	if (sweep && max_len <= 152 && overlap_cfg >= 2 && n >= (1 << 20) && stream == ctx->stream)
+		return launch_lanes_overlap<8, 8>(ctx, n, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, overlap_cfg);
 	LanesState L = { ctx, n, stream == ctx->copy_stream ? 1 : 0, d_reads, d_meta, d_results, d_seq_nt, seq_stride, d_counters, stream, nullptr, nullptr, nullptr, 0 };
 	/* one class in batch order while every read fits the 160-nt kernels (or the hash join is asked for, which takes whole
 	 * batches of reads up to 256 nt); by length class otherwise */

@@ -61,7 +61,7 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
                       const uint8_t *__restrict__ reads, const pb_pair_meta *__restrict__ meta,
                       const uint32_t *__restrict__ seeds, const int *__restrict__ order, pb_pair_result *__restrict__ results, uint8_t *__restrict__ seq_nt, long long seq_stride,
                       unsigned long long *__restrict__ counters, int *__restrict__ defer_list, int *__restrict__ defer_count,
-                      unsigned long long *__restrict__ defer_total, unsigned *__restrict__ next_batch, const int *__restrict__ order_n) {
+                      unsigned long long *__restrict__ defer_total, unsigned *__restrict__ next_batch, const int *__restrict__ order_n, int pair_base) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	using LA = LaneArea<ML>;
 	double *s_rec = reinterpret_cast<double *>(smem_raw);                 /* recon[2][48][48], row = quality a + 48 * match */
@@ -598,7 +598,7 @@ assemble_lanes_kernel(const pb_device_params *__restrict__ prm, int n,
 		if (m_defer) {
 			dbase = __shfl_sync(FULL, dbase, 0);
 			if (status == ST_DEFER)
-				defer_list[dbase + __popc(m_defer & pb::lanemask_lt())] = pair;
+				defer_list[dbase + __popc(m_defer & pb::lanemask_lt())] = pair + pair_base;      /* the list is the whole batch's: a slice's kernel counts from the slice */
 		}
 		__syncwarp();      /* every lane is done with its record before the next batch lands on it */
 		batch = batch1;

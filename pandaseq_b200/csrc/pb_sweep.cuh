@@ -337,13 +337,17 @@ template <int NW, typename PL> struct Resolver {
 namespace pbs {
 
 /* Per-warp shared memory: the 32 pairs' packed bases as the bulk copies land them, and the pairs' planes, word-major
- * (word w of lane l at [w][l]) so that a warp reading one word index never collides. */
+ * (word w of lane l at [w][l]) so that a warp reading one word index never collides.  The two share their memory: the bases
+ * are dead once every lane has built its planes (a __syncwarp() apart), and the next batch's copies are issued only after
+ * every lane is done with its planes. */
 template <int NW> struct SweepArea {
 	static constexpr int ML = 32 * NW;
 	static constexpr int NT_BYTES = ML;                                  /* 2 reads x ML / 2 bytes */
 	static constexpr int STRIDE = (((NT_BYTES + 15) / 16) | 1) * 16;     /* odd number of 16-byte units */
-	alignas(128) uint8_t nt[32 * STRIDE];
-	alignas(16) uint32_t planes[PlaneIndex<NW>::WORDS][32];
+	union alignas(128) {
+		uint8_t nt[32 * STRIDE];
+		uint32_t planes[PlaneIndex<NW>::WORDS][32];
+	};
 	alignas(8) uint64_t bar;
 };
 
@@ -411,6 +415,8 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 		const int fw = (F + 7) >> 3, rw = (R + 7) >> 3;
 		const unsigned bytes = flags ? 0u : (unsigned) ((fw + rw) * 4 + 15) & ~15u;
 		const unsigned total = __reduce_add_sync(pb::FULL, bytes);
+		/* the copies below (async proxy) land where this warp's lanes wrote their planes of the previous batch (generic proxy) */
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 		if (lane == 0)
 			pb::mbar_expect_tx(&wa.bar, total);
 		__syncwarp();
@@ -429,6 +435,7 @@ sweep_seed_kernel(const pb_device_params *__restrict__ prm, int n, const uint8_t
 			build_planes<NW>(nt + fw, Re, t0, t1, bad);
 			if (bad)
 				flags |= SEED_GENERAL;
+			__syncwarp();      /* the planes go where the bases were: every lane has read its own */
 #pragma unroll
 			for (int j = 0; j < NW; j++) {
 				fv[j] = lowbits(min(max(Fe - 32 * j, 0), 32));
