@@ -150,3 +150,9 @@ def test_reads_that_carry_their_primer_are_settled_after_one_sum():
         assert got == want == at + P + 1
         cases += 1
     assert stats["short"] >= cases - 3 and stats["exact"] <= cases + 30, (stats, cases)
+
+
+def test_what_the_bound_rests_on():
+    # every addend is a log-probability (<= 0), and qual_score_err falls with the quality: emax is its value at the read's lowest quality
+    assert (SCORE[:47] <= 0).all() and (SCORE_ERR[:47] <= 0).all()
+    assert (np.diff(SCORE_ERR[:47]) <= 0).all()
